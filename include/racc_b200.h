@@ -1,0 +1,162 @@
+/* racc_b200.h -- the drop-in boundary: C-ABI of the B200 ray-intersection engine.
+ *
+ * Plain C types only (pointers, sizes, opaque handles); no C++ or torch types cross it. The
+ * C++ `racc::` API in include/RayAccelerator.h (same names and layouts as the reference's
+ * /root/reference/RayAccelerator/RayAccelerator.h:25-116) is a thin caller of these entry points,
+ * and so are the Python mirror in rayaccel_b200/ and bench.py. Every entry point below names the
+ * reference interface it replaces. 0 = success unless stated; on failure racc_cuda_last_error()
+ * returns a thread-local message. Nothing here falls back to the CPU: without a CUDA device every
+ * compute entry point fails.
+ *
+ * Implemented in rayaccel_b200/csrc/ (capi.cu, traverse.cu, scene_build.cpp); built into
+ * rayaccel_b200/libracc_b200.so by __graft_entry__.build().
+ */
+#ifndef RACC_B200_H
+#define RACC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RACC_CUDA_ABI_VERSION 1
+
+typedef struct racc_cuda_scene racc_cuda_scene;   /* replaces racc::Scene        (Scene.h:15-21) */
+typedef struct racc_cuda_env racc_cuda_env;       /* replaces racc::Environment  (Environment.h:16-24) */
+
+/* One ray stream handed to the tester: replaces racc_internal::GpuRayStream
+ * (RayAccelerator.cpp:36-40) = racc::RayStream + its two cl_mem views. rays: count x 32 B
+ * racc::Ray; results: count x 16 B racc::Result, index-parallel to rays. */
+typedef struct {
+	const void* rays;
+	void* results;
+	uint32_t count;
+	uint32_t flags; /* RACC_CUDA_STREAM_* */
+} racc_cuda_stream_desc;
+
+#define RACC_CUDA_STREAM_DEVICE 0u /* rays/results are device pointers on the current device */
+#define RACC_CUDA_STREAM_HOST 1u   /* host pointers; the engine stages them (H2D, trace, D2H) */
+
+typedef struct {
+	uint32_t node_count;      /* inner nodes, 64 B each */
+	uint32_t pair_count;      /* triangle pairs incl. tail padding, 48 B each */
+	uint32_t real_pair_count; /* pairs referenced by leaves */
+	uint32_t remap_count;     /* 4 B words */
+	uint32_t depth;
+	uint32_t triangle_count;
+	float bounds_min[3];
+	float bounds_max[3];
+} racc_cuda_scene_info;
+
+/* Aggregate visit counters of a traced batch: the inputs of the algorithmic-bytes roofline
+ * (B_ray = 32 + 16 + 64*inner + 48*pairs + 4*[hit] + 64*[miss]). */
+typedef struct {
+	uint64_t rays;
+	uint64_t hits;
+	uint64_t inner_nodes;
+	uint64_t pairs_tested;
+} racc_cuda_counters;
+
+/* replaces racc::init() + the OpenCL device pick (RayAccelerator.cpp:417-423,463-478;
+ * Renderer/main.cpp:68-115). devices == NULL or n == 0: use the current CUDA device.
+ * Only devices[0] is bound to the calling process (one process per GPU). */
+int racc_cuda_init(const int* devices, int n);
+
+/* CUDA devices visible, or -1 if the runtime cannot be initialised (no fallback exists). */
+int racc_cuda_device_count(void);
+
+int racc_cuda_abi_version(void);
+
+const char* racc_cuda_last_error(void);
+
+/* replaces racc::createScene()'s GPU branch (Scene.cpp:216-349): host SAH build, pair merge,
+ * node packing, upload. verts4: nverts x float4 (w ignored); indices: nindices (multiple of 3).
+ * The caller keeps ownership of its arrays. NULL on failure. */
+racc_cuda_scene* racc_cuda_scene_create(const float* verts4, uint32_t nverts, const uint32_t* indices, uint32_t nindices);
+
+/* Upload prebuilt images (same byte formats) instead of building; used to trace the reference's
+ * own images and by the multi-GPU path to replicate one build. */
+racc_cuda_scene* racc_cuda_scene_create_from_images(const void* nodes, uint32_t node_count, const void* pairs,
+                                                    uint32_t pair_count, const uint32_t* remap, uint32_t remap_count);
+
+/* Host-only half of racc_cuda_scene_create (no CUDA call is made): builds the three images in
+ * host memory. Lets the scene build be checked against the reference builder on a machine without
+ * a GPU, and lets one build be uploaded to several devices. */
+typedef struct racc_cuda_host_images racc_cuda_host_images;
+racc_cuda_host_images* racc_cuda_build_images(const float* verts4, uint32_t nverts, const uint32_t* indices, uint32_t nindices);
+int racc_cuda_host_images_get_info(const racc_cuda_host_images* images, racc_cuda_scene_info* info);
+int racc_cuda_host_images_copy(const racc_cuda_host_images* images, void* nodes, void* pairs, uint32_t* remap);
+void racc_cuda_host_images_destroy(racc_cuda_host_images* images);
+
+/* replaces racc::destroy(Scene*) (Scene.cpp:359-372) */
+void racc_cuda_scene_destroy(racc_cuda_scene* scene);
+
+int racc_cuda_scene_get_info(const racc_cuda_scene* scene, racc_cuda_scene_info* info);
+
+/* Copies the host images out (any pointer may be NULL): what the reference keeps in
+ * scene->gpuNodes / gpuTriangles / gpuTriangleIndices (Scene.cpp:342-346). */
+int racc_cuda_scene_download(const racc_cuda_scene* scene, void* nodes, void* pairs, uint32_t* remap);
+
+/* replaces racc::createEnvironment() (Environment.cpp:13-60): rgba = width*height RGBA32F. */
+racc_cuda_env* racc_cuda_env_create(const float* rgba, uint32_t width, uint32_t height);
+
+/* replaces racc::destroy(Environment*) (Environment.cpp:62-67) */
+void racc_cuda_env_destroy(racc_cuda_env* env);
+
+/* replaces the body of gpuWorkerThread: 7x clSetKernelArg + clEnqueueNDRangeKernel
+ * (RayAccelerator.cpp:377-401) for one OR MORE ray streams in a single launch. env may be NULL
+ * (misses then return r=g=b=0). cuda_stream: a cudaStream_t (NULL = default stream).
+ * Asynchronous for DEVICE streams; HOST streams are staged through pinned memory on the same
+ * CUDA stream and are complete when racc_cuda_sync() returns. */
+int racc_cuda_trace(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_stream_desc* streams,
+                    uint32_t nstreams, void* cuda_stream);
+
+/* Same, additionally accumulating visit counters into *device_counters (a device pointer to a
+ * racc_cuda_counters that the caller zeroed). Slower; used for the roofline accounting only. */
+int racc_cuda_trace_counted(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_stream_desc* streams,
+                            uint32_t nstreams, void* cuda_stream, void* device_counters);
+
+/* replaces clFinish(queue) (RayAccelerator.cpp:403) */
+int racc_cuda_sync(void* cuda_stream);
+
+/* Number of engine kernels launched by this process so far (bench.py's gpu_launches). */
+uint64_t racc_cuda_launch_count(void);
+
+/* Engine tuning knob (not in the reference): which traversal kernel variant racc_cuda_trace uses.
+ * 0 = default. See DESIGN.md section 5. Returns the previous value. */
+int racc_cuda_set_variant(int variant);
+
+/* Launch-shape knobs for benchmark sweeps: key 0 variant, 1 threads per CTA (128/256/512/1024),
+ * 2 CTAs per SM (0 = as many as fit), 3 inner nodes staged in shared memory (-1 = as many as
+ * fit), 4 refill threshold (idle lanes per warp). Returns the previous value. Also settable
+ * through RACC_B200_VARIANT / _BLOCK / _CTAS_PER_SM / _SMEM_NODES / _FETCH_THRESHOLD. */
+int racc_cuda_set_tuning(int key, int value);
+
+/* ---- synthetic ray streams for the benchmark; not on the hot path ---- */
+
+/* Camera as Renderer/Camera.cpp:13-25 builds it; rays as Camera.cpp:55-114 (minT 0, maxT 1e6). */
+typedef struct {
+	float origin[3];
+	float view[3];
+	float right[3];
+	float up[3];
+} racc_cuda_camera;
+
+/* Primary rays for a width x height grid, `spp` samples per pixel, written to device memory
+ * (count = width*height*spp, sample-major). jitter_seed == 0: pixel centres. */
+int racc_cuda_generate_primary(const racc_cuda_camera* camera, uint32_t width, uint32_t height, uint32_t spp,
+                               uint32_t jitter_seed, void* device_rays, void* cuda_stream);
+
+/* One diffuse bounce (Renderer/PathTracingRenderer.cpp:405-422): for every HIT in results[],
+ * a cosine-hemisphere ray about the geometric normal flipped against the incoming direction,
+ * origin = hit + 1e-4*n, minT 1e-3, maxT 1e6; compacted, in arrival order, into device_out_rays.
+ * *device_out_count (device uint32, zeroed by the caller) receives the number written. */
+int racc_cuda_generate_bounce(const racc_cuda_scene* scene, const void* device_rays, const void* device_results,
+                              uint32_t count, uint32_t seed, void* device_out_rays, uint32_t* device_out_count,
+                              void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,195 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes bindings for the parity checker.
+
+`oracle/liboracle.so` is our CPU restatement of the reference hot path (racc_oracle.c, which
+cites /root/reference/RayAccelerator/Kernels.h line by line) and `oracle/_ref/libracc_ref.so`
+is the UNMODIFIED reference scene builder + light-probe sampler compiled with stand-in headers
+(oracle/ref_shim/). Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this package; the product (rayaccel_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "liboracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libracc_ref.so")
+
+INVALID = 0xFFFFFFFF
+
+RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("minT", "<f4"), ("dir", "<f4", 3), ("maxT", "<f4")])
+RESULT_DTYPE = np.dtype([("triangle", "<u4"), ("a", "<f4"), ("b", "<f4"), ("c", "<f4")])
+COUNTER_DTYPE = np.dtype([("inner", "<u2"), ("pairs", "<u2"), ("max_stack", "<u2"), ("hit", "<u2")])
+
+
+def build(ref: bool = True) -> None:
+    """Compile the checker (and, when /root/reference is present, oracle/_ref)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"] + (["ref"] if ref else []))
+
+
+class _Scene(ctypes.Structure):
+    _fields_ = [
+        ("nodes", ctypes.c_void_p), ("node_count", ctypes.c_uint32),
+        ("pairs", ctypes.c_void_p), ("pair_count", ctypes.c_uint32),
+        ("remap", ctypes.c_void_p), ("remap_count", ctypes.c_uint32),
+        ("env", ctypes.c_void_p), ("env_width", ctypes.c_uint32), ("env_height", ctypes.c_uint32),
+    ]
+
+
+class _RefImages(ctypes.Structure):
+    _fields_ = [
+        ("nodes", ctypes.c_void_p), ("nodes_bytes", ctypes.c_uint64),
+        ("pairs", ctypes.c_void_p), ("pairs_bytes", ctypes.c_uint64),
+        ("remap", ctypes.c_void_p), ("remap_bytes", ctypes.c_uint64),
+    ]
+
+
+_lib = None
+_ref = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        _lib = ctypes.CDLL(ORACLE_SO)
+        _lib.oracle_acosf.restype = ctypes.c_float
+        _lib.oracle_acosf.argtypes = [ctypes.c_float]
+    return _lib
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def ref() -> ctypes.CDLL:
+    global _ref
+    if _ref is None:
+        _ref = ctypes.CDLL(REF_SO)
+    return _ref
+
+
+def _p(a: np.ndarray) -> ctypes.c_void_p:
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class SceneImages:
+    """Host copies of the three scene images (+ optional light probe) the oracle traverses."""
+
+    def __init__(self, nodes: np.ndarray, pairs: np.ndarray, remap: np.ndarray, env: np.ndarray | None = None):
+        self.nodes = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1, 16)
+        self.pairs = np.ascontiguousarray(pairs, dtype=np.float32).reshape(-1, 12)
+        self.remap = np.ascontiguousarray(remap, dtype=np.uint32).reshape(-1)
+        self.env = None if env is None else np.ascontiguousarray(env, dtype=np.float32)
+        if self.env is not None:
+            assert self.env.ndim == 3 and self.env.shape[2] == 4
+
+    def c_struct(self) -> _Scene:
+        s = _Scene()
+        s.nodes, s.node_count = _p(self.nodes), self.nodes.shape[0]
+        s.pairs, s.pair_count = _p(self.pairs), self.pairs.shape[0]
+        s.remap, s.remap_count = _p(self.remap), self.remap.shape[0]
+        if self.env is not None:
+            s.env, s.env_height, s.env_width = _p(self.env), self.env.shape[0], self.env.shape[1]
+        return s
+
+    def digest(self) -> dict:
+        d = (ctypes.c_uint64 * 16)()
+        s = self.c_struct()
+        rc = lib().oracle_scene_digest(ctypes.byref(s), d)
+        if rc:
+            raise RuntimeError("oracle_scene_digest: malformed scene image")
+        return {
+            "inner": int(d[0]), "leaves": int(d[1]), "pairs": int(d[2]), "depth": int(d[3]),
+            "singletons": int(d[4]), "leaf_hist": [int(d[5 + i]) for i in range(7)], "hash": int(d[12]),
+        }
+
+
+def traverse(scene: SceneImages, rays: np.ndarray, counters: bool = False, threads: int = 0):
+    rays = np.ascontiguousarray(rays)
+    assert rays.dtype == RAY_DTYPE
+    n = rays.shape[0]
+    res = np.zeros(n, dtype=RESULT_DTYPE)
+    cnt = np.zeros(n, dtype=COUNTER_DTYPE) if counters else None
+    s = scene.c_struct()
+    rc = lib().oracle_traverse(ctypes.byref(s), _p(rays), ctypes.c_uint32(n), _p(res),
+                               _p(cnt) if counters else None, ctypes.c_int(threads))
+    if rc:
+        raise RuntimeError("oracle_traverse failed (stack overflow or malformed scene)")
+    return (res, cnt) if counters else res
+
+
+def env_sample(env: np.ndarray, dirs: np.ndarray) -> np.ndarray:
+    env = np.ascontiguousarray(env, dtype=np.float32)
+    dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+    out = np.zeros((dirs.shape[0], 3), dtype=np.float32)
+    f = lib().oracle_env_sample
+    for i in range(dirs.shape[0]):
+        f(_p(env), ctypes.c_uint32(env.shape[1]), ctypes.c_uint32(env.shape[0]), _p(dirs[i]), _p(out[i]))
+    return out
+
+
+def acosf(x: np.ndarray) -> np.ndarray:
+    f = lib().oracle_acosf
+    return np.array([f(float(v)) for v in np.asarray(x, dtype=np.float32).ravel()], dtype=np.float32)
+
+
+def brute_f64(verts4: np.ndarray, indices: np.ndarray, rays: np.ndarray, threads: int = 0):
+    verts4 = np.ascontiguousarray(verts4, dtype=np.float32).reshape(-1, 4)
+    indices = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+    rays = np.ascontiguousarray(rays)
+    n = rays.shape[0]
+    t = np.zeros(n, dtype=np.float64)
+    tri = np.zeros(n, dtype=np.uint32)
+    lib().oracle_brute_f64(_p(verts4), ctypes.c_uint32(verts4.shape[0]), _p(indices), ctypes.c_uint32(indices.shape[0] // 3),
+                           _p(rays), ctypes.c_uint32(n), _p(t), _p(tri), ctypes.c_int(threads))
+    return t, tri
+
+
+def tri_t_f64(verts4: np.ndarray, indices: np.ndarray, rays: np.ndarray, tri_ids: np.ndarray) -> np.ndarray:
+    verts4 = np.ascontiguousarray(verts4, dtype=np.float32).reshape(-1, 4)
+    indices = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+    rays = np.ascontiguousarray(rays)
+    tri_ids = np.ascontiguousarray(tri_ids, dtype=np.uint32)
+    t = np.zeros(rays.shape[0], dtype=np.float64)
+    lib().oracle_tri_t_f64(_p(verts4), _p(indices), _p(rays), _p(tri_ids), ctypes.c_uint32(rays.shape[0]), _p(t))
+    return t
+
+
+# ---- the unmodified reference (oracle/_ref) ------------------------------------------------
+
+def ref_build_scene(verts4: np.ndarray, indices: np.ndarray) -> SceneImages:
+    """racc::createScene() of the unmodified reference -> its GPU upload images."""
+    verts4 = np.ascontiguousarray(verts4, dtype=np.float32).reshape(-1, 4)
+    indices = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+    img = _RefImages()
+    rc = ref().ref_build_scene(_p(verts4), ctypes.c_uint32(verts4.shape[0]), _p(indices),
+                               ctypes.c_uint32(indices.shape[0]), ctypes.byref(img))
+    if rc:
+        raise RuntimeError("ref_build_scene failed")
+    try:
+        def grab(ptr, nbytes, dtype):
+            buf = (ctypes.c_char * nbytes).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype).copy()
+        return SceneImages(grab(img.nodes, img.nodes_bytes, np.float32),
+                           grab(img.pairs, img.pairs_bytes, np.float32),
+                           grab(img.remap, img.remap_bytes, np.uint32))
+    finally:
+        ref().ref_free_scene_images(ctypes.byref(img))
+
+
+def ref_env_sample(env: np.ndarray, dirs: np.ndarray) -> np.ndarray:
+    """racc_internal::sample() of the unmodified reference (Environment.h:27-82)."""
+    env = np.ascontiguousarray(env, dtype=np.float32)
+    d4 = np.zeros((np.asarray(dirs).reshape(-1, 3).shape[0], 4), dtype=np.float32)
+    d4[:, :3] = np.asarray(dirs, dtype=np.float32).reshape(-1, 3)
+    out = np.zeros_like(d4)
+    rc = ref().ref_env_sample(_p(env), ctypes.c_uint32(env.shape[1]), ctypes.c_uint32(env.shape[0]),
+                              _p(d4), ctypes.c_uint32(d4.shape[0]), _p(out))
+    if rc:
+        raise RuntimeError("ref_env_sample failed")
+    return out[:, :3]

@@ -1,0 +1,530 @@
+/* racc_oracle.c -- TEST INFRASTRUCTURE ONLY (the parity checker). See racc_oracle.h for the
+ * scope, the pin status ("parity unpinned" for traversal: the reference cannot execute here) and
+ * the pinned-arithmetic rules. Every function cites the reference lines it restates; paths are
+ * relative to /root/reference/.
+ *
+ * Build: oracle/Makefile (gcc -O2 -mfma -ffp-contract=off, pthreads). */
+#include "racc_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <xmmintrin.h>
+#include <pmmintrin.h>
+#include <pthread.h>
+#include <unistd.h>
+
+/* ------------------------------------------------------------------------------------------ */
+/* bit helpers                                                                                 */
+
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+/* Reference threads run with FTZ+DAZ (Threading.h:77-79, RayAccelerator.cpp:417-420). */
+static inline unsigned ftz_on(void) {
+	unsigned saved = _mm_getcsr();
+	_MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
+	_MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_ON);
+	return saved;
+}
+
+static inline float flush(float x) {
+	uint32_t u = f2u(x);
+	return (u & 0x7f800000u) ? x : u2f(u & 0x80000000u);
+}
+
+/* minNum / maxNum with -0 < +0 and subnormal inputs flushed: the semantics of the GPU's
+ * min.ftz.f32 / max.ftz.f32, which OpenCL fmin/fmax (Kernels.h:125-129) map onto. */
+static inline float pmin(float a, float b) {
+	a = flush(a); b = flush(b);
+	if (a != a) return b;
+	if (b != b) return a;
+	if (a < b) return a;
+	if (b < a) return b;
+	return u2f(f2u(a) | f2u(b)); /* equal: only +-0 can differ, prefer -0 */
+}
+static inline float pmax(float a, float b) {
+	a = flush(a); b = flush(b);
+	if (a != a) return b;
+	if (b != b) return a;
+	if (a > b) return a;
+	if (b > a) return b;
+	return u2f(f2u(a) & f2u(b)); /* equal: prefer +0 */
+}
+
+typedef struct { float x, y, z; } v3;
+
+/* dot(a,b), association pinned (racc_oracle.h) */
+static inline float dot3(v3 a, v3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+
+/* mad_cross, Kernels.h:23-25:  mad(e1.y,e2.z, -e1.z*e2.y), ... */
+static inline v3 mad_cross(v3 e1, v3 e2) {
+	v3 r;
+	r.x = fmaf(e1.y, e2.z, -(e1.z * e2.y));
+	r.y = fmaf(e1.z, e2.x, -(e1.x * e2.z));
+	r.z = fmaf(e1.x, e2.y, -(e1.y * e2.x));
+	return r;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* pinned acos                                                                                 */
+
+/* acos(x) for the light-probe angular map (Kernels.h:217). fdlibm-style: a rational
+ * approximation R(z) ~ (asin(sqrt z)/sqrt z - 1) on z in [0, 0.25], evaluated with a fixed
+ * sequence of binary32 operations so that CPU and GPU agree bit for bit. |error| < 2 ulp
+ * (checked against double acos in tests/test_oracle_kat.py). */
+float oracle_acosf(float x) {
+	const float pio2 = 1.57079637050628662109375f;  /* 0x3fc90fdb */
+	const float pi   = 3.1415927410125732421875f;   /* 0x40490fdb */
+	const float pS0 =  1.6666586697e-01f;
+	const float pS1 = -4.2743422091e-02f;
+	const float pS2 = -8.6563630030e-03f;
+	const float qS1 = -7.0662963390e-01f;
+	float ax = fabsf(x);
+	if (!(ax < 1.0f)) {
+		if (x != x) return x;
+		return x > 0.0f ? 0.0f : pi;
+	}
+	if (ax <= 0.5f) {
+		float z = x * x;
+		float p = z * fmaf(z, fmaf(z, pS2, pS1), pS0);
+		float q = fmaf(z, qS1, 1.0f);
+		float r = p / q;
+		return pio2 - fmaf(x, r, x);
+	}
+	{
+		float z = (1.0f - ax) * 0.5f;
+		float s = sqrtf(z);
+		float p = z * fmaf(z, fmaf(z, pS2, pS1), pS0);
+		float q = fmaf(z, qS1, 1.0f);
+		float r = p / q;
+		float w = 2.0f * fmaf(s, r, s);
+		return x > 0.0f ? w : pi - w;
+	}
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* light probe, Kernels.h:137,213-221                                                          */
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* floor(x) to int for the texel index, saturated well outside the image so the int conversion
+ * is defined for any finite or infinite x. NaN maps to 0. */
+static inline int texel_floor(float x, float* frac) {
+	float f = floorf(x);
+	*frac = x - f;
+	if (!(f > -4.0f)) { if (f != f) { *frac = 0.0f; return 0; } return -4; }
+	if (f > 1.0e9f) return 1000000000;
+	return (int)f;
+}
+
+void oracle_env_sample(const float* env, uint32_t width, uint32_t height, const float d[3], float rgb[3]) {
+	unsigned saved = ftz_on();
+	/* Kernels.h:216  rlen = native_rsqrt(d.y*d.y + d.z*d.z) */
+	float s = d[1] * d[1] + d[2] * d[2];
+	float rlen = 1.0f / sqrtf(s);
+	/* Kernels.h:217  r = (rlen > 1e+6f) ? 0 : acos(-d.x)*(1/(2*3.141593f))*rlen */
+	const float inv2pi = 1.0f / (2.0f * 3.141593f);
+	float r = (rlen > 1e+6f) ? 0.0f : (oracle_acosf(-d[0]) * inv2pi) * rlen;
+	/* Kernels.h:218-219 */
+	float u = 0.5f - r * d[2];
+	float v = 0.5f - r * d[1];
+	/* read_imagef, normalized coords, CLK_ADDRESS_CLAMP_TO_EDGE, CLK_FILTER_LINEAR
+	 * (OpenCL 1.2 spec 8.2): i0 = floor(u*w - 0.5), a = frac(u*w - 0.5), clamp indices. */
+	float fu = u * (float)(int)width - 0.5f;
+	float fv = v * (float)(int)height - 0.5f;
+	float a, b;
+	int i0 = texel_floor(fu, &a);
+	int j0 = texel_floor(fv, &b);
+	int i1 = clampi(i0 + 1, 0, (int)width - 1);
+	int j1 = clampi(j0 + 1, 0, (int)height - 1);
+	i0 = clampi(i0, 0, (int)width - 1);
+	j0 = clampi(j0, 0, (int)height - 1);
+	const float* t00 = env + 4 * ((size_t)j0 * width + (size_t)i0);
+	const float* t10 = env + 4 * ((size_t)j0 * width + (size_t)i1);
+	const float* t01 = env + 4 * ((size_t)j1 * width + (size_t)i0);
+	const float* t11 = env + 4 * ((size_t)j1 * width + (size_t)i1);
+	float na = 1.0f - a, nb = 1.0f - b;
+	float w00 = na * nb, w10 = a * nb, w01 = na * b, w11 = a * b;
+	for (int c = 0; c < 3; ++c)
+		rgb[c] = ((w00 * t00[c] + w10 * t10[c]) + w01 * t01[c]) + w11 * t11[c];
+	_mm_setcsr(saved);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* intersection primitives                                                                     */
+
+typedef struct {
+	v3 o, d;       /* origin; direction after the epsilon clamp */
+	float tNear;   /* RAY_NEAR */
+	float tFar;    /* RAY_FAR: shrinks as hits are found */
+} ray_state;
+
+typedef struct { uint32_t index; float t, u, v; } hit_state;
+
+/* trianglePairIntersect, Kernels.h:36-115. Returns the new RAY_FAR. */
+static inline float pair_intersect(const float* pairs, uint32_t index, const ray_state* ray, hit_state* hit) {
+	const float* t0 = pairs + 12 * (size_t)index;
+	const float* t1 = t0 + 4;
+	const float* t2 = t0 + 8;
+
+	float tNear = ray->tNear;
+	float tMax = ray->tFar;
+	v3 ro = ray->o, rd = ray->d;
+
+	v3 e1 = { t0[0], t0[1], t0[2] };
+	v3 e2 = { t1[0], t1[1], t1[2] };
+	v3 e3 = { t0[3], t1[3], t2[3] };
+	v3 v0 = { t2[0], t2[1], t2[2] };
+
+	v3 n1 = mad_cross(e1, e2);
+	v3 n2 = mad_cross(e3, e1);
+
+	v3 C = { v0.x - ro.x, v0.y - ro.y, v0.z - ro.z };
+	v3 R = mad_cross(rd, C);
+
+	float det1 = dot3(n1, rd);
+	float det2 = dot3(n2, rd);
+
+	uint32_t sgnDet1 = f2u(det1) & 0x80000000u;
+	uint32_t sgnDet2 = f2u(det2) & 0x80000000u;
+
+	float dRe1 = dot3(R, e1);
+	int32_t iU1 = (int32_t)(f2u(dot3(R, e2)) ^ sgnDet1);
+	int32_t iV1 = (int32_t)(f2u(dRe1) ^ sgnDet1);
+	int32_t iU2 = (int32_t)(f2u(-dRe1) ^ sgnDet2);
+	int32_t iV2 = (int32_t)(f2u(-dot3(R, e3)) ^ sgnDet2);
+
+	if (((iU1 | iV1) & (iU2 | iV2)) < 0)
+		return tMax;
+
+	int outside1 = (iU1 | iV1) < 0;
+	int outside2 = (iU2 | iV2) < 0;
+
+	float U1 = u2f((uint32_t)iU1), V1 = u2f((uint32_t)iV1);
+	float U2 = u2f((uint32_t)iU2), V2 = u2f((uint32_t)iV2);
+
+	float absDet1 = fabsf(det1);
+	float absDet2 = fabsf(det2);
+
+	float W1 = (absDet1 - U1) - V1;
+	float W2 = (absDet2 - U2) - V2;
+
+	float T1 = u2f(f2u(dot3(n1, C)) ^ sgnDet1);
+	float T2 = u2f(f2u(dot3(n2, C)) ^ sgnDet2);
+
+	outside1 = outside1 || (W1 < 0.0f || T1 <= absDet1 * tNear || T1 > absDet1 * tMax);
+	outside2 = outside2 || (W2 < 0.0f || T2 <= absDet2 * tNear || T2 > absDet2 * tMax);
+
+	if (outside1 && outside2)
+		return tMax;
+
+	index = index * 2;
+
+	if ((!outside2 && outside1) || (!outside1 && !outside2 && T1 * absDet2 > T2 * absDet1)) {
+		absDet1 = absDet2;
+		T1 = T2;
+		U1 = U2;
+		V1 = V2;
+		++index;
+	}
+
+	float rcpAbsDet1 = 1.0f / absDet1; /* native_recip, pinned to IEEE division */
+	float t = T1 * rcpAbsDet1;
+	float u = U1 * rcpAbsDet1;
+	float v = V1 * rcpAbsDet1;
+
+	hit->index = index;
+	hit->t = t;
+	hit->u = u;
+	hit->v = v;
+	return t;
+}
+
+/* aabbIntersect, Kernels.h:117-135 */
+static inline float aabb_intersect(v3 mn, v3 mx, float t0, float t1, v3 invDir, v3 OoD) {
+	float rayFar = t1;
+	float nx = fmaf(mn.x, invDir.x, OoD.x), ny = fmaf(mn.y, invDir.y, OoD.y), nz = fmaf(mn.z, invDir.z, OoD.z);
+	float fx = fmaf(mx.x, invDir.x, OoD.x), fy = fmaf(mx.y, invDir.y, OoD.y), fz = fmaf(mx.z, invDir.z, OoD.z);
+	float minx = pmin(nx, fx), miny = pmin(ny, fy), minz = pmin(nz, fz);
+	float maxx = pmax(nx, fx), maxy = pmax(ny, fy), maxz = pmax(nz, fz);
+	t0 = pmax(pmax(t0, minx), pmax(miny, minz));
+	t1 = pmin(pmin(t1, maxx), pmin(maxy, maxz));
+	if (t0 > t1)
+		return rayFar;
+	return t0;
+}
+
+#define ORACLE_STACK 64 /* Kernels.h:166 */
+
+/* traversal, Kernels.h:141-242, one ray. Returns 0, or -1 on stack overflow / bad reference. */
+static int traverse_one(const oracle_scene* sc, const oracle_ray* in, oracle_result* out, oracle_counters* cnt) {
+	ray_state ray;
+	ray.o.x = in->origin[0]; ray.o.y = in->origin[1]; ray.o.z = in->origin[2];
+	ray.d.x = in->dir[0]; ray.d.y = in->dir[1]; ray.d.z = in->dir[2];
+	ray.tNear = in->minT;
+	ray.tFar = in->maxT;
+
+	/* Kernels.h:149-157 */
+	const float epsilon = 1e-10f;
+	if (fabsf(ray.d.x) < epsilon) ray.d.x = copysignf(epsilon, ray.d.x);
+	if (fabsf(ray.d.y) < epsilon) ray.d.y = copysignf(epsilon, ray.d.y);
+	if (fabsf(ray.d.z) < epsilon) ray.d.z = copysignf(epsilon, ray.d.z);
+
+	/* Kernels.h:159-160 */
+	v3 invDir = { 1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z };
+	v3 OoD = { -ray.o.x * invDir.x, -ray.o.y * invDir.y, -ray.o.z * invDir.z };
+
+	hit_state hit = { 0xffffffffu, ray.tFar, 0.0f, 0.0f }; /* Kernels.h:162 */
+
+	uint32_t node = 0x80000000u; /* Kernels.h:164 */
+	uint32_t stack[ORACLE_STACK];
+	unsigned stackHead = 0;
+	unsigned nInner = 0, nPairs = 0, maxStack = 0;
+	const uint32_t* nodesU = (const uint32_t*)sc->nodes;
+
+	for (;;) {
+		if (node & 0x80000000u) {
+			node &= ~0x80000000u;
+			if (node >= sc->node_count) return -1;
+			const float* d = sc->nodes + 16 * (size_t)node;
+			uint32_t childFirst = nodesU[16 * (size_t)node + 2];
+			uint32_t childLast = nodesU[16 * (size_t)node + 3];
+			++nInner;
+
+			v3 firstMin = { d[4], d[5], d[6] };
+			v3 firstMax = { d[7], d[8], d[9] };
+			v3 lastMin = { d[10], d[11], d[12] };
+			v3 lastMax = { d[13], d[14], d[15] };
+
+			float tRay = ray.tFar;
+			float tFirst = aabb_intersect(firstMin, firstMax, ray.tNear, ray.tFar, invDir, OoD);
+			float tLast = aabb_intersect(lastMin, lastMax, ray.tNear, ray.tFar, invDir, OoD);
+
+			float firstDiff = tRay - tFirst;
+			float lastDiff = tRay - tLast;
+			if (firstDiff + lastDiff != 0.0f) { /* Kernels.h:192 */
+				int sgn = (f2u(tLast - tFirst) >> 31) != 0; /* signbit, Kernels.h:193 */
+				if (pmax(tFirst, tLast) != tRay) { /* both hit: push the far one, Kernels.h:194-195 */
+					if (stackHead >= ORACLE_STACK) return -1;
+					stack[stackHead++] = sgn ? childFirst : childLast;
+					if (stackHead > maxStack) maxStack = stackHead;
+				}
+				node = sgn ? childLast : childFirst; /* Kernels.h:196 */
+				continue;
+			}
+		}
+		else {
+			uint32_t first = node & 0xffffffu; /* Kernels.h:201-204 */
+			uint32_t last = first + (node >> 24);
+			if (last > sc->pair_count) return -1;
+			for (uint32_t i = first; i < last; ++i) {
+				ray.tFar = pair_intersect(sc->pairs, i, &ray, &hit);
+				++nPairs;
+			}
+		}
+		if (!stackHead)
+			break;
+		node = stack[--stackHead];
+	}
+
+	if (hit.index == 0xffffffffu) { /* Kernels.h:213-222 */
+		float d[3] = { ray.d.x, ray.d.y, ray.d.z };
+		float rgb[3] = { 0.0f, 0.0f, 0.0f };
+		if (sc->env)
+			oracle_env_sample(sc->env, sc->env_width, sc->env_height, d, rgb);
+		out->triangle = ORACLE_INVALID_TRIANGLE;
+		out->a = rgb[0]; out->b = rgb[1]; out->c = rgb[2];
+	}
+	else { /* Kernels.h:223-239 */
+		if (hit.index >= sc->remap_count) return -1;
+		uint32_t index = sc->remap[hit.index];
+		uint32_t edge = index >> 30;
+		index &= 0x3fffffffu;
+		float bx = hit.u, by = hit.v, bz = (1.0f - hit.u) - hit.v;
+		float u = bx, v = by;
+		if (edge == 1) { u = bz; v = bx; }      /* barys.zxy */
+		else if (edge == 2) { u = by; v = bz; } /* barys.yzx */
+		out->triangle = index;
+		out->a = hit.t; out->b = u; out->c = v;
+	}
+	if (cnt) {
+		cnt->inner = (uint16_t)(nInner > 65535 ? 65535 : nInner);
+		cnt->pairs = (uint16_t)(nPairs > 65535 ? 65535 : nPairs);
+		cnt->max_stack = (uint16_t)maxStack;
+		cnt->hit = hit.index != 0xffffffffu;
+	}
+	return 0;
+}
+
+/* minimal fork-join helper (pthreads; no OpenMP dependency) */
+typedef struct {
+	void (*body)(void* ctx, int64_t chunk);
+	void* ctx;
+	int64_t nchunks;
+	volatile int64_t next;
+} pfor_job;
+
+static void* pfor_worker(void* p) {
+	pfor_job* job = (pfor_job*)p;
+	unsigned saved = ftz_on();
+	for (;;) {
+		int64_t c = __sync_fetch_and_add(&job->next, 1);
+		if (c >= job->nchunks) break;
+		job->body(job->ctx, c);
+	}
+	_mm_setcsr(saved);
+	return 0;
+}
+
+static void parallel_for(int threads, int64_t nchunks, void (*body)(void*, int64_t), void* ctx) {
+	if (threads <= 0) threads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+	if (threads < 1) threads = 1;
+	if (threads > 256) threads = 256;
+	if ((int64_t)threads > nchunks) threads = nchunks > 0 ? (int)nchunks : 1;
+	pfor_job job = { body, ctx, nchunks, 0 };
+	pthread_t tid[256];
+	for (int i = 1; i < threads; ++i) pthread_create(&tid[i], 0, pfor_worker, &job);
+	pfor_worker(&job);
+	for (int i = 1; i < threads; ++i) pthread_join(tid[i], 0);
+}
+
+int oracle_hardware_threads(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); }
+
+typedef struct {
+	const oracle_scene* scene; const oracle_ray* rays; uint32_t count;
+	oracle_result* results; oracle_counters* counters; volatile int err;
+} trav_ctx;
+
+/* chunks of 1024 rays, the reference's cpuTestBatch (RayAccelerator.cpp:438) */
+#define TRAV_CHUNK 1024
+
+static void trav_body(void* p, int64_t c) {
+	trav_ctx* t = (trav_ctx*)p;
+	int64_t lo = c * TRAV_CHUNK, hi = lo + TRAV_CHUNK < (int64_t)t->count ? lo + TRAV_CHUNK : (int64_t)t->count;
+	for (int64_t i = lo; i < hi; ++i)
+		if (traverse_one(t->scene, t->rays + i, t->results + i, t->counters ? t->counters + i : 0))
+			t->err = -1;
+}
+
+int oracle_traverse(const oracle_scene* scene, const oracle_ray* rays, uint32_t count,
+                    oracle_result* results, oracle_counters* counters, int threads) {
+	trav_ctx t = { scene, rays, count, results, counters, 0 };
+	parallel_for(threads, ((int64_t)count + TRAV_CHUNK - 1) / TRAV_CHUNK, trav_body, &t);
+	return t.err;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* independent fp64 arbiter (textbook Moller-Trumbore, no relation to the pair formulation)    */
+
+static inline double tri_t_f64(const float* verts4, const uint32_t* tri, const oracle_ray* r) {
+	const float* p0 = verts4 + 4 * (size_t)tri[0];
+	const float* p1 = verts4 + 4 * (size_t)tri[1];
+	const float* p2 = verts4 + 4 * (size_t)tri[2];
+	double e1x = (double)p1[0] - p0[0], e1y = (double)p1[1] - p0[1], e1z = (double)p1[2] - p0[2];
+	double e2x = (double)p2[0] - p0[0], e2y = (double)p2[1] - p0[1], e2z = (double)p2[2] - p0[2];
+	double dx = r->dir[0], dy = r->dir[1], dz = r->dir[2];
+	double px = dy * e2z - dz * e2y, py = dz * e2x - dx * e2z, pz = dx * e2y - dy * e2x;
+	double det = e1x * px + e1y * py + e1z * pz;
+	if (det == 0.0) return INFINITY;
+	double inv = 1.0 / det;
+	double tx = (double)r->origin[0] - p0[0], ty = (double)r->origin[1] - p0[1], tz = (double)r->origin[2] - p0[2];
+	double u = (tx * px + ty * py + tz * pz) * inv;
+	if (u < 0.0 || u > 1.0) return INFINITY;
+	double qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+	double v = (dx * qx + dy * qy + dz * qz) * inv;
+	if (v < 0.0 || u + v > 1.0) return INFINITY;
+	double t = (e2x * qx + e2y * qy + e2z * qz) * inv;
+	if (!(t > (double)r->minT) || !(t <= (double)r->maxT)) return INFINITY; /* Kernels.h:88 interval */
+	return t;
+}
+
+typedef struct {
+	const float* verts4; const uint32_t* indices; uint32_t ntris;
+	const oracle_ray* rays; uint32_t count; double* t_min; uint32_t* tri_min;
+} brute_ctx;
+
+#define BRUTE_CHUNK 16
+
+static void brute_body(void* p, int64_t c) {
+	brute_ctx* b = (brute_ctx*)p;
+	int64_t lo = c * BRUTE_CHUNK, hi = lo + BRUTE_CHUNK < (int64_t)b->count ? lo + BRUTE_CHUNK : (int64_t)b->count;
+	for (int64_t i = lo; i < hi; ++i) {
+		double best = INFINITY;
+		uint32_t id = ORACLE_INVALID_TRIANGLE;
+		for (uint32_t k = 0; k < b->ntris; ++k) {
+			double t = tri_t_f64(b->verts4, b->indices + 3 * (size_t)k, b->rays + i);
+			if (t < best) { best = t; id = k; }
+		}
+		b->t_min[i] = best;
+		b->tri_min[i] = id;
+	}
+}
+
+int oracle_brute_f64(const float* verts4, uint32_t nverts, const uint32_t* indices, uint32_t ntris,
+                     const oracle_ray* rays, uint32_t count, double* t_min, uint32_t* tri_min, int threads) {
+	(void)nverts;
+	brute_ctx b = { verts4, indices, ntris, rays, count, t_min, tri_min };
+	parallel_for(threads, ((int64_t)count + BRUTE_CHUNK - 1) / BRUTE_CHUNK, brute_body, &b);
+	return 0;
+}
+
+int oracle_tri_t_f64(const float* verts4, const uint32_t* indices, const oracle_ray* rays,
+                     const uint32_t* tri_ids, uint32_t count, double* t_out) {
+	for (uint32_t i = 0; i < count; ++i)
+		t_out[i] = tri_ids[i] == ORACLE_INVALID_TRIANGLE ? INFINITY
+		         : tri_t_f64(verts4, indices + 3 * (size_t)tri_ids[i], rays + i);
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* numbering-independent structural digest                                                     */
+
+static inline uint64_t fnv(uint64_t h, const void* p, size_t n) {
+	const unsigned char* b = (const unsigned char*)p;
+	for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+	return h;
+}
+
+int oracle_scene_digest(const oracle_scene* sc, uint64_t digest[16]) {
+	memset(digest, 0, 16 * sizeof(uint64_t));
+	if (!sc->node_count) return -1;
+	typedef struct { uint32_t ref; uint32_t depth; } item;
+	size_t cap = (size_t)sc->node_count * 2 + 16;
+	item* st = (item*)malloc(cap * sizeof(item));
+	size_t top = 0;
+	uint64_t h = 14695981039346656037ull;
+	const uint32_t* nodesU = (const uint32_t*)sc->nodes;
+	st[top].ref = 0x80000000u; st[top].depth = 1; ++top;
+	int rc = 0;
+	while (top) {
+		item it = st[--top];
+		if (it.depth > digest[3]) digest[3] = it.depth;
+		if (it.ref & 0x80000000u) {
+			uint32_t n = it.ref & 0x7fffffffu;
+			if (n >= sc->node_count || top + 2 > cap) { rc = -1; break; }
+			digest[0]++;
+			h = fnv(h, sc->nodes + 16 * (size_t)n + 4, 48); /* the two child boxes */
+			/* visit first child before last child */
+			st[top].ref = nodesU[16 * (size_t)n + 3]; st[top].depth = it.depth + 1; ++top;
+			st[top].ref = nodesU[16 * (size_t)n + 2]; st[top].depth = it.depth + 1; ++top;
+		}
+		else {
+			uint32_t first = it.ref & 0xffffffu, cnt = it.ref >> 24;
+			if (first + cnt > sc->pair_count) { rc = -1; break; }
+			digest[1]++;
+			digest[2] += cnt;
+			if (cnt >= 1 && cnt <= 7) digest[4 + cnt]++;
+			h = fnv(h, &cnt, 4);
+			for (uint32_t i = first; i < first + cnt; ++i) {
+				const float* p = sc->pairs + 12 * (size_t)i;
+				if (p[3] == -p[0] && p[7] == -p[1] && p[11] == -p[2]) digest[4]++; /* p3 == p1 */
+				h = fnv(h, p, 48);
+				h = fnv(h, sc->remap + 2 * (size_t)i, 8);
+			}
+		}
+	}
+	digest[12] = h;
+	free(st);
+	return rc;
+}

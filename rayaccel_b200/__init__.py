@@ -1,0 +1,11 @@
+"""rayaccel_b200 -- B200-native wavefront ray-intersection engine behind the RayAccelerator API.
+
+The package holds only the hot path of rasmusbarr/rayaccel: scene images (BVH2 + triangle pairs),
+the sm_100a traversal kernels and the C-ABI (csrc/, include/racc_b200.h), plus this thin Python
+mirror of the reference's interface. There is no CPU fallback.
+"""
+from .api import (INVALID_TRIANGLE, RAY_DTYPE, RESULT_DTYPE, Environment, HostImages, Scene, create_environment,  # noqa: F401
+                  create_scene, create_scene_from_images, device_count, generate_bounce, generate_primary, init,
+                  launch_count, set_tuning, sync, trace_device, trace_host)
+from ._lib import EngineError  # noqa: F401
+from .scene_io import Camera, SceneFile, load_scene, synthetic_triangles  # noqa: F401

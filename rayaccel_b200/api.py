@@ -1,0 +1,221 @@
+"""Python mirror of the reference's public interface for the intersection path.
+
+Names and argument meaning follow /root/reference/RayAccelerator/RayAccelerator.h:95-115
+(`create_scene` = racc::createScene, `create_environment` = racc::createEnvironment,
+`destroy`, and ray streams of racc::Ray / racc::Result records). Everything is executed by the
+CUDA engine behind the C-ABI in include/racc_b200.h; this file only marshals pointers.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import Counters, EngineError, SceneInfo, StreamDesc
+from .scene_io import Camera
+
+INVALID_TRIANGLE = 0xFFFFFFFF  # racc::invalidTriangle, RayAccelerator.h:26
+
+# racc::Ray (RayAccelerator.h:59-64) and racc::Result (:66-76)
+RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("minT", "<f4"), ("dir", "<f4", 3), ("maxT", "<f4")])
+RESULT_DTYPE = np.dtype([("triangle", "<u4"), ("a", "<f4"), ("b", "<f4"), ("c", "<f4")])
+
+NODE_BYTES, PAIR_BYTES = 64, 48
+
+
+def init(device: int | None = None) -> None:
+    """racc::init(): binds the calling process to one CUDA device."""
+    lib = _lib.load()
+    if device is None:
+        _lib.check(lib.racc_cuda_init(None, 0), "racc_cuda_init")
+    else:
+        arr = (ctypes.c_int * 1)(device)
+        _lib.check(lib.racc_cuda_init(arr, 1), "racc_cuda_init")
+
+
+def device_count() -> int:
+    return _lib.load().racc_cuda_device_count()
+
+
+def _ptr(a: np.ndarray) -> ctypes.c_void_p:
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _info_dict(info: SceneInfo) -> dict:
+    return {
+        "node_count": info.node_count, "pair_count": info.pair_count, "real_pair_count": info.real_pair_count,
+        "remap_count": info.remap_count, "depth": info.depth, "triangle_count": info.triangle_count,
+        "bounds_min": tuple(info.bounds_min), "bounds_max": tuple(info.bounds_max),
+    }
+
+
+class HostImages:
+    """The three scene images in host memory (no CUDA involved): racc_cuda_build_images."""
+
+    def __init__(self, vertices: np.ndarray, indices: np.ndarray):
+        lib = _lib.load()
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 4)
+        i = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        self._h = _lib.check_ptr(lib.racc_cuda_build_images(_ptr(v), v.shape[0], _ptr(i), i.shape[0]), "racc_cuda_build_images")
+        info = SceneInfo()
+        _lib.check(lib.racc_cuda_host_images_get_info(self._h, ctypes.byref(info)), "racc_cuda_host_images_get_info")
+        self.info = _info_dict(info)
+        self.nodes = np.zeros((info.node_count, 16), dtype=np.float32)
+        self.pairs = np.zeros((info.pair_count, 12), dtype=np.float32)
+        self.remap = np.zeros(info.remap_count, dtype=np.uint32)
+        _lib.check(lib.racc_cuda_host_images_copy(self._h, _ptr(self.nodes), _ptr(self.pairs), _ptr(self.remap)), "racc_cuda_host_images_copy")
+        lib.racc_cuda_host_images_destroy(self._h)
+        self._h = None
+
+
+class Scene:
+    """racc::Scene. Immutable after creation; may be shared by successive traces."""
+
+    def __init__(self, handle):
+        self._h = handle
+        info = SceneInfo()
+        _lib.check(_lib.load().racc_cuda_scene_get_info(self._h, ctypes.byref(info)), "racc_cuda_scene_get_info")
+        self.info = _info_dict(info)
+
+    def download(self):
+        """(nodes, pairs, remap) as the kernel sees them (read back from the device)."""
+        nodes = np.zeros((self.info["node_count"], 16), dtype=np.float32)
+        pairs = np.zeros((self.info["pair_count"], 12), dtype=np.float32)
+        remap = np.zeros(self.info["remap_count"], dtype=np.uint32)
+        _lib.check(_lib.load().racc_cuda_scene_download(self._h, _ptr(nodes), _ptr(pairs), _ptr(remap)), "racc_cuda_scene_download")
+        return nodes, pairs, remap
+
+    def destroy(self) -> None:
+        if self._h:
+            _lib.load().racc_cuda_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Environment:
+    """racc::Environment: an angular-map light probe (RGBA32F)."""
+
+    def __init__(self, handle, width: int, height: int):
+        self._h, self.width, self.height = handle, width, height
+
+    def destroy(self) -> None:
+        if self._h:
+            _lib.load().racc_cuda_env_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def create_scene(vertices: np.ndarray, indices: np.ndarray) -> Scene:
+    """racc::createScene(context, vertices, vertexCount, indices, indexCount) (RayAccelerator.h:107).
+    vertices: (V,4) float32, indices: (3T,) uint32. Arrays are copied; the caller may free them."""
+    v = np.ascontiguousarray(vertices, dtype=np.float32)
+    if v.ndim != 2 or v.shape[1] != 4:
+        raise ValueError("vertices must be (V, 4) float32 (racc::Vertex)")
+    i = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+    if i.shape[0] % 3:
+        raise ValueError("indexCount % 3 != 0")  # Scene.cpp:186
+    lib = _lib.load()
+    return Scene(_lib.check_ptr(lib.racc_cuda_scene_create(_ptr(v), v.shape[0], _ptr(i), i.shape[0]), "racc_cuda_scene_create"))
+
+
+def create_scene_from_images(nodes: np.ndarray, pairs: np.ndarray, remap: np.ndarray) -> Scene:
+    n = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1, 16)
+    p = np.ascontiguousarray(pairs, dtype=np.float32).reshape(-1, 12)
+    r = np.ascontiguousarray(remap, dtype=np.uint32).reshape(-1)
+    lib = _lib.load()
+    return Scene(_lib.check_ptr(lib.racc_cuda_scene_create_from_images(_ptr(n), n.shape[0], _ptr(p), p.shape[0], _ptr(r), r.shape[0]),
+                                "racc_cuda_scene_create_from_images"))
+
+
+def create_environment(colors: np.ndarray) -> Environment:
+    """racc::createEnvironment(context, colors, width, height) (RayAccelerator.h:111). colors: (H,W,4) float32."""
+    c = np.ascontiguousarray(colors, dtype=np.float32)
+    if c.ndim != 3 or c.shape[2] != 4:
+        raise ValueError("colors must be (H, W, 4) float32 (racc::Color)")
+    lib = _lib.load()
+    return Environment(_lib.check_ptr(lib.racc_cuda_env_create(_ptr(c), c.shape[1], c.shape[0]), "racc_cuda_env_create"), c.shape[1], c.shape[0])
+
+
+def _cuda_stream_handle(stream) -> ctypes.c_void_p:
+    if stream is None:
+        return ctypes.c_void_p(0)
+    if hasattr(stream, "cuda_stream"):  # torch.cuda.Stream
+        return ctypes.c_void_p(stream.cuda_stream)
+    return ctypes.c_void_p(int(stream))
+
+
+def trace_host(scene: Scene, environment: Environment | None, rays: np.ndarray, results: np.ndarray | None = None,
+               stream=None, sync: bool = True) -> np.ndarray:
+    """One ray stream in HOST memory through the engine: H2D, traversal, D2H (what gpuWorkerThread
+    does per stream, RayAccelerator.cpp:369-410). rays: RAY_DTYPE array. Returns RESULT_DTYPE array."""
+    rays = np.ascontiguousarray(rays)
+    if rays.dtype != RAY_DTYPE:
+        raise ValueError("rays must have RAY_DTYPE")
+    if results is None:
+        results = np.zeros(rays.shape[0], dtype=RESULT_DTYPE)
+    desc = StreamDesc(rays.ctypes.data, results.ctypes.data, rays.shape[0], _lib.STREAM_HOST)
+    lib = _lib.load()
+    h = _cuda_stream_handle(stream)
+    _lib.check(lib.racc_cuda_trace(scene._h, environment._h if environment else None, ctypes.byref(desc), 1, h), "racc_cuda_trace")
+    if sync:
+        _lib.check(lib.racc_cuda_sync(h), "racc_cuda_sync")
+    return results
+
+
+def trace_device(scene: Scene, environment: Environment | None, streams, stream=None, counters_ptr: int | None = None) -> None:
+    """Launch ONE traversal over a list of device-resident streams [(rays_ptr, results_ptr, count), ...].
+    Asynchronous on `stream`. counters_ptr: device pointer to a zeroed Counters record (slower)."""
+    n = len(streams)
+    arr = (StreamDesc * n)()
+    for k, (rp, op, cnt) in enumerate(streams):
+        arr[k] = StreamDesc(rp, op, cnt, _lib.STREAM_DEVICE)
+    lib = _lib.load()
+    h = _cuda_stream_handle(stream)
+    env = environment._h if environment else None
+    if counters_ptr is None:
+        _lib.check(lib.racc_cuda_trace(scene._h, env, arr, n, h), "racc_cuda_trace")
+    else:
+        _lib.check(lib.racc_cuda_trace_counted(scene._h, env, arr, n, h, ctypes.c_void_p(counters_ptr)), "racc_cuda_trace_counted")
+
+
+def sync(stream=None) -> None:
+    _lib.check(_lib.load().racc_cuda_sync(_cuda_stream_handle(stream)), "racc_cuda_sync")
+
+
+def launch_count() -> int:
+    return int(_lib.load().racc_cuda_launch_count())
+
+
+def set_tuning(**kw) -> None:
+    keys = {"variant": 0, "block": 1, "ctas_per_sm": 2, "smem_nodes": 3, "fetch_threshold": 4}
+    lib = _lib.load()
+    for k, v in kw.items():
+        lib.racc_cuda_set_tuning(keys[k], int(v))
+
+
+def generate_primary(camera: Camera, width: int, height: int, spp: int, jitter_seed: int, rays_ptr: int, stream=None) -> int:
+    cam = _lib.CameraStruct()
+    for k in range(3):
+        cam.origin[k] = float(camera.origin[k]); cam.view[k] = float(camera.view[k])
+        cam.right[k] = float(camera.right[k]); cam.up[k] = float(camera.up[k])
+    _lib.check(_lib.load().racc_cuda_generate_primary(ctypes.byref(cam), width, height, spp, jitter_seed,
+                                                       ctypes.c_void_p(rays_ptr), _cuda_stream_handle(stream)), "racc_cuda_generate_primary")
+    return width * height * spp
+
+
+def generate_bounce(scene: Scene, rays_ptr: int, results_ptr: int, count: int, seed: int, out_rays_ptr: int,
+                    out_count_ptr: int, stream=None) -> None:
+    _lib.check(_lib.load().racc_cuda_generate_bounce(scene._h, ctypes.c_void_p(rays_ptr), ctypes.c_void_p(results_ptr), count, seed,
+                                                      ctypes.c_void_p(out_rays_ptr), ctypes.c_void_p(out_count_ptr),
+                                                      _cuda_stream_handle(stream)), "racc_cuda_generate_bounce")

@@ -1,0 +1,444 @@
+// capi.cu -- implementation of the C-ABI declared in include/racc_b200.h.
+// Device management, scene/environment upload, stream staging and kernel launch. No CPU fallback:
+// every compute entry point fails with an error string when CUDA is unavailable.
+#include "../../include/racc_b200.h"
+
+#include "engine.h"
+#include "scene_build.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+using namespace racc_b200;
+
+namespace {
+
+thread_local char g_error[512] = "";
+std::mutex g_initMutex;
+bool g_initialised = false;
+int g_device = 0;
+int g_smCount = 0;
+Tuning g_tuning;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_error, sizeof(g_error), fmt, ap);
+	va_end(ap);
+	return -1;
+}
+
+#define RACC_CUDA_CHECK(call)                                                                              \
+	do {                                                                                                   \
+		cudaError_t e_ = (call);                                                                           \
+		if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+#define RACC_CUDA_CHECK_NULL(call)                                                                         \
+	do {                                                                                                   \
+		cudaError_t e_ = (call);                                                                           \
+		if (e_ != cudaSuccess) {                                                                           \
+			fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);              \
+			return nullptr;                                                                                \
+		}                                                                                                  \
+	} while (0)
+
+int envInt(const char* name, int fallback) {
+	const char* v = getenv(name);
+	return v && *v ? atoi(v) : fallback;
+}
+
+int ensureInit() {
+	std::lock_guard<std::mutex> lock(g_initMutex);
+	if (g_initialised) {
+		cudaError_t e = cudaSetDevice(g_device);
+		return e == cudaSuccess ? 0 : fail("cudaSetDevice(%d) failed: %s", g_device, cudaGetErrorString(e));
+	}
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count <= 0)
+		return fail("no CUDA device available (%s); the engine has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+	RACC_CUDA_CHECK(cudaGetDevice(&g_device));
+	RACC_CUDA_CHECK(cudaDeviceGetAttribute(&g_smCount, cudaDevAttrMultiProcessorCount, g_device));
+	g_tuning.variant = envInt("RACC_B200_VARIANT", g_tuning.variant);
+	g_tuning.blockThreads = envInt("RACC_B200_BLOCK", g_tuning.blockThreads);
+	g_tuning.ctasPerSm = envInt("RACC_B200_CTAS_PER_SM", g_tuning.ctasPerSm);
+	g_tuning.smemNodes = envInt("RACC_B200_SMEM_NODES", g_tuning.smemNodes);
+	g_tuning.fetchThreshold = envInt("RACC_B200_FETCH_THRESHOLD", g_tuning.fetchThreshold);
+	g_initialised = true;
+	return 0;
+}
+
+constexpr int kCursorRing = 256;
+
+} // namespace
+
+struct racc_cuda_scene {
+	SceneImages host;
+	uint32_t triangleCount = 0;
+	float4* dNodes = nullptr;
+	float4* dPairs = nullptr;
+	uint32_t* dRemap = nullptr;
+	float4* dVerts = nullptr;    // only for the synthetic bounce generator
+	uint32_t* dIndices = nullptr;
+	uint32_t* dCursors = nullptr;
+	std::atomic<uint32_t> nextCursor{0};
+	uint32_t* dBounceScratch = nullptr;
+	size_t bounceScratchWords = 0;
+};
+
+struct racc_cuda_host_images {
+	SceneImages images;
+	uint32_t triangleCount = 0;
+};
+
+struct racc_cuda_env {
+	float4* dTexels = nullptr;
+	uint32_t width = 0, height = 0;
+};
+
+namespace {
+
+racc_cuda_scene* uploadScene(racc_cuda_scene* s, const float* verts4, uint32_t nverts, const uint32_t* indices, uint32_t nindices) {
+	const SceneImages& h = s->host;
+	auto bail = [&]() -> racc_cuda_scene* { racc_cuda_scene_destroy(s); return nullptr; };
+	cudaError_t e;
+#define UP(dst, src, bytes)                                                                  \
+	if ((e = cudaMalloc(reinterpret_cast<void**>(&dst), (bytes) ? (bytes) : 16)) != cudaSuccess || \
+	    (e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {            \
+		fail("scene upload failed: %s", cudaGetErrorString(e));                               \
+		return bail();                                                                        \
+	}
+	UP(s->dNodes, h.nodes.data(), h.nodes.size() * sizeof(GpuNode))
+	UP(s->dPairs, h.pairs.data(), h.pairs.size() * sizeof(GpuPair))
+	UP(s->dRemap, h.remap.data(), h.remap.size() * sizeof(uint32_t))
+	if (verts4 && indices) {
+		UP(s->dVerts, verts4, (size_t)nverts * 16)
+		UP(s->dIndices, indices, (size_t)nindices * 4)
+	}
+#undef UP
+	if ((e = cudaMalloc(reinterpret_cast<void**>(&s->dCursors), kCursorRing * sizeof(uint32_t))) != cudaSuccess) {
+		fail("scene upload failed: %s", cudaGetErrorString(e));
+		return bail();
+	}
+	return s;
+}
+
+} // namespace
+
+extern "C" {
+
+int racc_cuda_abi_version(void) { return RACC_CUDA_ABI_VERSION; }
+
+const char* racc_cuda_last_error(void) { return g_error; }
+
+int racc_cuda_device_count(void) {
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess) {
+		fail("cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+		return -1;
+	}
+	return count;
+}
+
+int racc_cuda_init(const int* devices, int n) {
+	if (devices && n > 0) {
+		cudaError_t e = cudaSetDevice(devices[0]);
+		if (e != cudaSuccess)
+			return fail("cudaSetDevice(%d) failed: %s; the engine has no CPU fallback", devices[0], cudaGetErrorString(e));
+		std::lock_guard<std::mutex> lock(g_initMutex);
+		g_initialised = false;
+	}
+	return ensureInit();
+}
+
+int racc_cuda_set_variant(int variant) {
+	const int previous = g_tuning.variant;
+	g_tuning.variant = variant;
+	return previous;
+}
+
+// Extended tuning access for the benchmark sweeps: key 0 variant, 1 block threads, 2 CTAs/SM,
+// 3 staged nodes, 4 fetch threshold. Returns the previous value.
+int racc_cuda_set_tuning(int key, int value) {
+	int* slot = nullptr;
+	switch (key) {
+	case 0: slot = &g_tuning.variant; break;
+	case 1: slot = &g_tuning.blockThreads; break;
+	case 2: slot = &g_tuning.ctasPerSm; break;
+	case 3: slot = &g_tuning.smemNodes; break;
+	case 4: slot = &g_tuning.fetchThreshold; break;
+	default: return fail("unknown tuning key %d", key);
+	}
+	const int previous = *slot;
+	*slot = value;
+	return previous;
+}
+
+uint64_t racc_cuda_launch_count(void) { return g_launches.load(); }
+
+racc_cuda_scene* racc_cuda_scene_create(const float* verts4, uint32_t nverts, const uint32_t* indices, uint32_t nindices) {
+	if (!verts4 || !indices) { fail("racc_cuda_scene_create: null input"); return nullptr; }
+	if (ensureInit()) return nullptr;
+	racc_cuda_scene* s = new racc_cuda_scene();
+	const char* why = "";
+	if (!buildSceneImages(verts4, nverts, indices, nindices, envInt("RACC_B200_BUILD_THREADS", 0), &s->host, &why)) {
+		fail("racc_cuda_scene_create: %s", why);
+		delete s;
+		return nullptr;
+	}
+	s->triangleCount = nindices / 3;
+	return uploadScene(s, verts4, nverts, indices, nindices);
+}
+
+static void fillInfo(const SceneImages& h, uint32_t triangleCount, racc_cuda_scene_info* info) {
+	info->node_count = (uint32_t)h.nodes.size();
+	info->pair_count = (uint32_t)h.pairs.size();
+	info->real_pair_count = h.realPairs;
+	info->remap_count = (uint32_t)h.remap.size();
+	info->depth = h.depth;
+	info->triangle_count = triangleCount;
+	for (int k = 0; k < 3; ++k) {
+		info->bounds_min[k] = h.boundsMin[k];
+		info->bounds_max[k] = h.boundsMax[k];
+	}
+}
+
+racc_cuda_host_images* racc_cuda_build_images(const float* verts4, uint32_t nverts, const uint32_t* indices, uint32_t nindices) {
+	if (!verts4 || !indices) { fail("racc_cuda_build_images: null input"); return nullptr; }
+	racc_cuda_host_images* img = new racc_cuda_host_images();
+	const char* why = "";
+	if (!buildSceneImages(verts4, nverts, indices, nindices, envInt("RACC_B200_BUILD_THREADS", 0), &img->images, &why)) {
+		fail("racc_cuda_build_images: %s", why);
+		delete img;
+		return nullptr;
+	}
+	img->triangleCount = nindices / 3;
+	return img;
+}
+
+int racc_cuda_host_images_get_info(const racc_cuda_host_images* img, racc_cuda_scene_info* info) {
+	if (!img || !info) return fail("racc_cuda_host_images_get_info: null argument");
+	fillInfo(img->images, img->triangleCount, info);
+	return 0;
+}
+
+int racc_cuda_host_images_copy(const racc_cuda_host_images* img, void* nodes, void* pairs, uint32_t* remap) {
+	if (!img) return fail("racc_cuda_host_images_copy: null argument");
+	if (nodes) memcpy(nodes, img->images.nodes.data(), img->images.nodes.size() * sizeof(GpuNode));
+	if (pairs) memcpy(pairs, img->images.pairs.data(), img->images.pairs.size() * sizeof(GpuPair));
+	if (remap) memcpy(remap, img->images.remap.data(), img->images.remap.size() * sizeof(uint32_t));
+	return 0;
+}
+
+void racc_cuda_host_images_destroy(racc_cuda_host_images* img) { delete img; }
+
+racc_cuda_scene* racc_cuda_scene_create_from_images(const void* nodes, uint32_t node_count, const void* pairs,
+                                                    uint32_t pair_count, const uint32_t* remap, uint32_t remap_count) {
+	if (!nodes || !pairs || !remap || !node_count || !pair_count) { fail("racc_cuda_scene_create_from_images: null or empty image"); return nullptr; }
+	if (ensureInit()) return nullptr;
+	racc_cuda_scene* s = new racc_cuda_scene();
+	s->host.nodes.assign(static_cast<const GpuNode*>(nodes), static_cast<const GpuNode*>(nodes) + node_count);
+	s->host.pairs.assign(static_cast<const GpuPair*>(pairs), static_cast<const GpuPair*>(pairs) + pair_count);
+	s->host.remap.assign(remap, remap + remap_count);
+	s->host.realPairs = remap_count / 2;
+	// validate references so a malformed image cannot send the kernel out of bounds
+	for (const GpuNode& n : s->host.nodes) {
+		const uint32_t refs[2] = {n.first, n.last};
+		for (uint32_t r : refs) {
+			const bool ok = (r & 0x80000000u) ? (r & 0x7fffffffu) < node_count
+			                                  : ((r >> 24) > 0 && (r & 0xffffffu) + (r >> 24) <= pair_count && 2 * ((r & 0xffffffu) + (r >> 24)) <= remap_count);
+			if (!ok) {
+				fail("racc_cuda_scene_create_from_images: child reference 0x%08x out of range", r);
+				delete s;
+				return nullptr;
+			}
+		}
+	}
+	return uploadScene(s, nullptr, 0, nullptr, 0);
+}
+
+void racc_cuda_scene_destroy(racc_cuda_scene* s) {
+	if (!s) return;
+	cudaFree(s->dNodes);
+	cudaFree(s->dPairs);
+	cudaFree(s->dRemap);
+	cudaFree(s->dVerts);
+	cudaFree(s->dIndices);
+	cudaFree(s->dCursors);
+	cudaFree(s->dBounceScratch);
+	delete s;
+}
+
+int racc_cuda_scene_get_info(const racc_cuda_scene* s, racc_cuda_scene_info* info) {
+	if (!s || !info) return fail("racc_cuda_scene_get_info: null argument");
+	fillInfo(s->host, s->triangleCount, info);
+	return 0;
+}
+
+int racc_cuda_scene_download(const racc_cuda_scene* s, void* nodes, void* pairs, uint32_t* remap) {
+	if (!s) return fail("racc_cuda_scene_download: null scene");
+	// read back from the device so the test sees what the kernel sees
+	if (nodes) RACC_CUDA_CHECK(cudaMemcpy(nodes, s->dNodes, s->host.nodes.size() * sizeof(GpuNode), cudaMemcpyDeviceToHost));
+	if (pairs) RACC_CUDA_CHECK(cudaMemcpy(pairs, s->dPairs, s->host.pairs.size() * sizeof(GpuPair), cudaMemcpyDeviceToHost));
+	if (remap) RACC_CUDA_CHECK(cudaMemcpy(remap, s->dRemap, s->host.remap.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+racc_cuda_env* racc_cuda_env_create(const float* rgba, uint32_t width, uint32_t height) {
+	if (!rgba || !width || !height) { fail("racc_cuda_env_create: null or empty image"); return nullptr; }
+	if (ensureInit()) return nullptr;
+	racc_cuda_env* env = new racc_cuda_env();
+	env->width = width;
+	env->height = height;
+	const size_t bytes = (size_t)width * height * 16;
+	cudaError_t e;
+	if ((e = cudaMalloc(reinterpret_cast<void**>(&env->dTexels), bytes)) != cudaSuccess ||
+	    (e = cudaMemcpy(env->dTexels, rgba, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {
+		fail("environment upload failed: %s", cudaGetErrorString(e));
+		cudaFree(env->dTexels);
+		delete env;
+		return nullptr;
+	}
+	return env;
+}
+
+void racc_cuda_env_destroy(racc_cuda_env* env) {
+	if (!env) return;
+	cudaFree(env->dTexels);
+	delete env;
+}
+
+static int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams,
+                     void* cuda_stream, void* device_counters) {
+	if (!s) return fail("racc_cuda_trace: null scene");
+	if (!streams && nstreams) return fail("racc_cuda_trace: null stream list");
+	if (ensureInit()) return -1;
+	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+
+	struct Staged { void* dRays; void* dResults; void* hResults; size_t resultBytes; };
+	std::vector<StreamRef> refs;
+	std::vector<Staged> staged;
+	refs.reserve(nstreams);
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < nstreams; ++i) {
+		const racc_cuda_stream_desc& d = streams[i];
+		if (!d.count) continue;
+		if (!d.rays || !d.results) return fail("racc_cuda_trace: stream %u has null buffers", i);
+		StreamRef ref;
+		ref.begin = (uint32_t)total;
+		ref.count = d.count;
+		if (d.flags & RACC_CUDA_STREAM_HOST) {
+			Staged st;
+			st.resultBytes = (size_t)d.count * 16;
+			st.hResults = d.results;
+			RACC_CUDA_CHECK(cudaMallocAsync(&st.dRays, (size_t)d.count * 32, stream));
+			RACC_CUDA_CHECK(cudaMallocAsync(&st.dResults, st.resultBytes, stream));
+			RACC_CUDA_CHECK(cudaMemcpyAsync(st.dRays, d.rays, (size_t)d.count * 32, cudaMemcpyHostToDevice, stream));
+			staged.push_back(st);
+			ref.rays = static_cast<const DevRay*>(st.dRays);
+			ref.results = static_cast<float4*>(st.dResults);
+		}
+		else {
+			if ((reinterpret_cast<uintptr_t>(d.rays) & 15) || (reinterpret_cast<uintptr_t>(d.results) & 15))
+				return fail("racc_cuda_trace: stream %u buffers must be 16-byte aligned", i);
+			ref.rays = static_cast<const DevRay*>(d.rays);
+			ref.results = static_cast<float4*>(d.results);
+		}
+		refs.push_back(ref);
+		total += d.count;
+		if (total > 0x7fffffffull) return fail("racc_cuda_trace: more than 2^31-1 rays in one launch");
+	}
+	if (!total) return 0;
+
+	TraceParams p{};
+	p.nodes = s->dNodes;
+	p.pairs = s->dPairs;
+	p.remap = s->dRemap;
+	p.env = env ? env->dTexels : nullptr;
+	p.envWidth = env ? env->width : 0;
+	p.envHeight = env ? env->height : 0;
+	p.nodeCount = (uint32_t)s->host.nodes.size();
+	p.nstreams = (uint32_t)refs.size();
+	p.total = (uint32_t)total;
+	p.single = refs[0];
+	p.cursor = s->dCursors + (s->nextCursor.fetch_add(1) % kCursorRing);
+	p.counters = static_cast<unsigned long long*>(device_counters);
+	void* dRefs = nullptr;
+	if (refs.size() > 1) {
+		RACC_CUDA_CHECK(cudaMallocAsync(&dRefs, refs.size() * sizeof(StreamRef), stream));
+		RACC_CUDA_CHECK(cudaMemcpyAsync(dRefs, refs.data(), refs.size() * sizeof(StreamRef), cudaMemcpyHostToDevice, stream));
+		p.streams = static_cast<const StreamRef*>(dRefs);
+	}
+
+	int launches = 0;
+	RACC_CUDA_CHECK(launchTrace(p, g_tuning, device_counters != nullptr, g_smCount, stream, &launches));
+	g_launches.fetch_add((uint64_t)launches);
+
+	for (const Staged& st : staged) {
+		RACC_CUDA_CHECK(cudaMemcpyAsync(st.hResults, st.dResults, st.resultBytes, cudaMemcpyDeviceToHost, stream));
+		RACC_CUDA_CHECK(cudaFreeAsync(st.dRays, stream));
+		RACC_CUDA_CHECK(cudaFreeAsync(st.dResults, stream));
+	}
+	if (dRefs) RACC_CUDA_CHECK(cudaFreeAsync(dRefs, stream));
+	return 0;
+}
+
+int racc_cuda_trace(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams, void* cuda_stream) {
+	return traceImpl(scene, env, streams, nstreams, cuda_stream, nullptr);
+}
+
+int racc_cuda_trace_counted(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams,
+                            void* cuda_stream, void* device_counters) {
+	if (!device_counters) return fail("racc_cuda_trace_counted: null counter buffer");
+	return traceImpl(scene, env, streams, nstreams, cuda_stream, device_counters);
+}
+
+int racc_cuda_sync(void* cuda_stream) {
+	if (ensureInit()) return -1;
+	RACC_CUDA_CHECK(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+	return 0;
+}
+
+int racc_cuda_generate_primary(const racc_cuda_camera* camera, uint32_t width, uint32_t height, uint32_t spp,
+                               uint32_t jitter_seed, void* device_rays, void* cuda_stream) {
+	if (!camera || !device_rays) return fail("racc_cuda_generate_primary: null argument");
+	if (ensureInit()) return -1;
+	if ((uint64_t)width * height * spp > 0x7fffffffull) return fail("racc_cuda_generate_primary: too many rays");
+	int launches = 0;
+	RACC_CUDA_CHECK(launchGeneratePrimary(camera->origin, width, height, spp, jitter_seed, static_cast<DevRay*>(device_rays),
+	                                      static_cast<cudaStream_t>(cuda_stream), &launches));
+	g_launches.fetch_add((uint64_t)launches);
+	return 0;
+}
+
+int racc_cuda_generate_bounce(const racc_cuda_scene* scene_, const void* device_rays, const void* device_results, uint32_t count,
+                              uint32_t seed, void* device_out_rays, uint32_t* device_out_count, void* cuda_stream) {
+	racc_cuda_scene* s = const_cast<racc_cuda_scene*>(scene_);
+	if (!s || !device_rays || !device_results || !device_out_rays || !device_out_count) return fail("racc_cuda_generate_bounce: null argument");
+	if (!s->dVerts) return fail("racc_cuda_generate_bounce: scene was created from images and has no vertex data");
+	if (ensureInit()) return -1;
+	const size_t words = bounceScratchWords(count);
+	if (words > s->bounceScratchWords) {
+		RACC_CUDA_CHECK(cudaDeviceSynchronize());
+		cudaFree(s->dBounceScratch);
+		s->dBounceScratch = nullptr;
+		RACC_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->dBounceScratch), words * sizeof(uint32_t)));
+		s->bounceScratchWords = words;
+	}
+	int launches = 0;
+	RACC_CUDA_CHECK(launchGenerateBounce(s->dVerts, s->dIndices, static_cast<const DevRay*>(device_rays),
+	                                     static_cast<const float4*>(device_results), count, seed, static_cast<DevRay*>(device_out_rays),
+	                                     device_out_count, s->dBounceScratch, static_cast<cudaStream_t>(cuda_stream), &launches));
+	g_launches.fetch_add((uint64_t)launches);
+	return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,57 @@
+// engine.h -- internal declarations shared by capi.cu, traverse.cu and raygen.cu.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace racc_b200 {
+
+// racc::Ray (RayAccelerator.h:59-64) as two 16-byte halves, and racc::Result (:66-76).
+struct DevRay { float4 a; float4 b; };          // a = origin.xyz,minT   b = dir.xyz,maxT
+static_assert(sizeof(DevRay) == 32, "ray is 32 bytes");
+
+// One ray stream of a launch; `begin` is its first ray's index in the launch-wide numbering.
+struct StreamRef {
+	const DevRay* rays;
+	float4* results;
+	uint32_t begin;
+	uint32_t count;
+};
+
+struct TraceParams {
+	const float4* nodes;     // 4 x float4 per inner node
+	const float4* pairs;     // 3 x float4 per triangle pair
+	const uint32_t* remap;
+	const float4* env;       // RGBA32F texels, may be null
+	uint32_t envWidth, envHeight;
+	uint32_t nodeCount;
+	const StreamRef* streams; // device array, nstreams entries (unused when nstreams == 1)
+	uint32_t nstreams;
+	uint32_t total;           // rays in the launch
+	StreamRef single;         // the stream when nstreams == 1 (no indirection)
+	uint32_t* cursor;         // work cursor for the persistent kernels (zeroed before launch)
+	unsigned long long* counters; // 4 x u64 {rays,hits,inner,pairs} or null
+	uint32_t smemNodes;       // inner nodes staged in shared memory by the persistent kernel
+};
+
+// Tunables (racc_cuda_set_variant / RACC_B200_* environment variables), see DESIGN.md section 5.
+struct Tuning {
+	int variant = 0;        // 0 persistent while-while (default), 1 one-thread-per-ray
+	int blockThreads = 256; // threads per CTA
+	int ctasPerSm = 0;      // 0 = as many as fit
+	int smemNodes = -1;     // -1 = auto
+	int fetchThreshold = 12; // refill a warp when at least this many lanes are idle
+};
+
+cudaError_t launchTrace(const TraceParams& p, const Tuning& t, bool counted, int smCount, cudaStream_t stream, int* launches);
+
+cudaError_t launchGeneratePrimary(const float* camera12, uint32_t width, uint32_t height, uint32_t spp, uint32_t seed,
+                                  DevRay* rays, cudaStream_t stream, int* launches);
+
+cudaError_t launchGenerateBounce(const float4* verts, const uint32_t* indices, const DevRay* rays, const float4* results,
+                                 uint32_t count, uint32_t seed, DevRay* outRays, uint32_t* outCount, uint32_t* scratch,
+                                 cudaStream_t stream, int* launches);
+
+size_t bounceScratchWords(uint32_t count);
+
+} // namespace racc_b200

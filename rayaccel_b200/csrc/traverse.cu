@@ -1,0 +1,496 @@
+// traverse.cu -- the hot path: closest-hit BVH2 traversal + triangle-pair intersection over packed
+// ray streams, hand-written for sm_100a.
+//
+// WHAT it computes is fixed by the reference's OpenCL `traversal` kernel
+// (/root/reference/RayAccelerator/Kernels.h:36-242): same slab test, same triangle-pair test with
+// its accept/tie rules, same near-first order and push rule, same miss (light-probe) and hit
+// (remap + barycentric rotation) epilogues, in the pinned fp32 arithmetic of DESIGN.md section 3
+// (mad -> fmaf, everything else separately rounded, IEEE reciprocal, FTZ). Compiled with
+// -fmad=false -ftz=true -prec-div=true -prec-sqrt=true so the compiler adds or removes no rounding.
+//
+// HOW is B200-first, not the reference's one-work-item-per-ray NDRange:
+//   * persistent CTAs (grid = SMs x resident CTAs) pulling rays from a global cursor, one warp-
+//     aggregated atomic per refill, refilling idle lanes when enough of a warp has retired;
+//   * while-while traversal: every lane descends inner nodes until it holds a leaf, then the warp
+//     reconverges and tests triangle pairs, so the two instruction streams are not interleaved;
+//   * the hottest inner nodes (the scene builder orders nodes by surface area) are staged once per
+//     CTA into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier);
+//   * rays are read as 2 x LDG.128, nodes as 4 x 128-bit loads, pairs as 3 x LDG.128 through the
+//     read-only path; results leave as one STG.128 per ray, index-parallel to the rays;
+//   * no tensor cores: this is branchy scalar fp32.
+#include "engine.h"
+
+namespace racc_b200 {
+namespace {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr uint32_t kInnerBit = 0x80000000u;
+constexpr uint32_t kMiss = 0xffffffffu;
+constexpr int kStackSize = 64; // Kernels.h:166
+
+struct RayState {
+	float ox, oy, oz;
+	float dx, dy, dz;      // after the epsilon clamp (Kernels.h:149-157)
+	float ix, iy, iz;      // invDir (Kernels.h:159)
+	float px, py, pz;      // OoD = -origin * invDir (Kernels.h:160)
+	float tNear, tFar;
+};
+
+struct HitState {
+	uint32_t index; // pair-triangle index, kMiss if none (Kernels.h:162)
+	float t, u, v;
+};
+
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+	return fmaf(az, bz, fmaf(ay, by, ax * bx));
+}
+
+// mad_cross (Kernels.h:23-25)
+#define RACC_CROSS(rx, ry, rz, ax, ay, az, bx, by, bz) \
+	float rx = fmaf(ay, bz, -(az * by));               \
+	float ry = fmaf(az, bx, -(ax * bz));               \
+	float rz = fmaf(ax, by, -(ay * bx));
+
+__device__ __forceinline__ void initRay(const DevRay* rays, uint32_t i, RayState& r, HitState& h) {
+	const float4 a = __ldg(&rays[i].a);
+	const float4 b = __ldg(&rays[i].b);
+	r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tNear = a.w;
+	r.dx = b.x; r.dy = b.y; r.dz = b.z; r.tFar = b.w;
+	const float epsilon = 1e-10f;
+	if (fabsf(r.dx) < epsilon) r.dx = copysignf(epsilon, r.dx);
+	if (fabsf(r.dy) < epsilon) r.dy = copysignf(epsilon, r.dy);
+	if (fabsf(r.dz) < epsilon) r.dz = copysignf(epsilon, r.dz);
+	r.ix = __frcp_rn(r.dx); r.iy = __frcp_rn(r.dy); r.iz = __frcp_rn(r.dz);
+	r.px = -r.ox * r.ix; r.py = -r.oy * r.iy; r.pz = -r.oz * r.iz;
+	h.index = kMiss; h.t = r.tFar; h.u = 0.0f; h.v = 0.0f;
+}
+
+// aabbIntersect (Kernels.h:117-135): entry distance, or tFar as the miss sentinel.
+__device__ __forceinline__ float slab(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const RayState& r) {
+	const float nx = fmaf(mnx, r.ix, r.px), ny = fmaf(mny, r.iy, r.py), nz = fmaf(mnz, r.iz, r.pz);
+	const float fx = fmaf(mxx, r.ix, r.px), fy = fmaf(mxy, r.iy, r.py), fz = fmaf(mxz, r.iz, r.pz);
+	const float t0 = fmaxf(fmaxf(r.tNear, fminf(nx, fx)), fmaxf(fminf(ny, fy), fminf(nz, fz)));
+	const float t1 = fminf(fminf(r.tFar, fmaxf(nx, fx)), fminf(fmaxf(ny, fy), fmaxf(nz, fz)));
+	return t0 > t1 ? r.tFar : t0;
+}
+
+// trianglePairIntersect (Kernels.h:36-115). Updates r.tFar and h on an accepted hit.
+__device__ __forceinline__ void pairTest(const float4* __restrict__ pairs, uint32_t index, RayState& r, HitState& h) {
+	const float4 t0 = __ldg(pairs + 3 * (size_t)index);
+	const float4 t1 = __ldg(pairs + 3 * (size_t)index + 1);
+	const float4 t2 = __ldg(pairs + 3 * (size_t)index + 2);
+	// e1 = t0.xyz, e2 = t1.xyz, e3 = (t0.w,t1.w,t2.w), v0 = t2.xyz
+	RACC_CROSS(n1x, n1y, n1z, t0.x, t0.y, t0.z, t1.x, t1.y, t1.z)
+	RACC_CROSS(n2x, n2y, n2z, t0.w, t1.w, t2.w, t0.x, t0.y, t0.z)
+	const float cx = t2.x - r.ox, cy = t2.y - r.oy, cz = t2.z - r.oz;
+	RACC_CROSS(Rx, Ry, Rz, r.dx, r.dy, r.dz, cx, cy, cz)
+
+	const float det1 = dot3(n1x, n1y, n1z, r.dx, r.dy, r.dz);
+	const float det2 = dot3(n2x, n2y, n2z, r.dx, r.dy, r.dz);
+	const uint32_t s1 = __float_as_uint(det1) & 0x80000000u;
+	const uint32_t s2 = __float_as_uint(det2) & 0x80000000u;
+
+	const float dRe1 = dot3(Rx, Ry, Rz, t0.x, t0.y, t0.z);
+	const int iU1 = (int)(__float_as_uint(dot3(Rx, Ry, Rz, t1.x, t1.y, t1.z)) ^ s1);
+	const int iV1 = (int)(__float_as_uint(dRe1) ^ s1);
+	const int iU2 = (int)(__float_as_uint(-dRe1) ^ s2);
+	const int iV2 = (int)(__float_as_uint(-dot3(Rx, Ry, Rz, t0.w, t1.w, t2.w)) ^ s2);
+
+	if (((iU1 | iV1) & (iU2 | iV2)) < 0)
+		return;
+
+	bool out1 = (iU1 | iV1) < 0;
+	bool out2 = (iU2 | iV2) < 0;
+	float U1 = __int_as_float(iU1), V1 = __int_as_float(iV1);
+	const float U2 = __int_as_float(iU2), V2 = __int_as_float(iV2);
+	float a1 = fabsf(det1);
+	const float a2 = fabsf(det2);
+	const float W1 = (a1 - U1) - V1;
+	const float W2 = (a2 - U2) - V2;
+	float T1 = __uint_as_float(__float_as_uint(dot3(n1x, n1y, n1z, cx, cy, cz)) ^ s1);
+	const float T2 = __uint_as_float(__float_as_uint(dot3(n2x, n2y, n2z, cx, cy, cz)) ^ s2);
+
+	out1 = out1 || (W1 < 0.0f || T1 <= a1 * r.tNear || T1 > a1 * r.tFar);
+	out2 = out2 || (W2 < 0.0f || T2 <= a2 * r.tNear || T2 > a2 * r.tFar);
+	if (out1 && out2)
+		return;
+
+	index *= 2;
+	if ((!out2 && out1) || (!out1 && !out2 && T1 * a2 > T2 * a1)) {
+		a1 = a2; T1 = T2; U1 = U2; V1 = V2;
+		++index;
+	}
+	const float rcp = __frcp_rn(a1); // native_recip pinned to the IEEE reciprocal
+	const float t = T1 * rcp;
+	h.index = index;
+	h.t = t;
+	h.u = U1 * rcp;
+	h.v = V1 * rcp;
+	r.tFar = t;
+}
+
+// pinned acos of the miss path; identical operation sequence to oracle_acosf (oracle/racc_oracle.c)
+__device__ __forceinline__ float acosPinned(float x) {
+	const float pio2 = 1.57079637050628662109375f;
+	const float pi = 3.1415927410125732421875f;
+	const float pS0 = 1.6666586697e-01f, pS1 = -4.2743422091e-02f, pS2 = -8.6563630030e-03f, qS1 = -7.0662963390e-01f;
+	const float ax = fabsf(x);
+	if (!(ax < 1.0f)) {
+		if (x != x) return x;
+		return x > 0.0f ? 0.0f : pi;
+	}
+	if (ax <= 0.5f) {
+		const float z = x * x;
+		const float p = z * fmaf(z, fmaf(z, pS2, pS1), pS0);
+		const float q = fmaf(z, qS1, 1.0f);
+		const float rr = __fdiv_rn(p, q);
+		return pio2 - fmaf(x, rr, x);
+	}
+	const float z = (1.0f - ax) * 0.5f;
+	const float s = __fsqrt_rn(z);
+	const float p = z * fmaf(z, fmaf(z, pS2, pS1), pS0);
+	const float q = fmaf(z, qS1, 1.0f);
+	const float rr = __fdiv_rn(p, q);
+	const float w = 2.0f * fmaf(s, rr, s);
+	return x > 0.0f ? w : pi - w;
+}
+
+__device__ __forceinline__ int texelFloor(float x, float& frac) {
+	const float f = floorf(x);
+	frac = x - f;
+	if (!(f > -4.0f)) {
+		if (f != f) { frac = 0.0f; return 0; }
+		return -4;
+	}
+	if (f > 1.0e9f) return 1000000000;
+	return (int)f;
+}
+
+// Miss epilogue (Kernels.h:213-221): angular-map lookup, bilinear, clamp-to-edge, written out with
+// the OpenCL 1.2 linear-filter formula so that the oracle can follow it bit for bit.
+__device__ __forceinline__ float4 missRadiance(const float4* __restrict__ env, uint32_t w, uint32_t hgt, const RayState& r) {
+	if (!env)
+		return make_float4(__uint_as_float(kMiss), 0.0f, 0.0f, 0.0f);
+	const float s = r.dy * r.dy + r.dz * r.dz;
+	const float rlen = __frcp_rn(__fsqrt_rn(s));
+	const float inv2pi = 1.0f / (2.0f * 3.141593f);
+	const float rr = (rlen > 1e+6f) ? 0.0f : (acosPinned(-r.dx) * inv2pi) * rlen;
+	const float u = 0.5f - rr * r.dz;
+	const float v = 0.5f - rr * r.dy;
+	const float fu = u * (float)(int)w - 0.5f;
+	const float fv = v * (float)(int)hgt - 0.5f;
+	float a, b;
+	int i0 = texelFloor(fu, a);
+	int j0 = texelFloor(fv, b);
+	const int i1 = min(max(i0 + 1, 0), (int)w - 1);
+	const int j1 = min(max(j0 + 1, 0), (int)hgt - 1);
+	i0 = min(max(i0, 0), (int)w - 1);
+	j0 = min(max(j0, 0), (int)hgt - 1);
+	const float4 t00 = __ldg(env + (size_t)j0 * w + i0);
+	const float4 t10 = __ldg(env + (size_t)j0 * w + i1);
+	const float4 t01 = __ldg(env + (size_t)j1 * w + i0);
+	const float4 t11 = __ldg(env + (size_t)j1 * w + i1);
+	const float na = 1.0f - a, nb = 1.0f - b;
+	const float w00 = na * nb, w10 = a * nb, w01 = na * b, w11 = a * b;
+	float4 o;
+	o.x = __uint_as_float(kMiss);
+	o.y = ((w00 * t00.x + w10 * t10.x) + w01 * t01.x) + w11 * t11.x;
+	o.z = ((w00 * t00.y + w10 * t10.y) + w01 * t01.y) + w11 * t11.y;
+	o.w = ((w00 * t00.z + w10 * t10.z) + w01 * t01.z) + w11 * t11.z;
+	return o;
+}
+
+// Hit epilogue (Kernels.h:223-239): original index + barycentric rotation by the edge code.
+__device__ __forceinline__ float4 hitResult(const uint32_t* __restrict__ remap, const HitState& h) {
+	uint32_t index = __ldg(remap + h.index);
+	const uint32_t edge = index >> 30;
+	index &= 0x3fffffffu;
+	const float bz = (1.0f - h.u) - h.v;
+	float u = h.u, v = h.v;
+	if (edge == 1) { u = bz; v = h.u; }
+	else if (edge == 2) { u = h.v; v = bz; }
+	return make_float4(__uint_as_float(index), h.t, u, v);
+}
+
+__device__ __forceinline__ float4 finishRay(const TraceParams& p, const RayState& r, const HitState& h) {
+	return h.index == kMiss ? missRadiance(p.env, p.envWidth, p.envHeight, r) : hitResult(p.remap, h);
+}
+
+// Launch-wide ray index -> (rays, results) of its stream.
+__device__ __forceinline__ void locate(const TraceParams& p, uint32_t idx, const DevRay*& rays, float4*& out, uint32_t& local) {
+	if (p.nstreams == 1) {
+		rays = p.single.rays; out = p.single.results; local = idx;
+		return;
+	}
+	uint32_t lo = 0, hi = p.nstreams - 1;
+	while (lo < hi) {
+		const uint32_t mid = (lo + hi + 1) >> 1;
+		if (__ldg(&p.streams[mid].begin) <= idx) lo = mid; else hi = mid - 1;
+	}
+	rays = p.streams[lo].rays; out = p.streams[lo].results; local = idx - p.streams[lo].begin;
+}
+
+// One inner-node step (Kernels.h:170-199). `np` points at the node's four float4s (shared or
+// global). Returns the next node reference, or 0 when neither child is hit and the stack is empty.
+__device__ __forceinline__ uint32_t innerStep(const float4* np, const RayState& r, uint32_t* stack, int& sp) {
+	const float4 d0 = np[0];
+	const float4 d1 = np[1];
+	const float4 d2 = np[2];
+	const float4 d3 = np[3];
+	const float tRay = r.tFar;
+	const float tFirst = slab(d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, r);
+	const float tLast = slab(d2.z, d2.w, d3.x, d3.y, d3.z, d3.w, r);
+	const float firstDiff = tRay - tFirst;
+	const float lastDiff = tRay - tLast;
+	if (firstDiff + lastDiff != 0.0f) {
+		const bool sgn = (__float_as_uint(tLast - tFirst) >> 31) != 0;
+		const uint32_t cf = __float_as_uint(d0.z), cl = __float_as_uint(d0.w);
+		if (fmaxf(tFirst, tLast) != tRay)
+			stack[sp++] = sgn ? cf : cl;
+		return sgn ? cl : cf;
+	}
+	return sp ? stack[--sp] : 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// variant 1: one thread per ray, the reference's launch shape (kept as the simple A/B baseline)
+
+template <bool kCount>
+__global__ void __launch_bounds__(256) traceSimpleKernel(const TraceParams p) {
+	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= p.total)
+		return;
+	const DevRay* rays; float4* out; uint32_t local;
+	locate(p, idx, rays, out, local);
+	RayState r; HitState h;
+	initRay(rays, local, r, h);
+	uint32_t stack[kStackSize];
+	int sp = 0;
+	uint32_t node = kInnerBit;
+	unsigned nInner = 0, nPairs = 0;
+	for (;;) {
+		if (node & kInnerBit) {
+			if (kCount) ++nInner;
+			node = innerStep(p.nodes + 4 * (size_t)(node & ~kInnerBit), r, stack, sp);
+			if (!node) break;
+			continue;
+		}
+		const uint32_t first = node & 0xffffffu, last = first + (node >> 24);
+		for (uint32_t i = first; i < last; ++i) {
+			pairTest(p.pairs, i, r, h);
+			if (kCount) ++nPairs;
+		}
+		if (!sp) break;
+		node = stack[--sp];
+	}
+	out[local] = finishRay(p, r, h);
+	if (kCount) {
+		atomicAdd(p.counters + 0, 1ull);
+		atomicAdd(p.counters + 1, h.index != kMiss ? 1ull : 0ull);
+		atomicAdd(p.counters + 2, (unsigned long long)nInner);
+		atomicAdd(p.counters + 3, (unsigned long long)nPairs);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// variant 0: persistent while-while kernel with TMA-staged tree top
+
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// TMA bulk copy of the first `bytes` of the node array into shared memory, completion on an
+// mbarrier (cp.async.bulk -> UBLKCP in SASS). One thread issues, all threads wait.
+__device__ __forceinline__ void stageNodes(float4* dst, const float4* src, uint32_t bytes, uint64_t* bar) {
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(bar)));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+		const uint32_t kChunk = 32768;
+		for (uint32_t off = 0; off < bytes; off += kChunk) {
+			const uint32_t n = min(kChunk, bytes - off);
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			             ::"r"(smemAddr(reinterpret_cast<char*>(dst) + off)), "l"(reinterpret_cast<const char*>(src) + off), "r"(n), "r"(smemAddr(bar))
+			             : "memory");
+		}
+	}
+	uint32_t done = 0;
+	while (!done) {
+		asm volatile(
+		    "{\n\t.reg .pred p;\n\t"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+		    "selp.u32 %0, 1, 0, p;\n\t}"
+		    : "=r"(done)
+		    : "r"(smemAddr(bar))
+		    : "memory");
+	}
+}
+
+template <bool kCount, int kBlock, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(const TraceParams p, const int fetchThreshold) {
+	extern __shared__ __align__(128) unsigned char smemRaw[];
+	__shared__ uint64_t stageBar;
+	float4* sNodes = reinterpret_cast<float4*>(smemRaw);
+	const uint32_t smemNodes = p.smemNodes;
+	if (smemNodes)
+		stageNodes(sNodes, p.nodes, smemNodes * 64u, &stageBar);
+
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned ltMask = (1u << lane) - 1u;
+
+	enum { kEmpty = 0, kTraversing = 1, kFinished = 2 };
+	int state = kEmpty;
+	bool exhausted = false; // warp-uniform: the cursor has run past the last ray
+
+	RayState r; HitState h;
+	uint32_t stack[kStackSize];
+	int sp = 0;
+	uint32_t node = 0;
+	float4* outPtr = nullptr;
+	unsigned long long cInner = 0, cPairs = 0, cRays = 0, cHits = 0;
+
+	for (;;) {
+		// ---- retire finished lanes and refill idle ones, warp-wide -----------------------------
+		const unsigned idle = __ballot_sync(kFullMask, state != kTraversing);
+		if (idle == kFullMask || (!exhausted && __popc(idle) >= fetchThreshold) || (exhausted && __ballot_sync(kFullMask, state == kFinished))) {
+			if (state == kFinished) {
+				*outPtr = finishRay(p, r, h);
+				if (kCount) { ++cRays; cHits += h.index != kMiss; }
+				state = kEmpty;
+			}
+			if (!exhausted) {
+				const int want = __popc(idle);
+				const int leader = __ffs(idle) - 1;
+				uint32_t base = 0;
+				if ((int)lane == leader) base = atomicAdd(p.cursor, (uint32_t)want);
+				base = __shfl_sync(kFullMask, base, leader);
+				if (state == kEmpty) {
+					const uint32_t idx = base + __popc(idle & ltMask);
+					if (idx < p.total) {
+						const DevRay* rays; uint32_t local;
+						locate(p, idx, rays, outPtr, local);
+						outPtr += local;
+						initRay(rays, local, r, h);
+						sp = 0;
+						node = kInnerBit;
+						state = kTraversing;
+					}
+				}
+				exhausted = base + (uint32_t)want >= p.total;
+			}
+			if (!__ballot_sync(kFullMask, state == kTraversing))
+				break;
+		}
+
+		// ---- while-while traversal ------------------------------------------------------------
+		if (state == kTraversing) {
+			while (node & kInnerBit) {
+				const uint32_t n = node & ~kInnerBit;
+				if (kCount) ++cInner;
+				const float4* np = n < smemNodes ? sNodes + 4 * n : p.nodes + 4 * (size_t)n;
+				node = innerStep(np, r, stack, sp);
+			}
+		}
+		__syncwarp();
+		if (state == kTraversing) {
+			if (node) {
+				const uint32_t first = node & 0xffffffu, last = first + (node >> 24);
+				for (uint32_t i = first; i < last; ++i) {
+					pairTest(p.pairs, i, r, h);
+					if (kCount) ++cPairs;
+				}
+				node = sp ? stack[--sp] : 0u;
+			}
+			if (!node)
+				state = kFinished;
+		}
+		__syncwarp();
+	}
+
+	if (kCount) {
+		for (int o = 16; o; o >>= 1) {
+			cRays += __shfl_xor_sync(kFullMask, cRays, o);
+			cHits += __shfl_xor_sync(kFullMask, cHits, o);
+			cInner += __shfl_xor_sync(kFullMask, cInner, o);
+			cPairs += __shfl_xor_sync(kFullMask, cPairs, o);
+		}
+		if (lane == 0) {
+			atomicAdd(p.counters + 0, cRays);
+			atomicAdd(p.counters + 1, cHits);
+			atomicAdd(p.counters + 2, cInner);
+			atomicAdd(p.counters + 3, cPairs);
+		}
+	}
+}
+
+template <bool kCount, int kBlock, int kMinBlocks>
+cudaError_t launchPersistent(const TraceParams& p, const Tuning& t, int smCount, cudaStream_t stream) {
+	auto kernel = tracePersistentKernel<kCount, kBlock, kMinBlocks>;
+	TraceParams q = p;
+	cudaError_t err;
+
+	// Shared-memory budget: stage as many hot nodes as fit while keeping the requested residency.
+	int device = 0;
+	cudaGetDevice(&device);
+	int maxOptin = 0;
+	cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+	int smPerSm = 0;
+	cudaDeviceGetAttribute(&smPerSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+	int ctas = t.ctasPerSm > 0 ? t.ctasPerSm : kMinBlocks;
+	uint32_t wantNodes = t.smemNodes >= 0 ? (uint32_t)t.smemNodes : 1024u;
+	if (wantNodes > p.nodeCount) wantNodes = p.nodeCount;
+	size_t budget = (size_t)smPerSm / (size_t)ctas;
+	budget = budget > 2048 ? budget - 2048 : 0; // static smem + per-CTA reservation
+	if (budget > (size_t)maxOptin - 1024) budget = (size_t)maxOptin - 1024;
+	if ((size_t)wantNodes * 64 > budget) wantNodes = (uint32_t)(budget / 64);
+	q.smemNodes = wantNodes;
+	const size_t smemBytes = (size_t)wantNodes * 64;
+
+	err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+	if (err != cudaSuccess) return err;
+	err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	if (err != cudaSuccess) return err;
+
+	int resident = 0;
+	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, kBlock, smemBytes);
+	if (err != cudaSuccess) return err;
+	if (resident < 1) resident = 1;
+	if (t.ctasPerSm > 0 && resident > t.ctasPerSm) resident = t.ctasPerSm;
+
+	// No more CTAs than there are warps' worth of work.
+	long long grid = (long long)smCount * resident;
+	const long long needed = ((long long)p.total + kBlock - 1) / kBlock;
+	if (grid > needed) grid = needed > 0 ? needed : 1;
+
+	err = cudaMemsetAsync(p.cursor, 0, sizeof(uint32_t), stream);
+	if (err != cudaSuccess) return err;
+	kernel<<<(unsigned)grid, kBlock, smemBytes, stream>>>(q, t.fetchThreshold);
+	return cudaGetLastError();
+}
+
+template <bool kCount>
+cudaError_t dispatch(const TraceParams& p, const Tuning& t, int smCount, cudaStream_t stream) {
+	if (t.variant == 1) {
+		const unsigned grid = (p.total + 255u) / 256u;
+		traceSimpleKernel<kCount><<<grid, 256, 0, stream>>>(p);
+		return cudaGetLastError();
+	}
+	switch (t.blockThreads) {
+	case 128: return launchPersistent<kCount, 128, 8>(p, t, smCount, stream);
+	case 512: return launchPersistent<kCount, 512, 2>(p, t, smCount, stream);
+	case 1024: return launchPersistent<kCount, 1024, 1>(p, t, smCount, stream);
+	default: return launchPersistent<kCount, 256, 4>(p, t, smCount, stream);
+	}
+}
+
+} // namespace
+
+cudaError_t launchTrace(const TraceParams& p, const Tuning& t, bool counted, int smCount, cudaStream_t stream, int* launches) {
+	if (!p.total)
+		return cudaSuccess;
+	if (launches) *launches += 1;
+	return counted ? dispatch<true>(p, t, smCount, stream) : dispatch<false>(p, t, smCount, stream);
+}
+
+} // namespace racc_b200
