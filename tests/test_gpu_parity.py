@@ -1,0 +1,260 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle on the same
+bytes. Bar: bit-exact triangle ids AND bit-exact t/u/v (hits) and r/g/b (misses) -- the kernel and
+the oracle use the same pinned fp32 operation sequence -- which implies the north_star's
+"|dt|/t <= 1e-4". All tests here need a GPU."""
+import numpy as np
+import pytest
+
+import oracle
+import rayaccel_b200 as rb
+from conftest import make_rays, random_rays
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+VARIANTS = [
+    dict(variant=0, block=256, smem_nodes=-1),
+    dict(variant=0, block=256, smem_nodes=0),
+    dict(variant=0, block=1024, smem_nodes=-1),
+    dict(variant=0, block=128, smem_nodes=64, fetch_threshold=1),
+    dict(variant=0, block=512, smem_nodes=-1, fetch_threshold=32),
+    dict(variant=1),
+]
+DEFAULT = dict(variant=0, block=256, ctas_per_sm=0, smem_nodes=-1, fetch_threshold=12)
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.cuda.set_device(0)
+    rb.init(0)
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def scene(gpu, battlefield):
+    s = rb.create_scene(battlefield.vertices, battlefield.indices)
+    yield s
+    s.destroy()
+
+
+@pytest.fixture(scope="module")
+def env(gpu, battlefield):
+    e = rb.create_environment(battlefield.environment)
+    yield e
+    e.destroy()
+
+
+@pytest.fixture(scope="module")
+def images(scene, battlefield):
+    nodes, pairs, remap = scene.download()  # what the kernel sees
+    return oracle.SceneImages(nodes, pairs, remap, battlefield.environment)
+
+
+def to_device(rays):
+    return torch.from_numpy(rays.view(np.float32).reshape(-1).copy()).cuda()
+
+
+def trace_dev(scene, env, rays_np):
+    d_rays = to_device(rays_np)
+    n = rays_np.shape[0]
+    d_res = torch.full((max(n, 1) * 4,), 7.0, dtype=torch.float32, device="cuda")
+    rb.trace_device(scene, env, [(d_rays.data_ptr(), d_res.data_ptr(), n)])
+    torch.cuda.synchronize()
+    return d_res[: n * 4].cpu().numpy().view(np.uint32).reshape(-1, 4)
+
+
+def assert_bit_exact(got_u32, want_struct, what):
+    want = want_struct.view(np.uint32).reshape(-1, 4)
+    if np.array_equal(got_u32, want):
+        return
+    bad = np.nonzero((got_u32 != want).any(axis=1))[0]
+    ids = (got_u32[bad, 0] != want[bad, 0]).sum()
+    raise AssertionError(f"{what}: {bad.size}/{want.shape[0]} results differ ({ids} in the triangle id); first at ray {bad[0]}: "
+                         f"got {got_u32[bad[0]]} want {want[bad[0]]}")
+
+
+def device_primary(battlefield, width, height, spp=1, seed=0):
+    cam = rb.Camera.for_scene(battlefield, width, height)
+    n = width * height * spp
+    d = torch.empty(n * 8, dtype=torch.float32, device="cuda")
+    rb.generate_primary(cam, width, height, spp, seed, d.data_ptr())
+    torch.cuda.synchronize()
+    return d
+
+
+def device_bounce(scene, d_rays, d_res, n, seed):
+    out = torch.empty(max(n, 1) * 8, dtype=torch.float32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rb.generate_bounce(scene, d_rays.data_ptr(), d_res.data_ptr(), n, seed, out.data_ptr(), cnt.data_ptr())
+    torch.cuda.synchronize()
+    m = int(cnt.item())
+    return out[: m * 8], m
+
+
+def test_scene_on_device_matches_host_build(scene, battlefield_images):
+    nodes, pairs, remap = scene.download()
+    assert np.array_equal(nodes.view(np.uint32), battlefield_images.nodes.view(np.uint32))
+    assert np.array_equal(pairs.view(np.uint32), battlefield_images.pairs.view(np.uint32))
+    assert np.array_equal(remap, battlefield_images.remap)
+
+
+@pytest.mark.parametrize("tuning", VARIANTS, ids=lambda t: "-".join(f"{k}{v}" for k, v in t.items()))
+def test_primary_and_bounces_bit_exact(tuning, scene, env, images, battlefield):
+    """C2/C3 shaped input at reduced size: 480x270 primaries, then 3 diffuse bounces."""
+    rb.set_tuning(**{**DEFAULT, **tuning})
+    try:
+        w, h = 480, 270
+        d_rays = device_primary(battlefield, w, h, 1, seed=1)
+        n = w * h
+        for bounce in range(4):
+            rays_np = d_rays[: n * 8].cpu().numpy().view(oracle.RAY_DTYPE)
+            d_res = torch.empty(n * 4, dtype=torch.float32, device="cuda")
+            rb.trace_device(scene, env, [(d_rays.data_ptr(), d_res.data_ptr(), n)])
+            torch.cuda.synchronize()
+            got = d_res.cpu().numpy().view(np.uint32).reshape(-1, 4)
+            assert_bit_exact(got, oracle.traverse(images, rays_np), f"bounce {bounce}")
+            d_rays, n = device_bounce(scene, d_rays, d_res, n, seed=2 + bounce)
+            assert n > 0
+    finally:
+        rb.set_tuning(**DEFAULT)
+
+
+def test_random_rays_bit_exact_and_brute_force(scene, env, images, battlefield):
+    lo = battlefield.vertices[:, :3].min(0)
+    hi = battlefield.vertices[:, :3].max(0)
+    rays = random_rays(300_000, lo, hi, seed=8)
+    got = trace_dev(scene, env, rays)
+    want = oracle.traverse(images, rays)
+    assert_bit_exact(got, want, "uniform random rays")
+    # independent arbiter on a subset: id in the fp64 tie set, t within 1e-4 relative
+    m = 3000
+    t64, id64 = oracle.brute_f64(battlefield.vertices, battlefield.indices, rays[:m])
+    ids = got[:m, 0]
+    hit = ids != rb.INVALID_TRIANGLE
+    assert np.array_equal(hit, np.isfinite(t64))
+    t_gpu = got[:m, 1].view(np.float32)
+    assert np.all(np.abs(t_gpu[hit] - t64[hit]) <= 1e-4 * t64[hit])
+    t_of_id = oracle.tri_t_f64(battlefield.vertices, battlefield.indices, rays[:m], np.where(hit, ids, rb.INVALID_TRIANGLE))
+    assert np.all(t_of_id[hit] <= t64[hit] * (1 + 1e-6) + 1e-9)
+
+
+def test_counters_match_oracle(scene, env, images, battlefield):
+    lo = battlefield.vertices[:, :3].min(0)
+    hi = battlefield.vertices[:, :3].max(0)
+    rays = random_rays(100_000, lo, hi, seed=3)
+    _, cnt = oracle.traverse(images, rays, counters=True)
+    for variant in (0, 1):
+        rb.set_tuning(**{**DEFAULT, "variant": variant})
+        d_rays = to_device(rays)
+        d_res = torch.empty(rays.shape[0] * 4, dtype=torch.float32, device="cuda")
+        d_cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+        rb.trace_device(scene, env, [(d_rays.data_ptr(), d_res.data_ptr(), rays.shape[0])], counters_ptr=d_cnt.data_ptr())
+        torch.cuda.synchronize()
+        c = d_cnt.cpu().numpy()
+        assert c[0] == rays.shape[0]
+        assert c[1] == int(cnt["hit"].sum())
+        assert c[2] == int(cnt["inner"].astype(np.int64).sum())
+        assert c[3] == int(cnt["pairs"].astype(np.int64).sum())
+    rb.set_tuning(**DEFAULT)
+
+
+def test_host_stream_path(scene, env, images, battlefield):
+    """The reference-facing call: host buffers in, host results out (H2D + trace + D2H)."""
+    lo = battlefield.vertices[:, :3].min(0)
+    hi = battlefield.vertices[:, :3].max(0)
+    rays = random_rays(50_000, lo, hi, seed=4)
+    res = rb.trace_host(scene, env, rays)
+    assert_bit_exact(res.view(np.uint32).reshape(-1, 4), oracle.traverse(images, rays), "host stream")
+
+
+def test_many_streams_one_launch_ragged(scene, env, images, battlefield):
+    """Several ray streams of ragged sizes (including empty ones) in a single launch."""
+    lo = battlefield.vertices[:, :3].min(0)
+    hi = battlefield.vertices[:, :3].max(0)
+    sizes = [1, 0, 31, 32, 33, 11264, 0, 27648, 7, 1000]
+    rays = [random_rays(s, lo, hi, seed=10 + k) for k, s in enumerate(sizes)]
+    d_rays = [to_device(r) if r.shape[0] else torch.empty(8, device="cuda") for r in rays]
+    d_res = [torch.full((max(s, 1) * 4,), 7.0, dtype=torch.float32, device="cuda") for s in sizes]
+    rb.trace_device(scene, env, [(a.data_ptr(), b.data_ptr(), s) for a, b, s in zip(d_rays, d_res, sizes)])
+    torch.cuda.synchronize()
+    for k, s in enumerate(sizes):
+        if s:
+            got = d_res[k][: s * 4].cpu().numpy().view(np.uint32).reshape(-1, 4)
+            assert_bit_exact(got, oracle.traverse(images, rays[k]), f"stream {k}")
+        else:
+            assert float(d_res[k][0]) == 7.0  # untouched
+
+
+def test_empty_launch_is_a_noop(scene, env):
+    rb.trace_device(scene, env, [])
+    rb.trace_device(scene, env, [(0, 0, 0)])
+    torch.cuda.synchronize()
+
+
+def test_no_environment_misses_return_zero(scene, images, battlefield):
+    rays = make_rays([[0, 500, 0]] * 64, [[0, 1, 0]] * 64)
+    got = trace_dev(scene, None, rays)
+    assert np.all(got[:, 0] == rb.INVALID_TRIANGLE)
+    assert np.all(got[:, 1:] == 0)
+
+
+def test_reference_built_images_give_identical_hits(gpu, env, battlefield):
+    """Trace the UNMODIFIED reference builder's own images with our kernel: results must equal the
+    ones from our build (the images are structurally identical, only the numbering differs)."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    ref_img = oracle.ref_build_scene(battlefield.vertices, battlefield.indices)
+    s_ref = rb.create_scene_from_images(ref_img.nodes, ref_img.pairs, ref_img.remap)
+    s_own = rb.create_scene(battlefield.vertices, battlefield.indices)
+    lo = battlefield.vertices[:, :3].min(0)
+    hi = battlefield.vertices[:, :3].max(0)
+    rays = random_rays(200_000, lo, hi, seed=5)
+    a = trace_dev(s_ref, env, rays)
+    b = trace_dev(s_own, env, rays)
+    assert np.array_equal(a, b)
+    ref_img.env = battlefield.environment
+    assert_bit_exact(a, oracle.traverse(ref_img, rays), "reference-built images")
+    s_ref.destroy()
+    s_own.destroy()
+
+
+def test_full_size_properties(scene, env, battlefield):
+    """BASELINE config 2 at full size (1920x1080x4 spp = 8.3 M rays): size-independent properties
+    instead of an oracle run -- idempotence (two launch shapes, same bits), every hit id in range,
+    t inside (minT, maxT], barycentrics in the triangle, and a shortened ray (maxT just past t)
+    re-hits the same triangle at the same t."""
+    w, h, spp = 1920, 1080, 4
+    n = w * h * spp
+    d_rays = device_primary(battlefield, w, h, spp, seed=1)
+    d_a = torch.empty(n * 4, dtype=torch.float32, device="cuda")
+    d_b = torch.empty(n * 4, dtype=torch.float32, device="cuda")
+    rb.set_tuning(**DEFAULT)
+    rb.trace_device(scene, env, [(d_rays.data_ptr(), d_a.data_ptr(), n)])
+    rb.set_tuning(**{**DEFAULT, "variant": 1})
+    rb.trace_device(scene, env, [(d_rays.data_ptr(), d_b.data_ptr(), n)])
+    rb.set_tuning(**DEFAULT)
+    torch.cuda.synchronize()
+    assert torch.equal(d_a.view(torch.int32), d_b.view(torch.int32))
+    res = d_a.view(-1, 4)
+    ids = res[:, 0].view(torch.int32)
+    hit = ids != -1
+    assert 0.5 < float(hit.float().mean()) < 0.95
+    assert int(ids[hit].max()) < battlefield.triangle_count and int(ids[hit].min()) >= 0
+    t, u, v = res[hit, 1], res[hit, 2], res[hit, 3]
+    assert bool((t > 0).all()) and bool((t <= 1e6).all())
+    assert bool((u >= -1e-6).all()) and bool((v >= -1e-6).all()) and bool((u + v <= 1 + 1e-5).all())
+    # shorten every hit ray to just past its hit: the closest hit must not change
+    rays2 = d_rays.view(-1, 8).clone()
+    rays2[hit, 7] = t * (1.0 + 1e-5)
+    d_c = torch.empty(n * 4, dtype=torch.float32, device="cuda")
+    rb.trace_device(scene, env, [(rays2.data_ptr(), d_c.data_ptr(), n)])
+    torch.cuda.synchronize()
+    res2 = d_c.view(-1, 4)
+    same_id = res2[:, 0].view(torch.int32) == ids
+    frac = float(same_id.float().mean())
+    assert frac > 0.9999, frac  # a different id is only legal when two triangles tie at exactly t
+    assert bool((res2[~hit, 0].view(torch.int32) == -1).all())
+    both = same_id & hit
+    assert torch.equal(res2[both, 1], res[both, 1])
