@@ -107,15 +107,19 @@ void racc_cuda_env_destroy(racc_cuda_env* env);
 /* replaces the body of gpuWorkerThread: 7x clSetKernelArg + clEnqueueNDRangeKernel
  * (RayAccelerator.cpp:377-401) for one OR MORE ray streams in a single launch. env may be NULL
  * (misses then return r=g=b=0). cuda_stream: a cudaStream_t (NULL = default stream).
- * Asynchronous for DEVICE streams; HOST streams are staged through pinned memory on the same
- * CUDA stream and are complete when racc_cuda_sync() returns. */
+ * Asynchronous. DEVICE streams of one call are traced by ONE launch. HOST streams
+ * (pinned memory recommended) are cut into chunks that alternate over internal CUDA streams so
+ * H2D, traversal and D2H overlap; cuda_stream waits for them, so everything is complete when
+ * racc_cuda_sync(cuda_stream) returns. */
 int racc_cuda_trace(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_stream_desc* streams,
                     uint32_t nstreams, void* cuda_stream);
 
-/* Same, additionally accumulating visit counters into *device_counters (a device pointer to a
- * racc_cuda_counters that the caller zeroed). Slower; used for the roofline accounting only. */
+/* Same, additionally accumulating into *device_counters (a device pointer to a racc_cuda_counters
+ * that the caller zeroed). detail == 0: rays and hits only (free: one atomic per warp; this is the
+ * per-frame hit count the multi-GPU reduction sums, and what racc::Stats reports). detail != 0:
+ * also inner-node and pair visits (slower; used for the roofline accounting only). */
 int racc_cuda_trace_counted(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_stream_desc* streams,
-                            uint32_t nstreams, void* cuda_stream, void* device_counters);
+                            uint32_t nstreams, void* cuda_stream, void* device_counters, int detail);
 
 /* replaces clFinish(queue) (RayAccelerator.cpp:403) */
 int racc_cuda_sync(void* cuda_stream);

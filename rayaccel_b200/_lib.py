@@ -55,7 +55,7 @@ SYMBOLS = {
     "racc_cuda_env_create": (_P, [_P, _U32, _U32]),
     "racc_cuda_env_destroy": (None, [_P]),
     "racc_cuda_trace": (ctypes.c_int, [_P, _P, ctypes.POINTER(StreamDesc), _U32, _P]),
-    "racc_cuda_trace_counted": (ctypes.c_int, [_P, _P, ctypes.POINTER(StreamDesc), _U32, _P, _P]),
+    "racc_cuda_trace_counted": (ctypes.c_int, [_P, _P, ctypes.POINTER(StreamDesc), _U32, _P, _P, ctypes.c_int]),
     "racc_cuda_sync": (ctypes.c_int, [_P]),
     "racc_cuda_launch_count": (ctypes.c_uint64, []),
     "racc_cuda_set_variant": (ctypes.c_int, [ctypes.c_int]),

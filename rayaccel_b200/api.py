@@ -155,6 +155,22 @@ def _cuda_stream_handle(stream) -> ctypes.c_void_p:
     return ctypes.c_void_p(int(stream))
 
 
+def trace_host_ptrs(scene: Scene, environment: Environment | None, streams, stream=None, counters_ptr: int | None = None) -> None:
+    """HOST ray streams by raw pointer [(rays_ptr, results_ptr, count), ...] (e.g. pinned torch tensors).
+    Asynchronous: complete after sync(stream)."""
+    n = len(streams)
+    arr = (StreamDesc * n)()
+    for k, (rp, op, cnt) in enumerate(streams):
+        arr[k] = StreamDesc(rp, op, cnt, _lib.STREAM_HOST)
+    lib = _lib.load()
+    h = _cuda_stream_handle(stream)
+    env = environment._h if environment else None
+    if counters_ptr is None:
+        _lib.check(lib.racc_cuda_trace(scene._h, env, arr, n, h), "racc_cuda_trace")
+    else:
+        _lib.check(lib.racc_cuda_trace_counted(scene._h, env, arr, n, h, ctypes.c_void_p(counters_ptr), 0), "racc_cuda_trace_counted")
+
+
 def trace_host(scene: Scene, environment: Environment | None, rays: np.ndarray, results: np.ndarray | None = None,
                stream=None, sync: bool = True) -> np.ndarray:
     """One ray stream in HOST memory through the engine: H2D, traversal, D2H (what gpuWorkerThread
@@ -173,9 +189,11 @@ def trace_host(scene: Scene, environment: Environment | None, rays: np.ndarray, 
     return results
 
 
-def trace_device(scene: Scene, environment: Environment | None, streams, stream=None, counters_ptr: int | None = None) -> None:
+def trace_device(scene: Scene, environment: Environment | None, streams, stream=None, counters_ptr: int | None = None,
+                 detail: bool = True) -> None:
     """Launch ONE traversal over a list of device-resident streams [(rays_ptr, results_ptr, count), ...].
-    Asynchronous on `stream`. counters_ptr: device pointer to a zeroed Counters record (slower)."""
+    Asynchronous on `stream`. counters_ptr: device pointer to a zeroed Counters record (4 x u64);
+    detail=False accumulates rays+hits only (free), detail=True also node/pair visits (slower)."""
     n = len(streams)
     arr = (StreamDesc * n)()
     for k, (rp, op, cnt) in enumerate(streams):
@@ -186,7 +204,8 @@ def trace_device(scene: Scene, environment: Environment | None, streams, stream=
     if counters_ptr is None:
         _lib.check(lib.racc_cuda_trace(scene._h, env, arr, n, h), "racc_cuda_trace")
     else:
-        _lib.check(lib.racc_cuda_trace_counted(scene._h, env, arr, n, h, ctypes.c_void_p(counters_ptr)), "racc_cuda_trace_counted")
+        _lib.check(lib.racc_cuda_trace_counted(scene._h, env, arr, n, h, ctypes.c_void_p(counters_ptr), 1 if detail else 0),
+                   "racc_cuda_trace_counted")
 
 
 def sync(stream=None) -> None:
@@ -198,7 +217,7 @@ def launch_count() -> int:
 
 
 def set_tuning(**kw) -> None:
-    keys = {"variant": 0, "block": 1, "ctas_per_sm": 2, "smem_nodes": 3, "fetch_threshold": 4}
+    keys = {"variant": 0, "block": 1, "ctas_per_sm": 2, "smem_nodes": 3, "fetch_threshold": 4, "leaf_threshold": 5, "carveout": 6}
     lib = _lib.load()
     for k, v in kw.items():
         lib.racc_cuda_set_tuning(keys[k], int(v))

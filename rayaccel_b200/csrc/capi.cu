@@ -71,6 +71,8 @@ int ensureInit() {
 	g_tuning.ctasPerSm = envInt("RACC_B200_CTAS_PER_SM", g_tuning.ctasPerSm);
 	g_tuning.smemNodes = envInt("RACC_B200_SMEM_NODES", g_tuning.smemNodes);
 	g_tuning.fetchThreshold = envInt("RACC_B200_FETCH_THRESHOLD", g_tuning.fetchThreshold);
+	g_tuning.leafThreshold = envInt("RACC_B200_LEAF_THRESHOLD", g_tuning.leafThreshold);
+	g_tuning.carveout = envInt("RACC_B200_CARVEOUT", g_tuning.carveout);
 	g_initialised = true;
 	return 0;
 }
@@ -175,6 +177,8 @@ int racc_cuda_set_tuning(int key, int value) {
 	case 2: slot = &g_tuning.ctasPerSm; break;
 	case 3: slot = &g_tuning.smemNodes; break;
 	case 4: slot = &g_tuning.fetchThreshold; break;
+	case 5: slot = &g_tuning.leafThreshold; break;
+	case 6: slot = &g_tuning.carveout; break;
 	default: return fail("unknown tuning key %d", key);
 	}
 	const int previous = *slot;
@@ -316,49 +320,61 @@ void racc_cuda_env_destroy(racc_cuda_env* env) {
 	delete env;
 }
 
-static int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams,
-                     void* cuda_stream, void* device_counters) {
-	if (!s) return fail("racc_cuda_trace: null scene");
-	if (!streams && nstreams) return fail("racc_cuda_trace: null stream list");
-	if (ensureInit()) return -1;
-	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+namespace {
 
-	struct Staged { void* dRays; void* dResults; void* hResults; size_t resultBytes; };
-	std::vector<StreamRef> refs;
-	std::vector<Staged> staged;
-	refs.reserve(nstreams);
-	uint64_t total = 0;
-	for (uint32_t i = 0; i < nstreams; ++i) {
-		const racc_cuda_stream_desc& d = streams[i];
-		if (!d.count) continue;
-		if (!d.rays || !d.results) return fail("racc_cuda_trace: stream %u has null buffers", i);
-		StreamRef ref;
-		ref.begin = (uint32_t)total;
-		ref.count = d.count;
-		if (d.flags & RACC_CUDA_STREAM_HOST) {
-			Staged st;
-			st.resultBytes = (size_t)d.count * 16;
-			st.hResults = d.results;
-			RACC_CUDA_CHECK(cudaMallocAsync(&st.dRays, (size_t)d.count * 32, stream));
-			RACC_CUDA_CHECK(cudaMallocAsync(&st.dResults, st.resultBytes, stream));
-			RACC_CUDA_CHECK(cudaMemcpyAsync(st.dRays, d.rays, (size_t)d.count * 32, cudaMemcpyHostToDevice, stream));
-			staged.push_back(st);
-			ref.rays = static_cast<const DevRay*>(st.dRays);
-			ref.results = static_cast<float4*>(st.dResults);
+// Staging pipeline for HOST ray streams: chunks alternate over a few internal CUDA streams so that
+// the H2D copy of chunk k+1, the traversal of chunk k and the D2H copy of chunk k-1 overlap (PCIe
+// is full duplex). One pipeline per calling host thread, so concurrent submitters never share
+// staging buffers. Replaces the reference's zero-copy CL_MEM_USE_HOST_PTR streams
+// (RayAccelerator.cpp:643-644), which a discrete GPU does not have.
+struct HostPipeline {
+	static constexpr int kLanes = 3;
+	bool ready = false;
+	int device = -1;
+	uint32_t chunkRays = 0;
+	cudaStream_t lane[kLanes] = {};
+	cudaEvent_t done[kLanes] = {};
+	cudaEvent_t fork = nullptr;
+	DevRay* dRays[kLanes] = {};
+	float4* dResults[kLanes] = {};
+
+	int init() {
+		if (ready && device == g_device) return 0;
+		release();
+		device = g_device;
+		chunkRays = (uint32_t)envInt("RACC_B200_HOST_CHUNK", 1 << 19);
+		if (chunkRays < 1024) chunkRays = 1024;
+		RACC_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+		for (int l = 0; l < kLanes; ++l) {
+			RACC_CUDA_CHECK(cudaStreamCreateWithFlags(&lane[l], cudaStreamNonBlocking));
+			RACC_CUDA_CHECK(cudaEventCreateWithFlags(&done[l], cudaEventDisableTiming));
+			RACC_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&dRays[l]), (size_t)chunkRays * sizeof(DevRay)));
+			RACC_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&dResults[l]), (size_t)chunkRays * sizeof(float4)));
 		}
-		else {
-			if ((reinterpret_cast<uintptr_t>(d.rays) & 15) || (reinterpret_cast<uintptr_t>(d.results) & 15))
-				return fail("racc_cuda_trace: stream %u buffers must be 16-byte aligned", i);
-			ref.rays = static_cast<const DevRay*>(d.rays);
-			ref.results = static_cast<float4*>(d.results);
-		}
-		refs.push_back(ref);
-		total += d.count;
-		if (total > 0x7fffffffull) return fail("racc_cuda_trace: more than 2^31-1 rays in one launch");
+		ready = true;
+		return 0;
 	}
-	if (!total) return 0;
 
-	TraceParams p{};
+	void release() {
+		if (!ready) return;
+		for (int l = 0; l < kLanes; ++l) {
+			if (lane[l]) { cudaStreamSynchronize(lane[l]); cudaStreamDestroy(lane[l]); }
+			if (done[l]) cudaEventDestroy(done[l]);
+			cudaFree(dRays[l]);
+			cudaFree(dResults[l]);
+			lane[l] = nullptr; done[l] = nullptr; dRays[l] = nullptr; dResults[l] = nullptr;
+		}
+		if (fork) cudaEventDestroy(fork);
+		fork = nullptr;
+		ready = false;
+	}
+
+	~HostPipeline() { /* process teardown: the context may already be gone, leak on purpose */ }
+};
+
+thread_local HostPipeline t_pipeline;
+
+void fillSceneParams(TraceParams& p, racc_cuda_scene* s, racc_cuda_env* env, void* device_counters) {
 	p.nodes = s->dNodes;
 	p.pairs = s->dPairs;
 	p.remap = s->dRemap;
@@ -366,39 +382,104 @@ static int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_str
 	p.envWidth = env ? env->width : 0;
 	p.envHeight = env ? env->height : 0;
 	p.nodeCount = (uint32_t)s->host.nodes.size();
-	p.nstreams = (uint32_t)refs.size();
-	p.total = (uint32_t)total;
-	p.single = refs[0];
-	p.cursor = s->dCursors + (s->nextCursor.fetch_add(1) % kCursorRing);
 	p.counters = static_cast<unsigned long long*>(device_counters);
-	void* dRefs = nullptr;
-	if (refs.size() > 1) {
-		RACC_CUDA_CHECK(cudaMallocAsync(&dRefs, refs.size() * sizeof(StreamRef), stream));
-		RACC_CUDA_CHECK(cudaMemcpyAsync(dRefs, refs.data(), refs.size() * sizeof(StreamRef), cudaMemcpyHostToDevice, stream));
-		p.streams = static_cast<const StreamRef*>(dRefs);
+}
+
+int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams,
+              void* cuda_stream, void* device_counters, bool fullCounters) {
+	if (!s) return fail("racc_cuda_trace: null scene");
+	if (!streams && nstreams) return fail("racc_cuda_trace: null stream list");
+	if (ensureInit()) return -1;
+	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+
+	std::vector<StreamRef> refs; // device-resident streams: one launch for all of them
+	std::vector<const racc_cuda_stream_desc*> hostStreams;
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < nstreams; ++i) {
+		const racc_cuda_stream_desc& d = streams[i];
+		if (!d.count) continue;
+		if (!d.rays || !d.results) return fail("racc_cuda_trace: stream %u has null buffers", i);
+		if (d.flags & RACC_CUDA_STREAM_HOST) {
+			hostStreams.push_back(&d);
+			continue;
+		}
+		if ((reinterpret_cast<uintptr_t>(d.rays) & 15) || (reinterpret_cast<uintptr_t>(d.results) & 15))
+			return fail("racc_cuda_trace: stream %u buffers must be 16-byte aligned", i);
+		StreamRef ref;
+		ref.begin = (uint32_t)total;
+		ref.count = d.count;
+		ref.rays = static_cast<const DevRay*>(d.rays);
+		ref.results = static_cast<float4*>(d.results);
+		refs.push_back(ref);
+		total += d.count;
+		if (total > 0x7fffffffull) return fail("racc_cuda_trace: more than 2^31-1 rays in one launch");
 	}
 
 	int launches = 0;
-	RACC_CUDA_CHECK(launchTrace(p, g_tuning, device_counters != nullptr, g_smCount, stream, &launches));
-	g_launches.fetch_add((uint64_t)launches);
-
-	for (const Staged& st : staged) {
-		RACC_CUDA_CHECK(cudaMemcpyAsync(st.hResults, st.dResults, st.resultBytes, cudaMemcpyDeviceToHost, stream));
-		RACC_CUDA_CHECK(cudaFreeAsync(st.dRays, stream));
-		RACC_CUDA_CHECK(cudaFreeAsync(st.dResults, stream));
+	if (total) {
+		TraceParams p{};
+		fillSceneParams(p, s, env, device_counters);
+		p.nstreams = (uint32_t)refs.size();
+		p.total = (uint32_t)total;
+		p.single = refs[0];
+		p.cursor = s->dCursors + (s->nextCursor.fetch_add(1) % kCursorRing);
+		void* dRefs = nullptr;
+		if (refs.size() > 1) {
+			RACC_CUDA_CHECK(cudaMallocAsync(&dRefs, refs.size() * sizeof(StreamRef), stream));
+			RACC_CUDA_CHECK(cudaMemcpyAsync(dRefs, refs.data(), refs.size() * sizeof(StreamRef), cudaMemcpyHostToDevice, stream));
+			p.streams = static_cast<const StreamRef*>(dRefs);
+		}
+		RACC_CUDA_CHECK(launchTrace(p, g_tuning, device_counters ? (fullCounters ? 2 : 1) : 0, g_smCount, stream, &launches));
+		if (dRefs) RACC_CUDA_CHECK(cudaFreeAsync(dRefs, stream));
 	}
-	if (dRefs) RACC_CUDA_CHECK(cudaFreeAsync(dRefs, stream));
+
+	if (!hostStreams.empty()) {
+		HostPipeline& pipe = t_pipeline;
+		if (pipe.init()) return -1;
+		RACC_CUDA_CHECK(cudaEventRecord(pipe.fork, stream));
+		for (int l = 0; l < HostPipeline::kLanes; ++l)
+			RACC_CUDA_CHECK(cudaStreamWaitEvent(pipe.lane[l], pipe.fork, 0));
+		unsigned chunk = 0;
+		for (const racc_cuda_stream_desc* d : hostStreams) {
+			const char* hRays = static_cast<const char*>(d->rays);
+			char* hResults = static_cast<char*>(d->results);
+			for (uint32_t begin = 0; begin < d->count; begin += pipe.chunkRays, ++chunk) {
+				const uint32_t n = d->count - begin < pipe.chunkRays ? d->count - begin : pipe.chunkRays;
+				const int l = (int)(chunk % HostPipeline::kLanes);
+				RACC_CUDA_CHECK(cudaMemcpyAsync(pipe.dRays[l], hRays + (size_t)begin * 32, (size_t)n * 32, cudaMemcpyHostToDevice, pipe.lane[l]));
+				TraceParams p{};
+				fillSceneParams(p, s, env, device_counters);
+				p.nstreams = 1;
+				p.total = n;
+				p.single.rays = pipe.dRays[l];
+				p.single.results = pipe.dResults[l];
+				p.single.begin = 0;
+				p.single.count = n;
+				p.cursor = s->dCursors + (s->nextCursor.fetch_add(1) % kCursorRing);
+				RACC_CUDA_CHECK(launchTrace(p, g_tuning, device_counters ? (fullCounters ? 2 : 1) : 0, g_smCount, pipe.lane[l], &launches));
+				RACC_CUDA_CHECK(cudaMemcpyAsync(hResults + (size_t)begin * 16, pipe.dResults[l], (size_t)n * 16, cudaMemcpyDeviceToHost, pipe.lane[l]));
+			}
+		}
+		const int used = chunk < (unsigned)HostPipeline::kLanes ? (int)chunk : HostPipeline::kLanes;
+		for (int l = 0; l < used; ++l) {
+			RACC_CUDA_CHECK(cudaEventRecord(pipe.done[l], pipe.lane[l]));
+			RACC_CUDA_CHECK(cudaStreamWaitEvent(stream, pipe.done[l], 0));
+		}
+	}
+	g_launches.fetch_add((uint64_t)launches);
 	return 0;
 }
 
+} // namespace
+
 int racc_cuda_trace(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams, void* cuda_stream) {
-	return traceImpl(scene, env, streams, nstreams, cuda_stream, nullptr);
+	return traceImpl(scene, env, streams, nstreams, cuda_stream, nullptr, false);
 }
 
 int racc_cuda_trace_counted(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams,
-                            void* cuda_stream, void* device_counters) {
+                            void* cuda_stream, void* device_counters, int detail) {
 	if (!device_counters) return fail("racc_cuda_trace_counted: null counter buffer");
-	return traceImpl(scene, env, streams, nstreams, cuda_stream, device_counters);
+	return traceImpl(scene, env, streams, nstreams, cuda_stream, device_counters, detail != 0);
 }
 
 int racc_cuda_sync(void* cuda_stream) {

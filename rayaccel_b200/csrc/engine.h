@@ -36,14 +36,17 @@ struct TraceParams {
 
 // Tunables (racc_cuda_set_variant / RACC_B200_* environment variables), see DESIGN.md section 5.
 struct Tuning {
-	int variant = 0;        // 0 persistent while-while (default), 1 one-thread-per-ray
+	int variant = 0;        // 0 persistent while-while (default), 1 one-thread-per-ray, 2 persistent phased
 	int blockThreads = 256; // threads per CTA
 	int ctasPerSm = 0;      // 0 = as many as fit
 	int smemNodes = -1;     // -1 = auto
 	int fetchThreshold = 12; // refill a warp when at least this many lanes are idle
+	int leafThreshold = 8;   // variant 2: run leaf tests when at least this many lanes wait at a leaf
+	int carveout = -1;       // shared-memory carveout percent, -1 = exactly what the CTAs need
 };
 
-cudaError_t launchTrace(const TraceParams& p, const Tuning& t, bool counted, int smCount, cudaStream_t stream, int* launches);
+// counterMode: 0 none, 1 rays+hits only, 2 rays, hits, inner-node and pair visits
+cudaError_t launchTrace(const TraceParams& p, const Tuning& t, int counterMode, int smCount, cudaStream_t stream, int* launches);
 
 cudaError_t launchGeneratePrimary(const float* camera12, uint32_t width, uint32_t height, uint32_t spp, uint32_t seed,
                                   DevRay* rays, cudaStream_t stream, int* launches);

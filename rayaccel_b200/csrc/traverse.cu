@@ -284,11 +284,25 @@ __global__ void __launch_bounds__(256) traceSimpleKernel(const TraceParams p) {
 		node = stack[--sp];
 	}
 	out[local] = finishRay(p, r, h);
-	if (kCount) {
-		atomicAdd(p.counters + 0, 1ull);
-		atomicAdd(p.counters + 1, h.index != kMiss ? 1ull : 0ull);
-		atomicAdd(p.counters + 2, (unsigned long long)nInner);
-		atomicAdd(p.counters + 3, (unsigned long long)nPairs);
+	if (p.counters) {
+		// warp-aggregated: one atomic per counter per warp
+		const unsigned active = __activemask();
+		const unsigned hits = __popc(__ballot_sync(active, h.index != kMiss));
+		unsigned long long sumInner = nInner, sumPairs = nPairs;
+		if (kCount) {
+			for (int o = 16; o; o >>= 1) {
+				sumInner += __shfl_xor_sync(active, sumInner, o);
+				sumPairs += __shfl_xor_sync(active, sumPairs, o);
+			}
+		}
+		if ((threadIdx.x & 31) == (unsigned)(__ffs(active) - 1)) {
+			atomicAdd(p.counters + 0, (unsigned long long)__popc(active));
+			atomicAdd(p.counters + 1, (unsigned long long)hits);
+			if (kCount) {
+				atomicAdd(p.counters + 2, sumInner);
+				atomicAdd(p.counters + 3, sumPairs);
+			}
+		}
 	}
 }
 
@@ -327,14 +341,44 @@ __device__ __forceinline__ void stageNodes(float4* dst, const float4* src, uint3
 	}
 }
 
-template <bool kCount, int kBlock, int kMinBlocks>
-__global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(const TraceParams p, const int fetchThreshold) {
+// The four float4s of inner node n. The hottest nodes live in shared memory (staged by TMA), the
+// rest in global memory behind L1/L2. Both bases are generic 64-bit addresses held in registers so
+// that picking one is two selects and the address one IMAD.WIDE.
+struct NodeBases {
+	const char* shared;
+	const char* global;
+	uint32_t sharedCount;
+};
+
+__device__ __forceinline__ const float4* nodeAddress(const NodeBases& nb, uint32_t n) {
+	const char* base = n < nb.sharedCount ? nb.shared : nb.global;
+	unsigned long long a;
+	asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(a) : "r"(n), "l"(reinterpret_cast<unsigned long long>(base)));
+	return reinterpret_cast<const float4*>(a);
+}
+
+// kMode 0: while-while (every lane walks inner nodes until it holds a leaf; then all leaves).
+// kMode 1: phased (each pass is EITHER one inner step for the lanes at inner nodes OR the leaf
+//          tests of the lanes at leaves; leaves run when at least `leafThreshold` lanes wait at one
+//          or no lane is at an inner node).
+template <bool kCount, int kBlock, int kMinBlocks, int kMode>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(const TraceParams p, const int fetchThreshold, const int leafThreshold) {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
 	__shared__ uint64_t stageBar;
 	float4* sNodes = reinterpret_cast<float4*>(smemRaw);
-	const uint32_t smemNodes = p.smemNodes;
-	if (smemNodes)
-		stageNodes(sNodes, p.nodes, smemNodes * 64u, &stageBar);
+	if (p.smemNodes)
+		stageNodes(sNodes, p.nodes, p.smemNodes * 64u, &stageBar);
+
+	NodeBases nb;
+	{
+		// materialise the generic address of the staging area once (otherwise the conversion is
+		// redone, S2R and all, in the traversal loop)
+		unsigned long long g;
+		asm volatile("cvta.shared.u64 %0, %1;" : "=l"(g) : "l"((unsigned long long)smemAddr(sNodes)));
+		nb.shared = reinterpret_cast<const char*>(g);
+		nb.global = reinterpret_cast<const char*>(p.nodes);
+		nb.sharedCount = p.smemNodes;
+	}
 
 	const unsigned lane = threadIdx.x & 31;
 	const unsigned ltMask = (1u << lane) - 1u;
@@ -348,15 +392,17 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(cons
 	int sp = 0;
 	uint32_t node = 0;
 	float4* outPtr = nullptr;
-	unsigned long long cInner = 0, cPairs = 0, cRays = 0, cHits = 0;
+	unsigned long long cInner = 0, cPairs = 0;
+	unsigned cRays = 0, cHits = 0;
 
 	for (;;) {
 		// ---- retire finished lanes and refill idle ones, warp-wide -----------------------------
 		const unsigned idle = __ballot_sync(kFullMask, state != kTraversing);
-		if (idle == kFullMask || (!exhausted && __popc(idle) >= fetchThreshold) || (exhausted && __ballot_sync(kFullMask, state == kFinished))) {
+		if (idle == kFullMask || __popc(idle) >= (exhausted ? 32 : fetchThreshold)) {
 			if (state == kFinished) {
 				*outPtr = finishRay(p, r, h);
-				if (kCount) { ++cRays; cHits += h.index != kMiss; }
+				++cRays;
+				cHits += h.index != kMiss;
 				state = kEmpty;
 			}
 			if (!exhausted) {
@@ -383,89 +429,146 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(cons
 				break;
 		}
 
-		// ---- while-while traversal ------------------------------------------------------------
-		if (state == kTraversing) {
-			while (node & kInnerBit) {
-				const uint32_t n = node & ~kInnerBit;
-				if (kCount) ++cInner;
-				const float4* np = n < smemNodes ? sNodes + 4 * n : p.nodes + 4 * (size_t)n;
-				node = innerStep(np, r, stack, sp);
-			}
-		}
-		__syncwarp();
-		if (state == kTraversing) {
-			if (node) {
-				const uint32_t first = node & 0xffffffu, last = first + (node >> 24);
-				for (uint32_t i = first; i < last; ++i) {
-					pairTest(p.pairs, i, r, h);
-					if (kCount) ++cPairs;
+		if (kMode == 0) {
+			// ---- while-while ---------------------------------------------------------------------
+			if (state == kTraversing) {
+				while (node & kInnerBit) {
+					if (kCount) ++cInner;
+					node = innerStep(nodeAddress(nb, node & ~kInnerBit), r, stack, sp);
 				}
-				node = sp ? stack[--sp] : 0u;
 			}
-			if (!node)
-				state = kFinished;
+			__syncwarp();
+			if (state == kTraversing) {
+				if (node) {
+					const uint32_t first = node & 0xffffffu, last = first + (node >> 24);
+					for (uint32_t i = first; i < last; ++i) {
+						pairTest(p.pairs, i, r, h);
+						if (kCount) ++cPairs;
+					}
+					node = sp ? stack[--sp] : 0u;
+				}
+				if (!node)
+					state = kFinished;
+			}
+			__syncwarp();
 		}
-		__syncwarp();
+		else {
+			// ---- phased: one inner step OR one round of leaf tests per pass -------------------------
+			const bool atInner = state == kTraversing && (node & kInnerBit);
+			const bool atLeaf = state == kTraversing && !(node & kInnerBit);
+			const unsigned innerMask = __ballot_sync(kFullMask, atInner);
+			const unsigned leafMask = __ballot_sync(kFullMask, atLeaf);
+			if (leafMask && (!innerMask || __popc(leafMask) >= leafThreshold)) {
+				if (atLeaf) {
+					const uint32_t first = node & 0xffffffu, last = first + (node >> 24);
+					for (uint32_t i = first; i < last; ++i) {
+						pairTest(p.pairs, i, r, h);
+						if (kCount) ++cPairs;
+					}
+					node = sp ? stack[--sp] : 0u;
+					if (!node)
+						state = kFinished;
+				}
+			}
+			else if (atInner) {
+				if (kCount) ++cInner;
+				node = innerStep(nodeAddress(nb, node & ~kInnerBit), r, stack, sp);
+				if (!node)
+					state = kFinished;
+			}
+			__syncwarp();
+		}
 	}
 
-	if (kCount) {
+	// Frame statistics (rays, hits): one atomic per warp, always on when a counter record is given;
+	// this is the value the multi-GPU hit reduction sums. Visit counters only in the kCount build.
+	if (p.counters) {
+		unsigned long long rays = cRays, hits = cHits;
 		for (int o = 16; o; o >>= 1) {
-			cRays += __shfl_xor_sync(kFullMask, cRays, o);
-			cHits += __shfl_xor_sync(kFullMask, cHits, o);
-			cInner += __shfl_xor_sync(kFullMask, cInner, o);
-			cPairs += __shfl_xor_sync(kFullMask, cPairs, o);
+			rays += __shfl_xor_sync(kFullMask, rays, o);
+			hits += __shfl_xor_sync(kFullMask, hits, o);
+			if (kCount) {
+				cInner += __shfl_xor_sync(kFullMask, cInner, o);
+				cPairs += __shfl_xor_sync(kFullMask, cPairs, o);
+			}
 		}
 		if (lane == 0) {
-			atomicAdd(p.counters + 0, cRays);
-			atomicAdd(p.counters + 1, cHits);
-			atomicAdd(p.counters + 2, cInner);
-			atomicAdd(p.counters + 3, cPairs);
+			atomicAdd(p.counters + 0, rays);
+			atomicAdd(p.counters + 1, hits);
+			if (kCount) {
+				atomicAdd(p.counters + 2, cInner);
+				atomicAdd(p.counters + 3, cPairs);
+			}
 		}
 	}
 }
 
-template <bool kCount, int kBlock, int kMinBlocks>
-cudaError_t launchPersistent(const TraceParams& p, const Tuning& t, int smCount, cudaStream_t stream) {
-	auto kernel = tracePersistentKernel<kCount, kBlock, kMinBlocks>;
-	TraceParams q = p;
-	cudaError_t err;
+// Launch shape of one kernel instantiation for one (device, tuning) pair; computed once.
+struct LaunchPlan {
+	bool valid = false;
+	int device = -1, ctasPerSm = -2, smemNodesWanted = -2, carveout = -2;
+	uint32_t nodeCount = 0;
+	uint32_t smemNodes = 0;
+	int resident = 1;
+};
 
-	// Shared-memory budget: stage as many hot nodes as fit while keeping the requested residency.
+template <bool kCount, int kBlock, int kMinBlocks, int kMode>
+cudaError_t launchPersistent(const TraceParams& p, const Tuning& t, int smCount, cudaStream_t stream) {
+	auto kernel = tracePersistentKernel<kCount, kBlock, kMinBlocks, kMode>;
+	static thread_local LaunchPlan plan;
+	cudaError_t err;
 	int device = 0;
 	cudaGetDevice(&device);
-	int maxOptin = 0;
-	cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-	int smPerSm = 0;
-	cudaDeviceGetAttribute(&smPerSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
-	int ctas = t.ctasPerSm > 0 ? t.ctasPerSm : kMinBlocks;
-	uint32_t wantNodes = t.smemNodes >= 0 ? (uint32_t)t.smemNodes : 1024u;
-	if (wantNodes > p.nodeCount) wantNodes = p.nodeCount;
-	size_t budget = (size_t)smPerSm / (size_t)ctas;
-	budget = budget > 2048 ? budget - 2048 : 0; // static smem + per-CTA reservation
-	if (budget > (size_t)maxOptin - 1024) budget = (size_t)maxOptin - 1024;
-	if ((size_t)wantNodes * 64 > budget) wantNodes = (uint32_t)(budget / 64);
-	q.smemNodes = wantNodes;
-	const size_t smemBytes = (size_t)wantNodes * 64;
+	if (!plan.valid || plan.device != device || plan.ctasPerSm != t.ctasPerSm || plan.smemNodesWanted != t.smemNodes || plan.nodeCount != p.nodeCount || plan.carveout != t.carveout) {
+		// Shared-memory budget: stage as many hot nodes as fit while keeping the requested residency.
+		int maxOptin = 0, smPerSm = 0;
+		cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+		cudaDeviceGetAttribute(&smPerSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+		const int ctas = t.ctasPerSm > 0 ? t.ctasPerSm : kMinBlocks;
+		uint32_t wantNodes = t.smemNodes >= 0 ? (uint32_t)t.smemNodes : 0xffffffffu;
+		if (wantNodes > p.nodeCount) wantNodes = p.nodeCount;
+		size_t budget = (size_t)smPerSm / (size_t)ctas;
+		budget = budget > 2048 ? budget - 2048 : 0; // static smem + the per-CTA system reservation
+		if (budget > (size_t)maxOptin - 1024) budget = (size_t)maxOptin - 1024;
+		if ((size_t)wantNodes * 64 > budget) wantNodes = (uint32_t)(budget / 64);
+		const size_t smemBytes = (size_t)wantNodes * 64;
+		err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+		if (err != cudaSuccess) return err;
+		// Give shared memory exactly what the resident CTAs need; the rest of the 228 KB stays L1,
+		// which caches the un-staged nodes, the triangle pairs and the per-thread traversal stacks.
+		{
+			const size_t perSm = (smemBytes + 1024 + 256) * (size_t)ctas;
+			int carveout = (int)((perSm * 100 + (size_t)smPerSm - 1) / (size_t)smPerSm);
+			if (t.carveout >= 0) carveout = t.carveout;
+			if (carveout > 100) carveout = 100;
+			err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+			if (err != cudaSuccess) return err;
+		}
+		int resident = 0;
+		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, kBlock, smemBytes);
+		if (err != cudaSuccess) return err;
+		if (resident < 1) resident = 1;
+		if (t.ctasPerSm > 0 && resident > t.ctasPerSm) resident = t.ctasPerSm;
+		plan.valid = true;
+		plan.device = device;
+		plan.ctasPerSm = t.ctasPerSm;
+		plan.smemNodesWanted = t.smemNodes;
+		plan.nodeCount = p.nodeCount;
+		plan.smemNodes = wantNodes;
+		plan.resident = resident;
+		plan.carveout = t.carveout;
+	}
+	TraceParams q = p;
+	q.smemNodes = plan.smemNodes;
 
-	err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
-	if (err != cudaSuccess) return err;
-	err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-	if (err != cudaSuccess) return err;
-
-	int resident = 0;
-	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, kBlock, smemBytes);
-	if (err != cudaSuccess) return err;
-	if (resident < 1) resident = 1;
-	if (t.ctasPerSm > 0 && resident > t.ctasPerSm) resident = t.ctasPerSm;
-
-	// No more CTAs than there are warps' worth of work.
-	long long grid = (long long)smCount * resident;
+	// Persistent grid: SMs x resident CTAs, but no more CTAs than there is work for.
+	long long grid = (long long)smCount * plan.resident;
 	const long long needed = ((long long)p.total + kBlock - 1) / kBlock;
 	if (grid > needed) grid = needed > 0 ? needed : 1;
 
 	err = cudaMemsetAsync(p.cursor, 0, sizeof(uint32_t), stream);
 	if (err != cudaSuccess) return err;
-	kernel<<<(unsigned)grid, kBlock, smemBytes, stream>>>(q, t.fetchThreshold);
+	kernel<<<(unsigned)grid, kBlock, (size_t)plan.smemNodes * 64, stream>>>(q, t.fetchThreshold, t.leafThreshold);
 	return cudaGetLastError();
 }
 
@@ -476,21 +579,33 @@ cudaError_t dispatch(const TraceParams& p, const Tuning& t, int smCount, cudaStr
 		traceSimpleKernel<kCount><<<grid, 256, 0, stream>>>(p);
 		return cudaGetLastError();
 	}
-	switch (t.blockThreads) {
-	case 128: return launchPersistent<kCount, 128, 8>(p, t, smCount, stream);
-	case 512: return launchPersistent<kCount, 512, 2>(p, t, smCount, stream);
-	case 1024: return launchPersistent<kCount, 1024, 1>(p, t, smCount, stream);
-	default: return launchPersistent<kCount, 256, 4>(p, t, smCount, stream);
+	const int mode = t.variant == 2 ? 1 : 0;
+#define RACC_LAUNCH(B, M) (mode ? launchPersistent<kCount, B, M, 1>(p, t, smCount, stream) : launchPersistent<kCount, B, M, 0>(p, t, smCount, stream))
+	switch (t.blockThreads * 100 + t.ctasPerSm) {
+	case 12800 + 8: case 12800: return RACC_LAUNCH(128, 8);
+	case 12800 + 10: return RACC_LAUNCH(128, 10);
+	case 12800 + 12: return RACC_LAUNCH(128, 12);
+	case 25600 + 5: return RACC_LAUNCH(256, 5);
+	case 25600 + 6: return RACC_LAUNCH(256, 6);
+	case 51200 + 2: case 51200: return RACC_LAUNCH(512, 2);
+	case 51200 + 3: return RACC_LAUNCH(512, 3);
+	case 102400 + 1: case 102400: return RACC_LAUNCH(1024, 1);
+	default:
+		if (t.blockThreads == 128) return RACC_LAUNCH(128, 8);
+		if (t.blockThreads == 512) return RACC_LAUNCH(512, 2);
+		if (t.blockThreads == 1024) return RACC_LAUNCH(1024, 1);
+		return RACC_LAUNCH(256, 4);
 	}
+#undef RACC_LAUNCH
 }
 
 } // namespace
 
-cudaError_t launchTrace(const TraceParams& p, const Tuning& t, bool counted, int smCount, cudaStream_t stream, int* launches) {
+cudaError_t launchTrace(const TraceParams& p, const Tuning& t, int counterMode, int smCount, cudaStream_t stream, int* launches) {
 	if (!p.total)
 		return cudaSuccess;
 	if (launches) *launches += 1;
-	return counted ? dispatch<true>(p, t, smCount, stream) : dispatch<false>(p, t, smCount, stream);
+	return counterMode == 2 ? dispatch<true>(p, t, smCount, stream) : dispatch<false>(p, t, smCount, stream);
 }
 
 } // namespace racc_b200

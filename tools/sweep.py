@@ -1,6 +1,6 @@
 """Kernel tuning sweep on one GPU: times the traversal launch alone (CUDA events, device-resident
-streams) for primary and diffuse-bounce ray sets over a grid of launch shapes. Development tool;
-writes JSON lines to gpurun_out/sweep.jsonl."""
+streams) for the bench batch (primary + 3 diffuse bounces) over a grid of launch shapes.
+Development tool; writes JSON lines to gpurun_out/sweep.jsonl.  usage: sweep.py [stage]"""
 import itertools
 import json
 import os
@@ -13,8 +13,10 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import rayaccel_b200 as rb  # noqa: E402
 
+BASE = dict(variant=0, block=256, ctas_per_sm=0, smem_nodes=-1, fetch_threshold=12, leaf_threshold=8, carveout=-1)
 
-def time_trace(scene, env, rays, res, n, iters=5, flush=None):
+
+def time_launch(scene, env, descs, iters=4, flush=None):
     stream = torch.cuda.current_stream()
     ts = []
     for _ in range(iters):
@@ -22,69 +24,84 @@ def time_trace(scene, env, rays, res, n, iters=5, flush=None):
             flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        rb.trace_device(scene, env, [(rays.data_ptr(), res.data_ptr(), n)], stream=stream)
+        rb.trace_device(scene, env, descs, stream=stream)
         b.record(stream)
         b.synchronize()
         ts.append(a.elapsed_time(b))
-    return min(ts), float(np.median(ts))
+    return min(ts)
+
+
+def grids(stage):
+    if stage == "a":   # launch shape x staging x refill, while-while
+        shapes = [(128, 0), (128, 10), (128, 12), (256, 0), (256, 5), (256, 6), (512, 0), (512, 3), (1024, 0)]
+        for (block, ctas), smem, thr in itertools.product(shapes, [0, 64, 256, 512, -1], [8, 16]):
+            yield dict(variant=0, block=block, ctas_per_sm=ctas, smem_nodes=smem, fetch_threshold=thr)
+        yield dict(variant=1)
+    elif stage == "b":  # phased kernel
+        for (block, ctas), smem, thr, leaf in itertools.product([(256, 0), (256, 5), (512, 0)], [0, 256, -1], [8, 16], [1, 4, 8, 12, 16, 24, 32]):
+            yield dict(variant=2, block=block, ctas_per_sm=ctas, smem_nodes=smem, fetch_threshold=thr, leaf_threshold=leaf)
+    else:
+        for kv in stage.split(";"):
+            yield {k: int(v) for k, v in (p.split("=") for p in kv.split(","))}
 
 
 def main():
-    out_path = os.path.join("gpurun_out", "sweep.jsonl")
+    stage = sys.argv[1] if len(sys.argv) > 1 else "a"
+    out_path = os.path.join("gpurun_out", f"sweep_{stage if len(stage) < 3 else 'custom'}.jsonl")
     os.makedirs("gpurun_out", exist_ok=True)
     torch.cuda.set_device(0)
     rb.init(0)
     sf = rb.load_scene()
-    t0 = time.time()
     scene = rb.create_scene(sf.vertices, sf.indices)
     env = rb.create_environment(sf.environment)
-    print("scene build+upload %.3fs" % (time.time() - t0), scene.info)
-    w, h, spp = 1920, 1080, int(os.environ.get("SWEEP_SPP", "4"))
+    w, h, spp = 1920, 1080, 4
     cam = rb.Camera.for_scene(sf, w, h)
-    n0 = w * h * spp
-    sets = []
-    rays = torch.empty(n0 * 8, dtype=torch.float32, device="cuda")
+    n = w * h * spp
+    rays = torch.empty(n * 8, dtype=torch.float32, device="cuda")
     rb.generate_primary(cam, w, h, spp, 1, rays.data_ptr())
-    n = n0
+    sets = []
     for bounce in range(4):
         res = torch.empty(n * 4, dtype=torch.float32, device="cuda")
         cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
-        rb.trace_device(scene, env, [(rays.data_ptr(), res.data_ptr(), n)], counters_ptr=cnt.data_ptr())
+        rb.trace_device(scene, env, [(rays.data_ptr(), res.data_ptr(), n)], counters_ptr=cnt.data_ptr(), detail=False)
         torch.cuda.synchronize()
-        c = cnt.cpu().numpy()
-        alg_bytes = 48 * n + 64 * int(c[2]) + 48 * int(c[3]) + 4 * int(c[1]) + 64 * (n - int(c[1]))
-        sets.append(dict(name="primary" if bounce == 0 else f"bounce{bounce}", rays=rays, res=res, n=n, alg_bytes=alg_bytes,
-                         inner=c[2] / n, pairs=c[3] / n, hit=c[1] / n))
-        print(sets[-1]["name"], n, "inner/ray %.2f pairs/ray %.2f hit %.3f bytes/ray %.0f" % (c[2] / n, c[3] / n, c[1] / n, alg_bytes / n))
-        nxt = torch.empty(max(int(c[1]), 1) * 8, dtype=torch.float32, device="cuda")
+        hits = int(cnt[1].item())
+        sets.append((rays, res, n))
+        nxt = torch.empty(max(hits, 1) * 8, dtype=torch.float32, device="cuda")
         k = torch.zeros(1, dtype=torch.int32, device="cuda")
         rb.generate_bounce(scene, rays.data_ptr(), res.data_ptr(), n, 2 + bounce, nxt.data_ptr(), k.data_ptr())
         torch.cuda.synchronize()
         rays, n = nxt, int(k.item())
+    descs = [(r.data_ptr(), o.data_ptr(), c) for r, o, c in sets]
+    n_all = sum(c for _, _, c in sets)
+    n_sec = n_all - sets[0][2]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
-
-    grid = []
-    grid.append(dict(variant=1))
-    for block, smem, thr in itertools.product([128, 256, 512, 1024], [0, -1], [1, 8, 16, 24, 32]):
-        grid.append(dict(variant=0, block=block, smem_nodes=smem, fetch_threshold=thr))
-    base = dict(variant=0, block=256, ctas_per_sm=0, smem_nodes=-1, fetch_threshold=12)
+    ref = [o.clone() for _, o, _ in sets]
+    rows = []
     with open(out_path, "w") as f:
-        for g in grid:
-            rb.set_tuning(**{**base, **g})
+        for g in grids(stage):
+            rb.set_tuning(**{**BASE, **g})
             row = dict(g)
-            tot_t, tot_n, tot_b = 0.0, 0, 0
-            for s in sets:
-                best, med = time_trace(scene, env, s["rays"], s["res"], s["n"], flush=flush)
-                row[s["name"] + "_mrays"] = round(s["n"] / best / 1e3, 1)
-                row[s["name"] + "_frac"] = round(s["alg_bytes"] / (best * 1e-3) / 6547.2e9, 4)
-                if s["name"] != "primary":
-                    tot_t += best; tot_n += s["n"]; tot_b += s["alg_bytes"]
-            row["secondary_mrays"] = round(tot_n / tot_t / 1e3, 1)
-            row["secondary_frac"] = round(tot_b / (tot_t * 1e-3) / 6547.2e9, 4)
-            print(json.dumps(row))
+            try:
+                t_all = time_launch(scene, env, descs, flush=flush)
+                t_pri = time_launch(scene, env, descs[:1], flush=flush)
+                t_sec = time_launch(scene, env, descs[1:], flush=flush)
+                ok = all(torch.equal(a.view(torch.int32), o.view(torch.int32)) for a, (_, o, _) in zip(ref, sets))
+                row.update(all_mrays=round(n_all / t_all / 1e3, 1), primary_mrays=round(sets[0][2] / t_pri / 1e3, 1),
+                           secondary_mrays=round(n_sec / t_sec / 1e3, 1), same_bits=ok)
+            except Exception as e:  # keep sweeping
+                row.update(error=str(e)[:200])
+            rows.append(row)
+            print(json.dumps(row), flush=True)
             f.write(json.dumps(row) + "\n")
             f.flush()
-    rb.set_tuning(**base)
+    rb.set_tuning(**BASE)
+    good = [r for r in rows if "all_mrays" in r]
+    for key in ("all_mrays", "secondary_mrays", "primary_mrays"):
+        best = sorted(good, key=lambda r: -r[key])[:5]
+        print("BEST by", key)
+        for r in best:
+            print("   ", json.dumps(r))
 
 
 if __name__ == "__main__":
