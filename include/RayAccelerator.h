@@ -1,0 +1,139 @@
+// RayAccelerator.h -- the public C++ API of the B200 engine.
+//
+// Same namespace, type names, field order/widths and function signatures as the reference's public
+// header (/root/reference/RayAccelerator/RayAccelerator.h:25-116), so that clients written against
+// the reference -- its example path tracer and Whitted renderer included -- compile and link
+// without edits. The reference header refuses to compile on Linux (:21-23) and pulls in OpenCL
+// only for the one `cl_context gpuContext` field (:33); here `cl_context` is an opaque token that
+// names a CUDA device (see racc::cudaDevice below). Everything behind these functions is
+// rayaccel_b200/csrc/racc_api.cpp, a client of the C-ABI in racc_b200.h.
+//
+// Differences a client can observe:
+//   * there is no CPU intersection back-end: createContext() fails (returns null after printing
+//     "RayAccelerator: ...") when configuration.gpuContext is null or no CUDA device is present;
+//     `allowCpuTracing` and `cpuTestBatch` are accepted and ignored;
+//   * ray streams live in pinned host memory and are moved to the GPU in aggregated launches
+//     (several streams per launch) instead of one zero-copy launch per stream.
+#ifndef RACC_B200_RAYACCELERATOR_H
+#define RACC_B200_RAYACCELERATOR_H
+
+#include <stdint.h>
+#include <immintrin.h>
+
+// the reference's clients rely on these arriving through this header (its OpenCL include did that)
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#if defined(_WIN32)
+#define RACC_ALIGNED(n) __declspec(align(n))
+#else
+#define RACC_ALIGNED(n) __attribute__((aligned(n)))
+#endif
+
+#ifndef RACC_B200_NO_CL_CONTEXT_TYPEDEF
+typedef struct _cl_context* cl_context; // opaque: non-null = "use the GPU engine", see cudaDevice()
+#endif
+
+namespace racc {
+	static const uint32_t invalidTriangle = ~(uint32_t)0; // Result.triangle of a miss
+
+	struct Context;
+	struct Scene;
+	struct Environment;
+
+	struct Configuration {
+		cl_context gpuContext;         // token from cudaDevice(); null is rejected (no CPU back-end)
+		bool allowCpuTracing;          // ignored: intersection always runs on the GPU
+		uint8_t cpuThreads;            // host threads running the spawn/shade callbacks
+		uint8_t gpuSubmissionThreads;  // host threads that gather ready streams and launch them
+		uint32_t maxRaysInFlight;      // cap on rays alive in the system
+		uint16_t maxRaysPerSpawn;      // most rays one spawn callback may append
+		uint16_t cpuTestBatch;         // ignored (was: CPU intersection slice)
+		uint16_t cpuShadeBatch;        // rays handed to one shade callback
+		uint16_t rayStreamBatchSize;   // fill level at which a stream is queued for intersection
+	};
+
+	struct ContextInfo {
+		uint16_t threadCount;     // callbacks receive thread in [0, threadCount)
+		uint16_t rayStreamCount;  // RayStream.index < rayStreamCount
+		uint32_t rayStreamSize;   // RayStream.count <= rayStreamSize
+		uint32_t maxRaysInFlight;
+	};
+
+	struct RACC_ALIGNED(16) Vertex {
+		float x, y, z, w;
+	};
+
+	struct RACC_ALIGNED(16) Color {
+		float r, g, b, a;
+	};
+
+	struct RACC_ALIGNED(32) Ray {
+		float origin[3];
+		float minT;
+		float dir[3];
+		float maxT;
+	};
+
+	struct RACC_ALIGNED(16) Result {
+		uint32_t triangle; // original triangle index, or invalidTriangle
+		union {
+			struct {
+				float t, u, v; // u, v weight the triangle's 2nd and 3rd vertex
+			} hit;
+			struct {
+				float r, g, b; // light-probe radiance along the ray
+			} miss;
+		};
+	};
+
+	struct RayStream {
+		uint32_t index;
+		uint32_t count;
+		Ray* rays;
+		Result* results; // index-parallel to rays, valid in shade()
+	};
+
+	struct Stats {
+		uint64_t raysTraced;
+	};
+
+	struct RenderCallbacks {
+		void* data;
+		bool (*spawn)(void* data, unsigned thread, RayStream* output);
+		void (*shade)(void* data, unsigned thread, const RayStream* input, unsigned start, unsigned end, RayStream* output);
+	};
+
+	void init();
+
+	void deinit();
+
+	Configuration defaultConfiguration(cl_context gpuContext);
+
+	Context* createContext(Configuration configuration);
+
+	void destroy(Context* context);
+
+	ContextInfo info(Context* context);
+
+	Scene* createScene(Context* context, const Vertex* vertices, unsigned vertexCount, const uint32_t* indices, unsigned indexCount);
+
+	void destroy(Scene* scene);
+
+	Environment* createEnvironment(Context* context, const Color* colors, unsigned width, unsigned height);
+
+	void destroy(Environment* environment);
+
+	Stats render(Context* context, Scene* scene, Environment* environment, RenderCallbacks callbacks);
+
+	// --- additions (not in the reference) -------------------------------------------------------
+
+	// The token to put in Configuration.gpuContext: selects CUDA device `ordinal` of this process.
+	// Stands in for the OpenCL context the reference's main.cpp creates (Renderer/main.cpp:68-115).
+	inline cl_context cudaDevice(int ordinal = 0) {
+		return reinterpret_cast<cl_context>(static_cast<uintptr_t>(ordinal) + 1);
+	}
+}
+
+#endif

@@ -14,6 +14,7 @@
 #ifndef RACC_B200_H
 #define RACC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -108,8 +109,8 @@ void racc_cuda_env_destroy(racc_cuda_env* env);
  * (RayAccelerator.cpp:377-401) for one OR MORE ray streams in a single launch. env may be NULL
  * (misses then return r=g=b=0). cuda_stream: a cudaStream_t (NULL = default stream).
  * Asynchronous. DEVICE streams of one call are traced by ONE launch. HOST streams
- * (pinned memory recommended) are cut into chunks that alternate over internal CUDA streams so
- * H2D, traversal and D2H overlap; cuda_stream waits for them, so everything is complete when
+ * (pinned memory recommended) are packed into staging chunks (several small streams share one
+ * chunk and one launch) that alternate over internal CUDA streams so H2D, traversal and D2H overlap; cuda_stream waits for them, so everything is complete when
  * racc_cuda_sync(cuda_stream) returns. */
 int racc_cuda_trace(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_stream_desc* streams,
                     uint32_t nstreams, void* cuda_stream);
@@ -120,6 +121,18 @@ int racc_cuda_trace(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_
  * also inner-node and pair visits (slower; used for the roofline accounting only). */
 int racc_cuda_trace_counted(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_stream_desc* streams,
                             uint32_t nstreams, void* cuda_stream, void* device_counters, int detail);
+
+/* Pinned (page-locked) host memory for ray streams: replaces the 4 KiB-aligned stream slab that the
+ * reference wraps in zero-copy CL_MEM_USE_HOST_PTR buffers (RayAccelerator.cpp:532-568,636-645).
+ * A discrete GPU has no zero-copy path; pinned memory is what lets HOST streams move at PCIe rate.
+ * NULL on failure. */
+void* racc_cuda_host_alloc(size_t bytes);
+void racc_cuda_host_free(void* ptr);
+
+/* One CUDA stream per submitter thread: replaces the per-thread cl_command_queue
+ * (RayAccelerator.cpp:711-717, released :774-779). Returns a cudaStream_t, NULL on failure. */
+void* racc_cuda_stream_create(void);
+void racc_cuda_stream_destroy(void* cuda_stream);
 
 /* replaces clFinish(queue) (RayAccelerator.cpp:403) */
 int racc_cuda_sync(void* cuda_stream);

@@ -56,6 +56,10 @@ SYMBOLS = {
     "racc_cuda_env_destroy": (None, [_P]),
     "racc_cuda_trace": (ctypes.c_int, [_P, _P, ctypes.POINTER(StreamDesc), _U32, _P]),
     "racc_cuda_trace_counted": (ctypes.c_int, [_P, _P, ctypes.POINTER(StreamDesc), _U32, _P, _P, ctypes.c_int]),
+    "racc_cuda_host_alloc": (_P, [ctypes.c_size_t]),
+    "racc_cuda_host_free": (None, [_P]),
+    "racc_cuda_stream_create": (_P, []),
+    "racc_cuda_stream_destroy": (None, [_P]),
     "racc_cuda_sync": (ctypes.c_int, [_P]),
     "racc_cuda_launch_count": (ctypes.c_uint64, []),
     "racc_cuda_set_variant": (ctypes.c_int, [ctypes.c_int]),

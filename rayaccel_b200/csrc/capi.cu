@@ -156,7 +156,8 @@ int racc_cuda_init(const int* devices, int n) {
 		if (e != cudaSuccess)
 			return fail("cudaSetDevice(%d) failed: %s; the engine has no CPU fallback", devices[0], cudaGetErrorString(e));
 		std::lock_guard<std::mutex> lock(g_initMutex);
-		g_initialised = false;
+		if (g_initialised && g_device != devices[0])
+			g_initialised = false; // re-bind the process (tuning is re-read from the environment)
 	}
 	return ensureInit();
 }
@@ -439,26 +440,43 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 		RACC_CUDA_CHECK(cudaEventRecord(pipe.fork, stream));
 		for (int l = 0; l < HostPipeline::kLanes; ++l)
 			RACC_CUDA_CHECK(cudaStreamWaitEvent(pipe.lane[l], pipe.fork, 0));
+		// Pack host streams into staging chunks: a chunk takes whole streams or slices of them until it
+		// holds chunkRays rays, so that many small API streams (<= 65 535 rays each under the
+		// RayAccelerator.h Configuration) still become ONE launch that fills the machine.
 		unsigned chunk = 0;
-		for (const racc_cuda_stream_desc* d : hostStreams) {
-			const char* hRays = static_cast<const char*>(d->rays);
-			char* hResults = static_cast<char*>(d->results);
-			for (uint32_t begin = 0; begin < d->count; begin += pipe.chunkRays, ++chunk) {
-				const uint32_t n = d->count - begin < pipe.chunkRays ? d->count - begin : pipe.chunkRays;
-				const int l = (int)(chunk % HostPipeline::kLanes);
-				RACC_CUDA_CHECK(cudaMemcpyAsync(pipe.dRays[l], hRays + (size_t)begin * 32, (size_t)n * 32, cudaMemcpyHostToDevice, pipe.lane[l]));
-				TraceParams p{};
-				fillSceneParams(p, s, env, device_counters);
-				p.nstreams = 1;
-				p.total = n;
-				p.single.rays = pipe.dRays[l];
-				p.single.results = pipe.dResults[l];
-				p.single.begin = 0;
-				p.single.count = n;
-				p.cursor = s->dCursors + (s->nextCursor.fetch_add(1) % kCursorRing);
-				RACC_CUDA_CHECK(launchTrace(p, g_tuning, device_counters ? (fullCounters ? 2 : 1) : 0, g_smCount, pipe.lane[l], &launches));
-				RACC_CUDA_CHECK(cudaMemcpyAsync(hResults + (size_t)begin * 16, pipe.dResults[l], (size_t)n * 16, cudaMemcpyDeviceToHost, pipe.lane[l]));
+		size_t si = 0;
+		uint32_t sBegin = 0;
+		while (si < hostStreams.size()) {
+			const int l = (int)(chunk % HostPipeline::kLanes);
+			struct Segment { char* hResults; uint32_t offset, n; };
+			Segment segs[64];
+			int nsegs = 0;
+			uint32_t filled = 0;
+			while (si < hostStreams.size() && filled < pipe.chunkRays && nsegs < 64) {
+				const racc_cuda_stream_desc* d = hostStreams[si];
+				const uint32_t left = d->count - sBegin;
+				const uint32_t room = pipe.chunkRays - filled;
+				const uint32_t n = left < room ? left : room;
+				RACC_CUDA_CHECK(cudaMemcpyAsync(pipe.dRays[l] + filled, static_cast<const char*>(d->rays) + (size_t)sBegin * 32, (size_t)n * 32,
+				                                cudaMemcpyHostToDevice, pipe.lane[l]));
+				segs[nsegs++] = Segment{static_cast<char*>(d->results) + (size_t)sBegin * 16, filled, n};
+				filled += n;
+				sBegin += n;
+				if (sBegin == d->count) { ++si; sBegin = 0; }
 			}
+			TraceParams p{};
+			fillSceneParams(p, s, env, device_counters);
+			p.nstreams = 1;
+			p.total = filled;
+			p.single.rays = pipe.dRays[l];
+			p.single.results = pipe.dResults[l];
+			p.single.begin = 0;
+			p.single.count = filled;
+			p.cursor = s->dCursors + (s->nextCursor.fetch_add(1) % kCursorRing);
+			RACC_CUDA_CHECK(launchTrace(p, g_tuning, device_counters ? (fullCounters ? 2 : 1) : 0, g_smCount, pipe.lane[l], &launches));
+			for (int k = 0; k < nsegs; ++k)
+				RACC_CUDA_CHECK(cudaMemcpyAsync(segs[k].hResults, pipe.dResults[l] + segs[k].offset, (size_t)segs[k].n * 16, cudaMemcpyDeviceToHost, pipe.lane[l]));
+			++chunk;
 		}
 		const int used = chunk < (unsigned)HostPipeline::kLanes ? (int)chunk : HostPipeline::kLanes;
 		for (int l = 0; l < used; ++l) {
@@ -480,6 +498,39 @@ int racc_cuda_trace_counted(racc_cuda_scene* scene, racc_cuda_env* env, const ra
                             void* cuda_stream, void* device_counters, int detail) {
 	if (!device_counters) return fail("racc_cuda_trace_counted: null counter buffer");
 	return traceImpl(scene, env, streams, nstreams, cuda_stream, device_counters, detail != 0);
+}
+
+// Pinned host memory for ray streams (replaces the 4 KiB-aligned slab of RayAccelerator.cpp:532-568
+// that the reference wraps in CL_MEM_USE_HOST_PTR buffers, :643-644).
+void* racc_cuda_host_alloc(size_t bytes) {
+	if (ensureInit()) return nullptr;
+	void* p = nullptr;
+	cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+	if (e != cudaSuccess) {
+		fail("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+		return nullptr;
+	}
+	return p;
+}
+
+void racc_cuda_host_free(void* p) {
+	if (p) cudaFreeHost(p);
+}
+
+// One CUDA stream per submitter (replaces the per-thread cl_command_queue, RayAccelerator.cpp:711-717).
+void* racc_cuda_stream_create(void) {
+	if (ensureInit()) return nullptr;
+	cudaStream_t s = nullptr;
+	cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+	if (e != cudaSuccess) {
+		fail("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+		return nullptr;
+	}
+	return s;
+}
+
+void racc_cuda_stream_destroy(void* cuda_stream) {
+	if (cuda_stream) cudaStreamDestroy(static_cast<cudaStream_t>(cuda_stream));
 }
 
 int racc_cuda_sync(void* cuda_stream) {
