@@ -27,7 +27,7 @@ COUNTER_DTYPE = np.dtype([("inner", "<u2"), ("pairs", "<u2"), ("max_stack", "<u2
 
 def build(ref: bool = True) -> None:
     """Compile the checker (and, when /root/reference is present, oracle/_ref)."""
-    subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"] + (["ref"] if ref else []), stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"] + (["ref", "renderer"] if ref else []), stdout=subprocess.DEVNULL)
 
 
 class _Scene(ctypes.Structure):

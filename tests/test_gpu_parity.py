@@ -258,3 +258,71 @@ def test_full_size_properties(scene, env, battlefield):
     assert bool((res2[~hit, 0].view(torch.int32) == -1).all())
     both = same_id & hit
     assert torch.equal(res2[both, 1], res[both, 1])
+
+
+def test_kat_scenes_on_gpu(gpu):
+    """Every hand-built tie / boundary case of tests/kat_scenes.py, on the CUDA path: equal to the
+    oracle bit for bit, and to the analytic answers."""
+    from kat_scenes import KAT_CASES, build_kat_scene
+    for case in KAT_CASES:
+        images, rays = build_kat_scene(case)
+        pad = (-images.pairs.shape[0] * 3) % 32 // 3 + (1 if (images.pairs.shape[0] * 3) % 32 == 0 else 0)
+        pairs = np.concatenate([images.pairs, np.repeat(images.pairs[:1], max(pad, 1), axis=0)])
+        s = rb.create_scene_from_images(images.nodes, pairs, images.remap)
+        for variant in (0, 1):
+            rb.set_tuning(**{**DEFAULT, "variant": variant})
+            got = trace_dev(s, None, rays)
+            assert_bit_exact(got, oracle.traverse(images, rays), f"{case['name']} variant {variant}")
+            for k, want in enumerate(case["expect"]):
+                if want is None:
+                    assert got[k, 0] == rb.INVALID_TRIANGLE, (case["name"], k)
+                else:
+                    assert got[k, 0] == want["triangle"], (case["name"], k)
+                    assert abs(float(got[k, 1:2].view(np.float32)[0]) - want["t"]) <= 1e-4 * want["t"], (case["name"], k)
+        rb.set_tuning(**DEFAULT)
+        s.destroy()
+
+
+def test_golden_rays_on_gpu(scene, env):
+    """The committed golden vectors (tests/golden/battlefield_rays.npz: oracle results on the
+    REFERENCE-built images + fp64 arbiter): bit-exact ids and t/u/v/r/g/b on the CUDA path."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "battlefield_rays.npz"))
+    rays = np.ascontiguousarray(g["rays"]).view(oracle.RAY_DTYPE).reshape(-1)
+    got = trace_dev(scene, env, rays)
+    assert np.array_equal(got, g["results"])
+    both = (got[:, 0] != rb.INVALID_TRIANGLE) & np.isfinite(g["t64"])
+    t = got[:, 1].copy().view(np.float32)
+    assert np.all(np.abs(t[both] - g["t64"][both]) <= 1e-4 * g["t64"][both])  # north_star: t within 1e-4 relative
+
+
+def test_host_streams_packed_into_shared_launches(scene, env, images, battlefield):
+    """Many small HOST streams (the sizes racc::render() submits) in one call: the engine packs them
+    into shared staging chunks; every stream's results must land in its own buffer, bit-exact."""
+    lo = battlefield.vertices[:, :3].min(0)
+    hi = battlefield.vertices[:, :3].max(0)
+    sizes = [11264, 27648, 1, 65535, 300, 49152, 7, 49152, 49152, 1000, 600000, 13]
+    rays = [random_rays(s, lo, hi, seed=40 + k) for k, s in enumerate(sizes)]
+    pinned_r = [torch.from_numpy(r.view(np.float32).reshape(-1).copy()).pin_memory() for r in rays]
+    pinned_o = [torch.full((s * 4,), 7.0, dtype=torch.float32).pin_memory() for s in sizes]
+    before = rb.launch_count()
+    rb.trace_host_ptrs(scene, env, [(a.data_ptr(), b.data_ptr(), s) for a, b, s in zip(pinned_r, pinned_o, sizes)])
+    rb.sync()
+    launches = rb.launch_count() - before
+    assert launches <= 3, f"{launches} launches for {sum(sizes)} rays: small streams were not packed"
+    for k, s in enumerate(sizes):
+        got = pinned_o[k].numpy().view(np.uint32).reshape(-1, 4)
+        assert_bit_exact(got, oracle.traverse(images, rays[k]), f"host stream {k}")
+
+
+def test_synthetic_soup_scene_bit_exact(gpu):
+    """BASELINE.json configs[4] at reduced size: random triangle soup + uniform random rays."""
+    v, i = rb.synthetic_triangles(200_000, seed=7, extent=1000.0, edge=2.0)
+    s = rb.create_scene(v, i)
+    nodes, pairs, remap = s.download()
+    img = oracle.SceneImages(nodes, pairs, remap)
+    rays = random_rays(400_000, np.zeros(3), np.full(3, 1000.0), seed=8)
+    got = trace_dev(s, None, rays)
+    assert_bit_exact(got, oracle.traverse(img, rays), "soup")
+    assert 0.001 < (got[:, 0] != rb.INVALID_TRIANGLE).mean() < 0.9
+    s.destroy()

@@ -1,0 +1,137 @@
+"""Scene build (SAH BVH2 + greedy pair merge + node packing) of the engine's host builder against the
+UNMODIFIED reference builder: live when oracle/_ref is present, and always against the committed
+digests that were produced by executing the reference (tests/golden/ref_scene_digests.json).
+CPU only -- racc_cuda_build_images makes no CUDA call."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+import rayaccel_b200 as rb
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+sys.path.insert(0, GOLDEN)
+from make_golden import synthetic_meshes  # noqa: E402
+
+
+def own_images(v, i):
+    h = rb.HostImages(v, i)
+    return oracle.SceneImages(h.nodes, h.pairs, h.remap), h.info
+
+
+@pytest.fixture(scope="module")
+def golden_digests():
+    with open(os.path.join(GOLDEN, "ref_scene_digests.json")) as f:
+        return json.load(f)
+
+
+def test_battlefield_digest_matches_reference_golden(battlefield, golden_digests):
+    img, info = own_images(battlefield.vertices, battlefield.indices)
+    assert img.digest() == golden_digests["battlefield"]
+    # the survey's structural facts
+    assert info["node_count"] == 19192 and info["real_pair_count"] == 35823 and info["depth"] == 21
+    assert info["pair_count"] == 35840 and info["remap_count"] == 71646
+
+
+@pytest.mark.parametrize("name", sorted(synthetic_meshes().keys()))
+def test_synthetic_digest_matches_reference_golden(name, golden_digests):
+    v, i = synthetic_meshes()[name]
+    img, _ = own_images(v, i)
+    assert img.digest() == golden_digests[name]
+
+
+def test_digest_matches_reference_live(battlefield):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    img, _ = own_images(battlefield.vertices, battlefield.indices)
+    assert img.digest() == oracle.ref_build_scene(battlefield.vertices, battlefield.indices).digest()
+    for seed in (21, 22):
+        v, i = rb.synthetic_triangles(5000 + seed, seed=seed, extent=50.0, edge=4.0)
+        assert own_images(v, i)[0].digest() == oracle.ref_build_scene(v, i).digest()
+
+
+def test_image_invariants(battlefield):
+    img, info = own_images(battlefield.vertices, battlefield.indices)
+    nodes_u = img.nodes.view(np.uint32)
+    refs = nodes_u[:, 2:4].ravel()
+    inner = refs[(refs & 0x80000000) != 0] & 0x7FFFFFFF
+    leaves = refs[(refs & 0x80000000) == 0]
+    # every inner node except the root is referenced exactly once; parents precede children (hot-first order)
+    assert np.array_equal(np.sort(inner), np.arange(1, info["node_count"]))
+    parent_of = np.repeat(np.arange(info["node_count"]), 2)[(refs & 0x80000000) != 0]
+    assert np.all(parent_of < inner)
+    # leaves tile the pair array without gaps or overlap
+    first, count = leaves & 0xFFFFFF, leaves >> 24
+    order = np.argsort(first)
+    assert first[order][0] == 0 and np.all(first[order][1:] == (first[order] + count[order])[:-1])
+    assert (first + count).max() == info["real_pair_count"] and count.min() >= 1 and count.max() <= 127
+    # remap: every original triangle appears exactly once; unused second slots hold 0
+    words = img.remap
+    singles = np.isclose(img.pairs[: info["real_pair_count"], [3, 7, 11]], -img.pairs[: info["real_pair_count"], [0, 1, 2]]).all(axis=1)
+    used = np.ones(words.shape[0], bool)
+    used[1::2] = ~singles
+    ids = words[used] & 0x3FFFFFFF
+    assert np.array_equal(np.sort(ids), np.arange(battlefield.triangle_count))
+    assert np.all(words[~used] == 0)
+    # pair array padded to a multiple of 32 float4 (Scene.cpp:335-338)
+    assert (info["pair_count"] * 3) % 32 == 0 and info["pair_count"] > info["real_pair_count"]
+    # child boxes: parent box contains both children's boxes
+    lo = np.minimum(img.nodes[:, 4:7], img.nodes[:, 10:13])
+    hi = np.maximum(img.nodes[:, 7:10], img.nodes[:, 13:16])
+    kids = np.nonzero((nodes_u[:, 2] & 0x80000000) != 0)[0]
+    c = nodes_u[kids, 2] & 0x7FFFFFFF
+    assert np.all(lo[c] >= img.nodes[kids, 4:7]) and np.all(hi[c] <= img.nodes[kids, 7:10])
+
+
+def test_pair_geometry_reconstructs_triangles(battlefield):
+    """Each pair triangle, rebuilt from (e1,e2,e3,p0) and un-rotated by its edge code, is the original
+    triangle (Scene.cpp:122-181)."""
+    img, info = own_images(battlefield.vertices, battlefield.indices)
+    n = info["real_pair_count"]
+    p = img.pairs[:n]
+    e1, e2, p0 = p[:, 0:3], p[:, 4:7], p[:, 8:11]
+    e3 = p[:, [3, 7, 11]]
+    p1, p2, p3 = p0 - e1, p0 + e2, p0 + e3
+    v = battlefield.vertices[:, :3]
+    tri = battlefield.indices.reshape(-1, 3)
+    for slot, (a, b, c) in enumerate(((p0, p1, p2), (p0, p3, p1))):
+        w = img.remap[slot::2][:n]
+        valid = np.ones(n, bool) if slot == 0 else ~np.isclose(p3, p1).all(axis=1)
+        ids, code = w & 0x3FFFFFFF, w >> 30
+        orig = v[tri[ids]]  # (n, 3 verts, 3)
+        # code k: pair verts (a,b,c) = original (v[k%3], v[(k+1)%3], v[(k+2)%3])  (reorder(), Scene.cpp:100-107)
+        perm = {0: (0, 1, 2), 3: (0, 1, 2), 1: (1, 2, 0), 2: (2, 0, 1)}  # code 3 = rotation by 3 = none (Scene.cpp:133)
+        for k, (i0, i1, i2) in perm.items():
+            m = valid & (code == k)
+            if not m.any():
+                continue
+            assert np.allclose(a[m], orig[m, i0], atol=2e-4) and np.allclose(b[m], orig[m, i1], atol=2e-4) and np.allclose(c[m], orig[m, i2], atol=2e-4), (slot, k)
+
+
+def test_invalid_inputs_are_rejected():
+    v, i = rb.synthetic_triangles(10, seed=1)
+    with pytest.raises(ValueError):
+        rb.create_scene(v, i[:-1])  # indexCount % 3 (Scene.cpp:186)
+    with pytest.raises(rb.EngineError, match="multiple of 3"):
+        rb.HostImages(v, i[:-1])
+    with pytest.raises(rb.EngineError, match="out of range"):
+        rb.HostImages(v[:5], i)
+    with pytest.raises(rb.EngineError, match="at least 3 triangles"):
+        rb.HostImages(v, i[:6])  # root must be an inner node (Scene.cpp:342 is UB in the reference)
+    with pytest.raises(rb.EngineError):
+        rb.HostImages(v, i[:0])
+
+
+def test_build_is_deterministic_and_thread_count_independent(battlefield):
+    a, _ = own_images(battlefield.vertices, battlefield.indices)
+    os.environ["RACC_B200_BUILD_THREADS"] = "1"
+    try:
+        b, _ = own_images(battlefield.vertices, battlefield.indices)
+    finally:
+        del os.environ["RACC_B200_BUILD_THREADS"]
+    assert np.array_equal(a.nodes.view(np.uint32), b.nodes.view(np.uint32))
+    assert np.array_equal(a.pairs.view(np.uint32), b.pairs.view(np.uint32))
+    assert np.array_equal(a.remap, b.remap)
