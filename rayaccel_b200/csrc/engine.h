@@ -38,8 +38,10 @@ struct TraceParams {
 struct Tuning {
 	int variant = 0;        // 0 persistent while-while (default), 1 one-thread-per-ray, 2 persistent phased
 	int blockThreads = 256; // threads per CTA
-	int ctasPerSm = 0;      // 0 = as many as fit
-	int smemNodes = -1;     // -1 = auto
+	int ctasPerSm = 5;      // 0 = as many as fit
+	int smemNodes = 0;      // inner nodes staged in shared memory by TMA: -1 = as many as fit, 0 = none. On
+	                        // battlefield (3.2 MB, L1/L2-resident) the un-staged instantiation measures ~4 %
+	                        // faster (profiles/r01_sweep_c_unstaged_256bit.jsonl), so it is the default.
 	int fetchThreshold = 12; // refill a warp when at least this many lanes are idle
 	int leafThreshold = 8;   // variant 2: run leaf tests when at least this many lanes wait at a leaf
 	int carveout = -1;       // shared-memory carveout percent, -1 = exactly what the CTAs need

@@ -230,13 +230,55 @@ __device__ __forceinline__ void locate(const TraceParams& p, uint32_t idx, const
 	rays = p.streams[lo].rays; out = p.streams[lo].results; local = idx - p.streams[lo].begin;
 }
 
-// One inner-node step (Kernels.h:170-199). `np` points at the node's four float4s (shared or
-// global). Returns the next node reference, or 0 when neither child is hit and the stack is empty.
-__device__ __forceinline__ uint32_t innerStep(const float4* np, const RayState& r, uint32_t* stack, int& sp) {
-	const float4 d0 = np[0];
-	const float4 d1 = np[1];
-	const float4 d2 = np[2];
-	const float4 d3 = np[3];
+// Per-ray traversal stack (Kernels.h:166: 64 entries) in local memory, addressed through a 32-bit
+// local-window address so that a push is one STL and a pop one LDL with no index arithmetic.
+struct LocalStack {
+	uint32_t base, top; // local-space byte addresses; top == base when empty
+	__device__ __forceinline__ void attach(uint32_t* storage) {
+		base = top = (uint32_t)__cvta_generic_to_local(storage);
+	}
+	__device__ __forceinline__ void reset() { top = base; }
+	__device__ __forceinline__ bool empty() const { return top == base; }
+	__device__ __forceinline__ void push(uint32_t v) {
+		asm volatile("st.local.u32 [%0], %1;" ::"l"((unsigned long long)top), "r"(v) : "memory");
+		top += 4;
+	}
+	__device__ __forceinline__ uint32_t pop() {
+		top -= 4;
+		uint32_t v;
+		asm volatile("ld.local.u32 %0, [%1];" : "=r"(v) : "l"((unsigned long long)top) : "memory");
+		return v;
+	}
+};
+
+// The four float4s of one inner node, all requested up front (the child references travel with the
+// boxes instead of being fetched after the hit test). kGlobal: read-only global path; else generic
+// (the node may live in shared memory).
+template <bool kGlobal>
+__device__ __forceinline__ void loadNode(const float4* np, float4& d0, float4& d1, float4& d2, float4& d3) {
+	if (kGlobal) {
+		// Blackwell 256-bit loads (LDG.E.ENL2.256): a 64-byte node is two load instructions instead of
+		// four, which halves the L1 wavefronts of a divergent node fetch (one wavefront per distinct
+		// line per instruction, whatever the width).
+		asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		             : "=f"(d0.x), "=f"(d0.y), "=f"(d0.z), "=f"(d0.w), "=f"(d1.x), "=f"(d1.y), "=f"(d1.z), "=f"(d1.w) : "l"(np));
+		asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+32];"
+		             : "=f"(d2.x), "=f"(d2.y), "=f"(d2.z), "=f"(d2.w), "=f"(d3.x), "=f"(d3.y), "=f"(d3.z), "=f"(d3.w) : "l"(np));
+	}
+	else {
+		asm volatile("ld.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(d0.x), "=f"(d0.y), "=f"(d0.z), "=f"(d0.w) : "l"(np));
+		asm volatile("ld.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(d1.x), "=f"(d1.y), "=f"(d1.z), "=f"(d1.w) : "l"(np));
+		asm volatile("ld.v4.f32 {%0,%1,%2,%3}, [%4+32];" : "=f"(d2.x), "=f"(d2.y), "=f"(d2.z), "=f"(d2.w) : "l"(np));
+		asm volatile("ld.v4.f32 {%0,%1,%2,%3}, [%4+48];" : "=f"(d3.x), "=f"(d3.y), "=f"(d3.z), "=f"(d3.w) : "l"(np));
+	}
+}
+
+// One inner-node step (Kernels.h:170-199). Returns the next node reference, or 0 when neither child
+// is hit and the stack is empty.
+template <bool kGlobal>
+__device__ __forceinline__ uint32_t innerStep(const float4* np, const RayState& r, LocalStack& stack) {
+	float4 d0, d1, d2, d3;
+	loadNode<kGlobal>(np, d0, d1, d2, d3);
 	const float tRay = r.tFar;
 	const float tFirst = slab(d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, r);
 	const float tLast = slab(d2.z, d2.w, d3.x, d3.y, d3.z, d3.w, r);
@@ -246,10 +288,10 @@ __device__ __forceinline__ uint32_t innerStep(const float4* np, const RayState& 
 		const bool sgn = (__float_as_uint(tLast - tFirst) >> 31) != 0;
 		const uint32_t cf = __float_as_uint(d0.z), cl = __float_as_uint(d0.w);
 		if (fmaxf(tFirst, tLast) != tRay)
-			stack[sp++] = sgn ? cf : cl;
+			stack.push(sgn ? cf : cl);
 		return sgn ? cl : cf;
 	}
-	return sp ? stack[--sp] : 0u;
+	return stack.empty() ? 0u : stack.pop();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -264,14 +306,15 @@ __global__ void __launch_bounds__(256) traceSimpleKernel(const TraceParams p) {
 	locate(p, idx, rays, out, local);
 	RayState r; HitState h;
 	initRay(rays, local, r, h);
-	uint32_t stack[kStackSize];
-	int sp = 0;
+	uint32_t stackStorage[kStackSize];
+	LocalStack stack;
+	stack.attach(stackStorage);
 	uint32_t node = kInnerBit;
 	unsigned nInner = 0, nPairs = 0;
 	for (;;) {
 		if (node & kInnerBit) {
 			if (kCount) ++nInner;
-			node = innerStep(p.nodes + 4 * (size_t)(node & ~kInnerBit), r, stack, sp);
+			node = innerStep<true>(p.nodes + 4 * (size_t)(node & ~kInnerBit), r, stack);
 			if (!node) break;
 			continue;
 		}
@@ -280,8 +323,8 @@ __global__ void __launch_bounds__(256) traceSimpleKernel(const TraceParams p) {
 			pairTest(p.pairs, i, r, h);
 			if (kCount) ++nPairs;
 		}
-		if (!sp) break;
-		node = stack[--sp];
+		if (stack.empty()) break;
+		node = stack.pop();
 	}
 	out[local] = finishRay(p, r, h);
 	if (p.counters) {
@@ -350,8 +393,9 @@ struct NodeBases {
 	uint32_t sharedCount;
 };
 
+template <bool kStage>
 __device__ __forceinline__ const float4* nodeAddress(const NodeBases& nb, uint32_t n) {
-	const char* base = n < nb.sharedCount ? nb.shared : nb.global;
+	const char* base = (kStage && n < nb.sharedCount) ? nb.shared : nb.global;
 	unsigned long long a;
 	asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(a) : "r"(n), "l"(reinterpret_cast<unsigned long long>(base)));
 	return reinterpret_cast<const float4*>(a);
@@ -361,12 +405,16 @@ __device__ __forceinline__ const float4* nodeAddress(const NodeBases& nb, uint32
 // kMode 1: phased (each pass is EITHER one inner step for the lanes at inner nodes OR the leaf
 //          tests of the lanes at leaves; leaves run when at least `leafThreshold` lanes wait at one
 //          or no lane is at an inner node).
-template <bool kCount, int kBlock, int kMinBlocks, int kMode>
+//
+// kStage: the first p.smemNodes inner nodes (the hottest: the builder orders nodes by surface area)
+// are served from shared memory, staged once per CTA by a TMA bulk copy; the un-staged
+// instantiation reads every node through L1/L2 and saves the per-step address select.
+template <bool kCount, int kBlock, int kMinBlocks, int kMode, bool kStage>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(const TraceParams p, const int fetchThreshold, const int leafThreshold) {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
 	__shared__ uint64_t stageBar;
 	float4* sNodes = reinterpret_cast<float4*>(smemRaw);
-	if (p.smemNodes)
+	if (kStage && p.smemNodes)
 		stageNodes(sNodes, p.nodes, p.smemNodes * 64u, &stageBar);
 
 	NodeBases nb;
@@ -377,7 +425,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(cons
 		asm volatile("cvta.shared.u64 %0, %1;" : "=l"(g) : "l"((unsigned long long)smemAddr(sNodes)));
 		nb.shared = reinterpret_cast<const char*>(g);
 		nb.global = reinterpret_cast<const char*>(p.nodes);
-		nb.sharedCount = p.smemNodes;
+		nb.sharedCount = kStage ? p.smemNodes : 0u;
 	}
 
 	const unsigned lane = threadIdx.x & 31;
@@ -388,8 +436,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(cons
 	bool exhausted = false; // warp-uniform: the cursor has run past the last ray
 
 	RayState r; HitState h;
-	uint32_t stack[kStackSize];
-	int sp = 0;
+	uint32_t stackStorage[kStackSize];
+	LocalStack stack;
+	stack.attach(stackStorage);
 	uint32_t node = 0;
 	float4* outPtr = nullptr;
 	unsigned long long cInner = 0, cPairs = 0;
@@ -418,7 +467,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(cons
 						locate(p, idx, rays, outPtr, local);
 						outPtr += local;
 						initRay(rays, local, r, h);
-						sp = 0;
+						stack.reset();
 						node = kInnerBit;
 						state = kTraversing;
 					}
@@ -434,7 +483,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(cons
 			if (state == kTraversing) {
 				while (node & kInnerBit) {
 					if (kCount) ++cInner;
-					node = innerStep(nodeAddress(nb, node & ~kInnerBit), r, stack, sp);
+					node = innerStep<!kStage>(nodeAddress<kStage>(nb, node & ~kInnerBit), r, stack);
 				}
 			}
 			__syncwarp();
@@ -445,7 +494,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(cons
 						pairTest(p.pairs, i, r, h);
 						if (kCount) ++cPairs;
 					}
-					node = sp ? stack[--sp] : 0u;
+					node = stack.empty() ? 0u : stack.pop();
 				}
 				if (!node)
 					state = kFinished;
@@ -465,14 +514,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(cons
 						pairTest(p.pairs, i, r, h);
 						if (kCount) ++cPairs;
 					}
-					node = sp ? stack[--sp] : 0u;
+					node = stack.empty() ? 0u : stack.pop();
 					if (!node)
 						state = kFinished;
 				}
 			}
 			else if (atInner) {
 				if (kCount) ++cInner;
-				node = innerStep(nodeAddress(nb, node & ~kInnerBit), r, stack, sp);
+				node = innerStep<!kStage>(nodeAddress<kStage>(nb, node & ~kInnerBit), r, stack);
 				if (!node)
 					state = kFinished;
 			}
@@ -512,9 +561,9 @@ struct LaunchPlan {
 	int resident = 1;
 };
 
-template <bool kCount, int kBlock, int kMinBlocks, int kMode>
+template <bool kCount, int kBlock, int kMinBlocks, int kMode, bool kStage>
 cudaError_t launchPersistent(const TraceParams& p, const Tuning& t, int smCount, cudaStream_t stream) {
-	auto kernel = tracePersistentKernel<kCount, kBlock, kMinBlocks, kMode>;
+	auto kernel = tracePersistentKernel<kCount, kBlock, kMinBlocks, kMode, kStage>;
 	static thread_local LaunchPlan plan;
 	cudaError_t err;
 	int device = 0;
@@ -525,7 +574,7 @@ cudaError_t launchPersistent(const TraceParams& p, const Tuning& t, int smCount,
 		cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
 		cudaDeviceGetAttribute(&smPerSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
 		const int ctas = t.ctasPerSm > 0 ? t.ctasPerSm : kMinBlocks;
-		uint32_t wantNodes = t.smemNodes >= 0 ? (uint32_t)t.smemNodes : 0xffffffffu;
+		uint32_t wantNodes = !kStage ? 0u : (t.smemNodes > 0 ? (uint32_t)t.smemNodes : 0xffffffffu);
 		if (wantNodes > p.nodeCount) wantNodes = p.nodeCount;
 		size_t budget = (size_t)smPerSm / (size_t)ctas;
 		budget = budget > 2048 ? budget - 2048 : 0; // static smem + the per-CTA system reservation
@@ -580,7 +629,10 @@ cudaError_t dispatch(const TraceParams& p, const Tuning& t, int smCount, cudaStr
 		return cudaGetLastError();
 	}
 	const int mode = t.variant == 2 ? 1 : 0;
-#define RACC_LAUNCH(B, M) (mode ? launchPersistent<kCount, B, M, 1>(p, t, smCount, stream) : launchPersistent<kCount, B, M, 0>(p, t, smCount, stream))
+	const bool stage = t.smemNodes != 0; // -1 = as many as fit, 0 = none (un-staged instantiation)
+#define RACC_LAUNCH(B, M)                                                                                 \
+	(mode ? (stage ? launchPersistent<kCount, B, M, 1, true>(p, t, smCount, stream) : launchPersistent<kCount, B, M, 1, false>(p, t, smCount, stream)) \
+	      : (stage ? launchPersistent<kCount, B, M, 0, true>(p, t, smCount, stream) : launchPersistent<kCount, B, M, 0, false>(p, t, smCount, stream)))
 	switch (t.blockThreads * 100 + t.ctasPerSm) {
 	case 12800 + 8: case 12800: return RACC_LAUNCH(128, 8);
 	case 12800 + 10: return RACC_LAUNCH(128, 10);

@@ -14,14 +14,15 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 VARIANTS = [
-    dict(variant=0, block=256, smem_nodes=-1),
+    dict(variant=0, block=256, smem_nodes=-1, ctas_per_sm=0),
     dict(variant=0, block=256, smem_nodes=0),
+    dict(variant=2, block=256, smem_nodes=-1, ctas_per_sm=0),
     dict(variant=0, block=1024, smem_nodes=-1),
     dict(variant=0, block=128, smem_nodes=64, fetch_threshold=1),
     dict(variant=0, block=512, smem_nodes=-1, fetch_threshold=32),
     dict(variant=1),
 ]
-DEFAULT = dict(variant=0, block=256, ctas_per_sm=0, smem_nodes=-1, fetch_threshold=12)
+DEFAULT = dict(variant=0, block=256, ctas_per_sm=5, smem_nodes=0, fetch_threshold=12)
 
 
 @pytest.fixture(scope="module")
