@@ -140,14 +140,21 @@ int racc_cuda_sync(void* cuda_stream);
 /* Number of engine kernels launched by this process so far (bench.py's gpu_launches). */
 uint64_t racc_cuda_launch_count(void);
 
+/* Diagnostics (not in the reference): warp-level loop statistics accumulated by the COUNTED traversal
+ * launches (racc_cuda_trace_counted with detail != 0) of the bail-out kernel variant: out8[0] outer
+ * rounds, [1] inner-loop iterations, [2] leaf-loop iterations, [3]/[4] lanes active summed over those
+ * iterations, [5] refills. Synchronises the device. reset != 0 zeroes them afterwards. */
+int racc_cuda_debug_warp_stats(uint64_t* out8, int reset);
+
 /* Engine tuning knob (not in the reference): which traversal kernel variant racc_cuda_trace uses.
  * 0 = default. See DESIGN.md section 5. Returns the previous value. */
 int racc_cuda_set_variant(int variant);
 
 /* Launch-shape knobs for benchmark sweeps: key 0 variant, 1 threads per CTA (128/256/512/1024),
  * 2 CTAs per SM (0 = as many as fit), 3 inner nodes staged in shared memory (-1 = as many as
- * fit), 4 refill threshold (idle lanes per warp). Returns the previous value. Also settable
- * through RACC_B200_VARIANT / _BLOCK / _CTAS_PER_SM / _SMEM_NODES / _FETCH_THRESHOLD. */
+ * fit, 0 = none), 4 refill threshold (idle lanes per warp), 5 leaf-loop bail-out, 6 shared-memory
+ * carve-out percent, 7 inner-loop bail-out. Returns the previous value. Also settable through
+ * RACC_B200_VARIANT / _BLOCK / _CTAS_PER_SM / _SMEM_NODES / _FETCH_THRESHOLD / _LEAF_BAIL / _INNER_BAIL. */
 int racc_cuda_set_tuning(int key, int value);
 
 /* ---- synthetic ray streams for the benchmark; not on the hot path ---- */

@@ -5,7 +5,7 @@ the sm_100a traversal kernels and the C-ABI (csrc/, include/racc_b200.h), plus t
 mirror of the reference's interface. There is no CPU fallback.
 """
 from .api import (INVALID_TRIANGLE, RAY_DTYPE, RESULT_DTYPE, Environment, HostImages, Scene, create_environment,  # noqa: F401
-                  create_scene, create_scene_from_images, device_count, generate_bounce, generate_primary, init,
+                  create_scene, create_scene_from_images, debug_warp_stats, device_count, generate_bounce, generate_primary, init,
                   launch_count, set_tuning, sync, trace_device, trace_host, trace_host_ptrs)
 from ._lib import EngineError  # noqa: F401
 from .scene_io import Camera, SceneFile, load_scene, synthetic_triangles  # noqa: F401

@@ -216,8 +216,14 @@ def launch_count() -> int:
     return int(_lib.load().racc_cuda_launch_count())
 
 
+def debug_warp_stats(reset: bool = True) -> list[int]:
+    out = (ctypes.c_uint64 * 8)()
+    _lib.check(_lib.load().racc_cuda_debug_warp_stats(out, 1 if reset else 0), "racc_cuda_debug_warp_stats")
+    return [int(x) for x in out]
+
+
 def set_tuning(**kw) -> None:
-    keys = {"variant": 0, "block": 1, "ctas_per_sm": 2, "smem_nodes": 3, "fetch_threshold": 4, "leaf_threshold": 5, "carveout": 6}
+    keys = {"variant": 0, "block": 1, "ctas_per_sm": 2, "smem_nodes": 3, "fetch_threshold": 4, "leaf_bail": 5, "carveout": 6, "inner_bail": 7}
     lib = _lib.load()
     for k, v in kw.items():
         lib.racc_cuda_set_tuning(keys[k], int(v))

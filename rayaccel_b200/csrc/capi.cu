@@ -71,7 +71,8 @@ int ensureInit() {
 	g_tuning.ctasPerSm = envInt("RACC_B200_CTAS_PER_SM", g_tuning.ctasPerSm);
 	g_tuning.smemNodes = envInt("RACC_B200_SMEM_NODES", g_tuning.smemNodes);
 	g_tuning.fetchThreshold = envInt("RACC_B200_FETCH_THRESHOLD", g_tuning.fetchThreshold);
-	g_tuning.leafThreshold = envInt("RACC_B200_LEAF_THRESHOLD", g_tuning.leafThreshold);
+	g_tuning.leafBail = envInt("RACC_B200_LEAF_BAIL", g_tuning.leafBail);
+	g_tuning.innerBail = envInt("RACC_B200_INNER_BAIL", g_tuning.innerBail);
 	g_tuning.carveout = envInt("RACC_B200_CARVEOUT", g_tuning.carveout);
 	g_initialised = true;
 	return 0;
@@ -178,7 +179,8 @@ int racc_cuda_set_tuning(int key, int value) {
 	case 2: slot = &g_tuning.ctasPerSm; break;
 	case 3: slot = &g_tuning.smemNodes; break;
 	case 4: slot = &g_tuning.fetchThreshold; break;
-	case 5: slot = &g_tuning.leafThreshold; break;
+	case 5: slot = &g_tuning.leafBail; break;
+	case 7: slot = &g_tuning.innerBail; break;
 	case 6: slot = &g_tuning.carveout; break;
 	default: return fail("unknown tuning key %d", key);
 	}
@@ -188,6 +190,14 @@ int racc_cuda_set_tuning(int key, int value) {
 }
 
 uint64_t racc_cuda_launch_count(void) { return g_launches.load(); }
+
+int racc_cuda_debug_warp_stats(uint64_t* out8, int reset) {
+	if (!out8) return fail("racc_cuda_debug_warp_stats: null argument");
+	if (ensureInit()) return -1;
+	RACC_CUDA_CHECK(cudaDeviceSynchronize());
+	RACC_CUDA_CHECK(readWarpStats(reinterpret_cast<unsigned long long*>(out8), reset != 0));
+	return 0;
+}
 
 racc_cuda_scene* racc_cuda_scene_create(const float* verts4, uint32_t nverts, const uint32_t* indices, uint32_t nindices) {
 	if (!verts4 || !indices) { fail("racc_cuda_scene_create: null input"); return nullptr; }

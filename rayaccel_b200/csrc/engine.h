@@ -36,19 +36,22 @@ struct TraceParams {
 
 // Tunables (racc_cuda_set_variant / RACC_B200_* environment variables), see DESIGN.md section 5.
 struct Tuning {
-	int variant = 0;        // 0 persistent while-while (default), 1 one-thread-per-ray, 2 persistent phased
+	int variant = 2;        // 0 persistent while-while, 1 one-thread-per-ray, 2 persistent while-while with bail-out (default)
 	int blockThreads = 256; // threads per CTA
 	int ctasPerSm = 5;      // 0 = as many as fit
 	int smemNodes = 0;      // inner nodes staged in shared memory by TMA: -1 = as many as fit, 0 = none. On
 	                        // battlefield (3.2 MB, L1/L2-resident) the un-staged instantiation measures ~4 %
 	                        // faster (profiles/r01_sweep_c_unstaged_256bit.jsonl), so it is the default.
-	int fetchThreshold = 12; // refill a warp when at least this many lanes are idle
-	int leafThreshold = 8;   // variant 2: run leaf tests when at least this many lanes wait at a leaf
+	int fetchThreshold = 16; // refill a warp when at least this many lanes are idle
+	int leafBail = 4;        // variant 2: leave the leaf loop when fewer lanes than this still have pairs to test
+	int innerBail = 12;      // variant 2: leave the inner loop when fewer lanes than this still descend
 	int carveout = -1;       // shared-memory carveout percent, -1 = exactly what the CTAs need
 };
 
 // counterMode: 0 none, 1 rays+hits only, 2 rays, hits, inner-node and pair visits
 cudaError_t launchTrace(const TraceParams& p, const Tuning& t, int counterMode, int smCount, cudaStream_t stream, int* launches);
+
+cudaError_t readWarpStats(unsigned long long* out8, bool reset);
 
 cudaError_t launchGeneratePrimary(const float* camera12, uint32_t width, uint32_t height, uint32_t spp, uint32_t seed,
                                   DevRay* rays, cudaStream_t stream, int* launches);

@@ -28,6 +28,12 @@ constexpr uint32_t kInnerBit = 0x80000000u;
 constexpr uint32_t kMiss = 0xffffffffu;
 constexpr int kStackSize = 64; // Kernels.h:166
 
+// Diagnostics of the counted (kCount) instantiations only: warp-level loop trip counts, for
+// lane-utilisation analysis (racc_cuda_debug_warp_stats). [0] outer rounds, [1] inner-loop
+// iterations, [2] leaf-loop iterations, [3] lanes active summed over inner iterations, [4] lanes
+// active summed over leaf iterations, [5] refills.
+__device__ unsigned long long g_warpStats[8];
+
 struct RayState {
 	float ox, oy, oz;
 	float dx, dy, dz;      // after the epsilon clamp (Kernels.h:149-157)
@@ -402,15 +408,15 @@ __device__ __forceinline__ const float4* nodeAddress(const NodeBases& nb, uint32
 }
 
 // kMode 0: while-while (every lane walks inner nodes until it holds a leaf; then all leaves).
-// kMode 1: phased (each pass is EITHER one inner step for the lanes at inner nodes OR the leaf
-//          tests of the lanes at leaves; leaves run when at least `leafThreshold` lanes wait at one
-//          or no lane is at an inner node).
+// kMode 1: while-while with bail-out (the inner loop stops once fewer than `innerBail` lanes still
+//          descend while others wait; the leaf loop tests one pair per iteration and stops once
+//          fewer than `leafBail` lanes still have pairs while others wait at inner nodes).
 //
 // kStage: the first p.smemNodes inner nodes (the hottest: the builder orders nodes by surface area)
 // are served from shared memory, staged once per CTA by a TMA bulk copy; the un-staged
 // instantiation reads every node through L1/L2 and saves the per-step address select.
 template <bool kCount, int kBlock, int kMinBlocks, int kMode, bool kStage>
-__global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(const TraceParams p, const int fetchThreshold, const int leafThreshold) {
+__global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(const TraceParams p, const int fetchThreshold, const int innerBail, const int leafBail) {
 	extern __shared__ __align__(128) unsigned char smemRaw[];
 	__shared__ uint64_t stageBar;
 	float4* sNodes = reinterpret_cast<float4*>(smemRaw);
@@ -502,30 +508,47 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(cons
 			__syncwarp();
 		}
 		else {
-			// ---- phased: one inner step OR one round of leaf tests per pass -------------------------
-			const bool atInner = state == kTraversing && (node & kInnerBit);
-			const bool atLeaf = state == kTraversing && !(node & kInnerBit);
-			const unsigned innerMask = __ballot_sync(kFullMask, atInner);
-			const unsigned leafMask = __ballot_sync(kFullMask, atLeaf);
-			if (leafMask && (!innerMask || __popc(leafMask) >= leafThreshold)) {
-				if (atLeaf) {
-					const uint32_t first = node & 0xffffffu, last = first + (node >> 24);
-					for (uint32_t i = first; i < last; ++i) {
-						pairTest(p.pairs, i, r, h);
-						if (kCount) ++cPairs;
-					}
-					node = stack.empty() ? 0u : stack.pop();
-					if (!node)
-						state = kFinished;
+			// ---- while-while with bail-out ----------------------------------------------------------
+			// Both phases run as warp-uniform loops that stop early once too few lanes still take part:
+			// in plain while-while a phase lasts as long as its slowest lane (7-8 inner steps while the
+			// median lane needs 2), which on incoherent rays leaves ~60 % of the issue slots masked
+			// off. A lane that is cut short keeps its place (node / remaining pairs) and simply
+			// continues in the next round, so every ray still sees exactly the same sequence of node
+			// and pair tests -- only the interleaving between lanes changes.
+			const bool live = state == kTraversing;
+			const unsigned liveMask = __ballot_sync(kFullMask, live);
+			if (kCount && lane == 0) atomicAdd(&g_warpStats[0], 1ull);
+			for (int steps = 0;; ++steps) {
+				const bool atInner = live && (node & kInnerBit);
+				const unsigned innerMask = __ballot_sync(kFullMask, atInner);
+				if (!innerMask)
+					break;
+				const int descending = __popc(innerMask);
+				if (descending < innerBail && innerMask != liveMask && (steps || 2 * descending <= __popc(liveMask)))
+					break;
+				if (kCount && lane == 0) { atomicAdd(&g_warpStats[1], 1ull); atomicAdd(&g_warpStats[3], (unsigned long long)descending); }
+				if (atInner) {
+					if (kCount) ++cInner;
+					node = innerStep<!kStage>(nodeAddress<kStage>(nb, node & ~kInnerBit), r, stack);
 				}
 			}
-			else if (atInner) {
-				if (kCount) ++cInner;
-				node = innerStep<!kStage>(nodeAddress<kStage>(nb, node & ~kInnerBit), r, stack);
-				if (!node)
-					state = kFinished;
+			for (int steps = 0;; ++steps) {
+				const bool atLeaf = live && node && !(node & kInnerBit);
+				const unsigned leafMask = __ballot_sync(kFullMask, atLeaf);
+				if (!leafMask)
+					break;
+				if (steps && __popc(leafMask) < leafBail && __ballot_sync(kFullMask, live && (node & kInnerBit)))
+					break;
+				if (kCount && lane == 0) { atomicAdd(&g_warpStats[2], 1ull); atomicAdd(&g_warpStats[4], (unsigned long long)__popc(leafMask)); }
+				if (atLeaf) {
+					pairTest(p.pairs, node & 0xffffffu, r, h);
+					if (kCount) ++cPairs;
+					// one pair of this leaf done: (count << 24 | first) -> (count-1 << 24 | first+1)
+					node = (node >> 24) > 1u ? node + 1u - 0x1000000u : (stack.empty() ? 0u : stack.pop());
+				}
 			}
-			__syncwarp();
+			if (live && !node)
+				state = kFinished;
 		}
 	}
 
@@ -617,7 +640,7 @@ cudaError_t launchPersistent(const TraceParams& p, const Tuning& t, int smCount,
 
 	err = cudaMemsetAsync(p.cursor, 0, sizeof(uint32_t), stream);
 	if (err != cudaSuccess) return err;
-	kernel<<<(unsigned)grid, kBlock, (size_t)plan.smemNodes * 64, stream>>>(q, t.fetchThreshold, t.leafThreshold);
+	kernel<<<(unsigned)grid, kBlock, (size_t)plan.smemNodes * 64, stream>>>(q, t.fetchThreshold, t.innerBail, t.leafBail);
 	return cudaGetLastError();
 }
 
@@ -652,6 +675,15 @@ cudaError_t dispatch(const TraceParams& p, const Tuning& t, int smCount, cudaStr
 }
 
 } // namespace
+
+cudaError_t readWarpStats(unsigned long long* out8, bool reset) {
+	cudaError_t e = cudaMemcpyFromSymbol(out8, g_warpStats, 8 * sizeof(unsigned long long));
+	if (e == cudaSuccess && reset) {
+		const unsigned long long zeros[8] = {};
+		e = cudaMemcpyToSymbol(g_warpStats, zeros, sizeof(zeros));
+	}
+	return e;
+}
 
 cudaError_t launchTrace(const TraceParams& p, const Tuning& t, int counterMode, int smCount, cudaStream_t stream, int* launches) {
 	if (!p.total)

@@ -13,7 +13,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import rayaccel_b200 as rb  # noqa: E402
 
-BASE = dict(variant=0, block=256, ctas_per_sm=5, smem_nodes=0, fetch_threshold=12, leaf_threshold=8, carveout=-1)
+BASE = dict(variant=2, block=256, ctas_per_sm=5, smem_nodes=0, fetch_threshold=16, leaf_bail=4, inner_bail=12, carveout=-1)
 
 
 def time_launch(scene, env, descs, iters=4, flush=None):
@@ -39,11 +39,15 @@ def grids(stage):
         yield dict(variant=1)
     elif stage == "b":  # phased kernel
         for (block, ctas), smem, thr, leaf in itertools.product([(256, 0), (256, 5), (512, 0)], [0, 256, -1], [8, 16], [1, 4, 8, 12, 16, 24, 32]):
-            yield dict(variant=2, block=block, ctas_per_sm=ctas, smem_nodes=smem, fetch_threshold=thr, leaf_threshold=leaf)
+            yield dict(variant=2, block=block, ctas_per_sm=ctas, smem_nodes=smem, fetch_threshold=thr, leaf_bail=leaf)
     elif stage == "c":  # staged vs un-staged instantiation x launch shape x refill
         shapes = [(128, 0), (128, 10), (128, 12), (256, 0), (256, 5), (256, 6), (512, 0), (512, 3), (1024, 0)]
         for (block, ctas), smem, thr in itertools.product(shapes, [0, -1], [8, 12, 16, 20]):
             yield dict(variant=0, block=block, ctas_per_sm=ctas, smem_nodes=smem, fetch_threshold=thr)
+    elif stage == "d":  # while-while with bail-out: inner/leaf thresholds x refill
+        yield dict(variant=0)
+        for ib, lb, thr in itertools.product([0, 8, 12, 16, 20, 24], [0, 4, 8, 12, 16], [8, 12, 16]):
+            yield dict(variant=2, inner_bail=ib, leaf_bail=lb, fetch_threshold=thr)
     else:
         for kv in stage.split(";"):
             yield {k: int(v) for k, v in (p.split("=") for p in kv.split(","))}
