@@ -39,6 +39,25 @@ WIDTH, HEIGHT, SPP, BOUNCES = 1920, 1080, 4, 3
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout() -> None:
+    """Keep stdout for the ONE JSON line: native libraries (NCCL prints its version banner to stdout)
+    write to fd 1, so fd 1 is pointed at stderr for the run and the line goes to the saved descriptor."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -197,7 +216,7 @@ def run_reference(args, rank: int, world: int) -> None:
         "e2e": {"value": round(mrays, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -404,7 +423,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
             line["parity_sample_bit_exact"] = parity
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -418,6 +437,7 @@ def main() -> None:
     ap.add_argument("--cpu-sample-rays", type=int, default=20_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
