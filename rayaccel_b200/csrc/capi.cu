@@ -66,6 +66,15 @@ int ensureInit() {
 		return fail("no CUDA device available (%s); the engine has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
 	RACC_CUDA_CHECK(cudaGetDevice(&g_device));
 	RACC_CUDA_CHECK(cudaDeviceGetAttribute(&g_smCount, cudaDevAttrMultiProcessorCount, g_device));
+	{
+		// stream-ordered scratch (stream tables, re-binning buffers) is recycled instead of being handed
+		// back to the driver at every synchronisation
+		cudaMemPool_t pool = nullptr;
+		if (cudaDeviceGetDefaultMemPool(&pool, g_device) == cudaSuccess && pool) {
+			unsigned long long keep = ~0ull;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+	}
 	g_tuning.variant = envInt("RACC_B200_VARIANT", g_tuning.variant);
 	g_tuning.blockThreads = envInt("RACC_B200_BLOCK", g_tuning.blockThreads);
 	g_tuning.ctasPerSm = envInt("RACC_B200_CTAS_PER_SM", g_tuning.ctasPerSm);
@@ -74,11 +83,16 @@ int ensureInit() {
 	g_tuning.leafBail = envInt("RACC_B200_LEAF_BAIL", g_tuning.leafBail);
 	g_tuning.innerBail = envInt("RACC_B200_INNER_BAIL", g_tuning.innerBail);
 	g_tuning.carveout = envInt("RACC_B200_CARVEOUT", g_tuning.carveout);
+	g_tuning.sortMode = envInt("RACC_B200_SORT", g_tuning.sortMode);
+	g_tuning.sortOriginBits = envInt("RACC_B200_SORT_ORIGIN_BITS", g_tuning.sortOriginBits);
+	g_tuning.sortDirBits = envInt("RACC_B200_SORT_DIR_BITS", g_tuning.sortDirBits);
+	g_tuning.sortDirMajor = envInt("RACC_B200_SORT_DIR_MAJOR", g_tuning.sortDirMajor);
 	g_initialised = true;
 	return 0;
 }
 
 constexpr int kCursorRing = 256;
+constexpr size_t kAutoSortSceneBytes = 256u << 20; // twice the 126 MB L2
 
 } // namespace
 
@@ -88,6 +102,8 @@ struct racc_cuda_scene {
 	float4* dNodes = nullptr;
 	float4* dPairs = nullptr;
 	uint32_t* dRemap = nullptr;
+	float4* dTNodes = nullptr;   // packed images walked by the default kernel (traverse_packed.cu)
+	float4* dTPairs = nullptr;
 	float4* dVerts = nullptr;    // only for the synthetic bounce generator
 	uint32_t* dIndices = nullptr;
 	uint32_t* dCursors = nullptr;
@@ -130,6 +146,16 @@ racc_cuda_scene* uploadScene(racc_cuda_scene* s, const float* verts4, uint32_t n
 		fail("scene upload failed: %s", cudaGetErrorString(e));
 		return bail();
 	}
+	// device-private packed copies of the node and pair images, derived on the device
+	int launches = 0;
+	if ((e = cudaMalloc(reinterpret_cast<void**>(&s->dTNodes), h.nodes.size() * 64 + 64)) != cudaSuccess ||
+	    (e = cudaMalloc(reinterpret_cast<void**>(&s->dTPairs), h.pairs.size() * 64 + 64)) != cudaSuccess ||
+	    (e = launchPackImages(s->dNodes, (uint32_t)h.nodes.size(), s->dPairs, (uint32_t)h.pairs.size(), s->dTNodes, s->dTPairs, nullptr, &launches)) != cudaSuccess ||
+	    (e = cudaDeviceSynchronize()) != cudaSuccess) {
+		fail("scene packing failed: %s", cudaGetErrorString(e));
+		return bail();
+	}
+	g_launches.fetch_add((uint64_t)launches);
 	return s;
 }
 
@@ -182,6 +208,10 @@ int racc_cuda_set_tuning(int key, int value) {
 	case 5: slot = &g_tuning.leafBail; break;
 	case 7: slot = &g_tuning.innerBail; break;
 	case 6: slot = &g_tuning.carveout; break;
+	case 8: slot = &g_tuning.sortMode; break;
+	case 9: slot = &g_tuning.sortOriginBits; break;
+	case 10: slot = &g_tuning.sortDirBits; break;
+	case 11: slot = &g_tuning.sortDirMajor; break;
 	default: return fail("unknown tuning key %d", key);
 	}
 	const int previous = *slot;
@@ -264,6 +294,14 @@ racc_cuda_scene* racc_cuda_scene_create_from_images(const void* nodes, uint32_t 
 	s->host.pairs.assign(static_cast<const GpuPair*>(pairs), static_cast<const GpuPair*>(pairs) + pair_count);
 	s->host.remap.assign(remap, remap + remap_count);
 	s->host.realPairs = remap_count / 2;
+	{
+		// scene bounds = union of the root's two child boxes (used only by the ray re-binning keys)
+		const GpuNode& root = s->host.nodes[0];
+		for (int k = 0; k < 3; ++k) {
+			s->host.boundsMin[k] = root.leftMin[k] < root.rightMin[k] ? root.leftMin[k] : root.rightMin[k];
+			s->host.boundsMax[k] = root.leftMax[k] > root.rightMax[k] ? root.leftMax[k] : root.rightMax[k];
+		}
+	}
 	// validate references so a malformed image cannot send the kernel out of bounds
 	for (const GpuNode& n : s->host.nodes) {
 		const uint32_t refs[2] = {n.first, n.last};
@@ -285,6 +323,8 @@ void racc_cuda_scene_destroy(racc_cuda_scene* s) {
 	cudaFree(s->dNodes);
 	cudaFree(s->dPairs);
 	cudaFree(s->dRemap);
+	cudaFree(s->dTNodes);
+	cudaFree(s->dTPairs);
 	cudaFree(s->dVerts);
 	cudaFree(s->dIndices);
 	cudaFree(s->dCursors);
@@ -394,6 +434,14 @@ void fillSceneParams(TraceParams& p, racc_cuda_scene* s, racc_cuda_env* env, voi
 	p.envHeight = env ? env->height : 0;
 	p.nodeCount = (uint32_t)s->host.nodes.size();
 	p.counters = static_cast<unsigned long long*>(device_counters);
+	p.tnodes = s->dTNodes;
+	p.tpairs = s->dTPairs;
+	p.perm = nullptr;
+}
+
+cudaError_t launchAny(const TraceParams& p, int counterMode, cudaStream_t stream, int* launches) {
+	return g_tuning.variant == 3 ? launchTracePacked(p, g_tuning, counterMode, g_smCount, stream, launches)
+	                             : launchTrace(p, g_tuning, counterMode, g_smCount, stream, launches);
 }
 
 int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams,
@@ -440,7 +488,18 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 			RACC_CUDA_CHECK(cudaMemcpyAsync(dRefs, refs.data(), refs.size() * sizeof(StreamRef), cudaMemcpyHostToDevice, stream));
 			p.streams = static_cast<const StreamRef*>(dRefs);
 		}
-		RACC_CUDA_CHECK(launchTrace(p, g_tuning, device_counters ? (fullCounters ? 2 : 1) : 0, g_smCount, stream, &launches));
+		void* sortScratch = nullptr;
+		const size_t sceneBytes = (s->host.nodes.size() + s->host.pairs.size()) * 64;
+		const bool rebin = g_tuning.variant == 3 && total >= 4096 &&
+		                   (g_tuning.sortMode == 1 || (g_tuning.sortMode == 2 && sceneBytes > kAutoSortSceneBytes && total >= (1u << 18)));
+		if (rebin) {
+			// re-bin the launch: visiting order by origin/direction key, results stay index-parallel
+			RACC_CUDA_CHECK(cudaMallocAsync(&sortScratch, raySortScratchBytes(p.total), stream));
+			RACC_CUDA_CHECK(launchRaySort(p, s->host.boundsMin, s->host.boundsMax, g_tuning.sortOriginBits, g_tuning.sortDirBits,
+			                              g_tuning.sortDirMajor, sortScratch, g_smCount, stream, &p.perm, &launches));
+		}
+		RACC_CUDA_CHECK(launchAny(p, device_counters ? (fullCounters ? 2 : 1) : 0, stream, &launches));
+		if (sortScratch) RACC_CUDA_CHECK(cudaFreeAsync(sortScratch, stream));
 		if (dRefs) RACC_CUDA_CHECK(cudaFreeAsync(dRefs, stream));
 	}
 
@@ -483,7 +542,7 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 			p.single.begin = 0;
 			p.single.count = filled;
 			p.cursor = s->dCursors + (s->nextCursor.fetch_add(1) % kCursorRing);
-			RACC_CUDA_CHECK(launchTrace(p, g_tuning, device_counters ? (fullCounters ? 2 : 1) : 0, g_smCount, pipe.lane[l], &launches));
+			RACC_CUDA_CHECK(launchAny(p, device_counters ? (fullCounters ? 2 : 1) : 0, pipe.lane[l], &launches));
 			for (int k = 0; k < nsegs; ++k)
 				RACC_CUDA_CHECK(cudaMemcpyAsync(segs[k].hResults, pipe.dResults[l] + segs[k].offset, (size_t)segs[k].n * 16, cudaMemcpyDeviceToHost, pipe.lane[l]));
 			++chunk;

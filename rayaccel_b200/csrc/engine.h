@@ -32,24 +32,47 @@ struct TraceParams {
 	uint32_t* cursor;         // work cursor for the persistent kernels (zeroed before launch)
 	unsigned long long* counters; // 4 x u64 {rays,hits,inner,pairs} or null
 	uint32_t smemNodes;       // inner nodes staged in shared memory by the persistent kernel
+	const float4* tnodes;     // packed images (traverse_packed.cu): 4 x float4 per inner node,
+	const float4* tpairs;     //   4 x float4 per triangle pair
+	const uint32_t* perm;     // optional visiting order (launch-wide ray indices), null = arrival order
 };
 
 // Tunables (racc_cuda_set_variant / RACC_B200_* environment variables), see DESIGN.md section 5.
 struct Tuning {
-	int variant = 2;        // 0 persistent while-while, 1 one-thread-per-ray, 2 persistent while-while with bail-out (default)
+	int variant = 3;        // 3 packed-format persistent while-while with bail-out (default, traverse_packed.cu);
+	                        // reference-format kernels of traverse.cu kept for A/B: 0 persistent while-while,
+	                        // 1 one-thread-per-ray, 2 persistent while-while with bail-out
 	int blockThreads = 256; // threads per CTA
 	int ctasPerSm = 5;      // 0 = as many as fit
 	int smemNodes = 0;      // inner nodes staged in shared memory by TMA: -1 = as many as fit, 0 = none. On
 	                        // battlefield (3.2 MB, L1/L2-resident) the un-staged instantiation measures ~4 %
 	                        // faster (profiles/r01_sweep_c_unstaged_256bit.jsonl), so it is the default.
 	int fetchThreshold = 16; // refill a warp when at least this many lanes are idle
-	int leafBail = 4;        // variant 2: leave the leaf loop when fewer lanes than this still have pairs to test
-	int innerBail = 12;      // variant 2: leave the inner loop when fewer lanes than this still descend
+	int leafBail = 4;        // variants 2, 3: leave the leaf loop when fewer lanes than this still have pairs to test
+	int innerBail = 8;       // variants 2, 3: leave the inner loop when fewer lanes than this still descend
 	int carveout = -1;       // shared-memory carveout percent, -1 = exactly what the CTAs need
+	// ray re-binning before traversal (raysort.cu; variant 3 only)
+	int sortMode = 2;        // 0 arrival order, 1 re-bin every device-resident launch, 2 auto: re-bin when the scene
+	                         // is far larger than L2 (traversal is then DRAM-bound and coherence pays for the sort)
+	int sortOriginBits = 5;  // Morton bits per axis of the ray origin inside the scene bounds
+	int sortDirBits = 3;     // Morton bits per axis of the direction on the unit cube
+	int sortDirMajor = 0;    // 0 origin-major key, 1 direction-major key
 };
 
 // counterMode: 0 none, 1 rays+hits only, 2 rays, hits, inner-node and pair visits
 cudaError_t launchTrace(const TraceParams& p, const Tuning& t, int counterMode, int smCount, cudaStream_t stream, int* launches);
+
+// variant 3 (traverse_packed.cu)
+cudaError_t launchTracePacked(const TraceParams& p, const Tuning& t, int counterMode, int smCount, cudaStream_t stream, int* launches);
+
+// reference-format images -> packed images, on the device (once per scene)
+cudaError_t launchPackImages(const float4* nodes, uint32_t nodeCount, const float4* pairs, uint32_t pairCount,
+                             float4* tnodes, float4* tpairs, cudaStream_t stream, int* launches);
+
+// ray re-binning (raysort.cu): builds a visiting order in scratch memory (raySortScratchBytes), see there
+size_t raySortScratchBytes(uint32_t total);
+cudaError_t launchRaySort(const TraceParams& p, const float boundsMin[3], const float boundsMax[3], int originBits, int dirBits,
+                          int dirMajor, void* scratch, int smCount, cudaStream_t stream, const uint32_t** perm, int* launches);
 
 cudaError_t readWarpStats(unsigned long long* out8, bool reset);
 

@@ -1,0 +1,370 @@
+// traverse_packed.cu -- the default traversal kernel: persistent while-while with bail-out over a
+// device-private "packed" copy of the scene images, written for sm_100a.
+//
+// WHAT it computes is unchanged (Kernels.h:36-242 in the pinned arithmetic of DESIGN.md section 3);
+// every ray sees exactly the same sequence of box and pair tests as in the reference-format kernels
+// of traverse.cu, so results stay bit-identical to the oracle. HOW differs in three places:
+//
+//   * node layout. The reference's 64-byte node (Scene.cpp:73-78) stores {lMin.xyz,lMax.x |
+//     lMax.yz,rMin.xy | rMin.z,rMax.xyz}. The packed node stores each axis' (min,max) side by side,
+//     {lx lX ly lY lz lZ rx rX | ry rY rz rZ first last - -}, so that one Blackwell packed-fp32
+//     instruction (fma.rn.ftz.f32x2 -> FFMA2 with the ray's invDir/OoD broadcast) evaluates the near
+//     and far plane of an axis at once: 6 FFMA2 per node instead of 12 FFMA. Same IEEE fma per
+//     component, so the same bits.
+//   * pair layout. 64 bytes instead of 48: {e1.xyz,e3.x | e2.xyz,e3.y | p0.xyz,e3.z | n1.xyz,-},
+//     where n1 = e1 x e2 is computed once per scene by packPairsKernel with the very instruction
+//     sequence the per-ray code used (mad_cross, Kernels.h:23-25). A pair is two aligned 256-bit
+//     loads that never straddle a cache line (the 48-byte stride does every third pair).
+//   * control. Child references keep the reference's encoding (bit 31 = inner), which makes the
+//     state tests single signed compares (<0 inner, >0 leaf, 0 none) and the node address one
+//     shift-add from a pre-biased base held in uniform registers; the push is a predicated STL.
+//
+// An optional permutation (TraceParams::perm, built by raysort.cu) makes the kernel visit the rays
+// in a coherence-improving order; results are still written index-parallel to the rays.
+#include "traverse_common.cuh"
+
+namespace racc_b200 {
+namespace {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+	u64 r;
+	asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+// (v,v): declared volatile so that the broadcast is not hoisted into a loop-invariant register pair;
+// ptxas folds it into the scalar-broadcast operand form of FFMA2 (Rn.F32) instead.
+__device__ __forceinline__ u64 splat2(float v) {
+	u64 r;
+	asm volatile("mov.b64 %0, {%1,%1};" : "=l"(r) : "f"(v));
+	return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+	asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// (a.lo*b.lo+c.lo, a.hi*b.hi+c.hi), each an IEEE fma with flush-to-zero: FFMA2
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+	u64 d;
+	asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reference-format images -> packed images (once per scene, on the device so that n1 is produced by
+// the same arithmetic the per-ray code would use)
+
+__global__ void packNodesKernel(const float4* __restrict__ nodes, uint32_t count, float4* __restrict__ out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	const float4 d0 = nodes[4 * (size_t)i], d1 = nodes[4 * (size_t)i + 1], d2 = nodes[4 * (size_t)i + 2], d3 = nodes[4 * (size_t)i + 3];
+	// left box: min (d1.x,d1.y,d1.z) max (d1.w,d2.x,d2.y); right box: min (d2.z,d2.w,d3.x) max (d3.y,d3.z,d3.w)
+	out[4 * (size_t)i + 0] = make_float4(d1.x, d1.w, d1.y, d2.x);
+	out[4 * (size_t)i + 1] = make_float4(d1.z, d2.y, d2.z, d3.y);
+	out[4 * (size_t)i + 2] = make_float4(d2.w, d3.z, d3.x, d3.w);
+	out[4 * (size_t)i + 3] = make_float4(d0.z, d0.w, 0.0f, 0.0f);
+}
+
+__global__ void packPairsKernel(const float4* __restrict__ pairs, uint32_t count, float4* __restrict__ out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	const float4 t0 = pairs[3 * (size_t)i], t1 = pairs[3 * (size_t)i + 1], t2 = pairs[3 * (size_t)i + 2];
+	RACC_CROSS(n1x, n1y, n1z, t0.x, t0.y, t0.z, t1.x, t1.y, t1.z)
+	out[4 * (size_t)i + 0] = t0;
+	out[4 * (size_t)i + 1] = t1;
+	out[4 * (size_t)i + 2] = t2;
+	out[4 * (size_t)i + 3] = make_float4(n1x, n1y, n1z, 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+
+// trianglePairIntersect (Kernels.h:36-115) on a packed pair; same operations as pairTest() of
+// traverse_common.cuh except that n1 arrives precomputed.
+__device__ __forceinline__ void pairTestPacked(u64 pairBase, uint32_t index, RayState& r, HitState& h) {
+	u64 a;
+	asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(a) : "r"(index), "l"(pairBase));
+	float4 t0, t1, t2, t3;
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(t0.x), "=f"(t0.y), "=f"(t0.z), "=f"(t0.w), "=f"(t1.x), "=f"(t1.y), "=f"(t1.z), "=f"(t1.w) : "l"(a));
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+32];"
+	             : "=f"(t2.x), "=f"(t2.y), "=f"(t2.z), "=f"(t2.w), "=f"(t3.x), "=f"(t3.y), "=f"(t3.z), "=f"(t3.w) : "l"(a));
+	const float n1x = t3.x, n1y = t3.y, n1z = t3.z;
+	RACC_CROSS(n2x, n2y, n2z, t0.w, t1.w, t2.w, t0.x, t0.y, t0.z)
+	const float cx = t2.x - r.ox, cy = t2.y - r.oy, cz = t2.z - r.oz;
+	RACC_CROSS(Rx, Ry, Rz, r.dx, r.dy, r.dz, cx, cy, cz)
+
+	const float det1 = dot3(n1x, n1y, n1z, r.dx, r.dy, r.dz);
+	const float det2 = dot3(n2x, n2y, n2z, r.dx, r.dy, r.dz);
+	const uint32_t s1 = __float_as_uint(det1) & 0x80000000u;
+	const uint32_t s2 = __float_as_uint(det2) & 0x80000000u;
+
+	const float dRe1 = dot3(Rx, Ry, Rz, t0.x, t0.y, t0.z);
+	const int iU1 = (int)(__float_as_uint(dot3(Rx, Ry, Rz, t1.x, t1.y, t1.z)) ^ s1);
+	const int iV1 = (int)(__float_as_uint(dRe1) ^ s1);
+	const int iU2 = (int)(__float_as_uint(-dRe1) ^ s2);
+	const int iV2 = (int)(__float_as_uint(-dot3(Rx, Ry, Rz, t0.w, t1.w, t2.w)) ^ s2);
+
+	if (((iU1 | iV1) & (iU2 | iV2)) < 0)
+		return;
+
+	bool out1 = (iU1 | iV1) < 0;
+	bool out2 = (iU2 | iV2) < 0;
+	float U1 = __int_as_float(iU1), V1 = __int_as_float(iV1);
+	const float U2 = __int_as_float(iU2), V2 = __int_as_float(iV2);
+	float a1 = fabsf(det1);
+	const float a2 = fabsf(det2);
+	const float W1 = (a1 - U1) - V1;
+	const float W2 = (a2 - U2) - V2;
+	float T1 = __uint_as_float(__float_as_uint(dot3(n1x, n1y, n1z, cx, cy, cz)) ^ s1);
+	const float T2 = __uint_as_float(__float_as_uint(dot3(n2x, n2y, n2z, cx, cy, cz)) ^ s2);
+
+	out1 = out1 || (W1 < 0.0f || T1 <= a1 * r.tNear || T1 > a1 * r.tFar);
+	out2 = out2 || (W2 < 0.0f || T2 <= a2 * r.tNear || T2 > a2 * r.tFar);
+	if (out1 && out2)
+		return;
+
+	index *= 2;
+	if ((!out2 && out1) || (!out1 && !out2 && T1 * a2 > T2 * a1)) {
+		a1 = a2; T1 = T2; U1 = U2; V1 = V2;
+		++index;
+	}
+	const float rcp = __frcp_rn(a1); // native_recip pinned to the IEEE reciprocal
+	const float t = T1 * rcp;
+	h.index = index;
+	h.t = t;
+	h.u = U1 * rcp;
+	h.v = V1 * rcp;
+	r.tFar = t;
+}
+
+// One inner-node step (Kernels.h:170-199) on a packed node. `node` has bit 31 set. Returns the next
+// reference: the nearer hit child, else the popped entry, else 0.
+__device__ __forceinline__ uint32_t innerStepPacked(u64 nodeBase, uint32_t node, const RayState& r, LocalStack& stack) {
+	u64 a;
+	asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(a) : "r"(node), "l"(nodeBase)); // nodeBase is biased by -(2^31 * 64)
+	u64 lx, ly, lz, rx, ry, rz, refs, unused;
+	asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(lx), "=l"(ly), "=l"(lz), "=l"(rx) : "l"(a));
+	asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4+32];" : "=l"(ry), "=l"(rz), "=l"(refs), "=l"(unused) : "l"(a));
+	const u64 ix2 = splat2(r.ix), iy2 = splat2(r.iy), iz2 = splat2(r.iz);
+	const u64 px2 = splat2(r.px), py2 = splat2(r.py), pz2 = splat2(r.pz);
+	float n0x, f0x, n0y, f0y, n0z, f0z, n1x, f1x, n1y, f1y, n1z, f1z;
+	unpack2(fma2(lx, ix2, px2), n0x, f0x);
+	unpack2(fma2(ly, iy2, py2), n0y, f0y);
+	unpack2(fma2(lz, iz2, pz2), n0z, f0z);
+	unpack2(fma2(rx, ix2, px2), n1x, f1x);
+	unpack2(fma2(ry, iy2, py2), n1y, f1y);
+	unpack2(fma2(rz, iz2, pz2), n1z, f1z);
+	const float tRay = r.tFar;
+	// aabbIntersect (Kernels.h:117-135), twice
+	const float a0 = fmaxf(fmaxf(r.tNear, fminf(n0x, f0x)), fmaxf(fminf(n0y, f0y), fminf(n0z, f0z)));
+	const float b0 = fminf(fminf(tRay, fmaxf(n0x, f0x)), fminf(fmaxf(n0y, f0y), fmaxf(n0z, f0z)));
+	const float a1 = fmaxf(fmaxf(r.tNear, fminf(n1x, f1x)), fmaxf(fminf(n1y, f1y), fminf(n1z, f1z)));
+	const float b1 = fminf(fminf(tRay, fmaxf(n1x, f1x)), fminf(fmaxf(n1y, f1y), fmaxf(n1z, f1z)));
+	const float tFirst = a0 > b0 ? tRay : a0;
+	const float tLast = a1 > b1 ? tRay : a1;
+	const float firstDiff = tRay - tFirst;
+	const float lastDiff = tRay - tLast;
+	const bool any = firstDiff + lastDiff != 0.0f;
+	const bool sgn = (int)__float_as_uint(tLast - tFirst) < 0;
+	const bool both = any && fmaxf(tFirst, tLast) != tRay;
+	uint32_t cf, cl;
+	asm("mov.b64 {%0,%1}, %2;" : "=r"(cf), "=r"(cl) : "l"(refs));
+	const uint32_t nearRef = sgn ? cl : cf, farRef = sgn ? cf : cl;
+	// The push is predicated (no branch around one STL); the pop is a real branch. A predicated pop
+	// measured 2x slower on DRAM-bound scenes (profiles/r01_c5_predicated_pop.md): an LDL issued with
+	// most or all lanes off still sits in the load pipeline behind the warp's outstanding misses.
+	uint32_t next = any ? nearRef : 0u;
+	asm volatile(
+	    "{\n\t.reg .pred pu;\n\t"
+	    "setp.ne.u32 pu, %2, 0;\n\t"
+	    "@pu st.local.u32 [%1], %3;\n\t"
+	    "@pu add.u32 %0, %0, 4;\n\t}"
+	    : "+r"(stack.top)
+	    : "l"((u64)stack.top), "r"((uint32_t)both), "r"(farRef)
+	    : "memory");
+	if (!any && !stack.empty())
+		next = stack.pop();
+	return next;
+}
+
+template <bool kCount, int kBlock, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const TraceParams p, const int fetchThreshold, const int innerBail, const int leafBail) {
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned ltMask = (1u << lane) - 1u;
+	// both bases are made opaque so that they stay in registers (otherwise they are re-derived from
+	// the constant bank, several instructions, at every step)
+	u64 nodeBase, pairBase;
+	asm volatile("mov.b64 %0, %1;" : "=l"(nodeBase) : "l"(reinterpret_cast<u64>(p.tnodes) - (0x80000000ull << 6)));
+	asm volatile("mov.b64 %0, %1;" : "=l"(pairBase) : "l"(reinterpret_cast<u64>(p.tpairs)));
+
+	bool exhausted = false; // warp-uniform: the cursor has run past the last ray
+	RayState r; HitState h;
+	uint32_t stackStorage[kStackSize];
+	LocalStack stack;
+	stack.attach(stackStorage);
+	uint32_t node = 0;         // 0: no ray in flight on this lane; bit 31: at an inner node; else at a leaf
+	float4* outPtr = nullptr;  // non-null: the lane holds a ray (in flight, or finished and not yet written)
+	unsigned long long cInner = 0, cPairs = 0;
+	unsigned cRays = 0, cHits = 0;
+
+	for (;;) {
+		// ---- retire finished lanes and refill idle ones, warp-wide -----------------------------
+		unsigned idle = __ballot_sync(kFullMask, node == 0);
+		if (idle == kFullMask || __popc(idle) >= (exhausted ? 32 : fetchThreshold)) {
+			if (node == 0 && outPtr) {
+				*outPtr = finishRay(p, r, h);
+				++cRays;
+				cHits += h.index != kMiss;
+				outPtr = nullptr;
+			}
+			if (!exhausted) {
+				const int want = __popc(idle);
+				const int leader = __ffs(idle) - 1;
+				uint32_t base = 0;
+				if ((int)lane == leader) base = atomicAdd(p.cursor, (uint32_t)want);
+				base = __shfl_sync(kFullMask, base, leader);
+				if (node == 0) {
+					uint32_t idx = base + __popc(idle & ltMask);
+					if (idx < p.total) {
+						if (p.perm) idx = __ldg(p.perm + idx);
+						const DevRay* rays; uint32_t local;
+						locate(p, idx, rays, outPtr, local);
+						outPtr += local;
+						initRay(rays, local, r, h);
+						stack.reset();
+						node = kInnerBit;
+					}
+				}
+				exhausted = base + (uint32_t)want >= p.total;
+			}
+			idle = __ballot_sync(kFullMask, node == 0);
+			if (idle == kFullMask)
+				break;
+		}
+		const unsigned liveMask = ~idle;
+
+		// ---- inner phase: warp-uniform loop, left once too few lanes still descend -------------
+		{
+			unsigned innerMask = __ballot_sync(kFullMask, (int)node < 0);
+			int descending = __popc(innerMask);
+			bool go = innerMask == liveMask || descending >= innerBail || 2 * descending > __popc(liveMask);
+			go = go && innerMask;
+			while (go) {
+				if ((int)node < 0) {
+					if (kCount) ++cInner;
+					node = innerStepPacked(nodeBase, node, r, stack);
+				}
+				innerMask = __ballot_sync(kFullMask, (int)node < 0);
+				go = innerMask == liveMask || __popc(innerMask) >= innerBail;
+			}
+		}
+		// ---- leaf phase: one pair per iteration, left once too few lanes still have pairs while
+		// others wait at inner nodes -----------------------------------------------------------
+		{
+			bool go = __ballot_sync(kFullMask, (int)node > 0) != 0;
+			while (go) {
+				if ((int)node > 0) {
+					pairTestPacked(pairBase, node & 0xffffffu, r, h);
+					if (kCount) ++cPairs;
+					// one pair of this leaf done: (count << 24 | first) -> (count-1 << 24 | first+1)
+					node = node >= 0x2000000u ? node + 1u - 0x1000000u : (stack.empty() ? 0u : stack.pop());
+				}
+				const unsigned leafMask = __ballot_sync(kFullMask, (int)node > 0);
+				go = leafMask != 0;
+				if (go && __popc(leafMask) < leafBail)
+					go = __ballot_sync(kFullMask, (int)node < 0) == 0;
+			}
+		}
+	}
+
+	// Frame statistics (rays, hits): one atomic per warp, always on when a counter record is given;
+	// this is the value the multi-GPU hit reduction sums. Visit counters only in the kCount build.
+	if (p.counters) {
+		unsigned long long rays = cRays, hits = cHits;
+		for (int o = 16; o; o >>= 1) {
+			rays += __shfl_xor_sync(kFullMask, rays, o);
+			hits += __shfl_xor_sync(kFullMask, hits, o);
+			if (kCount) {
+				cInner += __shfl_xor_sync(kFullMask, cInner, o);
+				cPairs += __shfl_xor_sync(kFullMask, cPairs, o);
+			}
+		}
+		if (lane == 0) {
+			atomicAdd(p.counters + 0, rays);
+			atomicAdd(p.counters + 1, hits);
+			if (kCount) {
+				atomicAdd(p.counters + 2, cInner);
+				atomicAdd(p.counters + 3, cPairs);
+			}
+		}
+	}
+}
+
+template <bool kCount, int kBlock, int kMinBlocks>
+cudaError_t launchPacked(const TraceParams& p, const Tuning& t, int smCount, cudaStream_t stream) {
+	auto kernel = tracePackedKernel<kCount, kBlock, kMinBlocks>;
+	static thread_local int plannedDevice = -1, plannedCarveout = -2, resident = 1;
+	int device = 0;
+	cudaGetDevice(&device);
+	cudaError_t err;
+	if (plannedDevice != device || plannedCarveout != t.carveout) {
+		// no shared memory at all: the whole 228 KB of each SM serves as L1 for nodes, pairs and stacks
+		err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, t.carveout >= 0 ? t.carveout : 0);
+		if (err != cudaSuccess) return err;
+		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, kBlock, 0);
+		if (err != cudaSuccess) return err;
+		if (resident < 1) resident = 1;
+		plannedDevice = device;
+		plannedCarveout = t.carveout;
+	}
+	int ctas = resident;
+	if (t.ctasPerSm > 0 && ctas > t.ctasPerSm) ctas = t.ctasPerSm;
+	long long grid = (long long)smCount * ctas;
+	const long long needed = ((long long)p.total + kBlock - 1) / kBlock;
+	if (grid > needed) grid = needed > 0 ? needed : 1;
+	err = cudaMemsetAsync(p.cursor, 0, sizeof(uint32_t), stream);
+	if (err != cudaSuccess) return err;
+	// innerBail 0 and 1 mean the same (stay while any lane descends); the loop test relies on >= 1
+	kernel<<<(unsigned)grid, kBlock, 0, stream>>>(p, t.fetchThreshold, t.innerBail < 1 ? 1 : t.innerBail, t.leafBail);
+	return cudaGetLastError();
+}
+
+template <bool kCount>
+cudaError_t dispatchPacked(const TraceParams& p, const Tuning& t, int smCount, cudaStream_t stream) {
+	switch (t.blockThreads * 100 + t.ctasPerSm) {
+	case 12800 + 8: return launchPacked<kCount, 128, 8>(p, t, smCount, stream);
+	case 12800 + 10: return launchPacked<kCount, 128, 10>(p, t, smCount, stream);
+	case 12800 + 12: return launchPacked<kCount, 128, 12>(p, t, smCount, stream);
+	case 25600 + 4: return launchPacked<kCount, 256, 4>(p, t, smCount, stream);
+	case 25600 + 6: return launchPacked<kCount, 256, 6>(p, t, smCount, stream);
+	case 51200 + 2: return launchPacked<kCount, 512, 2>(p, t, smCount, stream);
+	case 51200 + 3: return launchPacked<kCount, 512, 3>(p, t, smCount, stream);
+	default: return launchPacked<kCount, 256, 5>(p, t, smCount, stream);
+	}
+}
+
+} // namespace
+
+cudaError_t launchPackImages(const float4* nodes, uint32_t nodeCount, const float4* pairs, uint32_t pairCount,
+                             float4* tnodes, float4* tpairs, cudaStream_t stream, int* launches) {
+	if (nodeCount) {
+		packNodesKernel<<<(nodeCount + 255u) / 256u, 256, 0, stream>>>(nodes, nodeCount, tnodes);
+		if (launches) *launches += 1;
+	}
+	if (pairCount) {
+		packPairsKernel<<<(pairCount + 255u) / 256u, 256, 0, stream>>>(pairs, pairCount, tpairs);
+		if (launches) *launches += 1;
+	}
+	return cudaGetLastError();
+}
+
+cudaError_t launchTracePacked(const TraceParams& p, const Tuning& t, int counterMode, int smCount, cudaStream_t stream, int* launches) {
+	if (!p.total)
+		return cudaSuccess;
+	if (launches) *launches += 1;
+	return counterMode == 2 ? dispatchPacked<true>(p, t, smCount, stream) : dispatchPacked<false>(p, t, smCount, stream);
+}
+
+} // namespace racc_b200

@@ -24,8 +24,17 @@ VARIANTS = [
     dict(variant=0, block=128, smem_nodes=64, fetch_threshold=1),
     dict(variant=0, block=512, smem_nodes=-1, fetch_threshold=32),
     dict(variant=1),
+    dict(variant=2),
+    dict(variant=3, ctas_per_sm=4, fetch_threshold=1, inner_bail=32, leaf_bail=32),
+    dict(variant=3, block=128, ctas_per_sm=10, inner_bail=0, leaf_bail=0),
+    dict(variant=3, block=512, ctas_per_sm=2, inner_bail=20, leaf_bail=1, fetch_threshold=32),
+    dict(variant=3, sort=1),
+    dict(variant=3, sort=1, sort_origin_bits=10, sort_dir_bits=0),
+    dict(variant=3, sort=1, sort_origin_bits=0, sort_dir_bits=4, sort_dir_major=1),
+    dict(variant=3, sort=1, sort_origin_bits=6, sort_dir_bits=4, sort_dir_major=1, fetch_threshold=8),
 ]
-DEFAULT = dict(variant=2, block=256, ctas_per_sm=5, smem_nodes=0, fetch_threshold=16, inner_bail=12, leaf_bail=4)
+DEFAULT = dict(variant=3, block=256, ctas_per_sm=5, smem_nodes=0, fetch_threshold=16, inner_bail=8, leaf_bail=4,
+               sort=0, sort_origin_bits=5, sort_dir_bits=3, sort_dir_major=0)
 
 
 @pytest.fixture(scope="module")
@@ -149,7 +158,7 @@ def test_counters_match_oracle(scene, env, images, battlefield):
     hi = battlefield.vertices[:, :3].max(0)
     rays = random_rays(100_000, lo, hi, seed=3)
     _, cnt = oracle.traverse(images, rays, counters=True)
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         rb.set_tuning(**{**DEFAULT, "variant": variant})
         d_rays = to_device(rays)
         d_res = torch.empty(rays.shape[0] * 4, dtype=torch.float32, device="cuda")
@@ -273,7 +282,7 @@ def test_kat_scenes_on_gpu(gpu):
         pad = (-images.pairs.shape[0] * 3) % 32 // 3 + (1 if (images.pairs.shape[0] * 3) % 32 == 0 else 0)
         pairs = np.concatenate([images.pairs, np.repeat(images.pairs[:1], max(pad, 1), axis=0)])
         s = rb.create_scene_from_images(images.nodes, pairs, images.remap)
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3):
             rb.set_tuning(**{**DEFAULT, "variant": variant})
             got = trace_dev(s, None, rays)
             assert_bit_exact(got, oracle.traverse(images, rays), f"{case['name']} variant {variant}")

@@ -110,14 +110,25 @@ def c5(tris=10_000_000, nrays=100_000_000):
     rays[:, 7] = 1e6
     res = torch.empty(nrays * 4, dtype=torch.float32, device="cuda")
     c = counted(scene, None, rays, res, nrays)
-    ms = timed_trace(scene, None, [(rays.data_ptr(), res.data_ptr(), nrays)])
     b = alg_bytes(nrays, c)
     scene_mb = (info["node_count"] * 64 + info["pair_count"] * 48 + info["remap_count"] * 4) / 1e6
-    emit({"config": f"C5 synthetic soup {tris} triangles, {nrays} uniform random rays", "rays": nrays, "ms": round(ms, 3), "mrays": round(nrays / ms / 1e3, 1),
-          "hit_rate": round(c[1] / nrays, 4), "inner_per_ray": round(c[2] / nrays, 2), "pairs_per_ray": round(c[3] / nrays, 2),
-          "alg_bytes_per_ray": round(b / nrays, 1), "alg_gbs": round(b / ms / 1e6, 1), "frac_of_measured_hbm": round(b / ms / 1e6 / PEAK, 4),
-          "scene_mb": round(scene_mb, 1), "nodes": info["node_count"], "pairs": info["pair_count"], "depth": info["depth"],
-          "host_build_s": round(t_build, 2), "mesh_gen_s": round(t_gen, 2), "hbm_peak_gbs": PEAK})
+    ref = None
+    # RACC_CFG_TUNINGS="k=v,k=v;k=v": time the same rays under several tunings (one line each)
+    for spec in os.environ.get("RACC_CFG_TUNINGS", "").split(";"):
+        tuning = {k: int(v) for k, v in (kv.split("=") for kv in spec.split(",") if kv)}
+        rb.set_tuning(**tuning)
+        ms = timed_trace(scene, None, [(rays.data_ptr(), res.data_ptr(), nrays)])
+        same = None
+        if ref is None:
+            ref = res.clone()
+        else:
+            same = bool(torch.equal(ref.view(torch.int32), res.view(torch.int32)))
+        emit({"config": f"C5 synthetic soup {tris} triangles, {nrays} uniform random rays", "tuning": tuning, "same_bits_as_first": same,
+              "rays": nrays, "ms": round(ms, 3), "mrays": round(nrays / ms / 1e3, 1),
+              "hit_rate": round(c[1] / nrays, 4), "inner_per_ray": round(c[2] / nrays, 2), "pairs_per_ray": round(c[3] / nrays, 2),
+              "alg_bytes_per_ray": round(b / nrays, 1), "alg_gbs": round(b / ms / 1e6, 1), "frac_of_measured_hbm": round(b / ms / 1e6 / PEAK, 4),
+              "scene_mb": round(scene_mb, 1), "nodes": info["node_count"], "pairs": info["pair_count"], "depth": info["depth"],
+              "host_build_s": round(t_build, 2), "mesh_gen_s": round(t_gen, 2), "hbm_peak_gbs": PEAK})
 
 
 if __name__ == "__main__":
