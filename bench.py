@@ -407,14 +407,14 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             "breakdown": {"primary_mrays": round(streams[0][2] / ms_primary / 1e3, 1), "secondary_mrays": round(n_secondary / ms_secondary / 1e3, 1),
                           "primary_rays": streams[0][2], "secondary_rays": n_secondary, "note": "per GPU, separate launches, best of 5"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": traffic, "kernel": "tracePersistentKernel", "kernel_ms": round(kernel_ms, 4),
+                         "traffic": traffic, "kernel": "tracePackedKernel", "kernel_ms": round(kernel_ms, 4),
                          "algorithmic_bytes_per_launch": alg_bytes, "compulsory_bytes_per_launch": 48 * rays_per_step,
                          "peak_source": peak_src, "traffic_source": traffic_src,
                          "note": "algorithmic bytes = sum over rays of 32+16+64*N_inner+48*N_pair+4*[hit]+64*[miss] (SURVEY.md 8d), visits counted "
                                  "by the kernel itself. frac > 1 is expected here: battlefield's 3.2 MB scene is L1/L2-resident, so of the algorithmic "
                                  "bytes only the compulsory 48 B/ray (rays in, results out) reach DRAM -- `traffic` (ncu dram read+write per launch) "
                                  "equals compulsory_bytes_per_launch, i.e. no wasted re-reads; the kernel is issue/latency-bound, not HBM-bound "
-                                 "(profiles/r01_ncu_bench_launch.txt)"},
+                                 "(profiles/r01_ncu_bench_launch_packed.txt)"},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": 32 * rays_per_step, "d2h_bytes_per_step": 16 * rays_per_step,
                     "ms_per_step": round(e2e_ms, 3), "wall_ms_per_step": round(e2e_wall_ms / e2e_steps, 3), "steps": e2e_steps,
                     "results_match_device_run": e2e_ok, "path": "racc_cuda_trace with RACC_CUDA_STREAM_HOST descriptors, pinned host memory"},

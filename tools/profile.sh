@@ -6,5 +6,5 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/launches_run.log 2>&1
 # the top kernel, full set: -s 7 skips the 4 counted roofline-accounting launches and the 3 warm-ups,
 # -c 2 captures the two timed launches
-ncu --set full --clock-control none --import-source on -k regex:tracePersistentKernel -s 7 -c 2 -o gpurun_out/prof -f $CMD > gpurun_out/prof_run.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tracePackedKernel -s 7 -c 2 -o gpurun_out/prof -f $CMD > gpurun_out/prof_run.log 2>&1
 ls -la gpurun_out
