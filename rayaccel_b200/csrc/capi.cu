@@ -87,6 +87,7 @@ int ensureInit() {
 	g_tuning.sortOriginBits = envInt("RACC_B200_SORT_ORIGIN_BITS", g_tuning.sortOriginBits);
 	g_tuning.sortDirBits = envInt("RACC_B200_SORT_DIR_BITS", g_tuning.sortDirBits);
 	g_tuning.sortDirMajor = envInt("RACC_B200_SORT_DIR_MAJOR", g_tuning.sortDirMajor);
+	g_tuning.buildDevice = envInt("RACC_B200_BUILD_DEVICE", g_tuning.buildDevice);
 	g_initialised = true;
 	return 0;
 }
@@ -212,6 +213,7 @@ int racc_cuda_set_tuning(int key, int value) {
 	case 9: slot = &g_tuning.sortOriginBits; break;
 	case 10: slot = &g_tuning.sortDirBits; break;
 	case 11: slot = &g_tuning.sortDirMajor; break;
+	case 12: slot = &g_tuning.buildDevice; break;
 	default: return fail("unknown tuning key %d", key);
 	}
 	const int previous = *slot;
@@ -234,7 +236,12 @@ racc_cuda_scene* racc_cuda_scene_create(const float* verts4, uint32_t nverts, co
 	if (ensureInit()) return nullptr;
 	racc_cuda_scene* s = new racc_cuda_scene();
 	const char* why = "";
-	if (!buildSceneImages(verts4, nverts, indices, nindices, envInt("RACC_B200_BUILD_THREADS", 0), &s->host, &why)) {
+	bool built = false;
+	if (g_tuning.buildDevice) {
+		built = buildSceneImages(verts4, nverts, indices, nindices, 0, &s->host, &why, buildBvh2Device);
+		if (!built) fprintf(stderr, "RayAccelerator: device scene build declined (%s); building on the host\n", why);
+	}
+	if (!built && !buildSceneImages(verts4, nverts, indices, nindices, envInt("RACC_B200_BUILD_THREADS", 0), &s->host, &why)) {
 		fail("racc_cuda_scene_create: %s", why);
 		delete s;
 		return nullptr;

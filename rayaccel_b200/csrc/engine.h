@@ -57,6 +57,7 @@ struct Tuning {
 	int sortOriginBits = 5;  // Morton bits per axis of the ray origin inside the scene bounds
 	int sortDirBits = 3;     // Morton bits per axis of the direction on the unit cube
 	int sortDirMajor = 0;    // 0 origin-major key, 1 direction-major key
+	int buildDevice = 0;     // scene build: 0 SAH tree on the host threads, 1 on the GPU (bvh_build.cu); same tree
 };
 
 // counterMode: 0 none, 1 rays+hits only, 2 rays, hits, inner-node and pair visits
@@ -73,6 +74,11 @@ cudaError_t launchPackImages(const float4* nodes, uint32_t nodeCount, const floa
 size_t raySortScratchBytes(uint32_t total);
 cudaError_t launchRaySort(const TraceParams& p, const float boundsMin[3], const float boundsMax[3], int originBits, int dirBits,
                           int dirMajor, void* scratch, int smCount, cudaStream_t stream, const uint32_t** perm, int* launches);
+
+// stable LSD radix sort of (key, value) pairs, 8 bits per pass (raysort.cu); see there
+size_t radixSortHistWords();
+cudaError_t launchRadixSort(uint32_t* keys, uint32_t* vals, uint32_t* keysTmp, uint32_t* valsTmp, uint32_t* hist, uint32_t total,
+                            int keyBits, int smCount, cudaStream_t stream, uint32_t** keysOut, uint32_t** valsOut, int* launches);
 
 cudaError_t readWarpStats(unsigned long long* out8, bool reset);
 

@@ -201,10 +201,44 @@ __global__ void __launch_bounds__(kSortBlock) radixScatterKernel(const uint32_t*
 
 } // namespace
 
+size_t radixSortHistWords() { return (size_t)256 * 148 * 16 + 512; }
+
+// Stable LSD radix sort of (key, value) pairs on the low `keyBits` bits, 8 bits per pass. keys/vals
+// and keysTmp/valsTmp ping-pong; on return *keysOut / *valsOut point at the buffers holding the
+// sorted sequence (keysOut may be null; the last pass then skips writing keys). hist needs
+// radixSortHistWords() words.
+cudaError_t launchRadixSort(uint32_t* keys, uint32_t* vals, uint32_t* keysTmp, uint32_t* valsTmp, uint32_t* hist, uint32_t total,
+                            int keyBits, int smCount, cudaStream_t stream, uint32_t** keysOut, uint32_t** valsOut, int* launches) {
+	uint32_t warps = (uint32_t)smCount * 16u;
+	if (warps > 148u * 16u) warps = 148u * 16u;
+	uint32_t seg = (total + warps - 1) / warps;
+	seg = (seg + 31u) & ~31u;
+	if (seg < 512u) seg = 512u;
+	warps = (total + seg - 1) / seg;
+	uint32_t* rowTotal = hist + (size_t)256 * 148 * 16;
+	uint32_t* rowBase = rowTotal + 256;
+	const uint32_t blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+	const int passes = (keyBits + 7) / 8;
+	for (int pass = 0; pass < passes; ++pass) {
+		const int shift = 8 * pass;
+		const bool last = pass == passes - 1;
+		radixHistKernel<<<blocks, kSortBlock, 0, stream>>>(keys, total, seg, warps, shift, hist);
+		radixRowScanKernel<<<256, 1024, 0, stream>>>(hist, warps, rowTotal);
+		radixDigitScanKernel<<<1, 256, 0, stream>>>(rowTotal, rowBase);
+		radixScatterKernel<<<blocks, kSortBlock, 0, stream>>>(keys, vals, total, seg, warps, shift, hist, rowBase, (last && !keysOut) ? nullptr : keysTmp, valsTmp);
+		if (launches) *launches += 4;
+		uint32_t* t = keys; keys = keysTmp; keysTmp = t;
+		t = vals; vals = valsTmp; valsTmp = t;
+	}
+	if (keysOut) *keysOut = keys;
+	*valsOut = vals;
+	return cudaGetLastError();
+}
+
 size_t raySortScratchBytes(uint32_t total) {
 	// keys x2, vals x2, histogram (256 x warps), row totals and bases
 	const size_t n = ((size_t)total + 63) & ~(size_t)63;
-	return n * 4 * 4 + (size_t)256 * 148 * 16 * 4 + 4096;
+	return n * 4 * 4 + radixSortHistWords() * 4 + 4096;
 }
 
 // Builds the visiting order of the launch described by `p` into scratch memory and returns it in
@@ -224,14 +258,6 @@ cudaError_t launchRaySort(const TraceParams& p, const float boundsMin[3], const 
 	uint32_t* valsA = keysB + n;
 	uint32_t* valsB = valsA + n;
 	uint32_t* hist = valsB + n;
-	uint32_t warps = (uint32_t)smCount * 16u;
-	if (warps > 148u * 16u) warps = 148u * 16u;
-	uint32_t seg = (total + warps - 1) / warps;
-	seg = (seg + 31u) & ~31u;
-	if (seg < 512u) seg = 512u;
-	warps = (total + seg - 1) / seg;
-	uint32_t* rowTotal = hist + (size_t)256 * 148 * 16;
-	uint32_t* rowBase = rowTotal + 256;
 
 	KeyArgs a;
 	for (int k = 0; k < 3; ++k) {
@@ -244,22 +270,10 @@ cudaError_t launchRaySort(const TraceParams& p, const float boundsMin[3], const 
 	a.dirMajor = dirMajor;
 	rayKeyKernel<<<(total + 255u) / 256u, 256, 0, stream>>>(p, a, keysA, valsA);
 	if (launches) *launches += 1;
-
-	const uint32_t blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
-	const int passes = (keyBits + 7) / 8;
-	for (int pass = 0; pass < passes; ++pass) {
-		const int shift = 8 * pass;
-		const bool last = pass == passes - 1;
-		radixHistKernel<<<blocks, kSortBlock, 0, stream>>>(keysA, total, seg, warps, shift, hist);
-		radixRowScanKernel<<<256, 1024, 0, stream>>>(hist, warps, rowTotal);
-		radixDigitScanKernel<<<1, 256, 0, stream>>>(rowTotal, rowBase);
-		radixScatterKernel<<<blocks, kSortBlock, 0, stream>>>(keysA, valsA, total, seg, warps, shift, hist, rowBase, last ? nullptr : keysB, valsB);
-		if (launches) *launches += 4;
-		uint32_t* t = keysA; keysA = keysB; keysB = t;
-		t = valsA; valsA = valsB; valsB = t;
-	}
-	*perm = valsA;
-	return cudaGetLastError();
+	uint32_t* sorted = nullptr;
+	cudaError_t e = launchRadixSort(keysA, valsA, keysB, valsB, hist, total, keyBits, smCount, stream, nullptr, &sorted, launches);
+	*perm = sorted;
+	return e;
 }
 
 } // namespace racc_b200

@@ -9,6 +9,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -40,17 +42,6 @@ struct FtzScope {
 		_MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_ON);
 	}
 	~FtzScope() { _mm_setcsr(saved); }
-};
-
-// Sparse node as produced during the build. A subtree over n triangles owns the slot block
-// [slot, slot + 2n - 1): node at slot, left subtree right after it, right subtree after that.
-// This numbers nodes without an atomic counter, so the build is deterministic under threading.
-struct BuildNode {
-	uint32_t kind;
-	uint32_t parent;
-	uint32_t first, last;   // triangle range (always kept, also for inner nodes)
-	uint32_t left, right;   // child slots for inner nodes
-	float bounds[8];        // {-min.xyzw, max.xyzw}: one max() unions a box (Bvh2.cpp:82-126)
 };
 
 struct Builder {
@@ -255,8 +246,66 @@ inline uint32_t tiePosition(uint32_t i, uint32_t n) {
 
 } // namespace
 
+namespace {
+
+// compact: pre-order walk, parents before children, first child before last child
+void compactBvh2(const BuildNode* nodes, const uint32_t* sorted0, uint32_t n, Bvh2* out) {
+	out->nodes.clear();
+	out->nodes.reserve((size_t)n);
+	out->triangles.assign(sorted0, sorted0 + n);
+	std::vector<std::pair<uint32_t, uint32_t>> stack; // (slot, compact parent)
+	stack.emplace_back(0u, kNone);
+	while (!stack.empty()) {
+		auto [slot, parent] = stack.back();
+		stack.pop_back();
+		const BuildNode& bn = nodes[slot];
+		const uint32_t me = (uint32_t)out->nodes.size();
+		Bvh2::Node nd{};
+		nd.kind = bn.kind;
+		nd.parent = parent;
+		nd.first = bn.first;
+		nd.last = bn.last;
+		for (int k = 0; k < 3; ++k) {
+			nd.bbMin[k] = -bn.bounds[k];
+			nd.bbMax[k] = bn.bounds[4 + k];
+		}
+		out->nodes.push_back(nd);
+		if (parent != kNone) {
+			Bvh2::Node& pn = out->nodes[parent];
+			// children are visited first-then-last; the first to arrive fills `first`
+			if (pn.first == kNone) pn.first = me; else pn.last = me;
+		}
+		if (bn.kind) {
+			out->nodes[me].first = kNone;
+			out->nodes[me].last = kNone;
+			stack.emplace_back(bn.right, me);
+			stack.emplace_back(bn.left, me);
+		}
+	}
+}
+
+} // namespace
+
+bool fillRcpTable(float table[2048]) {
+	auto rcp = [](float x) { return _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(x))); };
+	auto fromBits = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+	for (uint32_t i = 0; i < 2048; ++i)
+		table[i] = rcp(fromBits(0x3f800000u | (i << 12)));
+	// the two properties the device relies on, sampled
+	uint32_t s = 12345u;
+	for (int k = 0; k < 200000; ++k) {
+		s = s * 1664525u + 1013904223u;
+		const uint32_t m = s >> 9, e = 1u + ((s >> 3) % 253u);
+		const float got = rcp(fromBits((e << 23) | m));
+		const float want = table[m >> 12] * fromBits((254u - e) << 23);
+		if (std::memcmp(&got, &want, 4) != 0 && e > 2 && e < 252)
+			return false;
+	}
+	return true;
+}
+
 bool buildBvh2(const float* vertices4, uint32_t vertexCount, const uint32_t* indices, uint32_t triangleCount,
-               int threads, Bvh2* out, const char** error) {
+               int threads, Bvh2* out, const char** error, DeviceBvhBuilder deviceBuilder) {
 	static const char* kEmpty = "scene has no triangles";
 	static const char* kIndex = "triangle index out of range";
 	static const char* kTooBig = "scene exceeds 2^30 triangles (remap word holds 30 index bits)";
@@ -264,6 +313,15 @@ bool buildBvh2(const float* vertices4, uint32_t vertexCount, const uint32_t* ind
 	if (triangleCount >= (1u << 30)) { if (error) *error = kTooBig; return false; }
 	for (size_t i = 0; i < (size_t)triangleCount * 3; ++i)
 		if (indices[i] >= vertexCount) { if (error) *error = kIndex; return false; }
+
+	if (deviceBuilder) {
+		std::vector<BuildNode> devNodes;
+		std::vector<uint32_t> devSorted;
+		if (!deviceBuilder(vertices4, vertexCount, indices, triangleCount, &devNodes, &devSorted, error))
+			return false;
+		compactBvh2(devNodes.data(), devSorted.data(), triangleCount, out);
+		return true;
+	}
 
 	FtzScope ftz;
 	const uint32_t n = triangleCount;
@@ -331,40 +389,7 @@ bool buildBvh2(const float* vertices4, uint32_t vertexCount, const uint32_t* ind
 	b.spareThreads.store(threads - 1);
 	b.build(0, true);
 
-	// compact: pre-order walk, parents before children, first child before last child
-	out->nodes.clear();
-	out->nodes.reserve((size_t)n);
-	out->triangles.assign(sorted[0], sorted[0] + n);
-	std::vector<std::pair<uint32_t, uint32_t>> stack; // (slot, compact parent)
-	std::vector<uint32_t> compactOf;                  // filled lazily through parents' child fields
-	stack.emplace_back(0u, kNone);
-	while (!stack.empty()) {
-		auto [slot, parent] = stack.back();
-		stack.pop_back();
-		const BuildNode& bn = nodes[slot];
-		const uint32_t me = (uint32_t)out->nodes.size();
-		Bvh2::Node nd{};
-		nd.kind = bn.kind;
-		nd.parent = parent;
-		nd.first = bn.first;
-		nd.last = bn.last;
-		for (int k = 0; k < 3; ++k) {
-			nd.bbMin[k] = -bn.bounds[k];
-			nd.bbMax[k] = bn.bounds[4 + k];
-		}
-		out->nodes.push_back(nd);
-		if (parent != kNone) {
-			Bvh2::Node& pn = out->nodes[parent];
-			// children are visited first-then-last; the first to arrive fills `first`
-			if (pn.first == kNone) pn.first = me; else pn.last = me;
-		}
-		if (bn.kind) {
-			out->nodes[me].first = kNone;
-			out->nodes[me].last = kNone;
-			stack.emplace_back(bn.right, me);
-			stack.emplace_back(bn.left, me);
-		}
-	}
+	compactBvh2(nodes.data(), sorted[0], n, out);
 	return true;
 }
 
@@ -444,17 +469,21 @@ inline float boxArea(const Bvh2::Node& n) {
 } // namespace
 
 bool buildSceneImages(const float* vertices4, uint32_t vertexCount, const uint32_t* indices, uint32_t indexCount,
-                      int threads, SceneImages* out, const char** error) {
+                      int threads, SceneImages* out, const char** error, DeviceBvhBuilder deviceBuilder) {
 	static const char* kMod3 = "index count is not a multiple of 3";
 	static const char* kTiny = "scene needs at least 3 triangles (root must be an inner node)";
 	static const char* kPairs = "scene exceeds 2^24 triangle pairs (leaf reference holds 24 index bits)";
 	if (indexCount % 3) { if (error) *error = kMod3; return false; }
+	const bool verbose = getenv("RACC_B200_BUILD_VERBOSE") != nullptr;
+	auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double t0 = now();
 	Bvh2 bvh;
-	if (!buildBvh2(vertices4, vertexCount, indices, indexCount / 3, threads, &bvh, error))
+	if (!buildBvh2(vertices4, vertexCount, indices, indexCount / 3, threads, &bvh, error, deviceBuilder))
 		return false;
 	if (!bvh.nodes[0].kind) { if (error) *error = kTiny; return false; }
 
 	const uint32_t nodeCount = (uint32_t)bvh.nodes.size();
+	const double t1 = now();
 
 	// Device order of inner nodes: largest surface area first. A child's box lies inside its
 	// parent's, so parents precede children and node 0 is the root; the first K nodes are the K
@@ -477,6 +506,7 @@ bool buildSceneImages(const float* vertices4, uint32_t vertexCount, const uint32
 		}
 	}
 
+	const double t2 = now();
 	out->nodes.resize(order.size());
 	out->pairs.clear();
 	out->remap.clear();
@@ -522,6 +552,7 @@ bool buildSceneImages(const float* vertices4, uint32_t vertexCount, const uint32
 		out->pairs.push_back(out->pairs[0]);
 	} while ((out->pairs.size() * 3) % 32 != 0);
 
+	const double t3 = now();
 	// depth + bounds
 	{
 		uint32_t depth = 0;
@@ -543,6 +574,9 @@ bool buildSceneImages(const float* vertices4, uint32_t vertexCount, const uint32
 			out->boundsMax[k] = bvh.nodes[0].bbMax[k];
 		}
 	}
+	if (verbose)
+		fprintf(stderr, "racc scene build: SAH tree (%s) %.1f ms, node order %.1f ms, pair merge + packing %.1f ms, depth %.1f ms\n",
+		        deviceBuilder ? "device, incl. compaction" : "host", (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (now() - t3) * 1e3);
 	return true;
 }
 

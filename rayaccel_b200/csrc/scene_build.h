@@ -56,13 +56,42 @@ struct SceneImages {
 	float boundsMax[3] = {0, 0, 0};
 };
 
+// Sparse node as produced during the build (host and device builders share it). A subtree over n
+// triangles owns the slot block [slot, slot + 2n - 1): node at slot, left subtree right after it,
+// right subtree after that. This numbers nodes without an atomic counter, so the build is
+// deterministic under any scheduling.
+struct BuildNode {
+	uint32_t kind;
+	uint32_t parent;
+	uint32_t first, last;   // triangle range (always kept, also for inner nodes)
+	uint32_t left, right;   // child slots for inner nodes
+	float bounds[8];        // {-min.xyzw, max.xyzw}: one max() unions a box (Bvh2.cpp:82-126)
+};
+static_assert(sizeof(BuildNode) == 56, "BuildNode is shared with the device builder");
+
+// Device SAH builder hook (bvh_build.cu): fills the sparse node array (2n slots) and the x-sorted
+// triangle list exactly as the host builder would. Returns false and sets *error on failure.
+typedef bool (*DeviceBvhBuilder)(const float* vertices4, uint32_t vertexCount, const uint32_t* indices, uint32_t triangleCount,
+                                 std::vector<BuildNode>* nodes, std::vector<uint32_t>* sorted0, const char** error);
+
+// The device builder itself (bvh_build.cu); uses the current CUDA device.
+bool buildBvh2Device(const float* vertices4, uint32_t vertexCount, const uint32_t* indices, uint32_t triangleCount,
+                     std::vector<BuildNode>* nodes, std::vector<uint32_t>* sorted0, const char** error);
+
+// The x86 RCPSS approximation of this host for the 2048 leading-mantissa patterns of [1,2): the
+// reference's leaf-cost test uses _mm_rcp_ss (Bvh2.cpp:462-467), whose bits the device builder
+// reproduces through this table (RCPSS depends on the top 11 mantissa bits only and scales exactly
+// with the exponent; checked at table-build time, false if this CPU behaves differently).
+bool fillRcpTable(float table[2048]);
+
 // vertices: float4 per vertex (w ignored for intersection but, as in the reference, it takes part in
 // the per-triangle bounds reduction and is harmless). indexCount must be a multiple of 3.
 // threads <= 0: use all hardware threads. Returns false (and sets *error) on invalid input.
+// deviceBuilder != nullptr: the SAH tree is built by it (on the GPU) instead of by the host threads.
 bool buildBvh2(const float* vertices4, uint32_t vertexCount, const uint32_t* indices, uint32_t triangleCount,
-               int threads, Bvh2* out, const char** error);
+               int threads, Bvh2* out, const char** error, DeviceBvhBuilder deviceBuilder = nullptr);
 
 bool buildSceneImages(const float* vertices4, uint32_t vertexCount, const uint32_t* indices, uint32_t indexCount,
-                      int threads, SceneImages* out, const char** error);
+                      int threads, SceneImages* out, const char** error, DeviceBvhBuilder deviceBuilder = nullptr);
 
 } // namespace racc_b200

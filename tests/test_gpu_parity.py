@@ -2,6 +2,8 @@
 bytes. Bar: bit-exact triangle ids AND bit-exact t/u/v (hits) and r/g/b (misses) -- the kernel and
 the oracle use the same pinned fp32 operation sequence -- which implies the north_star's
 "|dt|/t <= 1e-4". All tests here need a GPU."""
+import os
+
 import numpy as np
 import pytest
 
@@ -339,3 +341,49 @@ def test_synthetic_soup_scene_bit_exact(gpu):
     assert_bit_exact(got, oracle.traverse(img, rays), "soup")
     assert 0.001 < (got[:, 0] != rb.INVALID_TRIANGLE).mean() < 0.9
     s.destroy()
+
+
+# ---------------------------------------------------------------------------------------------
+# device SAH build (bvh_build.cu): byte equality of the device images with the host build, which the
+# CPU suite pins to the unmodified reference builder (tests/test_scene_build.py)
+
+def _images_with(build_device, v, i):
+    rb.set_tuning(build_device=build_device)
+    try:
+        s = rb.create_scene(v, i)
+        nodes, pairs, remap = s.download()
+        return nodes.view(np.uint32).copy(), pairs.view(np.uint32).copy(), remap.copy(), s.info
+    finally:
+        rb.set_tuning(build_device=0)
+
+
+def _assert_same_images(v, i, what):
+    hn, hp, hr, hinfo = _images_with(0, v, i)
+    dn, dp, dr, dinfo = _images_with(1, v, i)
+    assert hinfo["node_count"] == dinfo["node_count"] and hinfo["depth"] == dinfo["depth"], what
+    assert np.array_equal(hn, dn), f"{what}: node images differ"
+    assert np.array_equal(hp, dp), f"{what}: pair images differ"
+    assert np.array_equal(hr, dr), f"{what}: remap tables differ"
+
+
+def test_device_build_battlefield_identical_to_host(battlefield):
+    _assert_same_images(battlefield.vertices, battlefield.indices, "battlefield")
+
+
+def test_device_build_synthetic_identical_to_host():
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import synthetic_meshes
+    for name, (v, i) in sorted(synthetic_meshes().items()):
+        _assert_same_images(v, i, name)
+    # soups of awkward sizes: below one 8-block, around the warp/CTA hand-over, forced median splits
+    for n, seed, extent, edge in ((3, 1, 10.0, 1.0), (9, 2, 10.0, 1.0), (17, 3, 10.0, 3.0), (64, 4, 20.0, 2.0), (65, 5, 20.0, 2.0),
+                                  (127, 6, 0.0, 1.0), (300, 7, 0.0, 1.0), (1000, 8, 30.0, 5.0), (4097, 9, 100.0, 3.0), (50000, 10, 200.0, 2.0)):
+        v, i = rb.synthetic_triangles(n, seed=seed, extent=extent, edge=edge)
+        _assert_same_images(v, i, f"soup n={n}")
+
+
+@pytest.mark.slow
+def test_device_build_large_soup_identical_to_host():
+    v, i = rb.synthetic_triangles(1_000_000, seed=7, extent=1000.0, edge=2.0)
+    _assert_same_images(v, i, "soup n=1e6")
