@@ -28,13 +28,16 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 namespace racc_b200 {
 namespace {
 
 constexpr uint32_t kNone = 0xffffffffu;
-constexpr uint32_t kSmallNode = 64; // nodes up to this many triangles are built by one warp
+constexpr uint32_t kSmallNode = 64;  // nodes up to this many triangles are built by one warp
+constexpr uint32_t kWideNode = 4096; // nodes above this are built by 512 threads x 8 positions each
+constexpr int kWideThreads = 512;
 
 __constant__ float c_rcpTable[2048];
 
@@ -306,10 +309,269 @@ __device__ void splitList(const DevBuild& ctx, uint32_t* __restrict__ ids, uint3
 	__syncthreads();
 }
 
+
+// ---- wide variants: every thread owns 8 consecutive positions = exactly one 8-block of the sweep -----
+
+// Exclusive max-scan of one box per thread: returns the union of all earlier threads' boxes.
 template <int T>
+__device__ __forceinline__ Box6 ctaExclusiveScanMax(Box6 b, Box6& total, float (*sWarp)[6]) {
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+		for (int k = 0; k < 6; ++k) {
+			const float v = __shfl_up_sync(0xffffffffu, b.v[k], o);
+			if ((int)lane >= o) b.v[k] = fmaxf(b.v[k], v);
+		}
+	}
+	Box6 ex;
+#pragma unroll
+	for (int k = 0; k < 6; ++k) {
+		const float v = __shfl_up_sync(0xffffffffu, b.v[k], 1);
+		ex.v[k] = lane ? v : -INFINITY;
+	}
+	__syncthreads();
+	if (lane == 31) {
+#pragma unroll
+		for (int k = 0; k < 6; ++k) sWarp[warp][k] = b.v[k];
+	}
+	__syncthreads();
+	total = emptyBox();
+	for (unsigned w = 0; w < T / 32; ++w) {
+		Box6 x;
+#pragma unroll
+		for (int k = 0; k < 6; ++k) x.v[k] = sWarp[w][k];
+		if (w < warp) boxMax(ex, x);
+		boxMax(total, x);
+	}
+	return ex;
+}
+
+// Exclusive min-scan of one float per thread (identity +inf).
+template <int T>
+__device__ __forceinline__ float ctaExclusiveScanMin(float v, float* sWarp) {
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const float x = __shfl_up_sync(0xffffffffu, v, o);
+		if ((int)lane >= o) v = fminf(v, x);
+	}
+	float ex = __shfl_up_sync(0xffffffffu, v, 1);
+	if (!lane) ex = INFINITY;
+	__syncthreads();
+	if (lane == 31) sWarp[warp] = v;
+	__syncthreads();
+	for (unsigned w = 0; w < warp; ++w) ex = fminf(ex, sWarp[w]);
+	return ex;
+}
+
+// Exclusive sum-scan of one count per thread.
+template <int T>
+__device__ __forceinline__ uint32_t ctaExclusiveScanSum(uint32_t v, uint32_t* total, uint32_t* sWarp) {
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t incl = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+		if ((int)lane >= o) incl += x;
+	}
+	__syncthreads();
+	if (lane == 31) sWarp[warp] = incl;
+	__syncthreads();
+	uint32_t before = 0, all = 0;
+	for (unsigned w = 0; w < T / 32; ++w) {
+		const uint32_t c = sWarp[w];
+		if (w < warp) before += c;
+		all += c;
+	}
+	*total = all;
+	return before + incl - v;
+}
+
+template <int T>
+struct SharedWide {
+	float warpBox[T / 32][6];
+	float warpMin[T / 32];
+	uint32_t warpCount[T / 32];
+	uint32_t prune;
+	uint32_t term;
+	uint32_t lastBetter;
+	float best;
+	uint32_t pivot;
+	int done;
+};
+
+// sweepAxis with 8 positions per thread. Chunks start at `first` (forward) / at offset 0 from i0
+// (backward), so a thread's 8 positions are one block of the reference's 8-wide loops, and the
+// order-dependent replay runs in parallel: running best = exclusive prefix-min over the block minima,
+// termination = first block whose largest right cost exceeds it, pivot = last block at or before
+// the terminating one that strictly improves the running best.
+template <int T>
+__device__ uint32_t sweepAxisWide(const DevBuild& ctx, const uint32_t* __restrict__ ids, uint32_t first, uint32_t last, float& bestSah, SharedWide<T>& sh) {
+	constexpr uint32_t C = T * 8;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t count = last - first;
+	const uint32_t nb = count > 8 ? (count - 1) / 8 : 0;
+	const uint32_t blockEnd = first + 8 * nb;
+
+	if (tid == 0) sh.prune = kNone;
+	__syncthreads();
+	Box6 carry = emptyBox();
+	uint32_t prune = kNone;
+	for (uint32_t base = first; base + 1 < last; base += C) {
+		const uint32_t p0 = base + 8 * tid;
+		Box6 run[8];
+		Box6 acc = emptyBox();
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			if (p0 + j + 1 < last) boxMax(acc, loadBox(ctx.tb, ids[p0 + j]));
+			run[j] = acc;
+		}
+		Box6 total;
+		Box6 pre = ctaExclusiveScanMax<T>(acc, total, sh.warpBox);
+		boxMax(pre, carry);
+		boxMax(carry, total);
+		const bool inBlock = p0 < blockEnd;
+		uint32_t myPrune = kNone;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const uint32_t pos = p0 + j;
+			if (pos + 1 < last) {
+				Box6 b = run[j];
+				boxMax(b, pre);
+				const float sah = __fmul_rn(inBlock ? areaBlock(b) : areaScalar(b), (float)(pos - first + 1));
+				ctx.leftSah[pos] = sah;
+				if (inBlock && sah > bestSah && myPrune == kNone) myPrune = pos;
+			}
+		}
+		if (myPrune != kNone) atomicMin(&sh.prune, myPrune);
+		__syncthreads();
+		prune = sh.prune;
+		if (prune != kNone) break;
+	}
+
+	const uint32_t i0 = prune != kNone ? prune : last - 1;
+	Box6 run0;
+	if (prune == kNone) {
+		run0 = loadBox(ctx.tb, ids[last - 1]);
+	}
+	else {
+		Box6 acc = emptyBox();
+		for (uint32_t pos = i0 + tid; pos < last; pos += T) boxMax(acc, loadBox(ctx.tb, ids[pos]));
+		run0 = ctaReduceMax<T>(acc, sh.warpBox);
+	}
+	const uint32_t span = i0 - first;
+	const uint32_t blockSpan = (span / 8) * 8;
+	uint32_t bestPivot = kNone;
+	bool done = false;
+	carry = run0;
+	for (uint32_t off = 0; off < span && !done; off += C) {
+		const uint32_t o0 = off + 8 * tid;
+		Box6 run[8];
+		Box6 acc = emptyBox();
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			if (o0 + j < span) boxMax(acc, loadBox(ctx.tb, ids[i0 - (o0 + j)]));
+			run[j] = acc;
+		}
+		Box6 total;
+		Box6 pre = ctaExclusiveScanMax<T>(acc, total, sh.warpBox);
+		boxMax(pre, carry);
+		boxMax(carry, total);
+		const bool isBlock = o0 < blockSpan;          // 8 valid pivots of the 8-wide loop
+		const bool isTail = !isBlock && o0 < span;    // the one thread holding the <= 7 scalar-tail pivots
+		float sah[8];
+		float m = INFINITY, mr = -INFINITY;
+		int arg = 0;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			sah[j] = INFINITY;
+			if (o0 + j < span) {
+				const uint32_t q = i0 - (o0 + j);
+				Box6 b = run[j];
+				boxMax(b, pre);
+				const float r = __fmul_rn(isBlock ? areaBlock(b) : areaScalar(b), (float)(last - q));
+				const float sv = __fadd_rn(ctx.leftSah[q - 1], r);
+				sah[j] = sv;
+				if (isBlock) {
+					if (sv < m) { m = sv; arg = j; } // first lane holding the minimum
+					mr = fmaxf(mr, r);
+				}
+			}
+		}
+		if (tid == 0) { sh.term = kNone; sh.lastBetter = 0; sh.best = bestSah; sh.pivot = bestPivot; }
+		const float before = fminf(ctaExclusiveScanMin<T>(m, sh.warpMin), bestSah); // running best when this block starts
+		if (isBlock && mr > before) atomicMin(&sh.term, tid); // Bvh2.cpp:418
+		__syncthreads();
+		const uint32_t term = sh.term;
+		if (isBlock && m < before && tid <= term) atomicMax(&sh.lastBetter, tid + 1); // Bvh2.cpp:417,428
+		__syncthreads();
+		const uint32_t lb = sh.lastBetter;
+		if (lb && tid == lb - 1) { sh.best = m; sh.pivot = (i0 - o0) - (uint32_t)arg; }
+		__syncthreads();
+		if (isTail && term == kNone) {
+			// scalar tail (Bvh2.cpp:438-450): strict improvement, in order
+			float best = before;
+			uint32_t bp = sh.pivot;
+			bool changed = false;
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				if (o0 + j < span && sah[j] < best) { best = sah[j]; bp = i0 - (o0 + j); changed = true; }
+			}
+			if (changed) { sh.best = best; sh.pivot = bp; }
+		}
+		if (tid == 0) sh.done = (term != kNone || off + C >= span) ? 1 : 0;
+		__syncthreads();
+		bestSah = sh.best;
+		bestPivot = sh.pivot;
+		done = sh.done != 0;
+		__syncthreads();
+	}
+	__syncthreads();
+	return bestPivot;
+}
+
+template <int T>
+__device__ void splitListWide(const DevBuild& ctx, uint32_t* __restrict__ ids, uint32_t first, uint32_t pivot, uint32_t last, SharedWide<T>& sh) {
+	constexpr uint32_t C = T * 8;
+	const uint32_t tid = threadIdx.x;
+	uint32_t nL = 0, nR = 0;
+	for (uint32_t base = first; base < last; base += C) {
+		const uint32_t p0 = base + 8 * tid;
+		uint32_t t[8];
+		unsigned flags = 0;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			t[j] = 0;
+			if (p0 + j < last) {
+				t[j] = ids[p0 + j];
+				if (ctx.goesLeft[t[j]]) flags |= 1u << j;
+			}
+		}
+		uint32_t totalL;
+		const uint32_t exL = ctaExclusiveScanSum<T>(__popc(flags), &totalL, sh.warpCount);
+		const uint32_t chunk = min(C, last - base);
+		uint32_t dl = first + nL + exL;
+		uint32_t dr = pivot + nR + (8 * tid - exL);
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			if (p0 + j < last) {
+				if (flags & (1u << j)) ctx.scratch[dl++] = t[j];
+				else ctx.scratch[dr++] = t[j];
+			}
+		}
+		nL += totalL;
+		nR += chunk - totalL;
+	}
+	__syncthreads();
+	for (uint32_t pos = first + tid; pos < last; pos += T) ids[pos] = ctx.scratch[pos];
+	__syncthreads();
+}
+
+template <int T, int E>
 __global__ void __launch_bounds__(T) buildLevelKernel(const DevBuild ctx, const uint32_t* __restrict__ cur, uint32_t* __restrict__ nextBig,
-                                                     uint32_t* __restrict__ nextSmall, uint32_t* __restrict__ counts) {
-	__shared__ Shared<T> sh;
+                                                     uint32_t* __restrict__ nextSmall, uint32_t* __restrict__ nextWide, uint32_t* __restrict__ counts) {
+	__shared__ typename std::conditional<E == 8, SharedWide<T>, Shared<T>>::type sh;
 	const uint32_t tid = threadIdx.x;
 	const uint32_t slot = cur[blockIdx.x];
 	BuildNode* node = ctx.nodes + slot;
@@ -333,7 +595,9 @@ __global__ void __launch_bounds__(T) buildLevelKernel(const DevBuild ctx, const 
 	if (parentArea > 0.0f) {
 		float bestSah = INFINITY;
 		for (uint32_t dim = 0; dim < 3; ++dim) {
-			const uint32_t p = sweepAxis<T>(ctx, ctx.sorted[dim], first, last, bestSah, sh);
+			uint32_t p;
+			if constexpr (E == 8) p = sweepAxisWide<T>(ctx, ctx.sorted[dim], first, last, bestSah, sh);
+			else p = sweepAxis<T>(ctx, ctx.sorted[dim], first, last, bestSah, sh);
 			if (p != kNone) {
 				pivot = p;
 				bestDim = dim;
@@ -358,8 +622,14 @@ __global__ void __launch_bounds__(T) buildLevelKernel(const DevBuild ctx, const 
 		const uint32_t* ref = ctx.sorted[bestDim];
 		for (uint32_t pos = first + tid; pos < last; pos += T) ctx.goesLeft[ref[pos]] = pos < pivot ? 1 : 0;
 		__syncthreads();
-		splitList<T>(ctx, ctx.sorted[(bestDim + 1) % 3], first, pivot, last, sh);
-		splitList<T>(ctx, ctx.sorted[(bestDim + 2) % 3], first, pivot, last, sh);
+		if constexpr (E == 8) {
+			splitListWide<T>(ctx, ctx.sorted[(bestDim + 1) % 3], first, pivot, last, sh);
+			splitListWide<T>(ctx, ctx.sorted[(bestDim + 2) % 3], first, pivot, last, sh);
+		}
+		else {
+			splitList<T>(ctx, ctx.sorted[(bestDim + 1) % 3], first, pivot, last, sh);
+			splitList<T>(ctx, ctx.sorted[(bestDim + 2) % 3], first, pivot, last, sh);
+		}
 	}
 
 	if (tid == 0) {
@@ -376,7 +646,8 @@ __global__ void __launch_bounds__(T) buildLevelKernel(const DevBuild ctx, const 
 		const uint32_t child[2] = {left, right};
 		const uint32_t size[2] = {pivot - first, last - pivot};
 		for (int c = 0; c < 2; ++c) {
-			if (size[c] > kSmallNode) nextBig[atomicAdd(&counts[0], 1u)] = child[c];
+			if (size[c] > kWideNode) nextWide[atomicAdd(&counts[2], 1u)] = child[c];
+			else if (size[c] > kSmallNode) nextBig[atomicAdd(&counts[0], 1u)] = child[c];
 			else nextSmall[atomicAdd(&counts[1], 1u)] = child[c];
 		}
 	}
@@ -418,13 +689,15 @@ __global__ void boundsKeysKernel(const float4* __restrict__ verts, const uint32_
 	v0[j] = t; v1[j] = t; v2[j] = t;
 }
 
+// Scratch for one build, stream-ordered (default stream) so that repeated builds recycle the pool
+// instead of paying cudaMalloc/cudaFree each time.
 struct DeviceBuffers {
 	std::vector<void*> ptrs;
-	~DeviceBuffers() { for (void* p : ptrs) cudaFree(p); }
+	~DeviceBuffers() { for (void* p : ptrs) cudaFreeAsync(p, nullptr); }
 	template <typename Tp>
 	bool alloc(Tp** out, size_t count) {
 		void* p = nullptr;
-		if (cudaMalloc(&p, count * sizeof(Tp) + 256) != cudaSuccess) return false;
+		if (cudaMallocAsync(&p, count * sizeof(Tp) + 256, nullptr) != cudaSuccess) return false;
 		ptrs.push_back(p);
 		*out = static_cast<Tp*>(p);
 		return true;
@@ -435,41 +708,54 @@ std::once_flag g_rcpOnce;
 bool g_rcpOk = false;
 float g_rcpTable[2048];
 
-} // namespace
 
-// DeviceBvhBuilder (scene_build.h). Uses the current CUDA device.
-bool buildBvh2Device(const float* vertices4, uint32_t vertexCount, const uint32_t* indices, uint32_t triangleCount,
-                     std::vector<BuildNode>* outNodes, std::vector<uint32_t>* outSorted0, const char** error) {
-	static const char* kRcp = "device build unavailable: this CPU's RCPSS does not follow the table model";
-	static const char* kMem = "device build failed: out of device memory";
-	static const char* kCuda = "device build failed: CUDA error";
+// Everything the SAH build leaves on the device.
+struct SahOnDevice {
+	DeviceBuffers buf;
+	float4* verts = nullptr;
+	uint32_t* indices = nullptr;
+	BuildNode* nodes = nullptr;  // 2n slots; unused slots have kind == kNone
+	uint32_t* sorted0 = nullptr; // x-sorted triangle list, partitioned by the tree
+	uint32_t* hist = nullptr;    // radix-sort histogram scratch
+	uint32_t n = 0;
+	int levels = 0;              // = depth of the deepest leaf, root = 1
+	int smCount = 148;
+	double msPrepare = 0, msLevels = 0;
+};
+
+const char* const kErrRcp = "device build unavailable: this CPU's RCPSS does not follow the table model";
+const char* const kErrMem = "device build failed: out of device memory";
+const char* const kErrCuda = "device build failed: CUDA error";
+
+double nowSeconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+bool runSahOnDevice(const float* vertices4, uint32_t vertexCount, const uint32_t* indices, uint32_t triangleCount, SahOnDevice& out, const char** error) {
 	std::call_once(g_rcpOnce, [] { g_rcpOk = fillRcpTable(g_rcpTable); });
-	if (!g_rcpOk) { if (error) *error = kRcp; return false; }
+	if (!g_rcpOk) { if (error) *error = kErrRcp; return false; }
 	const uint32_t n = triangleCount;
-	const bool verbose = getenv("RACC_B200_BUILD_VERBOSE") != nullptr;
-	auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-	const double t0 = now();
+	const double t0 = nowSeconds();
 	int device = 0, smCount = 148;
 	cudaGetDevice(&device);
 	cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, device);
-	if (cudaMemcpyToSymbol(c_rcpTable, g_rcpTable, sizeof(g_rcpTable)) != cudaSuccess) { if (error) *error = kCuda; return false; }
+	if (cudaMemcpyToSymbol(c_rcpTable, g_rcpTable, sizeof(g_rcpTable)) != cudaSuccess) { if (error) *error = kErrCuda; return false; }
 
-	DeviceBuffers buf;
+	DeviceBuffers& buf = out.buf;
 	float4 *dVerts, *dTb;
-	uint32_t *dIdx, *keys[3], *vals[3], *keysTmp, *valsTmp, *hist, *scratch, *lists[4], *counts;
+	uint32_t *dIdx, *keys[3], *vals[3], *keysTmp, *valsTmp, *hist, *scratch, *lists[6], *counts;
 	float* leftSah;
 	uint8_t* goesLeft;
 	BuildNode* dNodes;
 	bool ok = buf.alloc(&dVerts, vertexCount) && buf.alloc(&dIdx, (size_t)n * 3) && buf.alloc(&dTb, (size_t)n * 2) && buf.alloc(&keysTmp, n) &&
 	          buf.alloc(&valsTmp, n) && buf.alloc(&hist, radixSortHistWords()) && buf.alloc(&scratch, n) && buf.alloc(&leftSah, n) &&
-	          buf.alloc(&goesLeft, n) && buf.alloc(&dNodes, (size_t)n * 2) && buf.alloc(&counts, 2);
+	          buf.alloc(&goesLeft, n) && buf.alloc(&dNodes, (size_t)n * 2) && buf.alloc(&counts, 4);
 	for (int d = 0; d < 3 && ok; ++d) ok = buf.alloc(&keys[d], n) && buf.alloc(&vals[d], n);
-	for (int l = 0; l < 4 && ok; ++l) ok = buf.alloc(&lists[l], n);
-	if (!ok) { if (error) *error = kMem; return false; }
+	for (int l = 0; l < 6 && ok; ++l) ok = buf.alloc(&lists[l], n);
+	if (!ok) { if (error) *error = kErrMem; return false; }
 
 	cudaError_t e = cudaMemcpy(dVerts, vertices4, (size_t)vertexCount * 16, cudaMemcpyHostToDevice);
 	if (e == cudaSuccess) e = cudaMemcpy(dIdx, indices, (size_t)n * 12, cudaMemcpyHostToDevice);
-	if (e != cudaSuccess) { if (error) *error = kCuda; return false; }
+	if (e == cudaSuccess) e = cudaMemsetAsync(dNodes, 0xff, (size_t)n * 2 * sizeof(BuildNode)); // kind == kNone: slot unused
+	if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
 
 	boundsKeysKernel<<<(n + 255u) / 256u, 256>>>(dVerts, dIdx, n, dTb, keys[0], keys[1], keys[2], vals[0], vals[1], vals[2]);
 	DevBuild ctx{};
@@ -482,47 +768,361 @@ bool buildBvh2Device(const float* vertices4, uint32_t vertexCount, const uint32_
 	for (int d = 0; d < 3; ++d) {
 		uint32_t* sortedVals = nullptr;
 		e = launchRadixSort(keys[d], vals[d], keysTmp, valsTmp, hist, n, 32, smCount, nullptr, nullptr, &sortedVals, nullptr);
-		if (e != cudaSuccess) { if (error) *error = kCuda; return false; }
-		// four passes: the result is back in vals[d]
-		ctx.sorted[d] = sortedVals;
+		if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
+		ctx.sorted[d] = sortedVals; // four passes: the result is back in vals[d]
 		if (sortedVals != vals[d]) { // defensive: keep the three lists in distinct buffers
 			e = cudaMemcpyAsync(vals[d], sortedVals, (size_t)n * 4, cudaMemcpyDeviceToDevice);
 			ctx.sorted[d] = vals[d];
 		}
 	}
+	cudaDeviceSynchronize();
+	const double t1 = nowSeconds();
 
-	if (verbose) cudaDeviceSynchronize();
-	const double t1 = now();
 	BuildNode root{};
 	root.kind = 0; root.parent = kNone; root.first = 0; root.last = n; root.left = kNone; root.right = kNone;
 	e = cudaMemcpy(dNodes, &root, sizeof(root), cudaMemcpyHostToDevice);
+	// level by level: lists[3*cur + {0,1,2}] = big / small / wide nodes of this level, the other three of the next
+	uint32_t have[3] = {0, 0, 0};
+	have[n > kWideNode ? 2 : (n > kSmallNode ? 0 : 1)] = 1;
 	const uint32_t zero = 0;
-	if (e == cudaSuccess) e = cudaMemcpy(lists[n > kSmallNode ? 0 : 1], &zero, 4, cudaMemcpyHostToDevice);
-	if (e != cudaSuccess) { if (error) *error = kCuda; return false; }
-
-	// level by level: lists[0]/[1] = big/small nodes of this level, lists[2]/[3] = of the next
-	uint32_t have[2] = {n > kSmallNode ? 1u : 0u, n > kSmallNode ? 0u : 1u};
+	if (e == cudaSuccess) e = cudaMemcpy(lists[n > kWideNode ? 2 : (n > kSmallNode ? 0 : 1)], &zero, 4, cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
 	int cur = 0, levels = 0;
-	for (int level = 0; level < 4096 && (have[0] || have[1]); ++level, ++levels) {
-		cudaMemsetAsync(counts, 0, 8);
-		uint32_t* big = lists[2 * cur], * small = lists[2 * cur + 1];
-		uint32_t* nextBig = lists[2 * (1 - cur)], * nextSmall = lists[2 * (1 - cur) + 1];
-		if (have[0]) buildLevelKernel<256><<<have[0], 256>>>(ctx, big, nextBig, nextSmall, counts);
-		if (have[1]) buildLevelKernel<32><<<have[1], 32>>>(ctx, small, nextBig, nextSmall, counts);
-		e = cudaMemcpy(have, counts, 8, cudaMemcpyDeviceToHost);
-		if (e != cudaSuccess) { if (error) *error = kCuda; return false; }
+	for (int level = 0; level < 4096 && (have[0] || have[1] || have[2]); ++level, ++levels) {
+		cudaMemsetAsync(counts, 0, 12);
+		uint32_t** in = lists + 3 * cur;
+		uint32_t** nxt = lists + 3 * (1 - cur);
+		if (have[2]) buildLevelKernel<kWideThreads, 8><<<have[2], kWideThreads>>>(ctx, in[2], nxt[0], nxt[1], nxt[2], counts);
+		if (have[0]) buildLevelKernel<256, 1><<<have[0], 256>>>(ctx, in[0], nxt[0], nxt[1], nxt[2], counts);
+		if (have[1]) buildLevelKernel<32, 1><<<have[1], 32>>>(ctx, in[1], nxt[0], nxt[1], nxt[2], counts);
+		e = cudaMemcpy(have, counts, 12, cudaMemcpyDeviceToHost);
+		if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
 		cur = 1 - cur;
 	}
+	out.verts = dVerts;
+	out.indices = dIdx;
+	out.nodes = dNodes;
+	out.sorted0 = ctx.sorted[0];
+	out.hist = hist;
+	out.n = n;
+	out.levels = levels;
+	out.smCount = smCount;
+	out.msPrepare = (t1 - t0) * 1e3;
+	out.msLevels = (nowSeconds() - t1) * 1e3;
+	return true;
+}
 
-	const double t2 = now();
+// ---------------------------------------------------------------------------------------------
+// From the sparse tree to the three device images, on the device (scene_build.cpp buildSceneImages /
+// Scene.cpp:223-338): inner nodes ordered by surface area (largest first, ties by tree order), leaves
+// packed in the order their parents appear, greedy edge-sharing pair merge per leaf, remap words.
+
+// exclusive prefix sum of n words: 8192 per CTA, then the CTA totals by one CTA (n <= 8192 * 8192)
+__global__ void __launch_bounds__(1024) scanBlocksKernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, uint32_t* __restrict__ blockSums) {
+	__shared__ uint32_t warpSums[32];
+	const uint32_t base = blockIdx.x * 8192u + threadIdx.x * 8u;
+	uint32_t v[8], sum = 0;
+#pragma unroll
+	for (int j = 0; j < 8; ++j) { v[j] = base + j < n ? in[base + j] : 0u; sum += v[j]; }
+	uint32_t total;
+	const uint32_t ex = ctaExclusiveScanSum<1024>(sum, &total, warpSums);
+	uint32_t run = ex;
+#pragma unroll
+	for (int j = 0; j < 8; ++j) { if (base + j < n) out[base + j] = run; run += v[j]; }
+	if (threadIdx.x == 0) blockSums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) scanSumsKernel(uint32_t* __restrict__ blockSums, uint32_t blocks, uint32_t* __restrict__ grandTotal) {
+	__shared__ uint32_t warpSums[32];
+	const uint32_t base = threadIdx.x * 8u;
+	uint32_t v[8], sum = 0;
+#pragma unroll
+	for (int j = 0; j < 8; ++j) { v[j] = base + j < blocks ? blockSums[base + j] : 0u; sum += v[j]; }
+	uint32_t total;
+	const uint32_t ex = ctaExclusiveScanSum<1024>(sum, &total, warpSums);
+	uint32_t run = ex;
+#pragma unroll
+	for (int j = 0; j < 8; ++j) { if (base + j < blocks) blockSums[base + j] = run; run += v[j]; }
+	if (threadIdx.x == 0) *grandTotal = total;
+}
+__global__ void __launch_bounds__(1024) scanAddKernel(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ blockSums) {
+	const uint32_t base = blockIdx.x * 8192u + threadIdx.x * 8u;
+	const uint32_t add = blockSums[blockIdx.x];
+#pragma unroll
+	for (int j = 0; j < 8; ++j) if (base + j < n) out[base + j] += add;
+}
+// out[i] = sum of in[0..i); *grandTotal (device) = sum of all. blockSums: >= ceil(n/8192) words.
+void exclusiveScan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* blockSums, uint32_t* grandTotal) {
+	const uint32_t blocks = (n + 8191u) / 8192u;
+	scanBlocksKernel<<<blocks, 1024>>>(in, out, n, blockSums);
+	scanSumsKernel<<<1, 1024>>>(blockSums, blocks, grandTotal);
+	scanAddKernel<<<blocks, 1024>>>(out, n, blockSums);
+}
+
+__global__ void innerFlagKernel(const BuildNode* __restrict__ nodes, uint32_t slots, uint32_t* __restrict__ flag) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s < slots) {
+		const uint32_t kind = nodes[s].kind;
+		flag[s] = (kind != kNone && kind != 0u) ? 1u : 0u;
+	}
+}
+// key = surface area, larger first (scene_build.cpp boxArea: dx*dy + dy*dz + dx*dz); root first
+__global__ void innerKeyKernel(const BuildNode* __restrict__ nodes, uint32_t slots, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ rank,
+                               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= slots || !flag[s])
+		return;
+	const BuildNode& nd = nodes[s];
+	// bbMax - bbMin with bbMin = -bounds[k]
+	const float dx = __fsub_rn(nd.bounds[4], -nd.bounds[0]), dy = __fsub_rn(nd.bounds[5], -nd.bounds[1]), dz = __fsub_rn(nd.bounds[6], -nd.bounds[2]);
+	const float area = __fadd_rn(__fadd_rn(__fmul_rn(dx, dy), __fmul_rn(dy, dz)), __fmul_rn(dx, dz));
+	// areas are >= 0: the bit pattern orders like the value; invert for "largest first"
+	keys[rank[s]] = s == 0 ? 0u : ~__float_as_uint(area);
+	vals[rank[s]] = s;
+}
+__global__ void deviceOfKernel(const uint32_t* __restrict__ order, uint32_t count, uint32_t* __restrict__ deviceOf) {
+	const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+	if (d < count) deviceOf[order[d]] = d;
+}
+__global__ void leafChildCountKernel(const BuildNode* __restrict__ nodes, const uint32_t* __restrict__ order, uint32_t count, uint32_t* __restrict__ leafChildren) {
+	const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+	if (d >= count)
+		return;
+	const BuildNode& nd = nodes[order[d]];
+	leafChildren[d] = (nodes[nd.left].kind == 0u ? 1u : 0u) + (nodes[nd.right].kind == 0u ? 1u : 0u);
+}
+
+// Directed edge (a[e0], a[e0+1]) of triangle a equals the reversed edge of b (Scene.cpp:109-120).
+__device__ __forceinline__ bool sharedEdgeDev(const uint32_t* a, const uint32_t* b, unsigned& e0, unsigned& e1) {
+	for (unsigned i = 0; i < 3; ++i)
+		for (unsigned j = 0; j < 3; ++j)
+			if (a[i] == b[(j + 1) % 3] && a[(i + 1) % 3] == b[j]) {
+				e0 = i;
+				e1 = j;
+				return true;
+			}
+	return false;
+}
+__device__ __forceinline__ void writePair(float4* pairs, uint32_t at, float4 p0, float4 p1, float4 p2, float4 p3) {
+	// e1 = p0 - p1, e2 = p2 - p0, e3 = p3 - p0 (Scene.cpp:149-153); layout Scene.cpp:80-87
+	pairs[3 * (size_t)at + 0] = make_float4(__fsub_rn(p0.x, p1.x), __fsub_rn(p0.y, p1.y), __fsub_rn(p0.z, p1.z), __fsub_rn(p3.x, p0.x));
+	pairs[3 * (size_t)at + 1] = make_float4(__fsub_rn(p2.x, p0.x), __fsub_rn(p2.y, p0.y), __fsub_rn(p2.z, p0.z), __fsub_rn(p3.y, p0.y));
+	pairs[3 * (size_t)at + 2] = make_float4(p0.x, p0.y, p0.z, __fsub_rn(p3.z, p0.z));
+}
+
+// Greedy pairing of one leaf's triangles in list order (Scene.cpp:122-181,251-256). One thread per
+// leaf. kWrite == false: only counts the pairs; kWrite == true: writes pairs and remap words at the
+// leaf's offset. Leaf l is the l-th leaf child in device order (first child before last child).
+template <bool kWrite>
+__global__ void leafMergeKernel(const BuildNode* __restrict__ nodes, const uint32_t* __restrict__ order, uint32_t innerCount,
+                                const uint32_t* __restrict__ leafBase, const uint32_t* __restrict__ sorted0, const uint32_t* __restrict__ indices,
+                                const float4* __restrict__ verts, uint32_t* __restrict__ pairCount, const uint32_t* __restrict__ pairStart,
+                                float4* __restrict__ pairs, uint32_t* __restrict__ remap) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= 2 * innerCount)
+		return;
+	const uint32_t d = t >> 1, c = t & 1u;
+	const BuildNode& nd = nodes[order[d]];
+	const uint32_t childSlot = c ? nd.right : nd.left;
+	const BuildNode& leaf = nodes[childSlot];
+	if (leaf.kind != 0u)
+		return;
+	const uint32_t l = leafBase[d] + ((c && nodes[nd.left].kind == 0u) ? 1u : 0u);
+	uint32_t cand[128];
+	uint32_t m = leaf.last - leaf.first;
+	for (uint32_t i = 0; i < m; ++i) cand[i] = sorted0[leaf.first + i];
+	uint32_t at = kWrite ? pairStart[l] : 0u, made = 0;
+	while (m) {
+		const uint32_t a = cand[0];
+		--m;
+		for (uint32_t i = 0; i < m; ++i) cand[i] = cand[i + 1];
+		uint32_t ta[3] = {indices[3 * (size_t)a], indices[3 * (size_t)a + 1], indices[3 * (size_t)a + 2]};
+		bool merged = false;
+		for (uint32_t i = 0; i < m; ++i) {
+			const uint32_t b = cand[i];
+			uint32_t tbv[3] = {indices[3 * (size_t)b], indices[3 * (size_t)b + 1], indices[3 * (size_t)b + 2]};
+			unsigned e0, e1;
+			if (!sharedEdgeDev(ta, tbv, e0, e1)) continue;
+			if (kWrite) {
+				remap[2 * (size_t)at] = a | (e0 << 30);
+				remap[2 * (size_t)at + 1] = b | ((e1 + 1) << 30); // 3 == "no rotation", same as 0 (Kernels.h:232-235)
+				writePair(pairs, at, verts[ta[e0]], verts[ta[(e0 + 1) % 3]], verts[ta[(e0 + 2) % 3]], verts[tbv[(e1 + 2) % 3]]);
+			}
+			++at; ++made;
+			--m;
+			for (uint32_t k = i; k < m; ++k) cand[k] = cand[k + 1];
+			merged = true;
+			break;
+		}
+		if (!merged) {
+			// singleton: second triangle degenerates to (p0, p1, p1), never hit (Scene.cpp:160-180)
+			if (kWrite) {
+				remap[2 * (size_t)at] = a;
+				remap[2 * (size_t)at + 1] = 0u;
+				const float4 p1 = verts[ta[1]];
+				writePair(pairs, at, verts[ta[0]], p1, verts[ta[2]], p1);
+			}
+			++at; ++made;
+		}
+	}
+	if (!kWrite) pairCount[l] = made;
+}
+
+// 64-byte inner node, both child boxes inline (Scene.cpp:73-78,274-332)
+__global__ void emitNodesKernel(const BuildNode* __restrict__ nodes, const uint32_t* __restrict__ order, uint32_t innerCount,
+                                const uint32_t* __restrict__ deviceOf, const uint32_t* __restrict__ leafBase, const uint32_t* __restrict__ pairCount,
+                                const uint32_t* __restrict__ pairStart, float4* __restrict__ out, uint32_t* __restrict__ overflow) {
+	const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+	if (d >= innerCount)
+		return;
+	const BuildNode& nd = nodes[order[d]];
+	const BuildNode& l = nodes[nd.left];
+	const BuildNode& r = nodes[nd.right];
+	uint32_t ref[2];
+	uint32_t leafIndex = leafBase[d];
+	const BuildNode* child[2] = {&l, &r};
+	const uint32_t childSlot[2] = {nd.left, nd.right};
+	for (int c = 0; c < 2; ++c) {
+		if (child[c]->kind != 0u) {
+			ref[c] = 0x80000000u | deviceOf[childSlot[c]];
+		}
+		else {
+			const uint32_t start = pairStart[leafIndex], count = pairCount[leafIndex];
+			if (start + count > (1u << 24)) *overflow = 1u;
+			ref[c] = (count << 24) | start; // Scene.cpp:298,308
+			++leafIndex;
+		}
+	}
+	const uint32_t parent = nd.parent == kNone ? kNone : deviceOf[nd.parent];
+	out[4 * (size_t)d + 0] = make_float4(__uint_as_float(nd.kind), __uint_as_float(parent), __uint_as_float(ref[0]), __uint_as_float(ref[1]));
+	out[4 * (size_t)d + 1] = make_float4(-l.bounds[0], -l.bounds[1], -l.bounds[2], l.bounds[4]);
+	out[4 * (size_t)d + 2] = make_float4(l.bounds[5], l.bounds[6], -r.bounds[0], -r.bounds[1]);
+	out[4 * (size_t)d + 3] = make_float4(-r.bounds[2], r.bounds[4], r.bounds[5], r.bounds[6]);
+}
+// tail padding: copies of pair 0 (Scene.cpp:335-338)
+__global__ void padPairsKernel(float4* __restrict__ pairs, uint32_t realPairs, uint32_t pairCount) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < (pairCount - realPairs) * 3u) pairs[3 * (size_t)realPairs + i] = pairs[i % 3u];
+}
+
+} // namespace
+
+// DeviceBvhBuilder (scene_build.h): SAH tree on the GPU, handed back to the host for packing.
+bool buildBvh2Device(const float* vertices4, uint32_t vertexCount, const uint32_t* indices, uint32_t triangleCount,
+                     std::vector<BuildNode>* outNodes, std::vector<uint32_t>* outSorted0, const char** error) {
+	SahOnDevice sah;
+	if (!runSahOnDevice(vertices4, vertexCount, indices, triangleCount, sah, error))
+		return false;
+	const uint32_t n = triangleCount;
+	const double t2 = nowSeconds();
 	outNodes->resize((size_t)n * 2);
 	outSorted0->resize(n);
-	e = cudaMemcpy(outNodes->data(), dNodes, (size_t)n * 2 * sizeof(BuildNode), cudaMemcpyDeviceToHost);
-	if (e == cudaSuccess) e = cudaMemcpy(outSorted0->data(), ctx.sorted[0], (size_t)n * 4, cudaMemcpyDeviceToHost);
-	if (e != cudaSuccess) { if (error) *error = kCuda; return false; }
-	if (verbose)
+	cudaError_t e = cudaMemcpy(outNodes->data(), sah.nodes, (size_t)n * 2 * sizeof(BuildNode), cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess) e = cudaMemcpy(outSorted0->data(), sah.sorted0, (size_t)n * 4, cudaMemcpyDeviceToHost);
+	if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
+	if (getenv("RACC_B200_BUILD_VERBOSE"))
 		fprintf(stderr, "racc device build: %u triangles: upload+bounds+3 sorts %.1f ms, %d levels %.1f ms, download %.1f ms\n", n,
-		        (t1 - t0) * 1e3, levels, (t2 - t1) * 1e3, (now() - t2) * 1e3);
+		        sah.msPrepare, sah.levels, sah.msLevels, (nowSeconds() - t2) * 1e3);
+	return true;
+}
+
+// The whole scene build on the device: SAH tree, node order, pair merge, node packing. The three
+// images stay in device memory (caller owns them, cudaFree); nothing but counters crosses PCIe.
+bool buildSceneImagesDevice(const float* vertices4, uint32_t vertexCount, const uint32_t* indices, uint32_t indexCount,
+                            DeviceSceneImages* out, const char** error) {
+	static const char* kMod3 = "index count is not a multiple of 3";
+	static const char* kEmpty = "scene has no triangles";
+	static const char* kIndex = "triangle index out of range";
+	static const char* kTooBig = "scene exceeds 2^30 triangles (remap word holds 30 index bits)";
+	static const char* kTiny = "scene needs at least 3 triangles (root must be an inner node)";
+	static const char* kPairs = "scene exceeds 2^24 triangle pairs (leaf reference holds 24 index bits)";
+	if (indexCount % 3) { if (error) *error = kMod3; return false; }
+	const uint32_t n = indexCount / 3;
+	if (!n) { if (error) *error = kEmpty; return false; }
+	if (n >= (1u << 30)) { if (error) *error = kTooBig; return false; }
+	for (size_t i = 0; i < (size_t)indexCount; ++i)
+		if (indices[i] >= vertexCount) { if (error) *error = kIndex; return false; }
+	if (n < 3) { if (error) *error = kTiny; return false; }
+
+	SahOnDevice sah;
+	if (!runSahOnDevice(vertices4, vertexCount, indices, n, sah, error))
+		return false;
+	const double t0 = nowSeconds();
+	const uint32_t slots = 2 * n;
+	DeviceBuffers& buf = sah.buf;
+	uint32_t *flag, *rank, *blockSums, *totals, *keys, *vals, *keysTmp, *valsTmp, *deviceOf, *leafChildren, *leafBase, *pairCount, *pairStart, *overflow;
+	bool ok = buf.alloc(&flag, slots) && buf.alloc(&rank, slots) && buf.alloc(&blockSums, 8192 + slots / 8192) && buf.alloc(&totals, 8) &&
+	          buf.alloc(&keys, n) && buf.alloc(&vals, n) && buf.alloc(&keysTmp, n) && buf.alloc(&valsTmp, n) && buf.alloc(&deviceOf, slots) &&
+	          buf.alloc(&leafChildren, n) && buf.alloc(&leafBase, n) && buf.alloc(&pairCount, n + 1) && buf.alloc(&pairStart, n + 1) && buf.alloc(&overflow, 1);
+	if (!ok) { if (error) *error = kErrMem; return false; }
+	cudaMemsetAsync(overflow, 0, 4);
+
+	// inner nodes in tree (slot) order, then ordered by area with a stable sort
+	innerFlagKernel<<<(slots + 255u) / 256u, 256>>>(sah.nodes, slots, flag);
+	exclusiveScan(flag, rank, slots, blockSums, totals + 0);
+	uint32_t innerCount = 0;
+	cudaError_t e = cudaMemcpy(&innerCount, totals + 0, 4, cudaMemcpyDeviceToHost);
+	if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
+	if (!innerCount) { if (error) *error = kTiny; return false; } // root is a leaf
+	innerKeyKernel<<<(slots + 255u) / 256u, 256>>>(sah.nodes, slots, flag, rank, keys, vals);
+	uint32_t* order = nullptr;
+	e = launchRadixSort(keys, vals, keysTmp, valsTmp, sah.hist, innerCount, 32, sah.smCount, nullptr, nullptr, &order, nullptr);
+	if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
+	deviceOfKernel<<<(innerCount + 255u) / 256u, 256>>>(order, innerCount, deviceOf);
+
+	// leaves in the order their parents appear, first child before last child
+	leafChildCountKernel<<<(innerCount + 255u) / 256u, 256>>>(sah.nodes, order, innerCount, leafChildren);
+	exclusiveScan(leafChildren, leafBase, innerCount, blockSums, totals + 1);
+	uint32_t leafCount = 0;
+	e = cudaMemcpy(&leafCount, totals + 1, 4, cudaMemcpyDeviceToHost);
+	if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
+	leafMergeKernel<false><<<(2 * innerCount + 127u) / 128u, 128>>>(sah.nodes, order, innerCount, leafBase, sah.sorted0, sah.indices, sah.verts,
+	                                                              pairCount, nullptr, nullptr, nullptr);
+	exclusiveScan(pairCount, pairStart, leafCount, blockSums, totals + 2);
+	uint32_t realPairs = 0;
+	e = cudaMemcpy(&realPairs, totals + 2, 4, cudaMemcpyDeviceToHost);
+	if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
+	if (realPairs > (1u << 24)) { if (error) *error = kPairs; return false; }
+	const uint32_t pad = 32u - (realPairs % 32u); // at least one pad pair, total a multiple of 32 float4 (Scene.cpp:335-338)
+	const uint32_t pairTotal = realPairs + pad;
+
+	float4 *dNodes = nullptr, *dPairs = nullptr;
+	uint32_t* dRemap = nullptr;
+	if (cudaMalloc(reinterpret_cast<void**>(&dNodes), (size_t)innerCount * 64) != cudaSuccess ||
+	    cudaMalloc(reinterpret_cast<void**>(&dPairs), (size_t)pairTotal * 48) != cudaSuccess ||
+	    cudaMalloc(reinterpret_cast<void**>(&dRemap), (size_t)realPairs * 8 + 16) != cudaSuccess) {
+		cudaFree(dNodes); cudaFree(dPairs); cudaFree(dRemap);
+		if (error) *error = kErrMem;
+		return false;
+	}
+	leafMergeKernel<true><<<(2 * innerCount + 127u) / 128u, 128>>>(sah.nodes, order, innerCount, leafBase, sah.sorted0, sah.indices, sah.verts,
+	                                                             pairCount, pairStart, dPairs, dRemap);
+	emitNodesKernel<<<(innerCount + 255u) / 256u, 256>>>(sah.nodes, order, innerCount, deviceOf, leafBase, pairCount, pairStart, dNodes, overflow);
+	padPairsKernel<<<(pad * 3u + 255u) / 256u, 256>>>(dPairs, realPairs, pairTotal);
+	uint32_t over = 0;
+	BuildNode root{};
+	e = cudaMemcpy(&over, overflow, 4, cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess) e = cudaMemcpy(&root, sah.nodes, sizeof(root), cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess) e = cudaDeviceSynchronize();
+	if (e != cudaSuccess || over) {
+		cudaFree(dNodes); cudaFree(dPairs); cudaFree(dRemap);
+		if (error) *error = over ? kPairs : kErrCuda;
+		return false;
+	}
+	out->nodes = dNodes;
+	out->pairs = dPairs;
+	out->remap = dRemap;
+	out->nodeCount = innerCount;
+	out->pairCount = pairTotal;
+	out->realPairs = realPairs;
+	out->remapCount = 2 * realPairs;
+	out->depth = (uint32_t)sah.levels;
+	for (int k = 0; k < 3; ++k) {
+		out->boundsMin[k] = -root.bounds[k];
+		out->boundsMax[k] = root.bounds[4 + k];
+	}
+	if (getenv("RACC_B200_BUILD_VERBOSE"))
+		fprintf(stderr, "racc device scene build: %u triangles: upload+bounds+3 sorts %.1f ms, %d levels %.1f ms, order+merge+packing %.1f ms -> %u nodes, %u pairs\n",
+		        n, sah.msPrepare, sah.levels, sah.msLevels, (nowSeconds() - t0) * 1e3, innerCount, realPairs);
 	return true;
 }
 

@@ -94,11 +94,13 @@ int ensureInit() {
 
 constexpr int kCursorRing = 256;
 constexpr size_t kAutoSortSceneBytes = 256u << 20; // twice the 126 MB L2
+constexpr uint32_t kAutoDeviceBuildTriangles = 4096; // tiny scenes: not worth a dozen kernel launches
 
 } // namespace
 
 struct racc_cuda_scene {
-	SceneImages host;
+	SceneImages host;            // host images; left empty when the scene was built on the device
+	racc_cuda_scene_info info{}; // counts, depth and bounds of what is on the device
 	uint32_t triangleCount = 0;
 	float4* dNodes = nullptr;
 	float4* dPairs = nullptr;
@@ -125,10 +127,40 @@ struct racc_cuda_env {
 
 namespace {
 
+void fillInfo(const SceneImages& h, uint32_t triangleCount, racc_cuda_scene_info* info) {
+	info->node_count = (uint32_t)h.nodes.size();
+	info->pair_count = (uint32_t)h.pairs.size();
+	info->real_pair_count = h.realPairs;
+	info->remap_count = (uint32_t)h.remap.size();
+	info->depth = h.depth;
+	info->triangle_count = triangleCount;
+	for (int k = 0; k < 3; ++k) {
+		info->bounds_min[k] = h.boundsMin[k];
+		info->bounds_max[k] = h.boundsMax[k];
+	}
+}
+
+// device-private packed copies of the node and pair images, derived on the device
+racc_cuda_scene* packScene(racc_cuda_scene* s) {
+	cudaError_t e;
+	int launches = 0;
+	if ((e = cudaMalloc(reinterpret_cast<void**>(&s->dTNodes), (size_t)s->info.node_count * 64 + 64)) != cudaSuccess ||
+	    (e = cudaMalloc(reinterpret_cast<void**>(&s->dTPairs), (size_t)s->info.pair_count * 64 + 64)) != cudaSuccess ||
+	    (e = launchPackImages(s->dNodes, s->info.node_count, s->dPairs, s->info.pair_count, s->dTNodes, s->dTPairs, nullptr, &launches)) != cudaSuccess ||
+	    (e = cudaDeviceSynchronize()) != cudaSuccess) {
+		fail("scene packing failed: %s", cudaGetErrorString(e));
+		racc_cuda_scene_destroy(s);
+		return nullptr;
+	}
+	g_launches.fetch_add((uint64_t)launches);
+	return s;
+}
+
 racc_cuda_scene* uploadScene(racc_cuda_scene* s, const float* verts4, uint32_t nverts, const uint32_t* indices, uint32_t nindices) {
 	const SceneImages& h = s->host;
 	auto bail = [&]() -> racc_cuda_scene* { racc_cuda_scene_destroy(s); return nullptr; };
 	cudaError_t e;
+	fillInfo(h, s->triangleCount, &s->info);
 #define UP(dst, src, bytes)                                                                  \
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&dst), (bytes) ? (bytes) : 16)) != cudaSuccess || \
 	    (e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {            \
@@ -147,17 +179,7 @@ racc_cuda_scene* uploadScene(racc_cuda_scene* s, const float* verts4, uint32_t n
 		fail("scene upload failed: %s", cudaGetErrorString(e));
 		return bail();
 	}
-	// device-private packed copies of the node and pair images, derived on the device
-	int launches = 0;
-	if ((e = cudaMalloc(reinterpret_cast<void**>(&s->dTNodes), h.nodes.size() * 64 + 64)) != cudaSuccess ||
-	    (e = cudaMalloc(reinterpret_cast<void**>(&s->dTPairs), h.pairs.size() * 64 + 64)) != cudaSuccess ||
-	    (e = launchPackImages(s->dNodes, (uint32_t)h.nodes.size(), s->dPairs, (uint32_t)h.pairs.size(), s->dTNodes, s->dTPairs, nullptr, &launches)) != cudaSuccess ||
-	    (e = cudaDeviceSynchronize()) != cudaSuccess) {
-		fail("scene packing failed: %s", cudaGetErrorString(e));
-		return bail();
-	}
-	g_launches.fetch_add((uint64_t)launches);
-	return s;
+	return packScene(s);
 }
 
 } // namespace
@@ -237,30 +259,45 @@ racc_cuda_scene* racc_cuda_scene_create(const float* verts4, uint32_t nverts, co
 	racc_cuda_scene* s = new racc_cuda_scene();
 	const char* why = "";
 	bool built = false;
-	if (g_tuning.buildDevice) {
+	s->triangleCount = nindices / 3;
+	if (g_tuning.buildDevice == 2 || (g_tuning.buildDevice == 3 && nindices / 3 >= kAutoDeviceBuildTriangles)) {
+		// the whole build on the device: the images never exist on the host
+		DeviceSceneImages img;
+		if (buildSceneImagesDevice(verts4, nverts, indices, nindices, &img, &why)) {
+			s->dNodes = static_cast<float4*>(img.nodes);
+			s->dPairs = static_cast<float4*>(img.pairs);
+			s->dRemap = img.remap;
+			s->info.node_count = img.nodeCount;
+			s->info.pair_count = img.pairCount;
+			s->info.real_pair_count = img.realPairs;
+			s->info.remap_count = img.remapCount;
+			s->info.depth = img.depth;
+			s->info.triangle_count = s->triangleCount;
+			for (int k = 0; k < 3; ++k) { s->info.bounds_min[k] = img.boundsMin[k]; s->info.bounds_max[k] = img.boundsMax[k]; }
+			cudaError_t e;
+			if ((e = cudaMalloc(reinterpret_cast<void**>(&s->dVerts), (size_t)nverts * 16)) != cudaSuccess ||
+			    (e = cudaMemcpy(s->dVerts, verts4, (size_t)nverts * 16, cudaMemcpyHostToDevice)) != cudaSuccess ||
+			    (e = cudaMalloc(reinterpret_cast<void**>(&s->dIndices), (size_t)nindices * 4)) != cudaSuccess ||
+			    (e = cudaMemcpy(s->dIndices, indices, (size_t)nindices * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+			    (e = cudaMalloc(reinterpret_cast<void**>(&s->dCursors), kCursorRing * sizeof(uint32_t))) != cudaSuccess) {
+				fail("scene upload failed: %s", cudaGetErrorString(e));
+				racc_cuda_scene_destroy(s);
+				return nullptr;
+			}
+			return packScene(s);
+		}
+		fprintf(stderr, "RayAccelerator: device scene build declined (%s); building on the host\n", why);
+	}
+	else if (g_tuning.buildDevice == 1) {
 		built = buildSceneImages(verts4, nverts, indices, nindices, 0, &s->host, &why, buildBvh2Device);
-		if (!built) fprintf(stderr, "RayAccelerator: device scene build declined (%s); building on the host\n", why);
+		if (!built) fprintf(stderr, "RayAccelerator: device SAH build declined (%s); building on the host\n", why);
 	}
 	if (!built && !buildSceneImages(verts4, nverts, indices, nindices, envInt("RACC_B200_BUILD_THREADS", 0), &s->host, &why)) {
 		fail("racc_cuda_scene_create: %s", why);
 		delete s;
 		return nullptr;
 	}
-	s->triangleCount = nindices / 3;
 	return uploadScene(s, verts4, nverts, indices, nindices);
-}
-
-static void fillInfo(const SceneImages& h, uint32_t triangleCount, racc_cuda_scene_info* info) {
-	info->node_count = (uint32_t)h.nodes.size();
-	info->pair_count = (uint32_t)h.pairs.size();
-	info->real_pair_count = h.realPairs;
-	info->remap_count = (uint32_t)h.remap.size();
-	info->depth = h.depth;
-	info->triangle_count = triangleCount;
-	for (int k = 0; k < 3; ++k) {
-		info->bounds_min[k] = h.boundsMin[k];
-		info->bounds_max[k] = h.boundsMax[k];
-	}
 }
 
 racc_cuda_host_images* racc_cuda_build_images(const float* verts4, uint32_t nverts, const uint32_t* indices, uint32_t nindices) {
@@ -341,16 +378,16 @@ void racc_cuda_scene_destroy(racc_cuda_scene* s) {
 
 int racc_cuda_scene_get_info(const racc_cuda_scene* s, racc_cuda_scene_info* info) {
 	if (!s || !info) return fail("racc_cuda_scene_get_info: null argument");
-	fillInfo(s->host, s->triangleCount, info);
+	*info = s->info;
 	return 0;
 }
 
 int racc_cuda_scene_download(const racc_cuda_scene* s, void* nodes, void* pairs, uint32_t* remap) {
 	if (!s) return fail("racc_cuda_scene_download: null scene");
 	// read back from the device so the test sees what the kernel sees
-	if (nodes) RACC_CUDA_CHECK(cudaMemcpy(nodes, s->dNodes, s->host.nodes.size() * sizeof(GpuNode), cudaMemcpyDeviceToHost));
-	if (pairs) RACC_CUDA_CHECK(cudaMemcpy(pairs, s->dPairs, s->host.pairs.size() * sizeof(GpuPair), cudaMemcpyDeviceToHost));
-	if (remap) RACC_CUDA_CHECK(cudaMemcpy(remap, s->dRemap, s->host.remap.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	if (nodes) RACC_CUDA_CHECK(cudaMemcpy(nodes, s->dNodes, (size_t)s->info.node_count * sizeof(GpuNode), cudaMemcpyDeviceToHost));
+	if (pairs) RACC_CUDA_CHECK(cudaMemcpy(pairs, s->dPairs, (size_t)s->info.pair_count * sizeof(GpuPair), cudaMemcpyDeviceToHost));
+	if (remap) RACC_CUDA_CHECK(cudaMemcpy(remap, s->dRemap, (size_t)s->info.remap_count * sizeof(uint32_t), cudaMemcpyDeviceToHost));
 	return 0;
 }
 
@@ -439,7 +476,7 @@ void fillSceneParams(TraceParams& p, racc_cuda_scene* s, racc_cuda_env* env, voi
 	p.env = env ? env->dTexels : nullptr;
 	p.envWidth = env ? env->width : 0;
 	p.envHeight = env ? env->height : 0;
-	p.nodeCount = (uint32_t)s->host.nodes.size();
+	p.nodeCount = s->info.node_count;
 	p.counters = static_cast<unsigned long long*>(device_counters);
 	p.tnodes = s->dTNodes;
 	p.tpairs = s->dTPairs;
@@ -496,13 +533,13 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 			p.streams = static_cast<const StreamRef*>(dRefs);
 		}
 		void* sortScratch = nullptr;
-		const size_t sceneBytes = (s->host.nodes.size() + s->host.pairs.size()) * 64;
+		const size_t sceneBytes = ((size_t)s->info.node_count + s->info.pair_count) * 64;
 		const bool rebin = g_tuning.variant == 3 && total >= 4096 &&
 		                   (g_tuning.sortMode == 1 || (g_tuning.sortMode == 2 && sceneBytes > kAutoSortSceneBytes && total >= (1u << 18)));
 		if (rebin) {
 			// re-bin the launch: visiting order by origin/direction key, results stay index-parallel
 			RACC_CUDA_CHECK(cudaMallocAsync(&sortScratch, raySortScratchBytes(p.total), stream));
-			RACC_CUDA_CHECK(launchRaySort(p, s->host.boundsMin, s->host.boundsMax, g_tuning.sortOriginBits, g_tuning.sortDirBits,
+			RACC_CUDA_CHECK(launchRaySort(p, s->info.bounds_min, s->info.bounds_max, g_tuning.sortOriginBits, g_tuning.sortDirBits,
 			                              g_tuning.sortDirMajor, sortScratch, g_smCount, stream, &p.perm, &launches));
 		}
 		RACC_CUDA_CHECK(launchAny(p, device_counters ? (fullCounters ? 2 : 1) : 0, stream, &launches));

@@ -57,7 +57,8 @@ struct Tuning {
 	int sortOriginBits = 5;  // Morton bits per axis of the ray origin inside the scene bounds
 	int sortDirBits = 3;     // Morton bits per axis of the direction on the unit cube
 	int sortDirMajor = 0;    // 0 origin-major key, 1 direction-major key
-	int buildDevice = 0;     // scene build: 0 SAH tree on the host threads, 1 on the GPU (bvh_build.cu); same tree
+	int buildDevice = 3;     // scene build (same images either way): 0 host threads; 1 SAH tree on the GPU, packing on the
+	                         // host; 2 everything on the GPU (bvh_build.cu); 3 auto = 2 from kAutoDeviceBuildTriangles up
 };
 
 // counterMode: 0 none, 1 rays+hits only, 2 rays, hits, inner-node and pair visits

@@ -78,6 +78,19 @@ typedef bool (*DeviceBvhBuilder)(const float* vertices4, uint32_t vertexCount, c
 bool buildBvh2Device(const float* vertices4, uint32_t vertexCount, const uint32_t* indices, uint32_t triangleCount,
                      std::vector<BuildNode>* nodes, std::vector<uint32_t>* sorted0, const char** error);
 
+// The whole scene build on the device (bvh_build.cu): the three images are produced in device
+// memory in the reference's byte formats; the caller owns the pointers (cudaFree).
+struct DeviceSceneImages {
+	void* nodes = nullptr;   // nodeCount x 64 B
+	void* pairs = nullptr;   // pairCount x 48 B (incl. tail padding)
+	uint32_t* remap = nullptr;
+	uint32_t nodeCount = 0, pairCount = 0, realPairs = 0, remapCount = 0, depth = 0;
+	float boundsMin[3] = {0, 0, 0};
+	float boundsMax[3] = {0, 0, 0};
+};
+bool buildSceneImagesDevice(const float* vertices4, uint32_t vertexCount, const uint32_t* indices, uint32_t indexCount,
+                            DeviceSceneImages* out, const char** error);
+
 // The x86 RCPSS approximation of this host for the 2048 leading-mantissa patterns of [1,2): the
 // reference's leaf-cost test uses _mm_rcp_ss (Bvh2.cpp:462-467), whose bits the device builder
 // reproduces through this table (RCPSS depends on the top 11 mantissa bits only and scales exactly

@@ -354,16 +354,18 @@ def _images_with(build_device, v, i):
         nodes, pairs, remap = s.download()
         return nodes.view(np.uint32).copy(), pairs.view(np.uint32).copy(), remap.copy(), s.info
     finally:
-        rb.set_tuning(build_device=0)
+        rb.set_tuning(build_device=3)
 
 
 def _assert_same_images(v, i, what):
+    """mode 1: SAH tree on the device, packing on the host; mode 2: everything on the device."""
     hn, hp, hr, hinfo = _images_with(0, v, i)
-    dn, dp, dr, dinfo = _images_with(1, v, i)
-    assert hinfo["node_count"] == dinfo["node_count"] and hinfo["depth"] == dinfo["depth"], what
-    assert np.array_equal(hn, dn), f"{what}: node images differ"
-    assert np.array_equal(hp, dp), f"{what}: pair images differ"
-    assert np.array_equal(hr, dr), f"{what}: remap tables differ"
+    for mode in (1, 2):
+        dn, dp, dr, dinfo = _images_with(mode, v, i)
+        assert hinfo == dinfo, f"{what} mode {mode}: scene info differs: {hinfo} vs {dinfo}"
+        assert np.array_equal(hn, dn), f"{what} mode {mode}: node images differ"
+        assert np.array_equal(hp, dp), f"{what} mode {mode}: pair images differ"
+        assert np.array_equal(hr, dr), f"{what} mode {mode}: remap tables differ"
 
 
 def test_device_build_battlefield_identical_to_host(battlefield):
@@ -387,3 +389,19 @@ def test_device_build_synthetic_identical_to_host():
 def test_device_build_large_soup_identical_to_host():
     v, i = rb.synthetic_triangles(1_000_000, seed=7, extent=1000.0, edge=2.0)
     _assert_same_images(v, i, "soup n=1e6")
+
+
+def test_device_built_scene_traces_bit_exact(battlefield, env, images):
+    """A scene whose images never existed on the host (build mode 2) gives the oracle's bits."""
+    rb.set_tuning(build_device=2)
+    try:
+        s = rb.create_scene(battlefield.vertices, battlefield.indices)
+    finally:
+        rb.set_tuning(build_device=3)
+    rays = random_rays(200_000, np.array(s.info["bounds_min"]) - 20, np.array(s.info["bounds_max"]) + 20, seed=77)
+    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1)).cuda()
+    d_res = torch.empty(rays.shape[0] * 4, dtype=torch.float32, device="cuda")
+    rb.trace_device(s, env, [(d_rays.data_ptr(), d_res.data_ptr(), rays.shape[0])])
+    torch.cuda.synchronize()
+    got = d_res.cpu().numpy().view(np.uint32).reshape(-1, 4)
+    assert_bit_exact(got, oracle.traverse(images, rays), "device-built scene")
