@@ -71,8 +71,8 @@ int racc_cuda_abi_version(void);
 
 const char* racc_cuda_last_error(void);
 
-/* replaces racc::createScene()'s GPU branch (Scene.cpp:216-349): host SAH build, pair merge,
- * node packing, upload. verts4: nverts x float4 (w ignored); indices: nindices (multiple of 3).
+/* replaces racc::createScene()'s GPU branch (Scene.cpp:216-349): SAH build, pair merge, node
+ * packing -- on the device by default (bvh_build.cu), on the host threads on request; same images. verts4: nverts x float4 (w ignored); indices: nindices (multiple of 3).
  * The caller keeps ownership of its arrays. NULL on failure. */
 racc_cuda_scene* racc_cuda_scene_create(const float* verts4, uint32_t nverts, const uint32_t* indices, uint32_t nindices);
 
@@ -153,8 +153,12 @@ int racc_cuda_set_variant(int variant);
 /* Launch-shape knobs for benchmark sweeps: key 0 variant, 1 threads per CTA (128/256/512/1024),
  * 2 CTAs per SM (0 = as many as fit), 3 inner nodes staged in shared memory (-1 = as many as
  * fit, 0 = none), 4 refill threshold (idle lanes per warp), 5 leaf-loop bail-out, 6 shared-memory
- * carve-out percent, 7 inner-loop bail-out. Returns the previous value. Also settable through
- * RACC_B200_VARIANT / _BLOCK / _CTAS_PER_SM / _SMEM_NODES / _FETCH_THRESHOLD / _LEAF_BAIL / _INNER_BAIL. */
+ * carve-out percent, 7 inner-loop bail-out, 8 ray re-binning (0 off, 1 on, 2 auto: scenes far larger than L2), 9 / 10
+ * Morton bits per axis of the re-binning key (origin / direction), 11 direction-major key, 12 scene build (0 host,
+ * 1 SAH tree on the device + host packing, 2 all on the device, 3 auto). Returns the previous value. Also settable through
+ * RACC_B200_VARIANT / _BLOCK / _CTAS_PER_SM / _SMEM_NODES / _FETCH_THRESHOLD / _LEAF_BAIL / _INNER_BAIL / _SORT /
+ * _SORT_ORIGIN_BITS / _SORT_DIR_BITS / _SORT_DIR_MAJOR / _BUILD_DEVICE. Variant 3 (default) is the packed-format kernel;
+ * 0-2 are the reference-format kernels kept for A/B. */
 int racc_cuda_set_tuning(int key, int value);
 
 /* ---- synthetic ray streams for the benchmark; not on the hot path ---- */
