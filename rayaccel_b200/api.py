@@ -189,15 +189,29 @@ def trace_host(scene: Scene, environment: Environment | None, rays: np.ndarray, 
     return results
 
 
-def trace_device(scene: Scene, environment: Environment | None, streams, stream=None, counters_ptr: int | None = None,
-                 detail: bool = True) -> None:
-    """Launch ONE traversal over a list of device-resident streams [(rays_ptr, results_ptr, count), ...].
-    Asynchronous on `stream`. counters_ptr: device pointer to a zeroed Counters record (4 x u64);
-    detail=False accumulates rays+hits only (free), detail=True also node/pair visits (slower)."""
+class PackedStreams:
+    """A stream list already marshalled into the C-ABI's descriptor array (pack_streams): lets a caller with
+    thousands of streams keep the Python loop out of a timed region."""
+
+    def __init__(self, arr, n):
+        self.arr, self.n = arr, n
+
+
+def pack_streams(streams) -> PackedStreams:
     n = len(streams)
     arr = (StreamDesc * n)()
     for k, (rp, op, cnt) in enumerate(streams):
         arr[k] = StreamDesc(rp, op, cnt, _lib.STREAM_DEVICE)
+    return PackedStreams(arr, n)
+
+
+def trace_device(scene: Scene, environment: Environment | None, streams, stream=None, counters_ptr: int | None = None,
+                 detail: bool = True) -> None:
+    """Launch ONE traversal over a list of device-resident streams [(rays_ptr, results_ptr, count), ...]
+    (or a PackedStreams). Asynchronous on `stream`. counters_ptr: device pointer to a zeroed Counters record
+    (4 x u64); detail=False accumulates rays+hits only (free), detail=True also node/pair visits (slower)."""
+    packed = streams if isinstance(streams, PackedStreams) else pack_streams(streams)
+    arr, n = packed.arr, packed.n
     lib = _lib.load()
     h = _cuda_stream_handle(stream)
     env = environment._h if environment else None

@@ -437,7 +437,7 @@ struct HostPipeline {
 		if (ready && device == g_device) return 0;
 		release();
 		device = g_device;
-		chunkRays = (uint32_t)envInt("RACC_B200_HOST_CHUNK", 1 << 19);
+		chunkRays = (uint32_t)envInt("RACC_B200_HOST_CHUNK", 1 << 20); // 32 MB of rays per H2D copy: best of 256K..4M (profiles/r01_e2e_chunk_sweep.txt)
 		if (chunkRays < 1024) chunkRays = 1024;
 		RACC_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
 		for (int l = 0; l < kLanes; ++l) {

@@ -58,3 +58,40 @@ def gather_results(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
     if all(s == longest for s in sizes):
         return gathered
     return torch.cat([gathered[r * longest * 4: r * longest * 4 + sizes[r] * 4] for r in range(world)])
+
+
+def interleaved_blocks(total: int, rank: int, world: int, block: int) -> list[tuple[int, int]]:
+    """Load-balanced alternative to shard_bounds: the index range is cut into runs of `block` rays and run b
+    belongs to rank b % world (a frame's sky rows are cheap and its ground rows expensive, so contiguous
+    slices of a pixel-ordered stream are unbalanced). Returns this rank's runs as [begin, end) pairs."""
+    if block <= 0 or not (0 <= rank < world):
+        raise ValueError("bad block size or rank")
+    return [(b, min(b + block, total)) for b in range(rank * block, total, world * block)]
+
+
+def gather_results_interleaved(local: torch.Tensor, total: int, block: int, group=None) -> torch.Tensor:
+    """All-gather for interleaved_blocks: `local` holds this rank's runs back to back (4 float32 words per
+    ray); returns the full index-parallel result array on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    counts = [sum(e - b for b, e in interleaved_blocks(total, r, world, block)) for r in range(world)]
+    if local.numel() != counts[rank] * 4:
+        raise ValueError(f"rank {rank} holds {local.numel() // 4} results, its runs hold {counts[rank]}")
+    if world == 1:
+        return local.clone()
+    longest = max(counts)
+    padded = torch.zeros(longest * 4, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    gathered = torch.empty(world * longest * 4, dtype=local.dtype, device=local.device).view(world, longest, 4)
+    dist.all_gather_into_tensor(gathered.view(-1), padded, group=group)
+    out = torch.empty(total, 4, dtype=local.dtype, device=local.device)
+    n_blocks = (total + block - 1) // block
+    for r in range(world):
+        # rank r's k-th run is global block r + k*world
+        mine = torch.arange(r, n_blocks, world, device=local.device)
+        if mine.numel() == 0:
+            continue
+        idx = (mine[:, None] * block + torch.arange(block, device=local.device)[None, :]).reshape(-1)
+        idx = idx[idx < total]
+        out[idx] = gathered[r, : idx.numel()]
+    return out.view(-1)

@@ -60,7 +60,13 @@ def _worker(rank, world, port, total, out_dir):
         counters = torch.tensor([hi - lo, int(cnt["hit"].sum()), int(cnt["inner"].astype(np.int64).sum()), int(cnt["pairs"].astype(np.int64).sum())],
                                 dtype=torch.int64)
         sharding.reduce_frame_counters(counters)
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), full=full.numpy().view(np.uint32).reshape(-1, 4), counters=counters.numpy())
+        # the load-balanced policy: runs of 500 rays dealt round-robin, traced run by run, gathered back in index order
+        runs = sharding.interleaved_blocks(total, rank, world, 500)
+        parts = [oracle.traverse(images, rays[b:e], threads=2).view(np.float32).reshape(-1) for b, e in runs]
+        local_i = torch.from_numpy(np.concatenate(parts).copy()) if parts else torch.zeros(0)
+        full_i = sharding.gather_results_interleaved(local_i, total, 500)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), full=full.numpy().view(np.uint32).reshape(-1, 4), counters=counters.numpy(),
+                 full_interleaved=full_i.numpy().view(np.uint32).reshape(-1, 4))
     finally:
         dist.destroy_process_group()
 
@@ -74,6 +80,7 @@ def test_two_rank_sharding_matches_single_process(tmp_path, total):
     for rank in range(world):
         out = np.load(tmp_path / f"rank{rank}.npz")
         assert np.array_equal(out["full"], want), f"rank {rank}: gathered results differ from the single-process golden run"
+        assert np.array_equal(out["full_interleaved"], want), f"rank {rank}: interleaved gather differs from the golden run"
         assert out["counters"][0] == total
         assert out["counters"][1] == int((want[:, 0] != 0xFFFFFFFF).sum())
         assert out["counters"][2] == int(g["inner"][:total].astype(np.int64).sum())
