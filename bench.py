@@ -58,6 +58,33 @@ def emit(line: dict) -> None:
     out.flush()
 
 
+def bind_near_gpu(local_rank: int):
+    """Multi-rank runs: pin this process to the CPUs of the NUMA node its GPU hangs off BEFORE any pinned host
+    buffer is allocated (first touch then places the staging pages next to the GPU's PCIe root). Without this the
+    8 ranks' H2D/D2H streams all cross the socket interconnect. Best effort: returns a note for the JSON line."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa node unknown"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return f"numa node {node}: none of its CPUs are available to this process"
+        os.sched_setaffinity(0, allowed)
+        return f"numa node {node}, {len(allowed)} CPUs"
+    except Exception as e:  # no sysfs, no permission, older torch: run unbound
+        return f"unbound ({type(e).__name__})"
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -232,6 +259,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    host_binding = bind_near_gpu(local_rank) if world > 1 else "single rank: unbound"
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     rb.init(local_rank)
@@ -417,7 +445,8 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
                                  "(profiles/r01_ncu_bench_launch_packed.txt)"},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": 32 * rays_per_step, "d2h_bytes_per_step": 16 * rays_per_step,
                     "ms_per_step": round(e2e_ms, 3), "wall_ms_per_step": round(e2e_wall_ms / e2e_steps, 3), "steps": e2e_steps,
-                    "results_match_device_run": e2e_ok, "path": "racc_cuda_trace with RACC_CUDA_STREAM_HOST descriptors, pinned host memory"},
+                    "results_match_device_run": e2e_ok, "host_binding": host_binding,
+                    "path": "racc_cuda_trace with RACC_CUDA_STREAM_HOST descriptors, pinned host memory"},
             "gpu_launches": int(launches), "clocks": clocks, "frame_hits_all_ranks": hits_all_ranks,
         }
         if cpu_baseline is not None:
