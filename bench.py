@@ -99,9 +99,9 @@ def ncu_traffic():
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_bench_traffic.json")) as f:
             t = json.load(f)
-        return float(t["dram_bytes_per_launch"]), t.get("source", "profiles/ncu_bench_traffic.json")
+        return float(t["dram_bytes_per_launch"]), t.get("source", "profiles/ncu_bench_traffic.json"), t.get("limiters")
     except Exception:
-        return None, None
+        return None, None, None
 
 
 def workload_name():
@@ -423,7 +423,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic()
+        traffic, traffic_src, limiters = ncu_traffic()
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -437,12 +437,13 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "kernel": "tracePackedKernel", "kernel_ms": round(kernel_ms, 4),
                          "algorithmic_bytes_per_launch": alg_bytes, "compulsory_bytes_per_launch": 48 * rays_per_step,
-                         "peak_source": peak_src, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "traffic_source": traffic_src, "ncu_limiters": limiters,
                          "note": "algorithmic bytes = sum over rays of 32+16+64*N_inner+48*N_pair+4*[hit]+64*[miss] (SURVEY.md 8d), visits counted "
                                  "by the kernel itself. frac > 1 is expected here: battlefield's 3.2 MB scene is L1/L2-resident, so of the algorithmic "
                                  "bytes only the compulsory 48 B/ray (rays in, results out) reach DRAM -- `traffic` (ncu dram read+write per launch) "
-                                 "equals compulsory_bytes_per_launch, i.e. no wasted re-reads; the kernel is issue/latency-bound, not HBM-bound "
-                                 "(profiles/r01_ncu_bench_launch_packed.txt)"},
+                                 "equals compulsory_bytes_per_launch, i.e. no wasted re-reads. What bounds the kernel is the L1 data pipe (ncu_limiters, from "
+                                 "the committed ncu --set full capture of this command: l1tex data-pipe wavefronts ~80 % of peak, issue slots ~66 %), "
+                                 "not HBM (profiles/r01_ncu_bench_launch_packed.txt)"},
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": 32 * rays_per_step, "d2h_bytes_per_step": 16 * rays_per_step,
                     "ms_per_step": round(e2e_ms, 3), "wall_ms_per_step": round(e2e_wall_ms / e2e_steps, 3), "steps": e2e_steps,
                     "results_match_device_run": e2e_ok, "host_binding": host_binding,
