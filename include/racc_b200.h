@@ -146,6 +146,13 @@ uint64_t racc_cuda_launch_count(void);
  * iterations, [5] refills. Synchronises the device. reset != 0 zeroes them afterwards. */
 int racc_cuda_debug_warp_stats(uint64_t* out8, int reset);
 
+/* Diagnostics (not in the reference): the 2048-entry table through which the device scene builder
+ * reproduces the host's _mm_rcp_ss (the reference's leaf-cost test, Bvh2.cpp:462-467): out2048[i] =
+ * RCPSS(1 + i/2048). Host only, no CUDA call. Returns 0 when this CPU's RCPSS follows the table
+ * model (result depends on the top 11 mantissa bits, scales exactly with the exponent), else 1 --
+ * the device builder then declines and scenes are built on the host threads. */
+int racc_cuda_debug_rcp_table(float* out2048);
+
 /* Engine tuning knob (not in the reference): which traversal kernel variant racc_cuda_trace uses.
  * 0 = default. See DESIGN.md section 5. Returns the previous value. */
 int racc_cuda_set_variant(int variant);

@@ -62,6 +62,7 @@ SYMBOLS = {
     "racc_cuda_stream_destroy": (None, [_P]),
     "racc_cuda_sync": (ctypes.c_int, [_P]),
     "racc_cuda_launch_count": (ctypes.c_uint64, []),
+    "racc_cuda_debug_rcp_table": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float)]),
     "racc_cuda_debug_warp_stats": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]),
     "racc_cuda_set_variant": (ctypes.c_int, [ctypes.c_int]),
     "racc_cuda_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),

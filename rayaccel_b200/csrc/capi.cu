@@ -245,6 +245,11 @@ int racc_cuda_set_tuning(int key, int value) {
 
 uint64_t racc_cuda_launch_count(void) { return g_launches.load(); }
 
+int racc_cuda_debug_rcp_table(float* out2048) {
+	if (!out2048) return fail("racc_cuda_debug_rcp_table: null argument");
+	return fillRcpTable(out2048) ? 0 : 1;
+}
+
 int racc_cuda_debug_warp_stats(uint64_t* out8, int reset) {
 	if (!out8) return fail("racc_cuda_debug_warp_stats: null argument");
 	if (ensureInit()) return -1;

@@ -135,3 +135,28 @@ def test_build_is_deterministic_and_thread_count_independent(battlefield):
     assert np.array_equal(a.nodes.view(np.uint32), b.nodes.view(np.uint32))
     assert np.array_equal(a.pairs.view(np.uint32), b.pairs.view(np.uint32))
     assert np.array_equal(a.remap, b.remap)
+
+
+def test_rcpss_table_model_of_the_device_builder():
+    """The device scene builder replays the reference's _mm_rcp_ss leaf-cost test (Bvh2.cpp:462-467) through a
+    table of this host's RCPSS values; check the table is a sane 12-bit reciprocal and that the model holds here."""
+    import ctypes
+    from rayaccel_b200 import _lib
+    table = (ctypes.c_float * 2048)()
+    rc = _lib.load().racc_cuda_debug_rcp_table(table)
+    t = np.frombuffer(table, dtype=np.float32)
+    x = 1.0 + np.arange(2048) / 2048.0
+    assert np.all(np.abs(t * x - 1.0) <= 1.5 * 2.0 ** -12 + 2.0 ** -11), "not a reciprocal approximation"
+    assert np.all(np.diff(t) <= 0), "RCPSS table must be monotone"
+    assert rc == 0, "this CPU's RCPSS does not follow the table model: the device builder will decline (host build is used)"
+
+
+def test_interleaved_blocks_partition():
+    from rayaccel_b200 import sharding
+    for total, world, block in ((10, 3, 4), (4097, 2, 500), (8294400, 8, 16384), (5, 8, 16)):
+        seen = np.zeros(total, dtype=np.int32)
+        for r in range(world):
+            for b, e in sharding.interleaved_blocks(total, r, world, block):
+                assert 0 <= b < e <= total and e - b <= block
+                seen[b:e] += 1
+        assert np.all(seen == 1)
