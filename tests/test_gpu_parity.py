@@ -252,6 +252,14 @@ def test_full_size_properties(scene, env, battlefield):
     rb.set_tuning(**DEFAULT)
     torch.cuda.synchronize()
     assert torch.equal(d_a.view(torch.int32), d_b.view(torch.int32))
+    # re-binned visiting order (raysort.cu) and the reference-format bail-out kernel: same bits again
+    for other in (dict(sort=1, sort_origin_bits=6, sort_dir_bits=4), dict(variant=2)):
+        d_b.zero_()
+        rb.set_tuning(**{**DEFAULT, **other})
+        rb.trace_device(scene, env, [(d_rays.data_ptr(), d_b.data_ptr(), n)])
+        rb.set_tuning(**DEFAULT)
+        torch.cuda.synchronize()
+        assert torch.equal(d_a.view(torch.int32), d_b.view(torch.int32)), other
     res = d_a.view(-1, 4)
     ids = res[:, 0].view(torch.int32)
     hit = ids != -1
