@@ -88,6 +88,7 @@ int ensureInit() {
 	g_tuning.sortDirBits = envInt("RACC_B200_SORT_DIR_BITS", g_tuning.sortDirBits);
 	g_tuning.sortDirMajor = envInt("RACC_B200_SORT_DIR_MAJOR", g_tuning.sortDirMajor);
 	g_tuning.buildDevice = envInt("RACC_B200_BUILD_DEVICE", g_tuning.buildDevice);
+	g_tuning.smemStack = envInt("RACC_B200_SMEM_STACK", g_tuning.smemStack);
 	g_initialised = true;
 	return 0;
 }
@@ -236,6 +237,7 @@ int racc_cuda_set_tuning(int key, int value) {
 	case 10: slot = &g_tuning.sortDirBits; break;
 	case 11: slot = &g_tuning.sortDirMajor; break;
 	case 12: slot = &g_tuning.buildDevice; break;
+	case 13: slot = &g_tuning.smemStack; break;
 	default: return fail("unknown tuning key %d", key);
 	}
 	const int previous = *slot;
@@ -488,9 +490,16 @@ void fillSceneParams(TraceParams& p, racc_cuda_scene* s, racc_cuda_env* env, voi
 	p.perm = nullptr;
 }
 
-cudaError_t launchAny(const TraceParams& p, int counterMode, cudaStream_t stream, int* launches) {
-	return g_tuning.variant == 3 ? launchTracePacked(p, g_tuning, counterMode, g_smCount, stream, launches)
-	                             : launchTrace(p, g_tuning, counterMode, g_smCount, stream, launches);
+bool sceneExceedsL2(const racc_cuda_scene* s) {
+	return ((size_t)s->info.node_count + s->info.pair_count) * 64 > kAutoSortSceneBytes;
+}
+
+cudaError_t launchAny(const racc_cuda_scene* s, const TraceParams& p, int counterMode, cudaStream_t stream, int* launches) {
+	if (g_tuning.variant != 3)
+		return launchTrace(p, g_tuning, counterMode, g_smCount, stream, launches);
+	Tuning t = g_tuning;
+	if (t.smemStack < 0) t.smemStack = sceneExceedsL2(s) ? 16 : 0;
+	return launchTracePacked(p, t, counterMode, g_smCount, stream, launches);
 }
 
 int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams,
@@ -538,16 +547,15 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 			p.streams = static_cast<const StreamRef*>(dRefs);
 		}
 		void* sortScratch = nullptr;
-		const size_t sceneBytes = ((size_t)s->info.node_count + s->info.pair_count) * 64;
 		const bool rebin = g_tuning.variant == 3 && total >= 4096 &&
-		                   (g_tuning.sortMode == 1 || (g_tuning.sortMode == 2 && sceneBytes > kAutoSortSceneBytes && total >= (1u << 18)));
+		                   (g_tuning.sortMode == 1 || (g_tuning.sortMode == 2 && sceneExceedsL2(s) && total >= (1u << 18)));
 		if (rebin) {
 			// re-bin the launch: visiting order by origin/direction key, results stay index-parallel
 			RACC_CUDA_CHECK(cudaMallocAsync(&sortScratch, raySortScratchBytes(p.total), stream));
 			RACC_CUDA_CHECK(launchRaySort(p, s->info.bounds_min, s->info.bounds_max, g_tuning.sortOriginBits, g_tuning.sortDirBits,
 			                              g_tuning.sortDirMajor, sortScratch, g_smCount, stream, &p.perm, &launches));
 		}
-		RACC_CUDA_CHECK(launchAny(p, device_counters ? (fullCounters ? 2 : 1) : 0, stream, &launches));
+		RACC_CUDA_CHECK(launchAny(s, p, device_counters ? (fullCounters ? 2 : 1) : 0, stream, &launches));
 		if (sortScratch) RACC_CUDA_CHECK(cudaFreeAsync(sortScratch, stream));
 		if (dRefs) RACC_CUDA_CHECK(cudaFreeAsync(dRefs, stream));
 	}
@@ -591,7 +599,7 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 			p.single.begin = 0;
 			p.single.count = filled;
 			p.cursor = s->dCursors + (s->nextCursor.fetch_add(1) % kCursorRing);
-			RACC_CUDA_CHECK(launchAny(p, device_counters ? (fullCounters ? 2 : 1) : 0, pipe.lane[l], &launches));
+			RACC_CUDA_CHECK(launchAny(s, p, device_counters ? (fullCounters ? 2 : 1) : 0, pipe.lane[l], &launches));
 			for (int k = 0; k < nsegs; ++k)
 				RACC_CUDA_CHECK(cudaMemcpyAsync(segs[k].hResults, pipe.dResults[l] + segs[k].offset, (size_t)segs[k].n * 16, cudaMemcpyDeviceToHost, pipe.lane[l]));
 			++chunk;

@@ -55,8 +55,11 @@ struct Tuning {
 	int sortMode = 2;        // 0 arrival order, 1 re-bin every device-resident launch, 2 auto: re-bin when the scene
 	                         // is far larger than L2 (traversal is then DRAM-bound and coherence pays for the sort)
 	int sortOriginBits = 5;  // Morton bits per axis of the ray origin inside the scene bounds
-	int sortDirBits = 3;     // Morton bits per axis of the direction on the unit cube
+	int sortDirBits = 0;     // Morton bits per axis of the direction on the unit cube (0: origin only, measured best on config 5)
 	int sortDirMajor = 0;    // 0 origin-major key, 1 direction-major key
+	int smemStack = -1;      // variant 3: entries of every traversal stack kept in shared memory: 0, 8, 16, or -1 = auto
+	                         // (16 when the scene is far larger than L2: the stacks then stop competing with the scene for
+	                         // L1 lines, +10 % on config 5; on L2-resident scenes the all-local stack is 4 % faster)
 	int buildDevice = 3;     // scene build (same images either way): 0 host threads; 1 SAH tree on the GPU, packing on the
 	                         // host; 2 everything on the GPU (bvh_build.cu); 3 auto = 2 from kAutoDeviceBuildTriangles up
 };

@@ -23,6 +23,8 @@
 // in a coherence-improving order; results are still written index-parallel to the rays.
 #include "traverse_common.cuh"
 
+#include <type_traits>
+
 namespace racc_b200 {
 namespace {
 
@@ -139,9 +141,57 @@ __device__ __forceinline__ void pairTestPacked(u64 pairBase, uint32_t index, Ray
 	r.tFar = t;
 }
 
+// Traversal stack whose first kSm entries live in shared memory, laid out [entry][thread] so that the
+// 32 lanes of a warp always hit 32 different banks whatever their depths: a push or pop is ONE data-pipe
+// wavefront per warp, where the thread-interleaved local-memory stack costs one per lane once the lanes'
+// depths differ (profiles/r01_l1_wavefront_microbench.md). Deeper entries spill to local memory
+// (Kernels.h:166 allows 64 in total).
+template <int kSm, int kBlock>
+struct HybridStack {
+	uint32_t sp;          // entries on the stack
+	uint32_t smAddr;      // shared-space byte address of entry 0 of this thread
+	uint32_t localAddr;   // local-space byte address of the first spilled entry
+	__device__ __forceinline__ void attach(uint32_t (*sm)[kBlock], uint32_t* spill) {
+		sp = 0;
+		smAddr = (uint32_t)__cvta_generic_to_shared(&sm[0][threadIdx.x]);
+		localAddr = (uint32_t)__cvta_generic_to_local(spill);
+	}
+	__device__ __forceinline__ void reset() { sp = 0; }
+	__device__ __forceinline__ bool empty() const { return sp == 0; }
+	__device__ __forceinline__ void pushIf(bool pred, uint32_t v) {
+		if (pred) {
+			if (sp < (uint32_t)kSm) asm volatile("st.shared.u32 [%0], %1;" ::"r"(smAddr + sp * (uint32_t)(kBlock * 4)), "r"(v) : "memory");
+			else asm volatile("st.local.u32 [%0], %1;" ::"l"((u64)(localAddr + (sp - kSm) * 4u)), "r"(v) : "memory");
+			++sp;
+		}
+	}
+	__device__ __forceinline__ uint32_t pop() {
+		--sp;
+		uint32_t v;
+		if (sp < (uint32_t)kSm) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smAddr + sp * (uint32_t)(kBlock * 4)) : "memory");
+		else asm volatile("ld.local.u32 %0, [%1];" : "=r"(v) : "l"((u64)(localAddr + (sp - kSm) * 4u)) : "memory");
+		return v;
+	}
+};
+
+// The all-local stack with the same interface (predicated STL, no branch around it).
+struct PlainStack : LocalStack {
+	__device__ __forceinline__ void pushIf(bool pred, uint32_t v) {
+		asm volatile(
+		    "{\n\t.reg .pred pu;\n\t"
+		    "setp.ne.u32 pu, %2, 0;\n\t"
+		    "@pu st.local.u32 [%1], %3;\n\t"
+		    "@pu add.u32 %0, %0, 4;\n\t}"
+		    : "+r"(top)
+		    : "l"((u64)top), "r"((uint32_t)pred), "r"(v)
+		    : "memory");
+	}
+};
+
 // One inner-node step (Kernels.h:170-199) on a packed node. `node` has bit 31 set. Returns the next
 // reference: the nearer hit child, else the popped entry, else 0.
-__device__ __forceinline__ uint32_t innerStepPacked(u64 nodeBase, uint32_t node, const RayState& r, LocalStack& stack) {
+template <typename Stack>
+__device__ __forceinline__ uint32_t innerStepPacked(u64 nodeBase, uint32_t node, const RayState& r, Stack& stack) {
 	u64 a;
 	asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(a) : "r"(node), "l"(nodeBase)); // nodeBase is biased by -(2^31 * 64)
 	u64 lx, ly, lz, rx, ry, rz, refs, unused;
@@ -176,20 +226,13 @@ __device__ __forceinline__ uint32_t innerStepPacked(u64 nodeBase, uint32_t node,
 	// measured 2x slower on DRAM-bound scenes (profiles/r01_c5_predicated_pop.md): an LDL issued with
 	// most or all lanes off still sits in the load pipeline behind the warp's outstanding misses.
 	uint32_t next = any ? nearRef : 0u;
-	asm volatile(
-	    "{\n\t.reg .pred pu;\n\t"
-	    "setp.ne.u32 pu, %2, 0;\n\t"
-	    "@pu st.local.u32 [%1], %3;\n\t"
-	    "@pu add.u32 %0, %0, 4;\n\t}"
-	    : "+r"(stack.top)
-	    : "l"((u64)stack.top), "r"((uint32_t)both), "r"(farRef)
-	    : "memory");
+	stack.pushIf(both, farRef);
 	if (!any && !stack.empty())
 		next = stack.pop();
 	return next;
 }
 
-template <bool kCount, int kBlock, int kMinBlocks>
+template <bool kCount, int kBlock, int kMinBlocks, int kSmStack>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const TraceParams p, const int fetchThreshold, const int innerBail, const int leafBail) {
 	const unsigned lane = threadIdx.x & 31;
 	const unsigned ltMask = (1u << lane) - 1u;
@@ -201,9 +244,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const Tr
 
 	bool exhausted = false; // warp-uniform: the cursor has run past the last ray
 	RayState r; HitState h;
-	uint32_t stackStorage[kStackSize];
-	LocalStack stack;
-	stack.attach(stackStorage);
+	__shared__ uint32_t smStack[kSmStack ? kSmStack : 1][kSmStack ? kBlock : 1];
+	uint32_t stackStorage[kStackSize - kSmStack];
+	typename std::conditional<(kSmStack > 0), HybridStack<(kSmStack > 0 ? kSmStack : 1), kBlock>, PlainStack>::type stack;
+	if constexpr (kSmStack > 0) stack.attach(smStack, stackStorage);
+	else stack.attach(stackStorage);
 	uint32_t node = 0;         // 0: no ray in flight on this lane; bit 31: at an inner node; else at a leaf
 	float4* outPtr = nullptr;  // non-null: the lane holds a ray (in flight, or finished and not yet written)
 	unsigned long long cInner = 0, cPairs = 0;
@@ -302,16 +347,23 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const Tr
 	}
 }
 
-template <bool kCount, int kBlock, int kMinBlocks>
+template <bool kCount, int kBlock, int kMinBlocks, int kSmStack = 0>
 cudaError_t launchPacked(const TraceParams& p, const Tuning& t, int smCount, cudaStream_t stream) {
-	auto kernel = tracePackedKernel<kCount, kBlock, kMinBlocks>;
+	auto kernel = tracePackedKernel<kCount, kBlock, kMinBlocks, kSmStack>;
 	static thread_local int plannedDevice = -1, plannedCarveout = -2, resident = 1;
 	int device = 0;
 	cudaGetDevice(&device);
 	cudaError_t err;
 	if (plannedDevice != device || plannedCarveout != t.carveout) {
-		// no shared memory at all: the whole 228 KB of each SM serves as L1 for nodes, pairs and stacks
-		err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, t.carveout >= 0 ? t.carveout : 0);
+		// shared memory only for the (optional) stack tops: the rest of the 228 KB of each SM serves as L1
+		int carve = 0;
+		if (kSmStack > 0) {
+			int smPerSm = 233472;
+			cudaDeviceGetAttribute(&smPerSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+			carve = (int)(((size_t)(kSmStack * kBlock * 4 + 1024) * kMinBlocks * 100 + smPerSm - 1) / smPerSm);
+			if (carve > 100) carve = 100;
+		}
+		err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, t.carveout >= 0 ? t.carveout : carve);
 		if (err != cudaSuccess) return err;
 		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, kBlock, 0);
 		if (err != cudaSuccess) return err;
@@ -333,6 +385,10 @@ cudaError_t launchPacked(const TraceParams& p, const Tuning& t, int smCount, cud
 
 template <bool kCount>
 cudaError_t dispatchPacked(const TraceParams& p, const Tuning& t, int smCount, cudaStream_t stream) {
+	if (t.smemStack > 0 && t.blockThreads == 256) { // stack tops in shared memory: 256 x 5 only
+		if (t.smemStack <= 8) return launchPacked<kCount, 256, 5, 8>(p, t, smCount, stream);
+		return launchPacked<kCount, 256, 5, 16>(p, t, smCount, stream);
+	}
 	switch (t.blockThreads * 100 + t.ctasPerSm) {
 	case 12800 + 8: return launchPacked<kCount, 128, 8>(p, t, smCount, stream);
 	case 12800 + 10: return launchPacked<kCount, 128, 10>(p, t, smCount, stream);

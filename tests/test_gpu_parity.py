@@ -30,13 +30,15 @@ VARIANTS = [
     dict(variant=3, ctas_per_sm=4, fetch_threshold=1, inner_bail=32, leaf_bail=32),
     dict(variant=3, block=128, ctas_per_sm=10, inner_bail=0, leaf_bail=0),
     dict(variant=3, block=512, ctas_per_sm=2, inner_bail=20, leaf_bail=1, fetch_threshold=32),
+    dict(variant=3, smem_stack=16),
+    dict(variant=3, smem_stack=8, fetch_threshold=4),
     dict(variant=3, sort=1),
     dict(variant=3, sort=1, sort_origin_bits=10, sort_dir_bits=0),
     dict(variant=3, sort=1, sort_origin_bits=0, sort_dir_bits=4, sort_dir_major=1),
     dict(variant=3, sort=1, sort_origin_bits=6, sort_dir_bits=4, sort_dir_major=1, fetch_threshold=8),
 ]
 DEFAULT = dict(variant=3, block=256, ctas_per_sm=5, smem_nodes=0, fetch_threshold=16, inner_bail=8, leaf_bail=4,
-               sort=0, sort_origin_bits=5, sort_dir_bits=3, sort_dir_major=0)
+               sort=0, sort_origin_bits=5, sort_dir_bits=0, sort_dir_major=0, smem_stack=0)
 
 
 @pytest.fixture(scope="module")

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import rayaccel_b200 as rb  # noqa: E402
 
 tuning = dict(variant=3, block=256, ctas_per_sm=5, smem_nodes=0, fetch_threshold=16, leaf_bail=4, inner_bail=8, carveout=-1,
-              sort=0, sort_origin_bits=5, sort_dir_bits=3, sort_dir_major=0)
+              sort=0, sort_origin_bits=5, sort_dir_bits=0, sort_dir_major=0, smem_stack=0)
 if len(sys.argv) > 1 and sys.argv[1]:
     tuning.update({k: int(v) for k, v in (p.split("=") for p in sys.argv[1].split(","))})
 repeat = int(sys.argv[2]) if len(sys.argv) > 2 else 2
