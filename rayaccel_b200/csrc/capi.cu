@@ -551,9 +551,15 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 		                   (g_tuning.sortMode == 1 || (g_tuning.sortMode == 2 && sceneExceedsL2(s) && total >= (1u << 18)));
 		if (rebin) {
 			// re-bin the launch: visiting order by origin/direction key, results stay index-parallel
-			RACC_CUDA_CHECK(cudaMallocAsync(&sortScratch, raySortScratchBytes(p.total), stream));
-			RACC_CUDA_CHECK(launchRaySort(p, s->info.bounds_min, s->info.bounds_max, g_tuning.sortOriginBits, g_tuning.sortDirBits,
-			                              g_tuning.sortDirMajor, sortScratch, g_smCount, stream, &p.perm, &launches));
+			// an optimisation only: when the scratch does not fit, trace in arrival order
+			if (cudaMallocAsync(&sortScratch, raySortScratchBytes(p.total), stream) != cudaSuccess) {
+				cudaGetLastError();
+				sortScratch = nullptr;
+			}
+			else {
+				RACC_CUDA_CHECK(launchRaySort(p, s->info.bounds_min, s->info.bounds_max, g_tuning.sortOriginBits, g_tuning.sortDirBits,
+				                              g_tuning.sortDirMajor, sortScratch, g_smCount, stream, &p.perm, &launches));
+			}
 		}
 		RACC_CUDA_CHECK(launchAny(s, p, device_counters ? (fullCounters ? 2 : 1) : 0, stream, &launches));
 		if (sortScratch) RACC_CUDA_CHECK(cudaFreeAsync(sortScratch, stream));
