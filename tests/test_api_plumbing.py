@@ -117,3 +117,22 @@ def test_reference_renderers_unchanged_gpu():
     assert out["nonblack_fraction"] > 0.9 and out["not_finite"] == 0
     rc, out = run_json([exe, "--whitted", "--width", "512", "--height", "512", "--depth", "1", "--frames", "2"])
     assert rc == 0 and out["nonblack_fraction"] > 0.9 and out["not_finite"] == 0
+
+
+def test_scheduler_under_thread_sanitizer(tmp_path):
+    """The scheduler state machine (racc_api.cpp) under ThreadSanitizer, contended configuration: no data race reports.
+    (The reference guards all of its scheduler state with one mutex, RayAccelerator.cpp:48-415, and was never checked.)"""
+    exe = str(tmp_path / "plumbing_tsan")
+    src = [os.path.join(HARNESS, "plumbing_client.cpp"), os.path.join(HARNESS, "fake_capi.cpp"),
+           os.path.join(ROOT, "rayaccel_b200", "csrc", "racc_api.cpp"), os.path.join(ROOT, "rayaccel_b200", "csrc", "scene_build.cpp")]
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-mavx2", "-mfma", "-ffp-contract=off", "-pthread", "-I", os.path.join(ROOT, "include")] + src + \
+          ["-L", os.path.dirname(oracle.ORACLE_SO), "-loracle", "-Wl,-rpath," + os.path.dirname(oracle.ORACLE_SO), "-o", exe]
+    built = subprocess.run(cmd, capture_output=True, text=True)
+    if built.returncode != 0:
+        pytest.skip("this toolchain cannot build with -fsanitize=thread: " + built.stderr[-200:])
+    for args in (["--threads", "8", "--submitters", "3", "--rays", "200000", "--frames", "2"],
+                 ["--spawn", "1000", "--shade", "333", "--batch", "777", "--inflight", "5000", "--rays", "40001"]):
+        p = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600, cwd=ROOT, env={**os.environ, "TSAN_OPTIONS": "halt_on_error=0"})
+        assert "WARNING: ThreadSanitizer" not in p.stderr, p.stderr[:2000]
+        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        assert p.returncode == 0 and lines and json.loads(lines[-1])["ok"]
