@@ -89,6 +89,7 @@ int ensureInit() {
 	g_tuning.sortDirMajor = envInt("RACC_B200_SORT_DIR_MAJOR", g_tuning.sortDirMajor);
 	g_tuning.buildDevice = envInt("RACC_B200_BUILD_DEVICE", g_tuning.buildDevice);
 	g_tuning.smemStack = envInt("RACC_B200_SMEM_STACK", g_tuning.smemStack);
+	g_tuning.hostZeroCopy = envInt("RACC_B200_HOST_ZERO_COPY", g_tuning.hostZeroCopy);
 	g_initialised = true;
 	return 0;
 }
@@ -238,6 +239,7 @@ int racc_cuda_set_tuning(int key, int value) {
 	case 11: slot = &g_tuning.sortDirMajor; break;
 	case 12: slot = &g_tuning.buildDevice; break;
 	case 13: slot = &g_tuning.smemStack; break;
+	case 14: slot = &g_tuning.hostZeroCopy; break;
 	default: return fail("unknown tuning key %d", key);
 	}
 	const int previous = *slot;
@@ -512,21 +514,43 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 	std::vector<StreamRef> refs; // device-resident streams: one launch for all of them
 	std::vector<const racc_cuda_stream_desc*> hostStreams;
 	uint64_t total = 0;
+	bool zeroCopy = false; // some stream of the launch lives in host memory: do not re-bin (random gathers over PCIe)
 	for (uint32_t i = 0; i < nstreams; ++i) {
 		const racc_cuda_stream_desc& d = streams[i];
 		if (!d.count) continue;
 		if (!d.rays || !d.results) return fail("racc_cuda_trace: stream %u has null buffers", i);
+		const void* rays = d.rays;
+		void* results = d.results;
 		if (d.flags & RACC_CUDA_STREAM_HOST) {
-			hostStreams.push_back(&d);
-			continue;
+			// Pinned, mapped host memory (racc_cuda_host_alloc, cudaHostAlloc, torch pin_memory) can be read and
+			// written by the kernel itself over PCIe: no staging copies, one launch, H2D and D2H traffic interleaved
+			// ray by ray. Anything else goes through the staging pipeline below.
+			bool direct = false;
+			if (g_tuning.hostZeroCopy && !((reinterpret_cast<uintptr_t>(d.rays) | reinterpret_cast<uintptr_t>(d.results)) & 15)) {
+				cudaPointerAttributes ar{}, ao{};
+				if (cudaPointerGetAttributes(&ar, d.rays) == cudaSuccess && cudaPointerGetAttributes(&ao, d.results) == cudaSuccess &&
+				    ar.type == cudaMemoryTypeHost && ao.type == cudaMemoryTypeHost && ar.devicePointer && ao.devicePointer) {
+					rays = ar.devicePointer;
+					results = ao.devicePointer;
+					direct = true;
+					zeroCopy = true;
+				}
+				else {
+					cudaGetLastError(); // unregistered host memory is reported as an error by older runtimes
+				}
+			}
+			if (!direct) {
+				hostStreams.push_back(&d);
+				continue;
+			}
 		}
-		if ((reinterpret_cast<uintptr_t>(d.rays) & 15) || (reinterpret_cast<uintptr_t>(d.results) & 15))
+		if ((reinterpret_cast<uintptr_t>(rays) & 15) || (reinterpret_cast<uintptr_t>(results) & 15))
 			return fail("racc_cuda_trace: stream %u buffers must be 16-byte aligned", i);
 		StreamRef ref;
 		ref.begin = (uint32_t)total;
 		ref.count = d.count;
-		ref.rays = static_cast<const DevRay*>(d.rays);
-		ref.results = static_cast<float4*>(d.results);
+		ref.rays = static_cast<const DevRay*>(rays);
+		ref.results = static_cast<float4*>(results);
 		refs.push_back(ref);
 		total += d.count;
 		if (total > 0x7fffffffull) return fail("racc_cuda_trace: more than 2^31-1 rays in one launch");
@@ -547,7 +571,7 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 			p.streams = static_cast<const StreamRef*>(dRefs);
 		}
 		void* sortScratch = nullptr;
-		const bool rebin = g_tuning.variant == 3 && total >= 4096 &&
+		const bool rebin = g_tuning.variant == 3 && total >= 4096 && !zeroCopy &&
 		                   (g_tuning.sortMode == 1 || (g_tuning.sortMode == 2 && sceneExceedsL2(s) && total >= (1u << 18)));
 		if (rebin) {
 			// re-bin the launch: visiting order by origin/direction key, results stay index-parallel

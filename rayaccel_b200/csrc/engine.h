@@ -60,6 +60,8 @@ struct Tuning {
 	int smemStack = -1;      // variant 3: entries of every traversal stack kept in shared memory: 0, 8, 16, or -1 = auto
 	                         // (16 when the scene is far larger than L2: the stacks then stop competing with the scene for
 	                         // L1 lines, +10 % on config 5; on L2-resident scenes the all-local stack is 4 % faster)
+	int hostZeroCopy = 0;    // HOST streams in pinned, mapped memory: 1 = the kernel reads rays / writes results over PCIe
+	                         // itself (one launch, no staging copies), 0 = staged H2D / trace / D2H pipeline
 	int buildDevice = 3;     // scene build (same images either way): 0 host threads; 1 SAH tree on the GPU, packing on the
 	                         // host; 2 everything on the GPU (bvh_build.cu); 3 auto = 2 from kAutoDeviceBuildTriangles up
 };

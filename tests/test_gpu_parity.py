@@ -340,6 +340,30 @@ def test_host_streams_packed_into_shared_launches(scene, env, images, battlefiel
         assert_bit_exact(got, oracle.traverse(images, rays[k]), f"host stream {k}")
 
 
+def test_host_streams_zero_copy(scene, env, images, battlefield):
+    """HOST streams in pinned memory read and written by the kernel itself (host_zero_copy=1): one launch, same bits;
+    pageable host memory still goes through the staging pipeline."""
+    lo = battlefield.vertices[:, :3].min(0)
+    hi = battlefield.vertices[:, :3].max(0)
+    sizes = [27648, 1, 65535, 300000]
+    rays = [random_rays(s, lo, hi, seed=60 + k) for k, s in enumerate(sizes)]
+    pinned_r = [torch.from_numpy(r.view(np.float32).reshape(-1).copy()).pin_memory() for r in rays]
+    pinned_o = [torch.full((s * 4,), 7.0, dtype=torch.float32).pin_memory() for s in sizes]
+    rb.set_tuning(host_zero_copy=1)
+    try:
+        before = rb.launch_count()
+        rb.trace_host_ptrs(scene, env, [(a.data_ptr(), b.data_ptr(), s) for a, b, s in zip(pinned_r, pinned_o, sizes)])
+        rb.sync()
+        assert rb.launch_count() - before == 1
+        for k, s in enumerate(sizes):
+            assert_bit_exact(pinned_o[k].numpy().view(np.uint32).reshape(-1, 4), oracle.traverse(images, rays[k]), f"zero-copy stream {k}")
+        pageable = random_rays(5000, lo, hi, seed=70)
+        res = rb.trace_host(scene, env, pageable)
+        assert_bit_exact(res.view(np.uint32).reshape(-1, 4), oracle.traverse(images, pageable), "pageable host stream")
+    finally:
+        rb.set_tuning(host_zero_copy=0)
+
+
 def test_synthetic_soup_scene_bit_exact(gpu):
     """BASELINE.json configs[4] at reduced size: random triangle soup + uniform random rays."""
     v, i = rb.synthetic_triangles(200_000, seed=7, extent=1000.0, edge=2.0)
