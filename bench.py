@@ -216,7 +216,7 @@ def run_reference(args, rank: int, world: int) -> None:
     images, streams, built_by = build_cpu_sample(sample_rows(60_000), seed=1)
     rays = np.concatenate(streams)
     t0 = time.perf_counter()
-    oracle.traverse(images, rays)
+    oracle.traverse_avx2(images, rays)
     rate = rays.shape[0] / (time.perf_counter() - t0)
     budget_s = 100.0
     target = int(min(WIDTH * HEIGHT * SPP * 2.05, max(60_000, rate * budget_s / max(1, args.steps + args.warmup))))
@@ -225,10 +225,10 @@ def run_reference(args, rank: int, world: int) -> None:
     rays = np.concatenate(streams)
     n = rays.shape[0]
     for _ in range(args.warmup):
-        oracle.traverse(images, rays)
+        oracle.traverse_avx2(images, rays)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.traverse(images, rays)
+        oracle.traverse_avx2(images, rays)
     dt = time.perf_counter() - t0
     mrays = n * args.steps / dt / 1e6
     sample = (f"{len(rows)} of {HEIGHT} pixel rows (evenly strided) of the {WIDTH}x{HEIGHT}x{SPP}spp batch, primary + {BOUNCES} "
@@ -238,7 +238,8 @@ def run_reference(args, rank: int, world: int) -> None:
         "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(), "rays_per_step": n, "note": "reference CPU path is Embree 2.7 (binary-only, macOS/Windows); "
-                   "timed here: the CPU restatement of the reference's own traversal kernel (oracle/racc_oracle.c), scalar, one ray per thread"},
+                   "timed here: the CPU restatement of the reference's own traversal kernel (oracle/racc_oracle.c), AVX2 node test (1 ray x 2 "
+                   "boxes, SURVEY.md 8d), one ray at a time per thread, all host threads; bit-identical to the scalar checker"},
         "cpu_baseline": {"value": round(mrays, 3), "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(mrays, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -411,13 +412,18 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             parts.append(r[: m * 8].cpu().numpy().view(oracle.RAY_DTYPE))
             gpu_parts.append(o[: m * 4].cpu().numpy().view(np.uint32).reshape(-1, 4))
         sample = np.concatenate(parts)
-        oracle.traverse(images, sample[: 20000])  # warm the library and the caches
+        oracle.traverse_avx2(images, sample[: 20000])  # warm the library and the caches
         t0 = time.perf_counter()
-        want = oracle.traverse(images, sample)
+        want = oracle.traverse_avx2(images, sample)
         dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        checker = oracle.traverse(images, sample[: 2_000_000])  # the scalar parity checker on a prefix, for the record
+        dt_checker = time.perf_counter() - t0
+        assert np.array_equal(checker.view(np.uint32), want[: checker.shape[0]].view(np.uint32)), "AVX2 baseline differs from the scalar checker"
         cpu_baseline = {"value": round(sample.shape[0] / dt / 1e6, 3), "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": "port",
                         "sample": f"first {frac * 100:.1f}% of each of the {len(streams)} ray streams of the batch ({sample.shape[0]} rays), "
-                                  f"scalar C restatement of the reference kernel, all host threads, {dt:.1f} s"}
+                                  f"C restatement of the reference kernel with an AVX2 node test (1 ray x 2 boxes), all host threads, {dt:.1f} s; "
+                                  f"the scalar parity checker runs at {min(sample.shape[0], 2_000_000) / dt_checker / 1e6:.1f} Mrays/s on the same cores"}
         parity = bool(np.array_equal(np.concatenate(gpu_parts), want.view(np.uint32).reshape(-1, 4)))
 
     if rank == 0:

@@ -123,6 +123,19 @@ def traverse(scene: SceneImages, rays: np.ndarray, counters: bool = False, threa
     return (res, cnt) if counters else res
 
 
+def traverse_avx2(scene: SceneImages, rays: np.ndarray, threads: int = 0) -> np.ndarray:
+    """CPU BASELINE (bench.py only): the same traversal with an AVX2 node test, all host threads by default."""
+    rays = np.ascontiguousarray(rays)
+    assert rays.dtype == RAY_DTYPE
+    n = rays.shape[0]
+    res = np.zeros(n, dtype=RESULT_DTYPE)
+    s = scene.c_struct()
+    rc = lib().oracle_traverse_avx2(ctypes.byref(s), _p(rays), ctypes.c_uint32(n), _p(res), ctypes.c_int(threads))
+    if rc:
+        raise RuntimeError("oracle_traverse_avx2 failed (stack overflow or malformed scene)")
+    return res
+
+
 def env_sample(env: np.ndarray, dirs: np.ndarray) -> np.ndarray:
     env = np.ascontiguousarray(env, dtype=np.float32)
     dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)

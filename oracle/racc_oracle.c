@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <immintrin.h>
 #include <xmmintrin.h>
 #include <pmmintrin.h>
 #include <pthread.h>
@@ -255,6 +256,33 @@ static inline float aabb_intersect(v3 mn, v3 mx, float t0, float t1, v3 invDir, 
 	return t0;
 }
 
+/* miss (Kernels.h:213-222) and hit (Kernels.h:223-239) epilogues */
+static int finish_ray(const oracle_scene* sc, const ray_state* rayp, const hit_state* hitp, oracle_result* out) {
+	const ray_state ray = *rayp;
+	const hit_state hit = *hitp;
+	if (hit.index == 0xffffffffu) { /* Kernels.h:213-222 */
+		float d[3] = { ray.d.x, ray.d.y, ray.d.z };
+		float rgb[3] = { 0.0f, 0.0f, 0.0f };
+		if (sc->env)
+			oracle_env_sample(sc->env, sc->env_width, sc->env_height, d, rgb);
+		out->triangle = ORACLE_INVALID_TRIANGLE;
+		out->a = rgb[0]; out->b = rgb[1]; out->c = rgb[2];
+	}
+	else { /* Kernels.h:223-239 */
+		if (hit.index >= sc->remap_count) return -1;
+		uint32_t index = sc->remap[hit.index];
+		uint32_t edge = index >> 30;
+		index &= 0x3fffffffu;
+		float bx = hit.u, by = hit.v, bz = (1.0f - hit.u) - hit.v;
+		float u = bx, v = by;
+		if (edge == 1) { u = bz; v = bx; }      /* barys.zxy */
+		else if (edge == 2) { u = by; v = bz; } /* barys.yzx */
+		out->triangle = index;
+		out->a = hit.t; out->b = u; out->c = v;
+	}
+	return 0;
+}
+
 #define ORACLE_STACK 64 /* Kernels.h:166 */
 
 /* traversal, Kernels.h:141-242, one ray. Returns 0, or -1 on stack overflow / bad reference. */
@@ -328,26 +356,8 @@ static int traverse_one(const oracle_scene* sc, const oracle_ray* in, oracle_res
 		node = stack[--stackHead];
 	}
 
-	if (hit.index == 0xffffffffu) { /* Kernels.h:213-222 */
-		float d[3] = { ray.d.x, ray.d.y, ray.d.z };
-		float rgb[3] = { 0.0f, 0.0f, 0.0f };
-		if (sc->env)
-			oracle_env_sample(sc->env, sc->env_width, sc->env_height, d, rgb);
-		out->triangle = ORACLE_INVALID_TRIANGLE;
-		out->a = rgb[0]; out->b = rgb[1]; out->c = rgb[2];
-	}
-	else { /* Kernels.h:223-239 */
-		if (hit.index >= sc->remap_count) return -1;
-		uint32_t index = sc->remap[hit.index];
-		uint32_t edge = index >> 30;
-		index &= 0x3fffffffu;
-		float bx = hit.u, by = hit.v, bz = (1.0f - hit.u) - hit.v;
-		float u = bx, v = by;
-		if (edge == 1) { u = bz; v = bx; }      /* barys.zxy */
-		else if (edge == 2) { u = by; v = bz; } /* barys.yzx */
-		out->triangle = index;
-		out->a = hit.t; out->b = u; out->c = v;
-	}
+	if (finish_ray(sc, &ray, &hit, out))
+		return -1;
 	if (cnt) {
 		cnt->inner = (uint16_t)(nInner > 65535 ? 65535 : nInner);
 		cnt->pairs = (uint16_t)(nPairs > 65535 ? 65535 : nPairs);
@@ -411,6 +421,109 @@ int oracle_traverse(const oracle_scene* scene, const oracle_ray* rays, uint32_t 
                     oracle_result* results, oracle_counters* counters, int threads) {
 	trav_ctx t = { scene, rays, count, results, counters, 0 };
 	parallel_for(threads, ((int64_t)count + TRAV_CHUNK - 1) / TRAV_CHUNK, trav_body, &t);
+	return t.err;
+}
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* CPU BASELINE (bench.py cpu_baseline / --impl reference only; SURVEY.md 8d "AVX2 restatement of the
+ * reference's own algorithm, 1 ray x 2 boxes"): the same traversal with both child boxes of a node
+ * tested in one AVX2 pass. Same fused multiply-adds, exact min/max; the only liberty is which zero
+ * (+0/-0) an intermediate min/max returns, which cannot reach the result while minT >= 0 (the final
+ * max takes minT as the tie winner). tests/test_oracle_kat.py checks it bit for bit against
+ * oracle_traverse on the golden rays. Not used as the parity checker. */
+typedef struct { __m128 inv1, inv2, inv3, ood1, ood2, ood3; } ray_simd;
+
+static inline void node_test_avx2(const float* d, const ray_simd* rs, float tNear, float tFar, float* tFirst, float* tLast) {
+	/* node floats 4..15 = lmn.xyz lmx.x | lmx.yz rmn.xy | rmn.z rmx.xyz; ray constants pre-permuted to match */
+	const __m128 t1 = _mm_fmadd_ps(_mm_loadu_ps(d + 4), rs->inv1, rs->ood1);
+	const __m128 t2 = _mm_fmadd_ps(_mm_loadu_ps(d + 8), rs->inv2, rs->ood2);
+	const __m128 t3 = _mm_fmadd_ps(_mm_loadu_ps(d + 12), rs->inv3, rs->ood3);
+	const __m128 al = _mm_shuffle_ps(t1, t1, _MM_SHUFFLE(2, 2, 1, 0));                 /* lmn.x lmn.y lmn.z lmn.z */
+	const __m128 tmp = _mm_shuffle_ps(t1, t2, _MM_SHUFFLE(1, 0, 3, 3));                /* lmx.x lmx.x lmx.y lmx.z */
+	const __m128 bl = _mm_shuffle_ps(tmp, tmp, _MM_SHUFFLE(3, 3, 2, 0));               /* lmx.x lmx.y lmx.z lmx.z */
+	const __m128 ar = _mm_shuffle_ps(t2, t3, _MM_SHUFFLE(0, 0, 3, 2));                 /* rmn.x rmn.y rmn.z rmn.z */
+	const __m128 br = _mm_shuffle_ps(t3, t3, _MM_SHUFFLE(3, 3, 2, 1));                 /* rmx.x rmx.y rmx.z rmx.z */
+	const __m256 a = _mm256_set_m128(ar, al), b = _mm256_set_m128(br, bl);
+	__m256 lo = _mm256_min_ps(a, b), hi = _mm256_max_ps(a, b);
+	lo = _mm256_max_ps(lo, _mm256_permute_ps(lo, _MM_SHUFFLE(1, 0, 3, 2)));
+	hi = _mm256_min_ps(hi, _mm256_permute_ps(hi, _MM_SHUFFLE(1, 0, 3, 2)));
+	lo = _mm256_max_ps(lo, _mm256_permute_ps(lo, _MM_SHUFFLE(2, 3, 0, 1)));
+	hi = _mm256_min_ps(hi, _mm256_permute_ps(hi, _MM_SHUFFLE(2, 3, 0, 1)));
+	const float e0l = _mm_cvtss_f32(_mm256_castps256_ps128(lo)), e0r = _mm_cvtss_f32(_mm256_extractf128_ps(lo, 1));
+	const float x1l = _mm_cvtss_f32(_mm256_castps256_ps128(hi)), x1r = _mm_cvtss_f32(_mm256_extractf128_ps(hi, 1));
+	const float t0l = e0l > tNear ? e0l : tNear, t0r = e0r > tNear ? e0r : tNear;
+	const float t1l = x1l < tFar ? x1l : tFar, t1r = x1r < tFar ? x1r : tFar;
+	*tFirst = t0l > t1l ? tFar : t0l;
+	*tLast = t0r > t1r ? tFar : t0r;
+}
+
+static int traverse_one_avx2(const oracle_scene* sc, const oracle_ray* in, oracle_result* out) {
+	ray_state ray;
+	ray.o.x = in->origin[0]; ray.o.y = in->origin[1]; ray.o.z = in->origin[2];
+	ray.d.x = in->dir[0]; ray.d.y = in->dir[1]; ray.d.z = in->dir[2];
+	ray.tNear = in->minT;
+	ray.tFar = in->maxT;
+	const float epsilon = 1e-10f;
+	if (fabsf(ray.d.x) < epsilon) ray.d.x = copysignf(epsilon, ray.d.x);
+	if (fabsf(ray.d.y) < epsilon) ray.d.y = copysignf(epsilon, ray.d.y);
+	if (fabsf(ray.d.z) < epsilon) ray.d.z = copysignf(epsilon, ray.d.z);
+	const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
+	const float px = -ray.o.x * ix, py = -ray.o.y * iy, pz = -ray.o.z * iz;
+	ray_simd rs;
+	rs.inv1 = _mm_setr_ps(ix, iy, iz, ix); rs.ood1 = _mm_setr_ps(px, py, pz, px);
+	rs.inv2 = _mm_setr_ps(iy, iz, ix, iy); rs.ood2 = _mm_setr_ps(py, pz, px, py);
+	rs.inv3 = _mm_setr_ps(iz, ix, iy, iz); rs.ood3 = _mm_setr_ps(pz, px, py, pz);
+	hit_state hit = { 0xffffffffu, ray.tFar, 0.0f, 0.0f };
+	uint32_t node = 0x80000000u;
+	uint32_t stack[ORACLE_STACK];
+	unsigned stackHead = 0;
+	const uint32_t* nodesU = (const uint32_t*)sc->nodes;
+	for (;;) {
+		if (node & 0x80000000u) {
+			node &= ~0x80000000u;
+			if (node >= sc->node_count) return -1;
+			const float* d = sc->nodes + 16 * (size_t)node;
+			const uint32_t childFirst = nodesU[16 * (size_t)node + 2], childLast = nodesU[16 * (size_t)node + 3];
+			const float tRay = ray.tFar;
+			float tFirst, tLast;
+			node_test_avx2(d, &rs, ray.tNear, tRay, &tFirst, &tLast);
+			if ((tRay - tFirst) + (tRay - tLast) != 0.0f) {
+				const int sgn = (f2u(tLast - tFirst) >> 31) != 0;
+				if ((tFirst > tLast ? tFirst : tLast) != tRay) {
+					if (stackHead >= ORACLE_STACK) return -1;
+					stack[stackHead++] = sgn ? childFirst : childLast;
+				}
+				node = sgn ? childLast : childFirst;
+				continue;
+			}
+		}
+		else {
+			const uint32_t first = node & 0xffffffu, last = first + (node >> 24);
+			if (last > sc->pair_count) return -1;
+			for (uint32_t i = first; i < last; ++i)
+				ray.tFar = pair_intersect(sc->pairs, i, &ray, &hit);
+		}
+		if (!stackHead)
+			break;
+		node = stack[--stackHead];
+	}
+	return finish_ray(sc, &ray, &hit, out);
+}
+
+static void trav_body_avx2(void* p, int64_t c) {
+	trav_ctx* t = (trav_ctx*)p;
+	unsigned saved = ftz_on(); /* the reference's threads run FTZ+DAZ; min/max then treat subnormals as zero */
+	int64_t lo = c * TRAV_CHUNK, hi = lo + TRAV_CHUNK < (int64_t)t->count ? lo + TRAV_CHUNK : (int64_t)t->count;
+	for (int64_t i = lo; i < hi; ++i)
+		if (traverse_one_avx2(t->scene, t->rays + i, t->results + i))
+			t->err = -1;
+	_mm_setcsr(saved);
+}
+
+int oracle_traverse_avx2(const oracle_scene* scene, const oracle_ray* rays, uint32_t count, oracle_result* results, int threads) {
+	trav_ctx t = { scene, rays, count, results, 0, 0 };
+	parallel_for(threads, ((int64_t)count + TRAV_CHUNK - 1) / TRAV_CHUNK, trav_body_avx2, &t);
 	return t.err;
 }
 

@@ -86,6 +86,10 @@ typedef struct {
 int oracle_traverse(const oracle_scene* scene, const oracle_ray* rays, uint32_t count,
                     oracle_result* results, oracle_counters* counters, int threads);
 
+/* CPU BASELINE only (not the checker): the same traversal with an AVX2 node test (1 ray x 2 boxes),
+ * multi-threaded; bit-identical to oracle_traverse for rays with minT >= 0. */
+int oracle_traverse_avx2(const oracle_scene* scene, const oracle_ray* rays, uint32_t count, oracle_result* results, int threads);
+
 /* online cores, as used when threads<=0 */
 int oracle_hardware_threads(void);
 
