@@ -419,6 +419,38 @@ def test_device_build_synthetic_identical_to_host():
         _assert_same_images(v, i, f"soup n={n}")
 
 
+def test_device_build_stress_meshes_identical_to_host():
+    """Meshes that lean on the order-dependent parts of the sweep: a large regular grid (thousands of equal centre keys
+    and equal costs: tie rules, wide kernel), thousands of coincident triangles (zero-extent parents: forced median
+    splits down to 126-triangle leaves), huge coordinates with needle triangles, and degenerate (zero-area) triangles."""
+    g = 300
+    xs, zs = np.meshgrid(np.arange(g + 1, dtype=np.float32), np.arange(g + 1, dtype=np.float32))
+    v = np.ones(((g + 1) * (g + 1), 4), np.float32)
+    v[:, 0], v[:, 1], v[:, 2] = xs.ravel(), 0.0, zs.ravel()
+    a = (np.arange(g)[:, None] * (g + 1) + np.arange(g)[None, :]).ravel().astype(np.uint32)
+    idx = np.stack([a, a + g + 1, a + 1, a + 1, a + g + 2 - 1, a + g + 2], axis=1).ravel().astype(np.uint32)
+    _assert_same_images(v, idx, "grid 300x300")
+
+    one = np.array([[0, 0, 0, 1], [1, 0, 0, 1], [0, 1, 0, 1]], np.float32)
+    n = 5000
+    _assert_same_images(np.tile(one, (n, 1)), np.arange(3 * n, dtype=np.uint32), "5000 coincident triangles")
+
+    rng = np.random.default_rng(99)
+    n = 30000
+    c = rng.uniform(-1e6, 1e6, size=(n, 1, 3))
+    d = rng.normal(size=(n, 1, 3)) * 1e4
+    t = np.concatenate([c, c + d, c + d * 1.0001 + rng.normal(size=(n, 1, 3)) * 1e-2], axis=1).astype(np.float32)
+    v = np.ones((3 * n, 4), np.float32)
+    v[:, :3] = t.reshape(-1, 3)
+    _assert_same_images(v, np.arange(3 * n, dtype=np.uint32), "needles at 1e6")
+
+    v, i = rb.synthetic_triangles(20000, seed=31, extent=50.0, edge=2.0)
+    v = v.copy()
+    v[3 * 5000 + 1: 3 * 9000: 3, :3] = v[3 * 5000: 3 * 9000: 3, :3]  # 4000 triangles with two equal vertices
+    v[2::9, 1] = 0.0
+    _assert_same_images(v, i, "soup with degenerate triangles")
+
+
 @pytest.mark.slow
 def test_device_build_large_soup_identical_to_host():
     v, i = rb.synthetic_triangles(1_000_000, seed=7, extent=1000.0, edge=2.0)
