@@ -164,7 +164,7 @@ racc_cuda_scene* uploadScene(racc_cuda_scene* s, const float* verts4, uint32_t n
 	cudaError_t e;
 	fillInfo(h, s->triangleCount, &s->info);
 #define UP(dst, src, bytes)                                                                  \
-	if ((e = cudaMalloc(reinterpret_cast<void**>(&dst), (bytes) ? (bytes) : 16)) != cudaSuccess || \
+	if ((e = cudaMalloc(reinterpret_cast<void**>(&dst), (bytes) != 0 ? (bytes) : 16)) != cudaSuccess || \
 	    (e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {            \
 		fail("scene upload failed: %s", cudaGetErrorString(e));                               \
 		return bail();                                                                        \
