@@ -30,11 +30,6 @@ namespace {
 
 typedef unsigned long long u64;
 
-__device__ __forceinline__ u64 pack2(float lo, float hi) {
-	u64 r;
-	asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
-	return r;
-}
 // (v,v): declared volatile so that the broadcast is not hoisted into a loop-invariant register pair;
 // ptxas folds it into the scalar-broadcast operand form of FFMA2 (Rn.F32) instead.
 __device__ __forceinline__ u64 splat2(float v) {
