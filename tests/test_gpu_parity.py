@@ -546,3 +546,42 @@ def test_fp64_brute_force_arbiter_at_scale(scene, env, battlefield):
     assert int(outside.sum()) <= 1e-5 * rays.shape[0] + 2, f"{int(outside.sum())} engine ids outside the fp64 tie set"
     print(f"fp64 arbiter: {rays.shape[0]} rays, {int(both.sum())} hits, {flips} grazing flips, {int(outside.sum())} ids outside the tie set, "
           f"max |dt|/t = {float(rel.max()):.3e}")
+
+
+@pytest.mark.timeout(120)
+def test_pathological_rays_terminate_and_match(scene, env, images, battlefield):
+    """Rays a client can produce by accident: zero and axis-parallel directions (epsilon clamp, Kernels.h:149-157),
+    empty intervals (minT >= maxT), huge and tiny magnitudes, and non-finite components. Finite rays must match the
+    oracle bit for bit; non-finite ones must simply come back (every variant), never hang the persistent kernel."""
+    lo = battlefield.vertices[:, :3].min(0)
+    hi = battlefield.vertices[:, :3].max(0)
+    base = random_rays(4096, lo, hi, seed=91)
+    finite = base.copy()
+    finite["dir"][0:256] = 0.0
+    finite["dir"][256:512, 0] = 0.0
+    finite["dir"][512:768, 1:] = 0.0
+    finite["minT"][768:1024] = 10.0
+    finite["maxT"][768:1024] = 10.0
+    finite["maxT"][1024:1280] = -1.0
+    finite["origin"][1280:1536] *= 1e20
+    finite["dir"][1536:1792] *= 1e-30
+    finite["dir"][1792:2048] *= 1e30
+    finite["maxT"][2048:2304] = 3.0e38
+    got = trace_dev(scene, env, finite)
+    assert_bit_exact(got, oracle.traverse(images, finite), "pathological finite rays")
+    weird = base.copy()
+    weird["origin"][0:512, 0] = np.nan
+    weird["dir"][512:1024, 1] = np.nan
+    weird["dir"][1024:1536, 2] = np.inf
+    weird["origin"][1536:2048] = -np.inf
+    weird["maxT"][2048:2560] = np.inf
+    weird["minT"][2560:3072] = np.nan
+    for tuning in (dict(), dict(variant=2), dict(variant=0, smem_nodes=-1), dict(variant=1), dict(sort=1, smem_stack=16)):
+        rb.set_tuning(**{**DEFAULT, **tuning})
+        try:
+            out = trace_dev(scene, env, weird)
+        finally:
+            rb.set_tuning(**DEFAULT)
+        assert out.shape == (4096, 4)
+        # the untouched tail of the batch is still right
+        assert np.array_equal(out[3072:], oracle.traverse(images, weird[3072:]).view(np.uint32).reshape(-1, 4))
