@@ -105,26 +105,45 @@ namespace racc {
 		void (*shade)(void* data, unsigned thread, const RayStream* input, unsigned start, unsigned end, RayStream* output);
 	};
 
+	// Process-wide set-up. Sets flush-to-zero / denormals-are-zero on the calling thread, as the reference
+	// does for every thread it starts (RayAccelerator.cpp:417-420, Threading.h:77-79): the shaders of a client
+	// inherit that. No device is touched before createContext().
 	void init();
 
 	void deinit();
 
+	// Defaults sized for one B200, not for the reference's integrated GPU
+	// (RayAccelerator.cpp:429-446): 65 536-ray streams, 2 M rays in flight, 2 submitter threads.
 	Configuration defaultConfiguration(cl_context gpuContext);
 
+	// Allocates the stream slab in pinned host memory and starts the callback and submitter threads
+	// (RayAccelerator.cpp:448-736). Returns null after printing "RayAccelerator: ..." on failure.
 	Context* createContext(Configuration configuration);
 
+	// Joins the threads and releases the slab (RayAccelerator.cpp:761-788). Scenes and environments created
+	// from the context must be destroyed first.
 	void destroy(Context* context);
 
+	// Sizes a client needs for its per-thread and per-stream side arrays (RayAccelerator.cpp:790-797).
 	ContextInfo info(Context* context);
 
+	// Builds the scene (full-sweep SAH BVH2, triangle pairs) and uploads it; vertices and indices are copied
+	// (Scene.cpp:183-357). vertices must be 16-byte aligned, indexCount a multiple of 3. Null on failure.
 	Scene* createScene(Context* context, const Vertex* vertices, unsigned vertexCount, const uint32_t* indices, unsigned indexCount);
 
 	void destroy(Scene* scene);
 
+	// An angular-map light probe of width x height RGBA32F texels, copied (Environment.cpp:13-60). Misses
+	// return its bilinearly filtered radiance in Result.miss.
 	Environment* createEnvironment(Context* context, const Color* colors, unsigned width, unsigned height);
 
 	void destroy(Environment* environment);
 
+	// One frame: runs spawn() until it returns false and shade() on every tested stream until no ray is left,
+	// then returns (RayAccelerator.cpp:738-759). Callbacks run concurrently, without any library lock held, each
+	// with a `thread` value no other running callback has. spawn appends at most maxRaysPerSpawn rays to
+	// `output`; shade reads input->rays/results[start, end) and appends at most end - start rays to `output`,
+	// which may already hold rays. One render() per context at a time.
 	Stats render(Context* context, Scene* scene, Environment* environment, RenderCallbacks callbacks);
 
 	// --- additions (not in the reference) -------------------------------------------------------
