@@ -453,7 +453,9 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": 32 * rays_per_step, "d2h_bytes_per_step": 16 * rays_per_step,
                     "ms_per_step": round(e2e_ms, 3), "wall_ms_per_step": round(e2e_wall_ms / e2e_steps, 3), "steps": e2e_steps,
                     "results_match_device_run": e2e_ok, "host_binding": host_binding,
-                    "path": "racc_cuda_trace with RACC_CUDA_STREAM_HOST descriptors, pinned host memory"},
+                    "path": "racc_cuda_trace with RACC_CUDA_STREAM_HOST descriptors, pinned host memory",
+                    "pcie_gbs": {"h2d": round(32 * world * rays_per_step / (e2e_ms * 1e-3) / 1e9 / world, 1), "d2h": round(16 * world * rays_per_step / (e2e_ms * 1e-3) / 1e9 / world, 1),
+                                 "note": "per GPU; plain pinned copies on this pool reach 52.6 + 26.3 GB/s with both directions busy (profiles/r01_pcie_copy_bandwidth.txt)"}},
             "gpu_launches": int(launches), "clocks": clocks, "frame_hits_all_ranks": hits_all_ranks,
         }
         if cpu_baseline is not None:
