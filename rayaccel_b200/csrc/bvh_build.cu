@@ -795,8 +795,12 @@ bool runSahOnDevice(const float* vertices4, uint32_t vertexCount, const uint32_t
 		if (have[2]) buildLevelKernel<kWideThreads, 8><<<have[2], kWideThreads>>>(ctx, in[2], nxt[0], nxt[1], nxt[2], counts);
 		if (have[0]) buildLevelKernel<256, 1><<<have[0], 256>>>(ctx, in[0], nxt[0], nxt[1], nxt[2], counts);
 		if (have[1]) buildLevelKernel<32, 1><<<have[1], 32>>>(ctx, in[1], nxt[0], nxt[1], nxt[2], counts);
+		const uint32_t had[3] = {have[0], have[1], have[2]};
+		const double tl = nowSeconds();
 		e = cudaMemcpy(have, counts, 12, cudaMemcpyDeviceToHost);
 		if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
+		if (getenv("RACC_B200_BUILD_VERBOSE") && atoi(getenv("RACC_B200_BUILD_VERBOSE")) > 1)
+			fprintf(stderr, "racc device build: level %d: %u wide + %u mid + %u small nodes, %.2f ms (wait)\n", level, had[2], had[0], had[1], (nowSeconds() - tl) * 1e3);
 		cur = 1 - cur;
 	}
 	out.verts = dVerts;
