@@ -9,8 +9,9 @@
 // the resulting device images with the host build (tests/test_gpu_parity.py::test_device_build_*).
 //
 // HOW is GPU-first. The reference recurses depth-first with a task pool; here the tree grows level
-// by level, one kernel launch per level, ONE CTA PER NODE of the level (256 threads for large nodes,
-// one warp for nodes of <= 64 triangles). Inside a CTA the sequential sweep becomes
+// by level: nodes above 131 072 triangles are built one at a time by the WHOLE GPU (cooperative launch,
+// grid-wide barriers between chunk-parallel phases), the others by ONE CTA PER NODE (512 threads x 8
+// positions above 4096 triangles, 256 threads above 64, one warp below). The sequential sweep becomes
 //   * prefix / suffix unions of the triangle boxes by chunked CTA-wide max-scans (max is exact and
 //     associative, so every position sees the very box the sequential loop would hold),
 //   * per-position cost in the arithmetic variant its position selects (block region vs scalar tail),
@@ -21,6 +22,8 @@
 // the radix sort of raysort.cu (stable; ties broken like the reference's packed key order).
 #include "engine.h"
 #include "scene_build.h"
+
+#include <cooperative_groups.h>
 
 #include <chrono>
 #include <cmath>
@@ -38,6 +41,7 @@ constexpr uint32_t kNone = 0xffffffffu;
 constexpr uint32_t kSmallNode = 64;  // nodes up to this many triangles are built by one warp
 constexpr uint32_t kWideNode = 4096; // nodes above this are built by 512 threads x 8 positions each
 constexpr int kWideThreads = 512;
+constexpr uint32_t kHugeNode = 131072; // nodes above this are built by the whole GPU, one node at a time (cooperative launch)
 
 __constant__ float c_rcpTable[2048];
 
@@ -50,6 +54,17 @@ struct DevBuild {
 	uint8_t* goesLeft;
 	BuildNode* nodes;
 };
+
+// Work lists of the next level, one per node class (index: 0 mid, 1 small, 2 wide, 3 huge).
+struct NextLists {
+	uint32_t* list[4];
+	uint32_t* counts;
+};
+__device__ __forceinline__ int nodeClass(uint32_t triangles);
+__device__ __forceinline__ void emitChild(const NextLists& nx, uint32_t slot, uint32_t triangles) {
+	const int c = nodeClass(triangles);
+	nx.list[c][atomicAdd(&nx.counts[c], 1u)] = slot;
+}
 
 struct Box6 { float v[6]; }; // -min.xyz, max.xyz
 
@@ -310,6 +325,10 @@ __device__ void splitList(const DevBuild& ctx, uint32_t* __restrict__ ids, uint3
 }
 
 
+__device__ __forceinline__ int nodeClass(uint32_t triangles) {
+	return triangles > kHugeNode ? 3 : (triangles > kWideNode ? 2 : (triangles > kSmallNode ? 0 : 1));
+}
+
 // ---- wide variants: every thread owns 8 consecutive positions = exactly one 8-block of the sweep -----
 
 // Exclusive max-scan of one box per thread: returns the union of all earlier threads' boxes.
@@ -568,9 +587,426 @@ __device__ void splitListWide(const DevBuild& ctx, uint32_t* __restrict__ ids, u
 	__syncthreads();
 }
 
+
+// ---- huge nodes: the whole GPU on one node ------------------------------------------------------------
+// With one CTA per node the first levels of a large tree run on 1, 2, 4 ... SMs. Nodes above kHugeNode
+// triangles are instead built one after the other by ALL resident CTAs of a cooperative launch. The sweep is
+// the wide one (8 positions per thread = one 8-block, 4096 positions per chunk), cut in chunk-parallel phases
+// separated by grid-wide barriers: chunk unions -> scan of the chunk unions by CTA 0 -> chunks again with their
+// carry; the order-dependent replay runs on per-block summaries kept in global memory (prefix-min over chunk
+// minima by CTA 0, then first terminating block / last improving block by atomics). Same values at every
+// position as the sequential sweep, so the same tree.
+namespace cg = cooperative_groups;
+
+struct CoopScratch {
+	float* chunkBox;      // [chunks][6] union of each chunk
+	float* chunkCarry;    // [chunks][6] union of everything before each chunk (incl. the initial box)
+	float* chunkMin;      // [chunks] minimum block cost of each chunk
+	float* chunkBefore;   // [chunks] running best when each chunk starts
+	uint32_t* chunkCount; // [2][chunks] lefts per chunk of the two lists being partitioned, then their prefix
+	float* partBox;       // [gridDim][6]
+	float* blkM;          // per 8-block: minimum cost
+	float* blkMr;         //              maximum right cost
+	float* blkBefore;     //              running best when the block starts
+	int* blkArg;          //              lane of the minimum
+	float* tailSah;       // [8] costs of the scalar-tail pivots
+	uint32_t* scal;       // 0 prune, 1 term, 2 lastBetter, 3 pivot, 4 best (float bits)
+	uint32_t maxChunks;
+};
+
+template <int T>
+__device__ Box6 gridUnion(cg::grid_group& grid, Box6 acc, const CoopScratch& sc, float (*sWarp)[6]) {
+	const Box6 mine = ctaReduceMax<T>(acc, sWarp);
+	if (threadIdx.x == 0) {
+#pragma unroll
+		for (int k = 0; k < 6; ++k) sc.partBox[6 * blockIdx.x + k] = mine.v[k];
+	}
+	grid.sync();
+	Box6 all = emptyBox();
+	for (unsigned g = 0; g < gridDim.x; ++g) {
+#pragma unroll
+		for (int k = 0; k < 6; ++k) all.v[k] = fmaxf(all.v[k], sc.partBox[6 * g + k]);
+	}
+	grid.sync();
+	return all;
+}
+
+// CTA 0: chunkCarry[c] = init U chunkBox[0..c)
+template <int T>
+__device__ void scanChunkBoxes(const CoopScratch& sc, uint32_t chunks, Box6 init, float (*sWarp)[6]) {
+	if (blockIdx.x != 0)
+		return;
+	Box6 carry = init;
+	for (uint32_t base = 0; base < chunks; base += T) {
+		const uint32_t c = base + threadIdx.x;
+		Box6 b = emptyBox();
+		if (c < chunks) {
+#pragma unroll
+			for (int k = 0; k < 6; ++k) b.v[k] = sc.chunkBox[6 * (size_t)c + k];
+		}
+		Box6 total;
+		Box6 ex = ctaExclusiveScanMax<T>(b, total, sWarp);
+		boxMax(ex, carry);
+		boxMax(carry, total);
+		if (c < chunks) {
+#pragma unroll
+			for (int k = 0; k < 6; ++k) sc.chunkCarry[6 * (size_t)c + k] = ex.v[k];
+		}
+	}
+}
+// CTA 0: chunkBefore[c] = min(init, chunkMin[0..c)); returns min over everything (uniform in CTA 0)
+template <int T>
+__device__ void scanChunkMins(const CoopScratch& sc, uint32_t chunks, float init, float* sWarpMin) {
+	if (blockIdx.x != 0)
+		return;
+	__shared__ float carryS;
+	if (threadIdx.x == 0) carryS = init;
+	__syncthreads();
+	for (uint32_t base = 0; base < chunks; base += T) {
+		const uint32_t c = base + threadIdx.x;
+		const float v = c < chunks ? sc.chunkMin[c] : INFINITY;
+		const float carry = carryS;
+		const float ex = fminf(ctaExclusiveScanMin<T>(v, sWarpMin), carry);
+		if (c < chunks) sc.chunkBefore[c] = ex;
+		__syncthreads();
+		if (threadIdx.x == T - 1) carryS = fminf(ex, v);
+		__syncthreads();
+	}
+}
+// CTA 0: in-place exclusive prefix sum of counts[0..chunks)
+template <int T>
+__device__ void scanChunkCounts(uint32_t* counts, uint32_t chunks, uint32_t* sWarp) {
+	if (blockIdx.x != 0)
+		return;
+	__shared__ uint32_t carryS;
+	if (threadIdx.x == 0) carryS = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < chunks; base += T) {
+		const uint32_t c = base + threadIdx.x;
+		const uint32_t v = c < chunks ? counts[c] : 0u;
+		uint32_t total;
+		const uint32_t ex = ctaExclusiveScanSum<T>(v, &total, sWarp);
+		const uint32_t carry = carryS;
+		if (c < chunks) counts[c] = carry + ex;
+		__syncthreads();
+		if (threadIdx.x == 0) carryS = carry + total;
+		__syncthreads();
+	}
+}
+
+// One axis of the sweep with the whole grid. bestSah / returned pivot are uniform over the grid.
+template <int T>
+__device__ uint32_t sweepAxisCoop(cg::grid_group& grid, const DevBuild& ctx, const CoopScratch& sc, const uint32_t* __restrict__ ids,
+                                  uint32_t first, uint32_t last, float& bestSah, SharedWide<T>& sh) {
+	constexpr uint32_t C = T * 8;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t count = last - first;
+	const uint32_t nb = count > 8 ? (count - 1) / 8 : 0;
+	const uint32_t blockEnd = first + 8 * nb;
+	const uint32_t chunksF = (count - 1 + C - 1) / C; // positions first .. last-2
+
+	// ---- forward ------------------------------------------------------------------------------------
+	for (uint32_t c = blockIdx.x; c < chunksF; c += gridDim.x) {
+		const uint32_t p0 = first + c * C + 8 * tid;
+		Box6 acc = emptyBox();
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			if (p0 + j + 1 < last) boxMax(acc, loadBox(ctx.tb, ids[p0 + j]));
+		const Box6 u = ctaReduceMax<T>(acc, sh.warpBox);
+		if (tid == 0) {
+#pragma unroll
+			for (int k = 0; k < 6; ++k) sc.chunkBox[6 * (size_t)c + k] = u.v[k];
+		}
+	}
+	if (blockIdx.x == 0 && tid == 0) { sc.scal[0] = kNone; sc.scal[1] = kNone; sc.scal[2] = 0u; }
+	grid.sync();
+	scanChunkBoxes<T>(sc, chunksF, emptyBox(), sh.warpBox);
+	grid.sync();
+	for (uint32_t c = blockIdx.x; c < chunksF; c += gridDim.x) {
+		const uint32_t p0 = first + c * C + 8 * tid;
+		Box6 run[8];
+		Box6 acc = emptyBox();
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			if (p0 + j + 1 < last) boxMax(acc, loadBox(ctx.tb, ids[p0 + j]));
+			run[j] = acc;
+		}
+		Box6 total;
+		Box6 pre = ctaExclusiveScanMax<T>(acc, total, sh.warpBox);
+		Box6 carry;
+#pragma unroll
+		for (int k = 0; k < 6; ++k) carry.v[k] = sc.chunkCarry[6 * (size_t)c + k];
+		boxMax(pre, carry);
+		const bool inBlock = p0 < blockEnd;
+		uint32_t myPrune = kNone;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const uint32_t pos = p0 + j;
+			if (pos + 1 < last) {
+				Box6 b = run[j];
+				boxMax(b, pre);
+				const float sah = __fmul_rn(inBlock ? areaBlock(b) : areaScalar(b), (float)(pos - first + 1));
+				ctx.leftSah[pos] = sah;
+				if (inBlock && sah > bestSah && myPrune == kNone) myPrune = pos;
+			}
+		}
+		if (myPrune != kNone) atomicMin(&sc.scal[0], myPrune);
+	}
+	grid.sync();
+	const uint32_t prune = sc.scal[0];
+
+	// ---- backward -----------------------------------------------------------------------------------
+	const uint32_t i0 = prune != kNone ? prune : last - 1;
+	Box6 run0;
+	if (prune == kNone) {
+		run0 = loadBox(ctx.tb, ids[last - 1]);
+	}
+	else {
+		Box6 acc = emptyBox();
+		for (uint32_t pos = i0 + blockIdx.x * T + tid; pos < last; pos += gridDim.x * T) boxMax(acc, loadBox(ctx.tb, ids[pos]));
+		run0 = gridUnion<T>(grid, acc, sc, sh.warpBox);
+	}
+	const uint32_t span = i0 - first;
+	const uint32_t blockSpan = (span / 8) * 8;
+	const uint32_t chunksB = (span + C - 1) / C;
+	uint32_t bestPivot = kNone;
+	if (span == 0) {
+		grid.sync();
+		return kNone;
+	}
+	for (uint32_t d = blockIdx.x; d < chunksB; d += gridDim.x) {
+		const uint32_t o0 = d * C + 8 * tid;
+		Box6 acc = emptyBox();
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			if (o0 + j < span) boxMax(acc, loadBox(ctx.tb, ids[i0 - (o0 + j)]));
+		const Box6 u = ctaReduceMax<T>(acc, sh.warpBox);
+		if (tid == 0) {
+#pragma unroll
+			for (int k = 0; k < 6; ++k) sc.chunkBox[6 * (size_t)d + k] = u.v[k];
+		}
+	}
+	grid.sync();
+	scanChunkBoxes<T>(sc, chunksB, run0, sh.warpBox);
+	grid.sync();
+	for (uint32_t d = blockIdx.x; d < chunksB; d += gridDim.x) {
+		const uint32_t o0 = d * C + 8 * tid;
+		Box6 run[8];
+		Box6 acc = emptyBox();
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			if (o0 + j < span) boxMax(acc, loadBox(ctx.tb, ids[i0 - (o0 + j)]));
+			run[j] = acc;
+		}
+		Box6 total;
+		Box6 pre = ctaExclusiveScanMax<T>(acc, total, sh.warpBox);
+		Box6 carry;
+#pragma unroll
+		for (int k = 0; k < 6; ++k) carry.v[k] = sc.chunkCarry[6 * (size_t)d + k];
+		boxMax(pre, carry);
+		const bool isBlock = o0 < blockSpan;
+		const bool isTail = !isBlock && o0 < span;
+		float m = INFINITY, mr = -INFINITY;
+		int arg = 0;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			float sv = INFINITY;
+			if (o0 + j < span) {
+				const uint32_t q = i0 - (o0 + j);
+				Box6 b = run[j];
+				boxMax(b, pre);
+				const float r = __fmul_rn(isBlock ? areaBlock(b) : areaScalar(b), (float)(last - q));
+				sv = __fadd_rn(ctx.leftSah[q - 1], r);
+				if (isBlock) {
+					if (sv < m) { m = sv; arg = j; }
+					mr = fmaxf(mr, r);
+				}
+			}
+			if (isTail) sc.tailSah[j] = sv;
+		}
+		const uint32_t gb = o0 / 8;
+		if (o0 < span) {
+			sc.blkM[gb] = m;
+			sc.blkMr[gb] = mr;
+			sc.blkArg[gb] = arg;
+		}
+		// minimum block cost of the chunk
+		float cm = m;
+#pragma unroll
+		for (int o = 16; o; o >>= 1) cm = fminf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+		__syncthreads();
+		if ((tid & 31) == 0) sh.warpMin[tid >> 5] = cm;
+		__syncthreads();
+		if (tid == 0) {
+			float x = INFINITY;
+			for (int w = 0; w < T / 32; ++w) x = fminf(x, sh.warpMin[w]);
+			sc.chunkMin[d] = x;
+		}
+	}
+	grid.sync();
+	scanChunkMins<T>(sc, chunksB, bestSah, sh.warpMin);
+	grid.sync();
+	for (uint32_t d = blockIdx.x; d < chunksB; d += gridDim.x) {
+		const uint32_t o0 = d * C + 8 * tid;
+		const uint32_t gb = o0 / 8;
+		const bool isBlock = o0 < blockSpan;
+		const float m = isBlock ? sc.blkM[gb] : INFINITY;
+		const float before = fminf(ctaExclusiveScanMin<T>(m, sh.warpMin), sc.chunkBefore[d]);
+		if (o0 < span) sc.blkBefore[gb] = before;
+		if (isBlock && sc.blkMr[gb] > before) atomicMin(&sc.scal[1], gb);
+	}
+	grid.sync();
+	const uint32_t term = sc.scal[1];
+	for (uint32_t gb = blockIdx.x * T + tid; gb * 8 < blockSpan; gb += gridDim.x * T) {
+		if (gb <= term && sc.blkM[gb] < sc.blkBefore[gb]) atomicMax(&sc.scal[2], gb + 1);
+	}
+	grid.sync();
+	if (blockIdx.x == 0 && tid == 0) {
+		const uint32_t lb = sc.scal[2];
+		float best = bestSah;
+		uint32_t bp = kNone;
+		if (lb) {
+			best = sc.blkM[lb - 1];
+			bp = (i0 - 8 * (lb - 1)) - (uint32_t)sc.blkArg[lb - 1];
+		}
+		if (term == kNone && blockSpan < span) {
+			// scalar tail: its running best is the minimum over all blocks
+			const uint32_t tb = blockSpan / 8;
+			float before = sc.blkBefore[tb];
+			if (before < best) best = before; // (equal by construction when any block improved)
+			for (uint32_t j = 0; j < 8 && blockSpan + j < span; ++j) {
+				const float sv = sc.tailSah[j];
+				if (sv < best) { best = sv; bp = i0 - (blockSpan + j); }
+			}
+		}
+		sc.scal[3] = bp;
+		sc.scal[4] = __float_as_uint(best);
+	}
+	grid.sync();
+	bestPivot = sc.scal[3];
+	bestSah = __uint_as_float(sc.scal[4]);
+	grid.sync();
+	return bestPivot;
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) buildHugeLevelKernel(const DevBuild ctx, const uint32_t* __restrict__ cur, uint32_t curCount, const NextLists next,
+                                                         const CoopScratch sc) {
+	cg::grid_group grid = cg::this_grid();
+	__shared__ SharedWide<T> sh;
+	constexpr uint32_t C = T * 8;
+	const uint32_t tid = threadIdx.x;
+	for (uint32_t item = 0; item < curCount; ++item) {
+		const uint32_t slot = cur[item];
+		BuildNode* node = ctx.nodes + slot;
+		const uint32_t first = node->first, last = node->last;
+		const uint32_t count = last - first;
+
+		Box6 acc = emptyBox();
+		for (uint32_t pos = first + blockIdx.x * T + tid; pos < last; pos += gridDim.x * T) boxMax(acc, loadBox(ctx.tb, ctx.sorted[0][pos]));
+		const Box6 bounds = gridUnion<T>(grid, acc, sc, sh.warpBox);
+		if (blockIdx.x == 0 && tid == 0) {
+			node->bounds[0] = bounds.v[0]; node->bounds[1] = bounds.v[1]; node->bounds[2] = bounds.v[2]; node->bounds[3] = 0.0f;
+			node->bounds[4] = bounds.v[3]; node->bounds[5] = bounds.v[4]; node->bounds[6] = bounds.v[5]; node->bounds[7] = 0.0f;
+		}
+		const float parentArea = areaScalar(bounds);
+		uint32_t bestDim = kNone, pivot = kNone;
+		bool split = false;
+		if (parentArea > 0.0f) {
+			float bestSah = INFINITY;
+			for (uint32_t dim = 0; dim < 3; ++dim) {
+				const uint32_t p = sweepAxisCoop<T>(grid, ctx, sc, ctx.sorted[dim], first, last, bestSah, sh);
+				if (p != kNone) {
+					pivot = p;
+					bestDim = dim;
+				}
+			}
+			const float cost = __fadd_rn(2.0f, __fmul_rn(__fmul_rn(1.0f, rcpSS(parentArea)), bestSah));
+			split = !(cost > (float)(int)count) && pivot != kNone;
+		}
+		if (!split) { // count > kHugeNode >= 127: forced median split (Bvh2.cpp:468-471,478-480)
+			bestDim = 0;
+			pivot = (first + last) >> 1;
+		}
+
+		// partition the two other lists
+		const uint32_t* ref = ctx.sorted[bestDim];
+		for (uint32_t pos = first + blockIdx.x * T + tid; pos < last; pos += gridDim.x * T) ctx.goesLeft[ref[pos]] = pos < pivot ? 1 : 0;
+		grid.sync();
+		uint32_t* lists[2] = {ctx.sorted[(bestDim + 1) % 3], ctx.sorted[(bestDim + 2) % 3]};
+		const uint32_t chunks = (count + C - 1) / C;
+		for (int l = 0; l < 2; ++l) {
+			uint32_t* cnt = sc.chunkCount + (size_t)l * sc.maxChunks;
+			for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x) {
+				const uint32_t p0 = first + c * C + 8 * tid;
+				uint32_t mine = 0;
+#pragma unroll
+				for (int j = 0; j < 8; ++j)
+					if (p0 + j < last && ctx.goesLeft[lists[l][p0 + j]]) ++mine;
+				uint32_t total;
+				ctaExclusiveScanSum<T>(mine, &total, sh.warpCount);
+				if (tid == 0) cnt[c] = total;
+			}
+		}
+		grid.sync();
+		scanChunkCounts<T>(sc.chunkCount, chunks, sh.warpCount);
+		scanChunkCounts<T>(sc.chunkCount + sc.maxChunks, chunks, sh.warpCount);
+		grid.sync();
+		for (int l = 0; l < 2; ++l) {
+			const uint32_t* cnt = sc.chunkCount + (size_t)l * sc.maxChunks;
+			uint32_t* out = l == 0 ? ctx.scratch : reinterpret_cast<uint32_t*>(ctx.leftSah); // leftSah is free again: second scratch
+			for (uint32_t c = blockIdx.x; c < chunks; c += gridDim.x) {
+				const uint32_t p0 = first + c * C + 8 * tid;
+				uint32_t t[8];
+				unsigned flags = 0;
+#pragma unroll
+				for (int j = 0; j < 8; ++j) {
+					t[j] = 0;
+					if (p0 + j < last) {
+						t[j] = lists[l][p0 + j];
+						if (ctx.goesLeft[t[j]]) flags |= 1u << j;
+					}
+				}
+				uint32_t totalL;
+				const uint32_t exL = ctaExclusiveScanSum<T>(__popc(flags), &totalL, sh.warpCount);
+				const uint32_t nL = cnt[c];
+				const uint32_t nR = c * C - nL;
+				uint32_t dl = first + nL + exL;
+				uint32_t dr = pivot + nR + (8 * tid - exL);
+#pragma unroll
+				for (int j = 0; j < 8; ++j) {
+					if (p0 + j < last) {
+						if (flags & (1u << j)) out[dl++] = t[j];
+						else out[dr++] = t[j];
+					}
+				}
+			}
+		}
+		grid.sync();
+		for (int l = 0; l < 2; ++l) {
+			const uint32_t* in = l == 0 ? ctx.scratch : reinterpret_cast<const uint32_t*>(ctx.leftSah);
+			for (uint32_t pos = first + blockIdx.x * T + tid; pos < last; pos += gridDim.x * T) lists[l][pos] = in[pos];
+		}
+		if (blockIdx.x == 0 && tid == 0) {
+			const uint32_t left = slot + 1;
+			const uint32_t right = slot + 2 * (pivot - first);
+			node->kind = bestDim + 1;
+			node->left = left;
+			node->right = right;
+			BuildNode l{}, r{};
+			l.kind = 0; l.parent = slot; l.first = first; l.last = pivot; l.left = kNone; l.right = kNone;
+			r.kind = 0; r.parent = slot; r.first = pivot; r.last = last; r.left = kNone; r.right = kNone;
+			ctx.nodes[left] = l;
+			ctx.nodes[right] = r;
+			emitChild(next, left, pivot - first);
+			emitChild(next, right, last - pivot);
+		}
+		grid.sync();
+	}
+}
+
 template <int T, int E>
-__global__ void __launch_bounds__(T) buildLevelKernel(const DevBuild ctx, const uint32_t* __restrict__ cur, uint32_t* __restrict__ nextBig,
-                                                     uint32_t* __restrict__ nextSmall, uint32_t* __restrict__ nextWide, uint32_t* __restrict__ counts) {
+__global__ void __launch_bounds__(T) buildLevelKernel(const DevBuild ctx, const uint32_t* __restrict__ cur, const NextLists next) {
 	__shared__ typename std::conditional<E == 8, SharedWide<T>, Shared<T>>::type sh;
 	const uint32_t tid = threadIdx.x;
 	const uint32_t slot = cur[blockIdx.x];
@@ -643,13 +1079,8 @@ __global__ void __launch_bounds__(T) buildLevelKernel(const DevBuild ctx, const 
 		r.kind = 0; r.parent = slot; r.first = pivot; r.last = last; r.left = kNone; r.right = kNone;
 		ctx.nodes[left] = l;
 		ctx.nodes[right] = r;
-		const uint32_t child[2] = {left, right};
-		const uint32_t size[2] = {pivot - first, last - pivot};
-		for (int c = 0; c < 2; ++c) {
-			if (size[c] > kWideNode) nextWide[atomicAdd(&counts[2], 1u)] = child[c];
-			else if (size[c] > kSmallNode) nextBig[atomicAdd(&counts[0], 1u)] = child[c];
-			else nextSmall[atomicAdd(&counts[1], 1u)] = child[c];
-		}
+		emitChild(next, left, pivot - first);
+		emitChild(next, right, last - pivot);
 	}
 }
 
@@ -741,7 +1172,7 @@ bool runSahOnDevice(const float* vertices4, uint32_t vertexCount, const uint32_t
 
 	DeviceBuffers& buf = out.buf;
 	float4 *dVerts, *dTb;
-	uint32_t *dIdx, *keys[3], *vals[3], *keysTmp, *valsTmp, *hist, *scratch, *lists[6], *counts;
+	uint32_t *dIdx, *keys[3], *vals[3], *keysTmp, *valsTmp, *hist, *scratch, *lists[8], *counts;
 	float* leftSah;
 	uint8_t* goesLeft;
 	BuildNode* dNodes;
@@ -749,7 +1180,7 @@ bool runSahOnDevice(const float* vertices4, uint32_t vertexCount, const uint32_t
 	          buf.alloc(&valsTmp, n) && buf.alloc(&hist, radixSortHistWords()) && buf.alloc(&scratch, n) && buf.alloc(&leftSah, n) &&
 	          buf.alloc(&goesLeft, n) && buf.alloc(&dNodes, (size_t)n * 2) && buf.alloc(&counts, 4);
 	for (int d = 0; d < 3 && ok; ++d) ok = buf.alloc(&keys[d], n) && buf.alloc(&vals[d], n);
-	for (int l = 0; l < 6 && ok; ++l) ok = buf.alloc(&lists[l], n);
+	for (int l = 0; l < 8 && ok; ++l) ok = buf.alloc(&lists[l], n);
 	if (!ok) { if (error) *error = kErrMem; return false; }
 
 	cudaError_t e = cudaMemcpy(dVerts, vertices4, (size_t)vertexCount * 16, cudaMemcpyHostToDevice);
@@ -781,26 +1212,54 @@ bool runSahOnDevice(const float* vertices4, uint32_t vertexCount, const uint32_t
 	BuildNode root{};
 	root.kind = 0; root.parent = kNone; root.first = 0; root.last = n; root.left = kNone; root.right = kNone;
 	e = cudaMemcpy(dNodes, &root, sizeof(root), cudaMemcpyHostToDevice);
-	// level by level: lists[3*cur + {0,1,2}] = big / small / wide nodes of this level, the other three of the next
-	uint32_t have[3] = {0, 0, 0};
-	have[n > kWideNode ? 2 : (n > kSmallNode ? 0 : 1)] = 1;
+	// level by level: lists[4*cur + {0,1,2,3}] = mid / small / wide / huge nodes of this level, the other four of the next
+	auto classOf = [](uint32_t t) { return t > kHugeNode ? 3 : (t > kWideNode ? 2 : (t > kSmallNode ? 0 : 1)); };
+	uint32_t have[4] = {0, 0, 0, 0};
+	have[classOf(n)] = 1;
 	const uint32_t zero = 0;
-	if (e == cudaSuccess) e = cudaMemcpy(lists[n > kWideNode ? 2 : (n > kSmallNode ? 0 : 1)], &zero, 4, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(lists[classOf(n)], &zero, 4, cudaMemcpyHostToDevice);
 	if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
+
+	// the cooperative kernel for huge nodes: as many CTAs as are co-resident
+	CoopScratch sc{};
+	int coopGrid = 0;
+	if (n > kHugeNode) {
+		int perSm = 0;
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, buildHugeLevelKernel<kWideThreads>, kWideThreads, 0);
+		coopGrid = perSm * smCount;
+		sc.maxChunks = n / (kWideThreads * 8) + 2;
+		const size_t blocks8 = (size_t)n / 8 + 8;
+		bool okc = coopGrid > 0 && buf.alloc(&sc.chunkBox, (size_t)sc.maxChunks * 6) && buf.alloc(&sc.chunkCarry, (size_t)sc.maxChunks * 6) &&
+		           buf.alloc(&sc.chunkMin, sc.maxChunks) && buf.alloc(&sc.chunkBefore, sc.maxChunks) && buf.alloc(&sc.chunkCount, (size_t)sc.maxChunks * 2) &&
+		           buf.alloc(&sc.partBox, (size_t)coopGrid * 6) && buf.alloc(&sc.blkM, blocks8) && buf.alloc(&sc.blkMr, blocks8) &&
+		           buf.alloc(&sc.blkBefore, blocks8) && buf.alloc(&sc.blkArg, blocks8) && buf.alloc(&sc.tailSah, 8) && buf.alloc(&sc.scal, 16);
+		if (!okc) { if (error) *error = kErrMem; return false; }
+	}
+
 	int cur = 0, levels = 0;
-	for (int level = 0; level < 4096 && (have[0] || have[1] || have[2]); ++level, ++levels) {
-		cudaMemsetAsync(counts, 0, 12);
-		uint32_t** in = lists + 3 * cur;
-		uint32_t** nxt = lists + 3 * (1 - cur);
-		if (have[2]) buildLevelKernel<kWideThreads, 8><<<have[2], kWideThreads>>>(ctx, in[2], nxt[0], nxt[1], nxt[2], counts);
-		if (have[0]) buildLevelKernel<256, 1><<<have[0], 256>>>(ctx, in[0], nxt[0], nxt[1], nxt[2], counts);
-		if (have[1]) buildLevelKernel<32, 1><<<have[1], 32>>>(ctx, in[1], nxt[0], nxt[1], nxt[2], counts);
-		const uint32_t had[3] = {have[0], have[1], have[2]};
+	for (int level = 0; level < 4096 && (have[0] || have[1] || have[2] || have[3]); ++level, ++levels) {
+		cudaMemsetAsync(counts, 0, 16);
+		uint32_t** in = lists + 4 * cur;
+		NextLists nx;
+		for (int c = 0; c < 4; ++c) nx.list[c] = lists[4 * (1 - cur) + c];
+		nx.counts = counts;
+		if (have[3]) {
+			const uint32_t* list = in[3];
+			uint32_t cnt = have[3];
+			void* args[] = {(void*)&ctx, (void*)&list, (void*)&cnt, (void*)&nx, (void*)&sc};
+			e = cudaLaunchCooperativeKernel((void*)buildHugeLevelKernel<kWideThreads>, dim3(coopGrid), dim3(kWideThreads), args, 0, nullptr);
+			if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
+		}
+		if (have[2]) buildLevelKernel<kWideThreads, 8><<<have[2], kWideThreads>>>(ctx, in[2], nx);
+		if (have[0]) buildLevelKernel<256, 1><<<have[0], 256>>>(ctx, in[0], nx);
+		if (have[1]) buildLevelKernel<32, 1><<<have[1], 32>>>(ctx, in[1], nx);
+		const uint32_t had[4] = {have[0], have[1], have[2], have[3]};
 		const double tl = nowSeconds();
-		e = cudaMemcpy(have, counts, 12, cudaMemcpyDeviceToHost);
+		e = cudaMemcpy(have, counts, 16, cudaMemcpyDeviceToHost);
 		if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
 		if (getenv("RACC_B200_BUILD_VERBOSE") && atoi(getenv("RACC_B200_BUILD_VERBOSE")) > 1)
-			fprintf(stderr, "racc device build: level %d: %u wide + %u mid + %u small nodes, %.2f ms (wait)\n", level, had[2], had[0], had[1], (nowSeconds() - tl) * 1e3);
+			fprintf(stderr, "racc device build: level %d: %u huge + %u wide + %u mid + %u small nodes, %.2f ms (wait)\n", level, had[3], had[2], had[0], had[1],
+			        (nowSeconds() - tl) * 1e3);
 		cur = 1 - cur;
 	}
 	out.verts = dVerts;
