@@ -1244,11 +1244,20 @@ bool runSahOnDevice(const float* vertices4, uint32_t vertexCount, const uint32_t
 		for (int c = 0; c < 4; ++c) nx.list[c] = lists[4 * (1 - cur) + c];
 		nx.counts = counts;
 		if (have[3]) {
-			const uint32_t* list = in[3];
-			uint32_t cnt = have[3];
-			void* args[] = {(void*)&ctx, (void*)&list, (void*)&cnt, (void*)&nx, (void*)&sc};
-			e = cudaLaunchCooperativeKernel((void*)buildHugeLevelKernel<kWideThreads>, dim3(coopGrid), dim3(kWideThreads), args, 0, nullptr);
-			if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
+			// Whole GPU per node, one node after the other (~0.35 ms of grid barriers each), or one CTA per node
+			// all at once (~15 ns per triangle of the largest node)? Measured on B200 (profiles/r01_build_levels_10M.txt):
+			// the cooperative kernel wins while the level has few, large nodes.
+			const double coopMs = have[3] * 0.35 + 1.5, wideMs = 1.5e-5 * (double)(n >> (level < 31 ? level : 31));
+			if (coopMs < wideMs) {
+				const uint32_t* list = in[3];
+				uint32_t cnt = have[3];
+				void* args[] = {(void*)&ctx, (void*)&list, (void*)&cnt, (void*)&nx, (void*)&sc};
+				e = cudaLaunchCooperativeKernel((void*)buildHugeLevelKernel<kWideThreads>, dim3(coopGrid), dim3(kWideThreads), args, 0, nullptr);
+				if (e != cudaSuccess) { if (error) *error = kErrCuda; return false; }
+			}
+			else {
+				buildLevelKernel<kWideThreads, 8><<<have[3], kWideThreads>>>(ctx, in[3], nx);
+			}
 		}
 		if (have[2]) buildLevelKernel<kWideThreads, 8><<<have[2], kWideThreads>>>(ctx, in[2], nx);
 		if (have[0]) buildLevelKernel<256, 1><<<have[0], 256>>>(ctx, in[0], nx);
