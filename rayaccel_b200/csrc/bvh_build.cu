@@ -1557,15 +1557,19 @@ bool buildSceneImagesDevice(const float* vertices4, uint32_t vertexCount, const 
 	const uint32_t pad = 32u - (realPairs % 32u); // at least one pad pair, total a multiple of 32 float4 (Scene.cpp:335-338)
 	const uint32_t pairTotal = realPairs + pad;
 
-	float4 *dNodes = nullptr, *dPairs = nullptr;
-	uint32_t* dRemap = nullptr;
+	float4 *dNodes = nullptr, *dPairs = nullptr, *dVertsOut = nullptr;
+	uint32_t *dRemap = nullptr, *dIndicesOut = nullptr;
 	if (cudaMalloc(reinterpret_cast<void**>(&dNodes), (size_t)innerCount * 64) != cudaSuccess ||
 	    cudaMalloc(reinterpret_cast<void**>(&dPairs), (size_t)pairTotal * 48) != cudaSuccess ||
-	    cudaMalloc(reinterpret_cast<void**>(&dRemap), (size_t)realPairs * 8 + 16) != cudaSuccess) {
-		cudaFree(dNodes); cudaFree(dPairs); cudaFree(dRemap);
+	    cudaMalloc(reinterpret_cast<void**>(&dRemap), (size_t)realPairs * 8 + 16) != cudaSuccess ||
+	    cudaMalloc(reinterpret_cast<void**>(&dVertsOut), (size_t)vertexCount * 16) != cudaSuccess ||
+	    cudaMalloc(reinterpret_cast<void**>(&dIndicesOut), (size_t)indexCount * 4) != cudaSuccess) {
+		cudaFree(dNodes); cudaFree(dPairs); cudaFree(dRemap); cudaFree(dVertsOut); cudaFree(dIndicesOut);
 		if (error) *error = kErrMem;
 		return false;
 	}
+	cudaMemcpyAsync(dVertsOut, sah.verts, (size_t)vertexCount * 16, cudaMemcpyDeviceToDevice);
+	cudaMemcpyAsync(dIndicesOut, sah.indices, (size_t)indexCount * 4, cudaMemcpyDeviceToDevice);
 	leafMergeKernel<true><<<(2 * innerCount + 127u) / 128u, 128>>>(sah.nodes, order, innerCount, leafBase, sah.sorted0, sah.indices, sah.verts,
 	                                                             pairCount, pairStart, dPairs, dRemap);
 	emitNodesKernel<<<(innerCount + 255u) / 256u, 256>>>(sah.nodes, order, innerCount, deviceOf, leafBase, pairCount, pairStart, dNodes, overflow);
@@ -1576,10 +1580,12 @@ bool buildSceneImagesDevice(const float* vertices4, uint32_t vertexCount, const 
 	if (e == cudaSuccess) e = cudaMemcpy(&root, sah.nodes, sizeof(root), cudaMemcpyDeviceToHost);
 	if (e == cudaSuccess) e = cudaDeviceSynchronize();
 	if (e != cudaSuccess || over) {
-		cudaFree(dNodes); cudaFree(dPairs); cudaFree(dRemap);
+		cudaFree(dNodes); cudaFree(dPairs); cudaFree(dRemap); cudaFree(dVertsOut); cudaFree(dIndicesOut);
 		if (error) *error = over ? kPairs : kErrCuda;
 		return false;
 	}
+	out->verts = dVertsOut;
+	out->indices = dIndicesOut;
 	out->nodes = dNodes;
 	out->pairs = dPairs;
 	out->remap = dRemap;

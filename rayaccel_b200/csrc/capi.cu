@@ -283,12 +283,10 @@ racc_cuda_scene* racc_cuda_scene_create(const float* verts4, uint32_t nverts, co
 			s->info.depth = img.depth;
 			s->info.triangle_count = s->triangleCount;
 			for (int k = 0; k < 3; ++k) { s->info.bounds_min[k] = img.boundsMin[k]; s->info.bounds_max[k] = img.boundsMax[k]; }
+			s->dVerts = static_cast<float4*>(img.verts);
+			s->dIndices = img.indices;
 			cudaError_t e;
-			if ((e = cudaMalloc(reinterpret_cast<void**>(&s->dVerts), (size_t)nverts * 16)) != cudaSuccess ||
-			    (e = cudaMemcpy(s->dVerts, verts4, (size_t)nverts * 16, cudaMemcpyHostToDevice)) != cudaSuccess ||
-			    (e = cudaMalloc(reinterpret_cast<void**>(&s->dIndices), (size_t)nindices * 4)) != cudaSuccess ||
-			    (e = cudaMemcpy(s->dIndices, indices, (size_t)nindices * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
-			    (e = cudaMalloc(reinterpret_cast<void**>(&s->dCursors), kCursorRing * sizeof(uint32_t))) != cudaSuccess) {
+			if ((e = cudaMalloc(reinterpret_cast<void**>(&s->dCursors), kCursorRing * sizeof(uint32_t))) != cudaSuccess) {
 				fail("scene upload failed: %s", cudaGetErrorString(e));
 				racc_cuda_scene_destroy(s);
 				return nullptr;

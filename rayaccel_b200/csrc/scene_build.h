@@ -84,6 +84,8 @@ struct DeviceSceneImages {
 	void* nodes = nullptr;   // nodeCount x 64 B
 	void* pairs = nullptr;   // pairCount x 48 B (incl. tail padding)
 	uint32_t* remap = nullptr;
+	void* verts = nullptr;   // device copies of the input mesh (the build uploaded them anyway)
+	uint32_t* indices = nullptr;
 	uint32_t nodeCount = 0, pairCount = 0, realPairs = 0, remapCount = 0, depth = 0;
 	float boundsMin[3] = {0, 0, 0};
 	float boundsMax[3] = {0, 0, 0};
