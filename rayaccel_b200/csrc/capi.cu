@@ -124,6 +124,7 @@ struct racc_cuda_host_images {
 
 struct racc_cuda_env {
 	float4* dTexels = nullptr;
+	float4* dTexelPairs = nullptr; // (width+1) x height pairs of horizontally adjacent texels (traverse_packed.cu)
 	uint32_t width = 0, height = 0;
 };
 
@@ -413,12 +414,22 @@ racc_cuda_env* racc_cuda_env_create(const float* rgba, uint32_t width, uint32_t 
 		delete env;
 		return nullptr;
 	}
+	int launches = 0;
+	if ((e = cudaMalloc(reinterpret_cast<void**>(&env->dTexelPairs), ((size_t)width + 1) * height * 32)) != cudaSuccess ||
+	    (e = launchPackEnv(env->dTexels, width, height, env->dTexelPairs, nullptr, &launches)) != cudaSuccess ||
+	    (e = cudaDeviceSynchronize()) != cudaSuccess) {
+		fail("environment packing failed: %s", cudaGetErrorString(e));
+		racc_cuda_env_destroy(env);
+		return nullptr;
+	}
+	g_launches.fetch_add((uint64_t)launches);
 	return env;
 }
 
 void racc_cuda_env_destroy(racc_cuda_env* env) {
 	if (!env) return;
 	cudaFree(env->dTexels);
+	cudaFree(env->dTexelPairs);
 	delete env;
 }
 
@@ -488,6 +499,7 @@ void fillSceneParams(TraceParams& p, racc_cuda_scene* s, racc_cuda_env* env, voi
 	p.tnodes = s->dTNodes;
 	p.tpairs = s->dTPairs;
 	p.perm = nullptr;
+	p.envPairs = env ? env->dTexelPairs : nullptr;
 }
 
 bool sceneExceedsL2(const racc_cuda_scene* s) {

@@ -35,6 +35,7 @@ struct TraceParams {
 	const float4* tnodes;     // packed images (traverse_packed.cu): 4 x float4 per inner node,
 	const float4* tpairs;     //   4 x float4 per triangle pair
 	const uint32_t* perm;     // optional visiting order (launch-wide ray indices), null = arrival order
+	const float4* envPairs;   // light probe as horizontally adjacent texel PAIRS: (envWidth+1) x envHeight x 32 B, or null
 };
 
 // Tunables (racc_cuda_set_variant / RACC_B200_* environment variables), see DESIGN.md section 5.
@@ -71,6 +72,9 @@ cudaError_t launchTrace(const TraceParams& p, const Tuning& t, int counterMode, 
 
 // variant 3 (traverse_packed.cu)
 cudaError_t launchTracePacked(const TraceParams& p, const Tuning& t, int counterMode, int smCount, cudaStream_t stream, int* launches);
+
+// light probe -> texel-pair table for the packed kernel (once per environment)
+cudaError_t launchPackEnv(const float4* texels, uint32_t width, uint32_t height, float4* pairsOut, cudaStream_t stream, int* launches);
 
 // reference-format images -> packed images, on the device (once per scene)
 cudaError_t launchPackImages(const float4* nodes, uint32_t nodeCount, const float4* pairs, uint32_t pairCount,

@@ -75,6 +75,57 @@ __global__ void packPairsKernel(const float4* __restrict__ pairs, uint32_t count
 	out[4 * (size_t)i + 3] = make_float4(n1x, n1y, n1z, 0.0f);
 }
 
+// Light probe as texel pairs: entry k of row j holds {texel(clamp(k-1)), texel(clamp(k))}, k in [0, width], so the two
+// horizontally adjacent texels of a bilinear footprint -- clamp-to-edge included -- are ONE aligned 256-bit load.
+__global__ void packEnvKernel(const float4* __restrict__ texels, uint32_t width, uint32_t height, float4* __restrict__ out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (width + 1) * height)
+		return;
+	const uint32_t j = i / (width + 1), k = i % (width + 1);
+	const uint32_t x0 = k ? k - 1 : 0, x1 = k < width ? k : width - 1;
+	out[2 * (size_t)i + 0] = texels[(size_t)j * width + x0];
+	out[2 * (size_t)i + 1] = texels[(size_t)j * width + x1];
+}
+
+// Miss epilogue (Kernels.h:213-221) on the texel-pair table: the arithmetic of missRadiance() of
+// traverse_common.cuh, two gathers instead of four.
+__device__ __forceinline__ float4 missRadiancePairs(const float4* __restrict__ envPairs, uint32_t w, uint32_t hgt, const RayState& r) {
+	const float s = r.dy * r.dy + r.dz * r.dz;
+	const float rlen = __frcp_rn(__fsqrt_rn(s));
+	const float inv2pi = 1.0f / (2.0f * 3.141593f);
+	const float rr = (rlen > 1e+6f) ? 0.0f : (acosPinned(-r.dx) * inv2pi) * rlen;
+	const float u = 0.5f - rr * r.dz;
+	const float v = 0.5f - rr * r.dy;
+	const float fu = u * (float)(int)w - 0.5f;
+	const float fv = v * (float)(int)hgt - 0.5f;
+	float a, b;
+	const int i0 = texelFloor(fu, a);
+	int j0 = texelFloor(fv, b);
+	const int j1 = min(max(j0 + 1, 0), (int)hgt - 1);
+	j0 = min(max(j0, 0), (int)hgt - 1);
+	const uint32_t k = (uint32_t)(min(max(i0, -1), (int)w - 1) + 1);
+	const float4* row0 = envPairs + 2 * ((size_t)j0 * (w + 1) + k);
+	const float4* row1 = envPairs + 2 * ((size_t)j1 * (w + 1) + k);
+	float4 t00, t10, t01, t11;
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(t00.x), "=f"(t00.y), "=f"(t00.z), "=f"(t00.w), "=f"(t10.x), "=f"(t10.y), "=f"(t10.z), "=f"(t10.w) : "l"(row0));
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(t01.x), "=f"(t01.y), "=f"(t01.z), "=f"(t01.w), "=f"(t11.x), "=f"(t11.y), "=f"(t11.z), "=f"(t11.w) : "l"(row1));
+	const float na = 1.0f - a, nb = 1.0f - b;
+	const float w00 = na * nb, w10 = a * nb, w01 = na * b, w11 = a * b;
+	float4 o;
+	o.x = __uint_as_float(kMiss);
+	o.y = ((w00 * t00.x + w10 * t10.x) + w01 * t01.x) + w11 * t11.x;
+	o.z = ((w00 * t00.y + w10 * t10.y) + w01 * t01.y) + w11 * t11.y;
+	o.w = ((w00 * t00.z + w10 * t10.z) + w01 * t01.z) + w11 * t11.z;
+	return o;
+}
+
+__device__ __forceinline__ float4 finishRayPacked(const TraceParams& p, const RayState& r, const HitState& h) {
+	if (h.index != kMiss) return hitResult(p.remap, h);
+	return p.envPairs ? missRadiancePairs(p.envPairs, p.envWidth, p.envHeight, r) : missRadiance(p.env, p.envWidth, p.envHeight, r);
+}
+
 // ---------------------------------------------------------------------------------------------
 
 // trianglePairIntersect (Kernels.h:36-115) on a packed pair; same operations as pairTest() of
@@ -254,7 +305,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const Tr
 		unsigned idle = __ballot_sync(kFullMask, node == 0);
 		if (idle == kFullMask || __popc(idle) >= (exhausted ? 32 : fetchThreshold)) {
 			if (node == 0 && outPtr) {
-				*outPtr = finishRay(p, r, h);
+				*outPtr = finishRayPacked(p, r, h);
 				++cRays;
 				cHits += h.index != kMiss;
 				outPtr = nullptr;
@@ -408,6 +459,13 @@ cudaError_t launchPackImages(const float4* nodes, uint32_t nodeCount, const floa
 		packPairsKernel<<<(pairCount + 255u) / 256u, 256, 0, stream>>>(pairs, pairCount, tpairs);
 		if (launches) *launches += 1;
 	}
+	return cudaGetLastError();
+}
+
+cudaError_t launchPackEnv(const float4* texels, uint32_t width, uint32_t height, float4* pairsOut, cudaStream_t stream, int* launches) {
+	const uint32_t n = (width + 1) * height;
+	packEnvKernel<<<(n + 255u) / 256u, 256, 0, stream>>>(texels, width, height, pairsOut);
+	if (launches) *launches += 1;
 	return cudaGetLastError();
 }
 
