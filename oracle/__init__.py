@@ -27,7 +27,7 @@ COUNTER_DTYPE = np.dtype([("inner", "<u2"), ("pairs", "<u2"), ("max_stack", "<u2
 
 def build(ref: bool = True) -> None:
     """Compile the checker (and, when /root/reference is present, oracle/_ref)."""
-    subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"] + (["ref", "renderer"] if ref else []), stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"] + (["ref", "kernel", "renderer"] if ref else []), stdout=subprocess.DEVNULL)
 
 
 class _Scene(ctypes.Structure):
@@ -64,6 +64,31 @@ def lib() -> ctypes.CDLL:
 
 def have_ref() -> bool:
     return os.path.exists(REF_SO)
+
+
+KERNEL_SO = os.path.join(_HERE, "_ref", "libkernel_ref.so")
+_kernel = None
+
+
+def have_ref_kernel() -> bool:
+    return os.path.exists(KERNEL_SO)
+
+
+def ref_kernel_traverse(scene: "SceneImages", rays: np.ndarray) -> np.ndarray:
+    """The reference's OpenCL `traversal` kernel, compiled from its own source text (Kernels.h) on top of
+    oracle/ref_shim/opencl_c.h, run on the CPU one work-item per ray (single thread)."""
+    global _kernel
+    if _kernel is None:
+        lib()  # liboracle.so provides oracle_acosf
+        _kernel = ctypes.CDLL(KERNEL_SO)
+    rays = np.ascontiguousarray(rays)
+    assert rays.dtype == RAY_DTYPE
+    n = rays.shape[0]
+    res = np.zeros(n, dtype=RESULT_DTYPE)
+    s = scene.c_struct()
+    _kernel.ref_kernel_traverse(ctypes.c_void_p(s.nodes), ctypes.c_void_p(s.pairs), ctypes.c_void_p(s.remap), ctypes.c_void_p(s.env),
+                                ctypes.c_uint32(s.env_width), ctypes.c_uint32(s.env_height), _p(rays), ctypes.c_uint32(n), _p(res))
+    return res
 
 
 def ref() -> ctypes.CDLL:

@@ -1,5 +1,5 @@
 /* racc_oracle.c -- TEST INFRASTRUCTURE ONLY (the parity checker). See racc_oracle.h for the
- * scope, the pin status ("parity unpinned" for traversal: the reference cannot execute here) and
+ * scope, the pin status (traversal pinned to the reference's own kernel source run on the CPU, oracle/_ref/libkernel_ref.so) and
  * the pinned-arithmetic rules. Every function cites the reference lines it restates; paths are
  * relative to /root/reference/.
  *

@@ -13,14 +13,22 @@
  *     compiled into oracle/_ref/libracc_ref.so (tests/test_scene_build.py).
  *   - light-probe lookup: pinned (float tolerance) against the reference's own CPU
  *     racc_internal::sample() (Environment.h:27-82) via oracle/_ref.
- *   - BVH traversal + triangle-pair test: the reference has NO golden vectors or tests, its GPU
- *     kernel is OpenCL JIT-compiled with -cl-fast-relaxed-math for an Intel iGPU and its CPU
- *     path is inside Embree 2.7.0 (binary-only, macOS/Windows). Neither can execute here, so for
- *     this part: **parity unpinned** against a running reference. It is anchored instead on
- *     (a) line-by-line restatement of Kernels.h with the arithmetic pinned as documented below,
- *     (b) an independent brute-force fp64 Moller-Trumbore arbiter over the ORIGINAL triangles
- *     (oracle_brute_f64), and (c) hand-built known-answer cases for every tie / boundary rule
- *     (tests/test_oracle_kat.py).
+ *   - BVH traversal + triangle-pair test: the reference has NO golden vectors or tests, no
+ *     OpenCL runtime exists here, and its CPU path is inside Embree 2.7.0 (binary-only,
+ *     macOS/Windows). What CAN run here is the reference's own kernel SOURCE: oracle/Makefile
+ *     target `kernel` extracts the `traversal` text from Kernels.h:9-242 at build time, compiles
+ *     it unmodified as C++ over a small OpenCL C language shim (oracle/ref_shim/opencl_c.h:
+ *     vector types, swizzles, built-ins) into oracle/_ref/libkernel_ref.so and runs it one
+ *     work-item at a time. The restatement is pinned, bit for bit (ids, t, u, v, r, g, b),
+ *     against that on the KAT scenes, the golden rays, random and edge-case rays and on
+ *     reference-BUILT images (tests/test_oracle_kat.py::test_oracle_matches_reference_kernel_*;
+ *     tests/golden/battlefield_rays.npz holds that library's outputs). So control flow, traversal
+ *     order, tie rules, edge codes and the operation sequence are the reference's own; what stays
+ *     a MODEL is only the bit behaviour of the built-ins the reference leaves implementation-
+ *     defined (-cl-fast-relaxed-math, native_*, read_imagef filtering; listed below), which the
+ *     shim and this file define identically. Additional anchors: (a) an independent brute-force
+ *     fp64 Moller-Trumbore arbiter over the ORIGINAL triangles (oracle_brute_f64), (b) hand-built
+ *     known-answer cases for every tie / boundary rule (tests/test_oracle_kat.py).
  *
  * PINNED ARITHMETIC (the "ideal reading" of the OpenCL source; the CUDA kernel uses the
  * identical operation sequence, so kernel-vs-oracle is bit-exact in IDs *and* t,u,v,r,g,b):

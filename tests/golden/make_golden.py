@@ -9,10 +9,11 @@ What is REFERENCE output (produced by executing the reference's own code):
   ref_scene_digests.json  numbering-independent digests of racc::createScene()'s GPU images
                           (Scene.cpp:183-357, Bvh2.cpp) for battlefield.bin and synthetic meshes
   ref_env_samples.npz     racc_internal::sample() (Environment.h:27-82) for 2048 directions
-What is ORACLE output pinned to those images (the reference's traversal cannot execute here --
-OpenCL JIT kernel / Embree binary, see oracle/racc_oracle.h "parity unpinned"):
-  battlefield_rays.npz    6144 rays (primary, diffuse bounce, uniform random) with the oracle's results
-                          on the REFERENCE-built images and the brute-force fp64 arbiter's (t, id)
+  battlefield_rays.npz    6144 rays (primary, diffuse bounce, uniform random) traced on the REFERENCE-built images
+                          by the reference's own traversal kernel SOURCE (Kernels.h:9-242, compiled as C++ over
+                          oracle/ref_shim/opencl_c.h into oracle/_ref/libkernel_ref.so by `make -C oracle kernel`
+                          and run on the CPU), asserted equal bit for bit to the oracle's results, plus the
+                          brute-force fp64 arbiter's (t, id)
 """
 import json
 import os
@@ -77,10 +78,16 @@ def main():
     rnd["minT"], rnd["maxT"] = 0.0, 1e6
     rays = np.concatenate([primary, bounce, rnd])
     results, counters = oracle.traverse(ref_img, rays, counters=True)
+    # `results` are the outputs of the REFERENCE ITSELF: its unmodified builder's images walked by its own traversal
+    # kernel, compiled from the source text of Kernels.h (oracle/_ref/libkernel_ref.so). The oracle must agree bit for bit.
+    assert oracle.have_ref_kernel(), "build oracle/_ref first (make -C oracle kernel)"
+    ref_results = oracle.ref_kernel_traverse(ref_img, rays)
+    assert np.array_equal(ref_results.view(np.uint32), results.view(np.uint32)), "oracle differs from the reference kernel"
     t64, id64 = oracle.brute_f64(sf.vertices, sf.indices, rays)
     np.savez_compressed(os.path.join(HERE, "battlefield_rays.npz"), rays=rays.view(np.float32).reshape(-1, 8),
-                        results=results.view(np.uint32).reshape(-1, 4), inner=counters["inner"], pairs=counters["pairs"],
-                        t64=t64, id64=id64, kinds=np.array([primary.shape[0], bounce.shape[0], rnd.shape[0]]))
+                        results=ref_results.view(np.uint32).reshape(-1, 4), inner=counters["inner"], pairs=counters["pairs"],
+                        t64=t64, id64=id64, kinds=np.array([primary.shape[0], bounce.shape[0], rnd.shape[0]]),
+                        results_by=np.array("reference builder + reference traversal kernel source (oracle/_ref), run on the CPU"))
     for fn in sorted(os.listdir(HERE)):
         print(f"{fn}: {os.path.getsize(os.path.join(HERE, fn))} bytes")
 
