@@ -231,6 +231,18 @@ def run_reference(args, rank: int, world: int) -> None:
         oracle.traverse_avx2(images, rays)
     dt = time.perf_counter() - t0
     mrays = n * args.steps / dt / 1e6
+    # beside it, the reference's own kernel SOURCE (Kernels.h compiled over oracle/ref_shim/opencl_c.h into oracle/_ref
+    # in the build container), all host threads, on a prefix of the same rays; reported, not the arm's value: the AVX2
+    # port above is the faster CPU implementation and therefore the stricter baseline
+    ref_kernel = None
+    if oracle.have_ref_kernel():
+        m = min(n, max(50_000, int(rate * 3.0)))
+        got = oracle.traverse_avx2(images, rays[:m])
+        t1 = time.perf_counter()
+        want = oracle.ref_kernel_traverse(images, rays[:m], threads=0)
+        ref_kernel = {"value": round(m / (time.perf_counter() - t1) / 1e6, 3), "unit": "Mrays/s", "cores": cores, "kind": "reference",
+                      "sample": f"first {m} rays of the step", "what": "reference traversal kernel source text run on the CPU through an "
+                      "OpenCL C shim, one work-item at a time per thread", "port_results_bit_identical": bool(got.tobytes() == want.tobytes())}
     sample = (f"{len(rows)} of {HEIGHT} pixel rows (evenly strided) of the {WIDTH}x{HEIGHT}x{SPP}spp batch, primary + {BOUNCES} "
               f"bounces = {n} rays per step; scene images by the {built_by}")
     line = {
@@ -244,6 +256,8 @@ def run_reference(args, rank: int, world: int) -> None:
         "e2e": {"value": round(mrays, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if ref_kernel is not None:
+        line["reference_kernel_source"] = ref_kernel
     emit(line)
 
 

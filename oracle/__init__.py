@@ -74,9 +74,10 @@ def have_ref_kernel() -> bool:
     return os.path.exists(KERNEL_SO)
 
 
-def ref_kernel_traverse(scene: "SceneImages", rays: np.ndarray) -> np.ndarray:
+def ref_kernel_traverse(scene: "SceneImages", rays: np.ndarray, threads: int = 1) -> np.ndarray:
     """The reference's OpenCL `traversal` kernel, compiled from its own source text (Kernels.h) on top of
-    oracle/ref_shim/opencl_c.h, run on the CPU one work-item per ray (single thread)."""
+    oracle/ref_shim/opencl_c.h, run on the CPU one work-item per ray; threads > 1 hands batches of 1024
+    work-items to that many threads, threads <= 0 uses every online core."""
     global _kernel
     if _kernel is None:
         lib()  # liboracle.so provides oracle_acosf
@@ -86,8 +87,11 @@ def ref_kernel_traverse(scene: "SceneImages", rays: np.ndarray) -> np.ndarray:
     n = rays.shape[0]
     res = np.zeros(n, dtype=RESULT_DTYPE)
     s = scene.c_struct()
-    _kernel.ref_kernel_traverse(ctypes.c_void_p(s.nodes), ctypes.c_void_p(s.pairs), ctypes.c_void_p(s.remap), ctypes.c_void_p(s.env),
-                                ctypes.c_uint32(s.env_width), ctypes.c_uint32(s.env_height), _p(rays), ctypes.c_uint32(n), _p(res))
+    if threads <= 0:
+        threads = os.cpu_count() or 1
+    _kernel.ref_kernel_traverse_mt(ctypes.c_void_p(s.nodes), ctypes.c_void_p(s.pairs), ctypes.c_void_p(s.remap), ctypes.c_void_p(s.env),
+                                   ctypes.c_uint32(s.env_width), ctypes.c_uint32(s.env_height), _p(rays), ctypes.c_uint32(n), _p(res),
+                                   ctypes.c_int(threads))
     return res
 
 
