@@ -193,6 +193,51 @@ int racc_cuda_generate_bounce(const racc_cuda_scene* scene, const void* device_r
                               uint32_t count, uint32_t seed, void* device_out_rays, uint32_t* device_out_count,
                               void* cuda_stream);
 
+/* ---- device-side wavefront path tracer ----
+ * The reference's example client (Renderer/PathTracingRenderer.cpp) shades on the host: every bounce crosses the
+ * spawn/shade callbacks of RayAccelerator.h:85-93, i.e. PCIe on a discrete GPU. These entry points run the same
+ * estimator with the shading on the device (rayaccel_b200/csrc/pathtrace.cu), so rays, hit records and path state stay
+ * in HBM from the camera to the framebuffer. They are an addition beside the drop-in API, not a replacement of it. */
+
+typedef struct racc_cuda_shading racc_cuda_shading;
+
+/* Host arrays of Renderer/SceneData.h:13-30 as main.cpp:154-180 loads them; copied to the device. */
+typedef struct {
+	const float* normals4;              /* per vertex, 4 floats (SceneData::normals) */
+	uint32_t vertex_count;
+	const float* triangle_normals4;     /* per triangle, 4 floats (SceneData::triangleNormals) */
+	const uint16_t* triangle_materials; /* per triangle (SceneData::triangleMaterials) */
+	uint32_t triangle_count;
+	const float* materials_ke4;         /* per material {r, g, b, eta}: ReflectiveDiffuseMaterial(k, eta), Materials.cpp:32-37 */
+	uint32_t material_count;
+} racc_cuda_shading_desc;
+
+/* NULL on failure (racc_cuda_last_error). */
+racc_cuda_shading* racc_cuda_shading_create(const racc_cuda_shading_desc* desc);
+void racc_cuda_shading_destroy(racc_cuda_shading* shading);
+
+#define RACC_CUDA_FRAMEBUFFER_HOST 1u /* framebuffer4 is a host pointer (copied in, accumulated, copied back, synchronised) */
+
+typedef struct {
+	uint32_t width, height;  /* every pixel is rendered (the reference's TiledRenderer covers whole 128-pixel tiles only) */
+	uint32_t sample_base;    /* index of the first sample: samples sample_base .. sample_base+spp-1 (ranks of a multi-GPU job
+	                            take disjoint ranges and sum their framebuffers) */
+	uint32_t spp;            /* paths per pixel; the reference renders one per frame and accumulates (TiledRenderer.cpp:40-48) */
+	uint32_t max_depth;      /* SceneData::maxDepth: a path is extended while its depth < max_depth (PathTracingRenderer.cpp:126) */
+	uint32_t seed;           /* 0 = primary rays through pixel centres */
+	uint32_t batch_spp;      /* samples traced together, 0 = about 8 M paths (128 B of device memory per path) */
+	uint32_t flags;
+} racc_cuda_path_desc;
+
+/* Adds the radiance sums of `spp` paths per pixel to framebuffer4 (width*height x {r,g,b,unused} floats; a DEVICE
+ * pointer unless RACC_CUDA_FRAMEBUFFER_HOST), like the reference's frameBuffer (PathTracingRenderer.cpp:540-543): sums,
+ * not means. wave_rays (host, may be NULL): [max_depth+1] counters, += rays traced at each depth; their total is
+ * Stats::raysTraced of the equivalent render() calls. The scene must have been created from triangles (not from images).
+ * Work is enqueued on cuda_stream; the call waits for each bounce's ray count, and a device framebuffer is complete once
+ * the stream has been synchronised. Results are bit-reproducible and equal oracle_path_trace's. 0 on success. */
+int racc_cuda_path_trace(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_shading* shading, const racc_cuda_camera* camera,
+                         const racc_cuda_path_desc* desc, float* framebuffer4, uint64_t* wave_rays, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

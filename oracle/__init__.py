@@ -235,3 +235,96 @@ def ref_env_sample(env: np.ndarray, dirs: np.ndarray) -> np.ndarray:
     if rc:
         raise RuntimeError("ref_env_sample failed")
     return out[:, :3]
+
+
+# ---- wavefront path tracer: checker for rayaccel_b200/csrc/pathtrace.cu -----------------
+
+class _Shading(ctypes.Structure):
+    _fields_ = [
+        ("indices", ctypes.c_void_p), ("triangle_count", ctypes.c_uint32),
+        ("normals4", ctypes.c_void_p), ("triangle_normals4", ctypes.c_void_p),
+        ("triangle_materials", ctypes.c_void_p), ("materials_ke4", ctypes.c_void_p), ("material_count", ctypes.c_uint32),
+    ]
+
+
+class _Camera(ctypes.Structure):
+    _fields_ = [("origin", ctypes.c_float * 3), ("view", ctypes.c_float * 3), ("right", ctypes.c_float * 3), ("up", ctypes.c_float * 3)]
+
+
+# the four materials the reference assigns to battlefield.bin (Renderer/main.cpp:165-168): {r, g, b, eta}
+BATTLEFIELD_MATERIALS = np.array([[0.8, 0.8, 0.8, 1.0 / 1.4], [0.1, 0.1, 0.1, 1.0 / 1.4], [0.6, 0.6, 0.6, 1.0 / 1.2], [0.3, 0.3, 0.3, 1.0 / 1.2]],
+                                 dtype=np.float32)
+
+
+class Shading:
+    """Host copies of what the reference's example path tracer shades with (Renderer/SceneData.h)."""
+
+    def __init__(self, indices, normals4, triangle_normals4, triangle_materials, materials_ke4=BATTLEFIELD_MATERIALS):
+        self.indices = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        self.normals = np.ascontiguousarray(normals4, dtype=np.float32).reshape(-1, 4)
+        self.triangle_normals = np.ascontiguousarray(triangle_normals4, dtype=np.float32).reshape(-1, 4)
+        self.triangle_materials = np.ascontiguousarray(triangle_materials, dtype=np.uint16).reshape(-1)
+        self.materials = np.ascontiguousarray(materials_ke4, dtype=np.float32).reshape(-1, 4)
+        assert self.indices.shape[0] == 3 * self.triangle_normals.shape[0] == 3 * self.triangle_materials.shape[0]
+
+    def c_struct(self) -> _Shading:
+        return _Shading(self.indices.ctypes.data, self.triangle_materials.shape[0], self.normals.ctypes.data,
+                        self.triangle_normals.ctypes.data, self.triangle_materials.ctypes.data, self.materials.ctypes.data,
+                        self.materials.shape[0])
+
+
+def _camera_struct(cam) -> _Camera:
+    get = (lambda k: cam[k]) if isinstance(cam, dict) else (lambda k: getattr(cam, k))
+    c = _Camera()
+    for k in range(3):
+        c.origin[k], c.view[k], c.right[k], c.up[k] = (float(get(n)[k]) for n in ("origin", "view", "right", "up"))
+    return c
+
+
+def material_sample(ke, rnd, normal, wo):
+    """oracle_material_sample for n lanes: (n,3) rnd / normal / wo -> (wi, color)."""
+    rnd, normal, wo = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in (rnd, normal, wo))
+    ke = np.ascontiguousarray(ke, dtype=np.float32).reshape(4)
+    wi, color = np.zeros_like(rnd), np.zeros_like(rnd)
+    fn = lib().oracle_material_sample
+    fn.restype = None
+    for i in range(rnd.shape[0]):
+        fn(_p(ke), _p(rnd[i]), _p(normal[i]), _p(wo[i]), ctypes.c_void_p(wi[i].ctypes.data), ctypes.c_void_p(color[i].ctypes.data))
+    return wi, color
+
+
+def path_trace(scene: SceneImages, shading: Shading, camera, width: int, height: int, spp: int, max_depth: int, seed: int,
+               sample_base: int = 0, framebuffer: np.ndarray | None = None, threads: int = 0):
+    """oracle_path_trace: returns (framebuffer (H, W, 4) float32 with the radiance sums added, rays traced per depth)."""
+    fb = np.zeros((height, width, 4), dtype=np.float32) if framebuffer is None else framebuffer
+    assert fb.dtype == np.float32 and fb.shape == (height, width, 4) and fb.flags.c_contiguous
+    waves = np.zeros(max_depth + 1, dtype=np.uint64)
+    s, sh, cam = scene.c_struct(), shading.c_struct(), _camera_struct(camera)
+    rc = lib().oracle_path_trace(ctypes.byref(s), ctypes.byref(sh), ctypes.byref(cam), ctypes.c_uint32(width), ctypes.c_uint32(height),
+                                 ctypes.c_uint32(sample_base), ctypes.c_uint32(spp), ctypes.c_uint32(max_depth), ctypes.c_uint32(seed),
+                                 _p(fb), _p(waves), ctypes.c_int(threads))
+    if rc:
+        raise RuntimeError("oracle_path_trace failed")
+    return fb, waves
+
+
+SHADE_SO = os.path.join(_HERE, "_ref", "libshade_ref.so")
+_shade = None
+
+
+def have_ref_shade() -> bool:
+    return os.path.exists(SHADE_SO)
+
+
+def ref_material_sample(ke, rnd, normal, wo):
+    """The reference's UNMODIFIED ReflectiveDiffuseMaterial::sample8 (Renderer/Materials.cpp, compiled into
+    oracle/_ref/libshade_ref.so by `make -C oracle renderer`), 8 lanes at a time."""
+    global _shade
+    if _shade is None:
+        _shade = ctypes.CDLL(SHADE_SO)
+    rnd, normal, wo = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in (rnd, normal, wo))
+    ke = np.ascontiguousarray(ke, dtype=np.float32).reshape(4)
+    n = rnd.shape[0]
+    wi, color = np.zeros_like(rnd), np.zeros_like(rnd)
+    _shade.ref_material_sample(_p(ke), _p(rnd), _p(normal), _p(wo), ctypes.c_uint32(n), _p(wi), _p(color))
+    return wi, color

@@ -641,3 +641,196 @@ int oracle_scene_digest(const oracle_scene* sc, uint64_t digest[16]) {
 	free(st);
 	return rc;
 }
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* Wavefront path tracer: CPU restatement of what the reference's example
+ * client computes per path -- Renderer/PathTracingRenderer.cpp:72-566 (shade),
+ * Renderer/Materials.cpp:11-151 (ReflectiveDiffuseMaterial::sample8 and its sin/cos parabolas),
+ * Renderer/Camera.cpp:55-114 (generateTileRays), Renderer/LightPath.cpp:11-39 -- one path at a
+ * time, in the arithmetic the CUDA renderer (rayaccel_b200/csrc/pathtrace.cu) uses, so that the
+ * two agree bit for bit. Departures from the reference, all of them where the reference is not
+ * reproducible itself: its random numbers come from an MWC generator seeded with libc rand() per
+ * call (SimdRandom.h:20-56, PathTracingRenderer.cpp:107, Camera.cpp:58), here from a counter-based
+ * hash of (pixel, sample, depth, seed); its _mm256_rsqrt_ps / _mm256_rcp_ps 12-bit approximations
+ * are exact 1/sqrt and 1/x here. The estimator (what is sampled with which probability and
+ * weight, when a path ends) is the reference's. */
+
+static inline uint32_t pcg_hash(uint32_t v) {
+	uint32_t s = v * 747796405u + 2891336453u;
+	uint32_t w = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
+	return (w >> 22u) ^ w;
+}
+static inline float unit_float(uint32_t h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
+static inline float xor_sign(float x, uint32_t signbit) { return u2f(f2u(x) ^ signbit); }
+
+/* Materials.cpp:11-22: parabola through sin(2 pi x), x in [0,1] */
+static inline float sin_approx(float x) {
+	float y = fmaf(-16.0f, x, 8.0f);
+	int gt = x >= 0.5f;
+	float xy = x * y;
+	if (gt) xy = -xy;
+	return xy + (gt ? y : 0.0f);
+}
+/* Materials.cpp:24-28 */
+static inline float cos_approx(float x) {
+	float y = x - 0.75f;
+	x = (f2u(y) & 0x80000000u) ? x + 0.25f : y;
+	return sin_approx(x);
+}
+
+/* Materials.cpp:39-151, one lane */
+void oracle_material_sample(const float ke[4], const float rnd[3], const float normal[3], const float wo[3], float wi[3], float color[3]) {
+	const float nx = normal[0], ny = normal[1], nz = normal[2];
+	const float eta = ke[3];
+	/* reflection vector and fresnel term, :57-80 */
+	float cosi = fmaf(nz, wo[2], fmaf(ny, wo[1], nx * wo[0]));
+	cosi = cosi > 0.0f ? cosi : 0.0f;
+	const float c2 = 2.0f * cosi;
+	const float rx = fmaf(c2, nx, -wo[0]), ry = fmaf(c2, ny, -wo[1]), rz = fmaf(c2, nz, -wo[2]);
+	const float cosi2m1 = fmaf(cosi, cosi, -1.0f);
+	const float eta2 = eta * eta;
+	const float k = fmaf(eta2, cosi2m1, 1.0f);
+	const float cost = sqrtf(k);
+	const float rper = fmaf(eta, cosi, -cost) * (1.0f / fmaf(eta, cosi, cost));
+	const float rpar = -(fmaf(eta, cost, -cosi) * (1.0f / fmaf(eta, cost, cosi)));
+	float fresnel = 0.5f * fmaf(rpar, rpar, rper * rper);
+	if (f2u(k) & 0x80000000u) fresnel = 1.0f;
+	/* diffuse direction, :82-120 */
+	const int wide = !(fabsf(nx) <= 0.1f);
+	float ux = wide ? -nz : 0.0f, uy = wide ? 0.0f : -nz, uz = wide ? nx : ny;
+	const float fb = 1.0f / sqrtf(fmaf(uz, uz, fmaf(uy, uy, ux * ux)));
+	ux *= fb; uy *= fb; uz *= fb;
+	const float vx = fmaf(ny, uz, -(nz * uy)), vy = fmaf(nz, ux, -(nx * uz)), vz = fmaf(nx, uy, -(ny * ux));
+	const float sinx = sin_approx(rnd[0]), cosx = cos_approx(rnd[0]);
+	const float r2s = sqrtf(rnd[1]);
+	const float sq = sqrtf(1.0f - rnd[1]);
+	float dx = fmaf(nx, sq, fmaf(ux, cosx, vx * sinx) * r2s);
+	float dy = fmaf(ny, sq, fmaf(uy, cosx, vy * sinx) * r2s);
+	float dz = fmaf(nz, sq, fmaf(uz, cosx, vz * sinx) * r2s);
+	const float fd = 1.0f / sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+	dx *= fd; dy *= fd; dz *= fd;
+	/* reflection or diffuse, :122-150 */
+	const float s0 = fresnel * 3.0f;
+	const float s1 = ke[2] + (ke[0] + ke[1]);
+	const float sum = s0 + s1;
+	const float uniform = rnd[2] * sum;
+	const int diffuse = uniform >= s0;
+	wi[0] = diffuse ? dx : rx; wi[1] = diffuse ? dy : ry; wi[2] = diffuse ? dz : rz;
+	const float r = diffuse ? ke[0] : fresnel, g = diffuse ? ke[1] : fresnel, b = diffuse ? ke[2] : fresnel;
+	const float scale = sum * (1.0f / (b + (r + g)));
+	color[0] = r * scale; color[1] = g * scale; color[2] = b * scale;
+}
+
+/* One bounce of one path, PathTracingRenderer.cpp:124-127 (who is shaded), :231-246 (shading normal),
+ * :376-466 (sample, weight, continuation test, next ray). Returns 1 when the path goes on. */
+static int shade_hit(const oracle_shading* sh, const oracle_ray* ray, const oracle_result* res, const float rnd[3], float weight[3],
+                     oracle_ray* next) {
+	const uint32_t tri = res->triangle;
+	const float t = res->a, u = res->b, v = res->c;
+	const uint32_t* idx = sh->indices + 3 * (size_t)tri;
+	const float* n0 = sh->normals4 + 4 * (size_t)idx[0];
+	const float* n1 = sh->normals4 + 4 * (size_t)idx[1];
+	const float* n2 = sh->normals4 + 4 * (size_t)idx[2];
+	const float w = 1.0f - (u + v);
+	float n[3];
+	for (int k = 0; k < 3; ++k) n[k] = fmaf(n2[k], v, fmaf(n1[k], u, n0[k] * w));
+	const float fn = 1.0f / sqrtf(fmaf(n[2], n[2], fmaf(n[1], n[1], n[0] * n[0])));
+	const float* gn = sh->triangle_normals4 + 4 * (size_t)tri;
+	const float rdgn = fmaf(ray->dir[2], gn[2], fmaf(ray->dir[1], gn[1], ray->dir[0] * gn[0]));
+	const uint32_t sgn0 = f2u(rdgn) & 0x80000000u;
+	float wo[3], pos[3];
+	for (int k = 0; k < 3; ++k) {
+		n[k] = xor_sign(n[k] * fn, sgn0);
+		wo[k] = -ray->dir[k];
+		pos[k] = fmaf(ray->dir[k], t, ray->origin[k]);
+	}
+	uint32_t m = sh->triangle_materials[tri];
+	if (m >= sh->material_count) m = 0;
+	float wi[3], color[3];
+	oracle_material_sample(sh->materials_ke4 + 4 * (size_t)m, rnd, n, wo, wi, color);
+	for (int k = 0; k < 3; ++k) weight[k] *= color[k];
+	int go = weight[0] > 0.01f || weight[1] > 0.01f || weight[2] > 0.01f;
+	const float sgn1 = fmaf(wi[2], gn[2], fmaf(wi[1], gn[1], wi[0] * gn[0]));
+	go &= ((f2u(sgn1) ^ sgn0) >> 31) != 0; /* leaves on the side it arrived from (no transmission in this material) */
+	const uint32_t flip = f2u(sgn1) & 0x80000000u;
+	for (int k = 0; k < 3; ++k) {
+		pos[k] = fmaf(xor_sign(gn[k], flip), 1e-4f, pos[k]);
+		go &= pos[k] == pos[k] && wi[k] == wi[k];
+		next->origin[k] = pos[k];
+		next->dir[k] = wi[k];
+	}
+	next->minT = 1e-3f;
+	next->maxT = 1e+6f;
+	return go;
+}
+
+typedef struct {
+	const oracle_scene* scene; const oracle_shading* sh; const oracle_camera* cam;
+	uint32_t width, height, sample_base, spp, max_depth, seed;
+	float* fb; uint64_t* waves; volatile int err;
+} pt_ctx;
+
+#define PT_CHUNK 256 /* pixels per task */
+
+static void pt_body(void* p, int64_t c) {
+	pt_ctx* x = (pt_ctx*)p;
+	const uint64_t pixels = (uint64_t)x->width * x->height;
+	uint64_t lo = (uint64_t)c * PT_CHUNK, hi = lo + PT_CHUNK < pixels ? lo + PT_CHUNK : pixels;
+	uint64_t waves[64] = { 0 };
+	for (uint64_t pixel = lo; pixel < hi; ++pixel) {
+		const uint32_t px_i = (uint32_t)(pixel % x->width), py_i = (uint32_t)(pixel / x->width);
+		float acc[3] = { x->fb[4 * pixel], x->fb[4 * pixel + 1], x->fb[4 * pixel + 2] };
+		for (uint32_t s = 0; s < x->spp; ++s) {
+			const uint32_t sample = x->sample_base + s;
+			/* primary ray: Camera.cpp:55-114 */
+			float jx = 0.5f, jy = 0.5f;
+			if (x->seed) {
+				uint32_t h = pcg_hash((uint32_t)pixel ^ pcg_hash(sample ^ pcg_hash(x->seed)));
+				jx = unit_float(h);
+				jy = unit_float(pcg_hash(h));
+			}
+			const float fx = (float)px_i + jx, fy = (float)py_i + jy;
+			oracle_ray ray;
+			float d[3];
+			for (int k = 0; k < 3; ++k) d[k] = fmaf(x->cam->right[k], fx, fmaf(x->cam->up[k], fy, x->cam->view[k]));
+			const float scale = 1.0f / sqrtf(fmaf(d[2], d[2], fmaf(d[1], d[1], d[0] * d[0])));
+			for (int k = 0; k < 3; ++k) { ray.origin[k] = x->cam->origin[k]; ray.dir[k] = d[k] * scale; }
+			ray.minT = 0.0f;
+			ray.maxT = 1e+6f;
+			float weight[3] = { 1.0f, 1.0f, 1.0f };
+			float contrib[3] = { 0.0f, 0.0f, 0.0f };
+			for (uint32_t depth = 0; depth <= x->max_depth; ++depth) {
+				oracle_result res;
+				if (traverse_one(x->scene, &ray, &res, 0)) { x->err = -1; break; }
+				waves[depth < 64 ? depth : 63]++;
+				if (res.triangle == ORACLE_INVALID_TRIANGLE) { /* PathTracingRenderer.cpp:468-566 */
+					contrib[0] = res.a * weight[0]; contrib[1] = res.b * weight[1]; contrib[2] = res.c * weight[2];
+					break;
+				}
+				if (!(res.triangle < x->sh->triangle_count && depth < x->max_depth)) break;
+				uint32_t h = pcg_hash((uint32_t)pixel ^ pcg_hash(sample ^ pcg_hash(x->seed ^ (0x9e3779b9u * (depth + 1u)))));
+				float rnd[3];
+				rnd[0] = unit_float(h); h = pcg_hash(h);
+				rnd[1] = unit_float(h); h = pcg_hash(h);
+				rnd[2] = unit_float(h);
+				oracle_ray next;
+				if (!shade_hit(x->sh, &ray, &res, rnd, weight, &next)) break;
+				ray = next;
+			}
+			for (int k = 0; k < 3; ++k) acc[k] += contrib[k];
+		}
+		for (int k = 0; k < 3; ++k) x->fb[4 * pixel + k] = acc[k];
+	}
+	if (x->waves)
+		for (uint32_t dpt = 0; dpt <= x->max_depth && dpt < 64; ++dpt) __sync_fetch_and_add(&x->waves[dpt], waves[dpt]);
+}
+
+int oracle_path_trace(const oracle_scene* scene, const oracle_shading* shading, const oracle_camera* camera, uint32_t width,
+                      uint32_t height, uint32_t sample_base, uint32_t spp, uint32_t max_depth, uint32_t seed, float* framebuffer4,
+                      uint64_t* wave_rays, int threads) {
+	if (max_depth > 62) return -1;
+	pt_ctx x = { scene, shading, camera, width, height, sample_base, spp, max_depth, seed, framebuffer4, wave_rays, 0 };
+	parallel_for(threads, ((int64_t)width * height + PT_CHUNK - 1) / PT_CHUNK, pt_body, &x);
+	return x.err;
+}

@@ -124,6 +124,36 @@ int oracle_tri_t_f64(const float* verts4, const uint32_t* indices, const oracle_
  * FNV-1a hash over (DFS order) child boxes, leaf pair bytes and remap words. Returns 0. */
 int oracle_scene_digest(const oracle_scene* scene, uint64_t digest[16]);
 
+/* ---- wavefront path tracer; checker for rayaccel_b200/csrc/pathtrace.cu ---- */
+
+/* What the reference's example renderer shades with (Renderer/SceneData.h:13-30, main.cpp:160-180). */
+typedef struct {
+	const uint32_t* indices;            /* 3 per triangle */
+	uint32_t triangle_count;
+	const float* normals4;              /* per vertex, 4 floats */
+	const float* triangle_normals4;     /* per triangle, 4 floats */
+	const uint16_t* triangle_materials; /* per triangle */
+	const float* materials_ke4;         /* per material {r,g,b,eta}: ReflectiveDiffuseMaterial, Materials.cpp:32-37 */
+	uint32_t material_count;
+} oracle_shading;
+
+/* Camera::lookAt's outputs (Camera.cpp:13-25) */
+typedef struct { float origin[3], view[3], right[3], up[3]; } oracle_camera;
+
+/* ReflectiveDiffuseMaterial::sample8 (Materials.cpp:39-151) for one lane: rnd in [0,1]^3, shading normal,
+ * wo = -ray direction -> sampled direction wi and the path-weight factor. Exact 1/x and 1/sqrt where the
+ * reference uses the 12-bit _mm256_rcp_ps / _mm256_rsqrt_ps. */
+void oracle_material_sample(const float ke[4], const float rnd[3], const float normal[3], const float wo[3], float wi[3], float color[3]);
+
+/* `spp` paths per pixel (samples sample_base .. sample_base+spp-1) of at most max_depth bounces each
+ * (PathTracingRenderer.cpp:72-566), radiance of escaping paths ADDED to framebuffer4 (width*height x 4
+ * floats, .w untouched) sample by sample in ascending order. wave_rays (may be NULL): [max_depth+1]
+ * counters, += rays traced at each depth. Random numbers: counter-based hash of (pixel, sample, depth,
+ * seed) -- see racc_oracle.c. seed 0 = pixel centres for the primary rays. */
+int oracle_path_trace(const oracle_scene* scene, const oracle_shading* shading, const oracle_camera* camera, uint32_t width,
+                      uint32_t height, uint32_t sample_base, uint32_t spp, uint32_t max_depth, uint32_t seed, float* framebuffer4,
+                      uint64_t* wave_rays, int threads);
+
 #ifdef __cplusplus
 }
 #endif

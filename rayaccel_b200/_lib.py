@@ -35,6 +35,19 @@ class CameraStruct(ctypes.Structure):
     _fields_ = [("origin", ctypes.c_float * 3), ("view", ctypes.c_float * 3), ("right", ctypes.c_float * 3), ("up", ctypes.c_float * 3)]
 
 
+class ShadingDesc(ctypes.Structure):
+    _fields_ = [("normals4", ctypes.c_void_p), ("vertex_count", ctypes.c_uint32), ("triangle_normals4", ctypes.c_void_p),
+                ("triangle_materials", ctypes.c_void_p), ("triangle_count", ctypes.c_uint32), ("materials_ke4", ctypes.c_void_p),
+                ("material_count", ctypes.c_uint32)]
+
+
+class PathDesc(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("sample_base", ctypes.c_uint32), ("spp", ctypes.c_uint32),
+                ("max_depth", ctypes.c_uint32), ("seed", ctypes.c_uint32), ("batch_spp", ctypes.c_uint32), ("flags", ctypes.c_uint32)]
+
+
+FRAMEBUFFER_HOST = 1
+
 # every symbol include/racc_b200.h declares: name -> (restype, argtypes)
 _P = ctypes.c_void_p
 _U32 = ctypes.c_uint32
@@ -68,6 +81,10 @@ SYMBOLS = {
     "racc_cuda_set_tuning": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "racc_cuda_generate_primary": (ctypes.c_int, [ctypes.POINTER(CameraStruct), _U32, _U32, _U32, _U32, _P, _P]),
     "racc_cuda_generate_bounce": (ctypes.c_int, [_P, _P, _P, _U32, _U32, _P, _P, _P]),
+    "racc_cuda_shading_create": (_P, [ctypes.POINTER(ShadingDesc)]),
+    "racc_cuda_shading_destroy": (None, [_P]),
+    "racc_cuda_path_trace": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(CameraStruct), ctypes.POINTER(PathDesc), _P,
+                                             ctypes.POINTER(ctypes.c_uint64), _P]),
 }
 
 _lib = None

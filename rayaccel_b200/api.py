@@ -259,3 +259,70 @@ def generate_bounce(scene: Scene, rays_ptr: int, results_ptr: int, count: int, s
     _lib.check(_lib.load().racc_cuda_generate_bounce(scene._h, ctypes.c_void_p(rays_ptr), ctypes.c_void_p(results_ptr), count, seed,
                                                       ctypes.c_void_p(out_rays_ptr), ctypes.c_void_p(out_count_ptr),
                                                       _cuda_stream_handle(stream)), "racc_cuda_generate_bounce")
+
+
+# ---- device-side wavefront path tracer (csrc/pathtrace.cu) ----------------------
+
+# the four materials the reference assigns to battlefield.bin (Renderer/main.cpp:165-168): {r, g, b, eta}
+BATTLEFIELD_MATERIALS = np.array([[0.8, 0.8, 0.8, 1.0 / 1.4], [0.1, 0.1, 0.1, 1.0 / 1.4], [0.6, 0.6, 0.6, 1.0 / 1.2], [0.3, 0.3, 0.3, 1.0 / 1.2]],
+                                 dtype=np.float32)
+
+
+class Shading:
+    """Device copies of what the reference's example path tracer shades with (Renderer/SceneData.h:13-30)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def destroy(self) -> None:
+        if self._h:
+            _lib.load().racc_cuda_shading_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def create_shading(normals: np.ndarray, triangle_normals: np.ndarray, triangle_materials: np.ndarray,
+                   materials: np.ndarray = BATTLEFIELD_MATERIALS) -> Shading:
+    """normals (V,4) float32, triangle_normals (T,4) float32, triangle_materials (T,) uint16, materials (M,4) float32 {r,g,b,eta}."""
+    n = np.ascontiguousarray(normals, dtype=np.float32)
+    tn = np.ascontiguousarray(triangle_normals, dtype=np.float32)
+    tm = np.ascontiguousarray(triangle_materials, dtype=np.uint16).reshape(-1)
+    m = np.ascontiguousarray(materials, dtype=np.float32)
+    if n.ndim != 2 or n.shape[1] != 4 or tn.ndim != 2 or tn.shape[1] != 4 or m.ndim != 2 or m.shape[1] != 4:
+        raise ValueError("normals, triangle_normals and materials must be (N, 4) float32")
+    if tn.shape[0] != tm.shape[0]:
+        raise ValueError("one geometric normal and one material index per triangle")
+    d = _lib.ShadingDesc(n.ctypes.data, n.shape[0], tn.ctypes.data, tm.ctypes.data, tm.shape[0], m.ctypes.data, m.shape[0])
+    return Shading(_lib.check_ptr(_lib.load().racc_cuda_shading_create(ctypes.byref(d)), "racc_cuda_shading_create"))
+
+
+def _camera_struct(camera: Camera) -> "_lib.CameraStruct":
+    cam = _lib.CameraStruct()
+    for k in range(3):
+        cam.origin[k] = float(camera.origin[k]); cam.view[k] = float(camera.view[k])
+        cam.right[k] = float(camera.right[k]); cam.up[k] = float(camera.up[k])
+    return cam
+
+
+def path_trace(scene: Scene, environment: Environment | None, shading: Shading, camera: Camera, width: int, height: int, spp: int,
+               max_depth: int, seed: int, framebuffer_ptr: int | None = None, sample_base: int = 0, batch_spp: int = 0, stream=None):
+    """`spp` paths per pixel of the reference's path tracer (PathTracingRenderer.cpp) with the shading on the device.
+    framebuffer_ptr: DEVICE pointer to width*height float4 radiance sums, added to in place; None = a fresh host array,
+    returned as (H, W, 4) float32. Returns (framebuffer or None, rays traced per depth)."""
+    waves = (ctypes.c_uint64 * (max_depth + 1))()
+    d = _lib.PathDesc(width, height, sample_base, spp, max_depth, seed, batch_spp, 0)
+    fb = None
+    if framebuffer_ptr is None:
+        fb = np.zeros((height, width, 4), dtype=np.float32)
+        d.flags = _lib.FRAMEBUFFER_HOST
+        framebuffer_ptr = fb.ctypes.data
+    cam = _camera_struct(camera)
+    _lib.check(_lib.load().racc_cuda_path_trace(scene._h, environment._h if environment is not None else None, shading._h, ctypes.byref(cam),
+                                                 ctypes.byref(d), ctypes.c_void_p(framebuffer_ptr), waves, _cuda_stream_handle(stream)),
+               "racc_cuda_path_trace")
+    return fb, [int(x) for x in waves]

@@ -104,12 +104,13 @@ struct racc_cuda_scene {
 	SceneImages host;            // host images; left empty when the scene was built on the device
 	racc_cuda_scene_info info{}; // counts, depth and bounds of what is on the device
 	uint32_t triangleCount = 0;
+	uint32_t vertexCount = 0;    // of dVerts (0 when the scene was created from images)
 	float4* dNodes = nullptr;
 	float4* dPairs = nullptr;
 	uint32_t* dRemap = nullptr;
 	float4* dTNodes = nullptr;   // packed images walked by the default kernel (traverse_packed.cu)
 	float4* dTPairs = nullptr;
-	float4* dVerts = nullptr;    // only for the synthetic bounce generator
+	float4* dVerts = nullptr;    // for the synthetic bounce generator and the device-side renderer (indices)
 	uint32_t* dIndices = nullptr;
 	uint32_t* dCursors = nullptr;
 	std::atomic<uint32_t> nextCursor{0};
@@ -126,6 +127,15 @@ struct racc_cuda_env {
 	float4* dTexels = nullptr;
 	float4* dTexelPairs = nullptr; // (width+1) x height pairs of horizontally adjacent texels (traverse_packed.cu)
 	uint32_t width = 0, height = 0;
+};
+
+// What the reference's example path tracer shades with (Renderer/SceneData.h), resident on the device.
+struct racc_cuda_shading {
+	float4* dNormals = nullptr;
+	float4* dTriangleNormals = nullptr;
+	uint16_t* dTriangleMaterials = nullptr;
+	float4* dMaterials = nullptr;
+	uint32_t vertexCount = 0, triangleCount = 0, materialCount = 0;
 };
 
 namespace {
@@ -270,6 +280,7 @@ racc_cuda_scene* racc_cuda_scene_create(const float* verts4, uint32_t nverts, co
 	const char* why = "";
 	bool built = false;
 	s->triangleCount = nindices / 3;
+	s->vertexCount = nverts;
 	if (g_tuning.buildDevice == 2 || (g_tuning.buildDevice == 3 && nindices / 3 >= kAutoDeviceBuildTriangles)) {
 		// the whole build on the device: the images never exist on the host
 		DeviceSceneImages img;
@@ -736,6 +747,124 @@ int racc_cuda_generate_bounce(const racc_cuda_scene* scene_, const void* device_
 	                                     static_cast<const float4*>(device_results), count, seed, static_cast<DevRay*>(device_out_rays),
 	                                     device_out_count, s->dBounceScratch, static_cast<cudaStream_t>(cuda_stream), &launches));
 	g_launches.fetch_add((uint64_t)launches);
+	return 0;
+}
+
+// ---- device-side wavefront path tracer (pathtrace.cu) ----
+
+racc_cuda_shading* racc_cuda_shading_create(const racc_cuda_shading_desc* d) {
+	if (!d || !d->normals4 || !d->triangle_normals4 || !d->triangle_materials || !d->materials_ke4) {
+		fail("racc_cuda_shading_create: null input");
+		return nullptr;
+	}
+	if (!d->material_count) { fail("racc_cuda_shading_create: no materials"); return nullptr; }
+	if (ensureInit()) return nullptr;
+	racc_cuda_shading* sh = new racc_cuda_shading();
+	sh->vertexCount = d->vertex_count;
+	sh->triangleCount = d->triangle_count;
+	sh->materialCount = d->material_count;
+	cudaError_t e;
+#define UP(dst, src, bytes)                                                                                 \
+	if ((e = cudaMalloc(reinterpret_cast<void**>(&dst), (bytes) != 0 ? (bytes) : 16)) != cudaSuccess ||     \
+	    (e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {                         \
+		fail("racc_cuda_shading_create: upload failed: %s", cudaGetErrorString(e));                         \
+		racc_cuda_shading_destroy(sh);                                                                      \
+		return nullptr;                                                                                     \
+	}
+	UP(sh->dNormals, d->normals4, (size_t)d->vertex_count * 16)
+	UP(sh->dTriangleNormals, d->triangle_normals4, (size_t)d->triangle_count * 16)
+	UP(sh->dTriangleMaterials, d->triangle_materials, (size_t)d->triangle_count * 2)
+	UP(sh->dMaterials, d->materials_ke4, (size_t)d->material_count * 16)
+#undef UP
+	return sh;
+}
+
+void racc_cuda_shading_destroy(racc_cuda_shading* sh) {
+	if (!sh) return;
+	cudaFree(sh->dNormals);
+	cudaFree(sh->dTriangleNormals);
+	cudaFree(sh->dTriangleMaterials);
+	cudaFree(sh->dMaterials);
+	delete sh;
+}
+
+int racc_cuda_path_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_shading* sh, const racc_cuda_camera* camera,
+                         const racc_cuda_path_desc* d, float* framebuffer4, uint64_t* wave_rays, void* cuda_stream) {
+	if (!s || !sh || !camera || !d || !framebuffer4) return fail("racc_cuda_path_trace: null argument");
+	if (!s->dIndices) return fail("racc_cuda_path_trace: scene was created from images and has no index data");
+	if (sh->triangleCount != s->triangleCount || sh->vertexCount < s->vertexCount)
+		return fail("racc_cuda_path_trace: shading data (%u triangles, %u vertices) does not match the scene (%u, %u)", sh->triangleCount,
+		            sh->vertexCount, s->triangleCount, s->vertexCount);
+	if (d->max_depth > 62) return fail("racc_cuda_path_trace: max_depth %u > 62", d->max_depth);
+	if (ensureInit()) return -1;
+	const uint64_t pixels = (uint64_t)d->width * d->height;
+	if (!pixels || !d->spp) return 0;
+	if (pixels > (1ull << 28)) return fail("racc_cuda_path_trace: viewport too large");
+	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+	// paths per batch: whole samples, about 8 M paths (128 B of device memory each) unless the caller says otherwise
+	uint32_t batchSpp = d->batch_spp ? d->batch_spp : (uint32_t)((8ull << 20) / pixels);
+	if (batchSpp < 1) batchSpp = 1;
+	if (batchSpp > d->spp) batchSpp = d->spp;
+	if (pixels * batchSpp > 0x7fffffffull) return fail("racc_cuda_path_trace: batch of %u samples is too large", batchSpp);
+	const size_t paths = (size_t)pixels * batchSpp;
+	const bool hostFb = (d->flags & RACC_CUDA_FRAMEBUFFER_HOST) != 0;
+
+	struct Buffers {
+		cudaStream_t stream;
+		void* p[8] = {};
+		~Buffers() { for (void* q : p) if (q) cudaFreeAsync(q, stream); }
+	} buf;
+	buf.stream = stream;
+	const size_t sizes[8] = {paths * 32, paths * 32, paths * 16, paths * 16, paths * 16, paths * 16, 64 * sizeof(uint32_t),
+	                         hostFb ? (size_t)pixels * 16 : 0};
+	for (int k = 0; k < 8; ++k)
+		if (sizes[k]) RACC_CUDA_CHECK(cudaMallocAsync(&buf.p[k], sizes[k], stream));
+	DevRay* rays[2] = {static_cast<DevRay*>(buf.p[0]), static_cast<DevRay*>(buf.p[1])};
+	float4* states[2] = {static_cast<float4*>(buf.p[2]), static_cast<float4*>(buf.p[3])};
+	float4* results = static_cast<float4*>(buf.p[4]);
+	float4* radiance = static_cast<float4*>(buf.p[5]);
+	uint32_t* counts = static_cast<uint32_t*>(buf.p[6]);
+	float4* fb = hostFb ? static_cast<float4*>(buf.p[7]) : reinterpret_cast<float4*>(framebuffer4);
+	if (hostFb) RACC_CUDA_CHECK(cudaMemcpyAsync(fb, framebuffer4, (size_t)pixels * 16, cudaMemcpyHostToDevice, stream));
+
+	int launches = 0;
+	for (uint32_t done = 0; done < d->spp; done += batchSpp) {
+		const uint32_t spp = d->spp - done < batchSpp ? d->spp - done : batchSpp;
+		const uint32_t sampleBase = d->sample_base + done;
+		uint32_t count = (uint32_t)(pixels * spp);
+		RACC_CUDA_CHECK(cudaMemsetAsync(radiance, 0, (size_t)count * 16, stream));
+		RACC_CUDA_CHECK(cudaMemsetAsync(counts, 0, 64 * sizeof(uint32_t), stream));
+		RACC_CUDA_CHECK(launchPathPrimary(camera->origin, d->width, d->height, sampleBase, spp, d->seed, rays[0], states[0], stream, &launches));
+		int cur = 0;
+		for (uint32_t depth = 0; depth <= d->max_depth && count; ++depth) {
+			if (wave_rays) wave_rays[depth] += count;
+			racc_cuda_stream_desc sd{};
+			sd.rays = rays[cur];
+			sd.results = results;
+			sd.count = count;
+			sd.flags = 0;
+			if (traceImpl(s, env, &sd, 1, stream, nullptr, false)) return -1;
+			PathShadeParams p{};
+			p.rays = rays[cur]; p.results = results; p.states = states[cur]; p.count = count;
+			p.depth = depth; p.maxDepth = d->max_depth; p.seed = d->seed; p.pixels = (uint32_t)pixels; p.sampleBase = sampleBase;
+			p.indices = s->dIndices; p.normals = sh->dNormals; p.triangleNormals = sh->dTriangleNormals;
+			p.triangleMaterials = sh->dTriangleMaterials; p.materials = sh->dMaterials;
+			p.triangleCount = sh->triangleCount; p.materialCount = sh->materialCount;
+			p.outRays = rays[cur ^ 1]; p.outStates = states[cur ^ 1]; p.outCount = counts + depth; p.radiance = radiance;
+			RACC_CUDA_CHECK(launchPathShade(p, stream, &launches));
+			if (depth == d->max_depth) break; // nothing is extended past the last bounce
+			// the size of the next wave decides its launch: the one host round trip per bounce
+			RACC_CUDA_CHECK(cudaMemcpyAsync(&count, counts + depth, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+			RACC_CUDA_CHECK(cudaStreamSynchronize(stream));
+			cur ^= 1;
+		}
+		RACC_CUDA_CHECK(launchPathAccumulate(radiance, (uint32_t)pixels, spp, fb, stream, &launches));
+	}
+	g_launches.fetch_add((uint64_t)launches);
+	if (hostFb) {
+		RACC_CUDA_CHECK(cudaMemcpyAsync(framebuffer4, fb, (size_t)pixels * 16, cudaMemcpyDeviceToHost, stream));
+		RACC_CUDA_CHECK(cudaStreamSynchronize(stream));
+	}
 	return 0;
 }
 

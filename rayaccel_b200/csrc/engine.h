@@ -101,4 +101,30 @@ cudaError_t launchGenerateBounce(const float4* verts, const uint32_t* indices, c
 
 size_t bounceScratchWords(uint32_t count);
 
+// device-side wavefront path tracer (pathtrace.cu), see there
+struct PathShadeParams {
+	const DevRay* rays;       // the wave just traced: rays, results, path states (weight rgb + path index in .w)
+	const float4* results;
+	const float4* states;
+	uint32_t count;
+	uint32_t depth, maxDepth; // bounce number of this wave; hits are extended while depth < maxDepth
+	uint32_t seed, pixels, sampleBase;
+	const uint32_t* indices;
+	const float4* normals;
+	const float4* triangleNormals;
+	const uint16_t* triangleMaterials;
+	const float4* materials;  // {r, g, b, eta} per material
+	uint32_t triangleCount, materialCount;
+	DevRay* outRays;          // next wave (compacted), its size in *outCount (zeroed by the caller)
+	float4* outStates;
+	uint32_t* outCount;
+	float4* radiance;         // one slot per path of the batch (zeroed by the caller), written when the path escapes
+};
+
+cudaError_t launchPathPrimary(const float* camera12, uint32_t width, uint32_t height, uint32_t sampleBase, uint32_t spp, uint32_t seed,
+                              DevRay* rays, float4* states, cudaStream_t stream, int* launches);
+cudaError_t launchPathShade(const PathShadeParams& p, cudaStream_t stream, int* launches);
+cudaError_t launchPathAccumulate(const float4* radiance, uint32_t pixels, uint32_t spp, float4* framebuffer, cudaStream_t stream,
+                                 int* launches);
+
 } // namespace racc_b200

@@ -6,20 +6,10 @@
 //   bounce rays  : the ray construction of /root/reference/Renderer/PathTracingRenderer.cpp:405-422
 //                  (origin = hit + 1e-4 * n_g, minT 1e-3, maxT 1e6) with a cosine-hemisphere
 //                  direction about the flipped geometric normal, i.e. a diffuse path-tracer bounce.
-#include "engine.h"
+#include "raygen.cuh"
 
 namespace racc_b200 {
 namespace {
-
-__device__ __forceinline__ uint32_t pcg(uint32_t v) {
-	uint32_t s = v * 747796405u + 2891336453u;
-	uint32_t w = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
-	return (w >> 22u) ^ w;
-}
-
-__device__ __forceinline__ float unitFloat(uint32_t h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
-
-struct CameraArgs { float origin[3], view[3], right[3], up[3]; };
 
 __global__ void primaryKernel(CameraArgs cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t seed, DevRay* rays) {
 	const uint64_t total = (uint64_t)width * height * spp;
@@ -27,22 +17,7 @@ __global__ void primaryKernel(CameraArgs cam, uint32_t width, uint32_t height, u
 	if (i >= total) return;
 	const uint32_t pixel = (uint32_t)(i % ((uint64_t)width * height));
 	const uint32_t sample = (uint32_t)(i / ((uint64_t)width * height));
-	const uint32_t x = pixel % width, y = pixel / width;
-	float jx = 0.5f, jy = 0.5f;
-	if (seed) {
-		const uint32_t h = pcg(pixel ^ pcg(sample ^ pcg(seed)));
-		jx = unitFloat(h);
-		jy = unitFloat(pcg(h));
-	}
-	const float px = (float)x + jx, py = (float)y + jy;
-	float dx = fmaf(cam.right[0], px, fmaf(cam.up[0], py, cam.view[0]));
-	float dy = fmaf(cam.right[1], px, fmaf(cam.up[1], py, cam.view[1]));
-	float dz = fmaf(cam.right[2], px, fmaf(cam.up[2], py, cam.view[2]));
-	const float scale = 1.0f / sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-	DevRay r;
-	r.a = make_float4(cam.origin[0], cam.origin[1], cam.origin[2], 0.0f);
-	r.b = make_float4(dx * scale, dy * scale, dz * scale, 1e+6f);
-	rays[i] = r;
+	rays[i] = primaryRay(cam, width, pixel, sample, seed);
 }
 
 constexpr int kTile = 1024; // rays per compaction tile (256 threads x 4)
@@ -154,13 +129,7 @@ __global__ void bounceWriteKernel(const float4* verts, const uint32_t* indices, 
 
 cudaError_t launchGeneratePrimary(const float* camera12, uint32_t width, uint32_t height, uint32_t spp, uint32_t seed,
                                   DevRay* rays, cudaStream_t stream, int* launches) {
-	CameraArgs cam;
-	for (int k = 0; k < 3; ++k) {
-		cam.origin[k] = camera12[k];
-		cam.view[k] = camera12[3 + k];
-		cam.right[k] = camera12[6 + k];
-		cam.up[k] = camera12[9 + k];
-	}
+	const CameraArgs cam = cameraArgs(camera12);
 	const uint64_t total = (uint64_t)width * height * spp;
 	if (!total) return cudaSuccess;
 	const unsigned grid = (unsigned)((total + 255) / 256);

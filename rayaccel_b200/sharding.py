@@ -95,3 +95,22 @@ def gather_results_interleaved(local: torch.Tensor, total: int, block: int, grou
         idx = idx[idx < total]
         out[idx] = gathered[r, : idx.numel()]
     return out.view(-1)
+
+
+def sample_range(spp: int, rank: int, world: int) -> tuple[int, int]:
+    """Device-side renderer across GPUs: the frame's samples are split, every rank renders all pixels for
+    samples [first, first + count) (racc_cuda_path_desc.sample_base / spp) and the framebuffers are summed."""
+    begin, end = shard_bounds(spp, rank, world)
+    return begin, end - begin
+
+
+def reduce_framebuffer(framebuffer: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the ranks' radiance sums (float32, width*height*4) over all ranks, in place: the one collective of the
+    device-side renderer (the reference accumulates one sample per frame into one host framebuffer,
+    PathTracingRenderer.cpp:540-543). The sum is associative up to float rounding, so an N-GPU image equals the
+    1-GPU image to a few ulp, not bit for bit."""
+    if framebuffer.dtype != torch.float32:
+        raise ValueError("the framebuffer holds float32 radiance sums")
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(framebuffer, op=dist.ReduceOp.SUM, group=group)
+    return framebuffer

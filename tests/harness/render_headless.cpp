@@ -9,7 +9,8 @@
 // is the reference's own: Stats.raysTraced / microseconds per render() (main.cpp:208-231).
 //
 //   racc_render_{gpu,cpu} [--whitted] [--width W --height H] [--frames N] [--depth D]
-//                         [--threads T] [--scene path] [--out image.ppm]
+//                         [--threads T] [--scene path] [--out image.ppm] [--dump framebuffer.f32]
+// --dump writes the raw float4 framebuffer (radiance sums over the frames, width*height*4 floats).
 // Prints one JSON line. `_gpu` links libracc_b200.so; `_cpu` links tests/harness/fake_capi.cpp
 // (oracle-backed, for plumbing checks on machines without a GPU -- BASELINE.json configs[0]).
 #include "Camera.h"
@@ -39,7 +40,7 @@ static T* alignedArray(size_t n) { return static_cast<T*>(_mm_malloc(n * sizeof(
 int main(int argc, char** argv) {
 	bool whitted = false;
 	int width = 0, height = 0, frames = 4, depth = -1, threads = 0, device = 0;
-	std::string scenePath = "data/battlefield.bin", outPath;
+	std::string scenePath = "data/battlefield.bin", outPath, dumpPath;
 	for (int i = 1; i < argc; ++i) {
 		auto next = [&]() { return i + 1 < argc ? argv[++i] : "0"; };
 		if (!strcmp(argv[i], "--whitted")) whitted = true;
@@ -51,6 +52,7 @@ int main(int argc, char** argv) {
 		else if (!strcmp(argv[i], "--device")) device = atoi(next());
 		else if (!strcmp(argv[i], "--scene")) scenePath = next();
 		else if (!strcmp(argv[i], "--out")) outPath = next();
+		else if (!strcmp(argv[i], "--dump")) dumpPath = next();
 		else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
 	}
 
@@ -148,6 +150,13 @@ int main(int argc, char** argv) {
 				const float c[3] = {p.x, p.y, p.z};
 				for (int k = 0; k < 3; ++k) fputc((int)std::fmin(255.0f, std::fmax(0.0f, c[k] * scale)), o);
 			}
+			fclose(o);
+		}
+	}
+	if (!dumpPath.empty()) {
+		FILE* o = fopen(dumpPath.c_str(), "wb");
+		if (o) {
+			fwrite(g_renderer->frameBuffer, sizeof(float4), (size_t)sd.viewportWidth * sd.viewportHeight, o);
 			fclose(o);
 		}
 	}
