@@ -498,6 +498,37 @@ struct HostPipeline {
 
 thread_local HostPipeline t_pipeline;
 
+// Internal streams of racc_cuda_path_trace (one set per calling host thread), see there.
+struct PathLanes {
+	static constexpr int kMax = 4;
+	bool ready = false;
+	int device = -1;
+	int count = 2;
+	cudaStream_t stream[kMax] = {};
+	cudaEvent_t done[kMax] = {};
+	cudaEvent_t fork = nullptr;
+	uint32_t* hostCounts = nullptr; // pinned: the next wave's size of each lane
+
+	int init() {
+		if (ready && device == g_device) return 0;
+		device = g_device;
+		count = envInt("RACC_B200_PATH_LANES", 2);
+		if (count < 1) count = 1;
+		if (count > kMax) count = kMax;
+		RACC_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+		RACC_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&hostCounts), kMax * sizeof(uint32_t), cudaHostAllocPortable));
+		for (int l = 0; l < kMax; ++l) {
+			RACC_CUDA_CHECK(cudaStreamCreateWithFlags(&stream[l], cudaStreamNonBlocking));
+			RACC_CUDA_CHECK(cudaEventCreateWithFlags(&done[l], cudaEventDisableTiming));
+		}
+		ready = true;
+		return 0;
+	}
+	~PathLanes() { /* process teardown: the context may already be gone, leak on purpose */ }
+};
+
+thread_local PathLanes t_pathLanes;
+
 void fillSceneParams(TraceParams& p, racc_cuda_scene* s, racc_cuda_env* env, void* device_counters) {
 	p.nodes = s->dNodes;
 	p.pairs = s->dPairs;
@@ -811,55 +842,112 @@ int racc_cuda_path_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda
 	const size_t paths = (size_t)pixels * batchSpp;
 	const bool hostFb = (d->flags & RACC_CUDA_FRAMEBUFFER_HOST) != 0;
 
+	// Lanes: a batch is cut into contiguous path ranges that advance bounce by bounce on their own streams. While the host
+	// waits for one lane's wave size, the other lane's launches are queued, and the tail of a traversal launch (few long
+	// paths left, most SMs idle) is filled by the other lane's kernels.
+	PathLanes& lanes = t_pathLanes;
+	if (lanes.init()) return -1;
+	const int nlanes = paths >= (size_t)lanes.count * 65536 ? lanes.count : 1;
+	const size_t lanePaths = (paths + nlanes - 1) / nlanes;
+
 	struct Buffers {
 		cudaStream_t stream;
 		void* p[8] = {};
 		~Buffers() { for (void* q : p) if (q) cudaFreeAsync(q, stream); }
 	} buf;
 	buf.stream = stream;
-	const size_t sizes[8] = {paths * 32, paths * 32, paths * 16, paths * 16, paths * 16, paths * 16, 64 * sizeof(uint32_t),
-	                         hostFb ? (size_t)pixels * 16 : 0};
+	const size_t sizes[8] = {lanePaths * nlanes * 32, lanePaths * nlanes * 32, lanePaths * nlanes * 16, lanePaths * nlanes * 16,
+	                         lanePaths * nlanes * 16, paths * 16, (size_t)PathLanes::kMax * 64 * sizeof(uint32_t), hostFb ? (size_t)pixels * 16 : 0};
 	for (int k = 0; k < 8; ++k)
 		if (sizes[k]) RACC_CUDA_CHECK(cudaMallocAsync(&buf.p[k], sizes[k], stream));
-	DevRay* rays[2] = {static_cast<DevRay*>(buf.p[0]), static_cast<DevRay*>(buf.p[1])};
-	float4* states[2] = {static_cast<float4*>(buf.p[2]), static_cast<float4*>(buf.p[3])};
-	float4* results = static_cast<float4*>(buf.p[4]);
 	float4* radiance = static_cast<float4*>(buf.p[5]);
 	uint32_t* counts = static_cast<uint32_t*>(buf.p[6]);
 	float4* fb = hostFb ? static_cast<float4*>(buf.p[7]) : reinterpret_cast<float4*>(framebuffer4);
 	if (hostFb) RACC_CUDA_CHECK(cudaMemcpyAsync(fb, framebuffer4, (size_t)pixels * 16, cudaMemcpyHostToDevice, stream));
 
+	struct Lane {
+		DevRay* rays[2];
+		float4* states[2];
+		float4* results;
+		uint32_t* counts; // device, one per depth
+		cudaStream_t stream;
+		uint32_t count, depth;
+		int cur;
+		bool busy;
+	} lane[PathLanes::kMax];
+	for (int l = 0; l < nlanes; ++l) {
+		lane[l].rays[0] = static_cast<DevRay*>(buf.p[0]) + (size_t)l * lanePaths;
+		lane[l].rays[1] = static_cast<DevRay*>(buf.p[1]) + (size_t)l * lanePaths;
+		lane[l].states[0] = static_cast<float4*>(buf.p[2]) + (size_t)l * lanePaths;
+		lane[l].states[1] = static_cast<float4*>(buf.p[3]) + (size_t)l * lanePaths;
+		lane[l].results = static_cast<float4*>(buf.p[4]) + (size_t)l * lanePaths;
+		lane[l].counts = counts + (size_t)l * 64;
+		lane[l].stream = nlanes > 1 ? lanes.stream[l] : stream;
+	}
+
 	int launches = 0;
 	for (uint32_t done = 0; done < d->spp; done += batchSpp) {
 		const uint32_t spp = d->spp - done < batchSpp ? d->spp - done : batchSpp;
 		const uint32_t sampleBase = d->sample_base + done;
-		uint32_t count = (uint32_t)(pixels * spp);
-		RACC_CUDA_CHECK(cudaMemsetAsync(radiance, 0, (size_t)count * 16, stream));
-		RACC_CUDA_CHECK(cudaMemsetAsync(counts, 0, 64 * sizeof(uint32_t), stream));
-		RACC_CUDA_CHECK(launchPathPrimary(camera->origin, d->width, d->height, sampleBase, spp, d->seed, rays[0], states[0], stream, &launches));
-		int cur = 0;
-		for (uint32_t depth = 0; depth <= d->max_depth && count; ++depth) {
-			if (wave_rays) wave_rays[depth] += count;
+		const uint32_t batchPaths = (uint32_t)(pixels * spp);
+		RACC_CUDA_CHECK(cudaMemsetAsync(radiance, 0, (size_t)batchPaths * 16, stream));
+		RACC_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)PathLanes::kMax * 64 * sizeof(uint32_t), stream));
+		if (nlanes > 1) {
+			RACC_CUDA_CHECK(cudaEventRecord(lanes.fork, stream));
+			for (int l = 0; l < nlanes; ++l) RACC_CUDA_CHECK(cudaStreamWaitEvent(lane[l].stream, lanes.fork, 0));
+		}
+		// one wave of one lane: trace, shade + compact, and (unless it was the last bounce) ask for the next wave's size
+		auto enqueue = [&](Lane& ln, int l) -> int {
+			if (wave_rays) wave_rays[ln.depth] += ln.count;
 			racc_cuda_stream_desc sd{};
-			sd.rays = rays[cur];
-			sd.results = results;
-			sd.count = count;
+			sd.rays = ln.rays[ln.cur];
+			sd.results = ln.results;
+			sd.count = ln.count;
 			sd.flags = 0;
-			if (traceImpl(s, env, &sd, 1, stream, nullptr, false)) return -1;
+			if (traceImpl(s, env, &sd, 1, ln.stream, nullptr, false)) return -1;
 			PathShadeParams p{};
-			p.rays = rays[cur]; p.results = results; p.states = states[cur]; p.count = count;
-			p.depth = depth; p.maxDepth = d->max_depth; p.seed = d->seed; p.pixels = (uint32_t)pixels; p.sampleBase = sampleBase;
+			p.rays = ln.rays[ln.cur]; p.results = ln.results; p.states = ln.states[ln.cur]; p.count = ln.count;
+			p.depth = ln.depth; p.maxDepth = d->max_depth; p.seed = d->seed; p.pixels = (uint32_t)pixels; p.sampleBase = sampleBase;
 			p.indices = s->dIndices; p.normals = sh->dNormals; p.triangleNormals = sh->dTriangleNormals;
 			p.triangleMaterials = sh->dTriangleMaterials; p.materials = sh->dMaterials;
 			p.triangleCount = sh->triangleCount; p.materialCount = sh->materialCount;
-			p.outRays = rays[cur ^ 1]; p.outStates = states[cur ^ 1]; p.outCount = counts + depth; p.radiance = radiance;
-			RACC_CUDA_CHECK(launchPathShade(p, stream, &launches));
-			if (depth == d->max_depth) break; // nothing is extended past the last bounce
-			// the size of the next wave decides its launch: the one host round trip per bounce
-			RACC_CUDA_CHECK(cudaMemcpyAsync(&count, counts + depth, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-			RACC_CUDA_CHECK(cudaStreamSynchronize(stream));
-			cur ^= 1;
+			p.outRays = ln.rays[ln.cur ^ 1]; p.outStates = ln.states[ln.cur ^ 1]; p.outCount = ln.counts + ln.depth; p.radiance = radiance;
+			RACC_CUDA_CHECK(launchPathShade(p, ln.stream, &launches));
+			if (ln.depth == d->max_depth) { ln.busy = false; return 0; } // nothing is extended past the last bounce
+			RACC_CUDA_CHECK(cudaMemcpyAsync(lanes.hostCounts + l, ln.counts + ln.depth, sizeof(uint32_t), cudaMemcpyDeviceToHost, ln.stream));
+			return 0;
+		};
+		int active = 0;
+		for (int l = 0; l < nlanes; ++l) {
+			Lane& ln = lane[l];
+			const size_t first = (size_t)l * lanePaths;
+			ln.count = first < batchPaths ? (uint32_t)(batchPaths - first < lanePaths ? batchPaths - first : lanePaths) : 0;
+			ln.depth = 0;
+			ln.cur = 0;
+			ln.busy = ln.count != 0;
+			if (!ln.busy) continue;
+			RACC_CUDA_CHECK(launchPathPrimary(camera->origin, d->width, d->height, sampleBase, (uint32_t)first, ln.count, d->seed, ln.rays[0],
+			                                  ln.states[0], ln.stream, &launches));
+			if (enqueue(ln, l)) return -1;
+			active += ln.busy;
 		}
+		// round robin: the size of a lane's next wave decides its launch -- the one host round trip per bounce and lane
+		for (int l = 0; active; l = (l + 1) % nlanes) {
+			Lane& ln = lane[l];
+			if (!ln.busy) continue;
+			RACC_CUDA_CHECK(cudaStreamSynchronize(ln.stream));
+			ln.count = lanes.hostCounts[l];
+			ln.depth += 1;
+			ln.cur ^= 1;
+			if (!ln.count) { ln.busy = false; --active; continue; }
+			if (enqueue(ln, l)) return -1;
+			if (!ln.busy) --active;
+		}
+		if (nlanes > 1)
+			for (int l = 0; l < nlanes; ++l) {
+				RACC_CUDA_CHECK(cudaEventRecord(lanes.done[l], lane[l].stream));
+				RACC_CUDA_CHECK(cudaStreamWaitEvent(stream, lanes.done[l], 0));
+			}
 		RACC_CUDA_CHECK(launchPathAccumulate(radiance, (uint32_t)pixels, spp, fb, stream, &launches));
 	}
 	g_launches.fetch_add((uint64_t)launches);

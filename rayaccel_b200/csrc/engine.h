@@ -121,8 +121,8 @@ struct PathShadeParams {
 	float4* radiance;         // one slot per path of the batch (zeroed by the caller), written when the path escapes
 };
 
-cudaError_t launchPathPrimary(const float* camera12, uint32_t width, uint32_t height, uint32_t sampleBase, uint32_t spp, uint32_t seed,
-                              DevRay* rays, float4* states, cudaStream_t stream, int* launches);
+cudaError_t launchPathPrimary(const float* camera12, uint32_t width, uint32_t height, uint32_t sampleBase, uint32_t firstPath, uint32_t count,
+                              uint32_t seed, DevRay* rays, float4* states, cudaStream_t stream, int* launches);
 cudaError_t launchPathShade(const PathShadeParams& p, cudaStream_t stream, int* launches);
 cudaError_t launchPathAccumulate(const float4* radiance, uint32_t pixels, uint32_t spp, float4* framebuffer, cudaStream_t stream,
                                  int* launches);

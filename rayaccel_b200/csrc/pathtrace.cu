@@ -12,8 +12,10 @@
 // Data in HBM per batch of R = width*height*spp_batch paths: two ray buffers (32 B/path), two path-state buffers
 // (16 B: weight rgb + path index), one result buffer (16 B), one radiance buffer (16 B, written at most once per path:
 // a path contributes only when it escapes to the light probe) -- 128 B per path. Compaction between bounces is one
-// atomic per CTA; paths keep their arrival order inside a CTA, CTAs land in completion order. The image does not depend
-// on that order: a ray's result does not depend on its neighbours, and every path owns its radiance slot, which
+// atomic per CTA; paths keep their arrival order inside a CTA, CTAs land in completion order. A batch is cut into lanes
+// (contiguous path ranges) that advance bounce by bounce on their own CUDA streams, so that the tail of one lane's
+// traversal launch is filled by the other lane's kernels (capi.cu: racc_cuda_path_trace). The image does not depend
+// on any of that order: a ray's result does not depend on its neighbours, and every path owns its radiance slot, which
 // pathAccumulateKernel adds to the framebuffer sample by sample in ascending order (so there are no float atomics and
 // the framebuffer is bit-reproducible, and equal to oracle_path_trace's).
 //
@@ -90,13 +92,15 @@ __device__ __forceinline__ void materialSample(const float4 ke, const float rnd[
 	color[0] = r * scale; color[1] = g * scale; color[2] = b * scale;
 }
 
-__global__ void pathPrimaryKernel(CameraArgs cam, uint32_t width, uint32_t pixels, uint32_t sampleBase, uint32_t count, uint32_t seed,
-                                  DevRay* rays, float4* states) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count) return;
+// paths [firstPath, firstPath + count) of a batch; path i is pixel i % pixels of sample sampleBase + i / pixels
+__global__ void pathPrimaryKernel(CameraArgs cam, uint32_t width, uint32_t pixels, uint32_t sampleBase, uint32_t firstPath, uint32_t count,
+                                  uint32_t seed, DevRay* rays, float4* states) {
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= count) return;
+	const uint32_t i = firstPath + k;
 	const uint32_t pixel = i % pixels, sample = sampleBase + i / pixels;
-	rays[i] = primaryRay(cam, width, pixel, sample, seed);
-	states[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(i));
+	rays[k] = primaryRay(cam, width, pixel, sample, seed);
+	states[k] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(i));
 }
 
 struct ShadeArgs {
@@ -217,11 +221,11 @@ __global__ void pathAccumulateKernel(const float4* radiance, uint32_t pixels, ui
 
 } // namespace
 
-cudaError_t launchPathPrimary(const float* camera12, uint32_t width, uint32_t height, uint32_t sampleBase, uint32_t spp, uint32_t seed,
-                              DevRay* rays, float4* states, cudaStream_t stream, int* launches) {
-	const uint32_t pixels = width * height, count = pixels * spp;
+cudaError_t launchPathPrimary(const float* camera12, uint32_t width, uint32_t height, uint32_t sampleBase, uint32_t firstPath, uint32_t count,
+                              uint32_t seed, DevRay* rays, float4* states, cudaStream_t stream, int* launches) {
 	if (!count) return cudaSuccess;
-	pathPrimaryKernel<<<(count + 255) / 256, 256, 0, stream>>>(cameraArgs(camera12), width, pixels, sampleBase, count, seed, rays, states);
+	pathPrimaryKernel<<<(count + 255) / 256, 256, 0, stream>>>(cameraArgs(camera12), width, width * height, sampleBase, firstPath, count, seed,
+	                                                           rays, states);
 	if (launches) *launches += 1;
 	return cudaGetLastError();
 }
