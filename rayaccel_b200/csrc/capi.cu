@@ -853,7 +853,11 @@ int racc_cuda_path_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda
 	struct Buffers {
 		cudaStream_t stream;
 		void* p[8] = {};
-		~Buffers() { for (void* q : p) if (q) cudaFreeAsync(q, stream); }
+		bool joined = false; // every lane's work is ordered before `stream`; false on an error return
+		~Buffers() {
+			if (!joined) cudaDeviceSynchronize(); // lanes may still be using the buffers
+			for (void* q : p) if (q) cudaFreeAsync(q, stream);
+		}
 	} buf;
 	buf.stream = stream;
 	const size_t sizes[8] = {lanePaths * nlanes * 32, lanePaths * nlanes * 32, lanePaths * nlanes * 16, lanePaths * nlanes * 16,
@@ -950,6 +954,7 @@ int racc_cuda_path_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda
 			}
 		RACC_CUDA_CHECK(launchPathAccumulate(radiance, (uint32_t)pixels, spp, fb, stream, &launches));
 	}
+	buf.joined = true;
 	g_launches.fetch_add((uint64_t)launches);
 	if (hostFb) {
 		RACC_CUDA_CHECK(cudaMemcpyAsync(framebuffer4, fb, (size_t)pixels * 16, cudaMemcpyDeviceToHost, stream));
