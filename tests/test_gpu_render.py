@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 import rayaccel_b200 as rb
-from test_render_oracle import camera_for, check_against_reference_image
+from test_render_oracle import camera_for, check_against_reference_image, synthetic_shading_case
 
 pytestmark = pytest.mark.gpu
 
@@ -70,6 +70,24 @@ def test_device_path_trace_equals_oracle(scene, env, shading, checker, battlefie
     assert waves == [int(x) for x in want_waves], "rays traced per bounce differ"
     bad = np.flatnonzero((got.view(np.uint32) != want.view(np.uint32)).reshape(-1, 4).any(axis=1))
     assert bad.size == 0, f"{bad.size} of {width * height} pixels differ, first {bad[:5]}: {got.reshape(-1, 4)[bad[:3]]} vs {want.reshape(-1, 4)[bad[:3]]}"
+
+
+def test_device_path_trace_equals_oracle_on_synthetic_scene(gpu):
+    """Branches battlefield never takes (tests/test_render_oracle.py::synthetic_shading_case): coloured materials,
+    eta >= 1, clamped material ids, shading normals far from the geometric ones, degenerate normals."""
+    verts, indices, normals, tri_normals, tri_materials, materials, env_img, cam = synthetic_shading_case()
+    scene = rb.create_scene(verts, indices)
+    env = rb.create_environment(env_img)
+    shading = rb.create_shading(normals, tri_normals, tri_materials, materials)
+    nodes, pairs, remap = scene.download()
+    images = oracle.SceneImages(nodes, pairs, remap, env_img)
+    sh = oracle.Shading(indices, normals, tri_normals, tri_materials, materials)
+    for spp, depth, seed in ((8, 6, 2), (3, 12, 0)):
+        want, want_waves = oracle.path_trace(images, sh, cam, 96, 64, spp, depth, seed)
+        got, waves = rb.path_trace(scene, env, shading, cam, 96, 64, spp, depth, seed)
+        assert waves == [int(x) for x in want_waves]
+        assert got.tobytes() == want.tobytes(), f"{(got.view(np.uint32) != want.view(np.uint32)).reshape(-1, 4).any(axis=1).sum()} pixels differ"
+    shading.destroy(); env.destroy(); scene.destroy()
 
 
 def test_device_framebuffer_accumulates_and_splits_by_sample(scene, env, shading, battlefield):

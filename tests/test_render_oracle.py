@@ -140,6 +140,54 @@ def test_path_trace_is_deterministic_and_additive(battlefield, battlefield_image
     assert np.array_equal(e.reshape(-1, 4)[:, 0] != 0, miss & (res["a"] != 0))
 
 
+def synthetic_shading_case(n_tris=5000, seed=17):
+    """A scene battlefield does not cover: a dense random soup with the camera inside, smooth random vertex normals that
+    disagree with the geometric ones, coloured materials (r != g != b), eta > 1 (the total-reflection branch of the
+    Fresnel term), an eta of exactly 1, material ids beyond the table (clamped to 0), and a few degenerate normals
+    (zero length -> NaN shading normal -> the path ends at the NaN test, PathTracingRenderer.cpp:436-439)."""
+    import rayaccel_b200 as rb
+    verts, indices = rb.synthetic_triangles(n_tris, seed=seed, extent=30.0, edge=4.0)
+    rng = np.random.default_rng(seed + 1)
+    tri = verts[indices.reshape(-1, 3), :3]
+    gn = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    gn /= np.maximum(np.linalg.norm(gn, axis=1, keepdims=True), 1e-20)
+    flip = rng.random(n_tris) < 0.5
+    gn[flip] = -gn[flip]
+    tri_normals = np.zeros((n_tris, 4), np.float32)
+    tri_normals[:, :3] = gn
+    normals = np.zeros((verts.shape[0], 4), np.float32)
+    # battlefield.bin's convention: SceneData::triangleNormals point against the vertex normals (shade() flips the
+    # shading normal by the sign of dir . triangleNormal, PathTracingRenderer.cpp:383-389)
+    normals[:, :3] = -np.repeat(gn, 3, axis=0) + 0.6 * rng.normal(size=(verts.shape[0], 3))
+    normals[::97, :3] = 0.0  # degenerate
+    materials = np.array([[0.9, 0.5, 0.1, 1 / 1.5], [0.2, 0.4, 0.6, 1.5], [0.7, 0.7, 0.2, 1.0], [0.05, 0.9, 0.9, 2.4], [0.99, 0.99, 0.99, 0.4]], np.float32)
+    tri_materials = rng.integers(0, 7, size=n_tris).astype(np.uint16)  # 5 and 6 are out of range
+    env = (rng.random((32, 64, 4)) * 3.0).astype(np.float32)
+    cam = scene_io.Camera.look_at(np.array([15.0, 15.0, 2.0], np.float32), np.array([15.0, 16.0, 30.0], np.float32),
+                                  np.array([0.0, 1.0, 0.0], np.float32), 60.0, 96, 64)
+    return verts, indices, normals, tri_normals, tri_materials, materials, env, cam
+
+
+def test_path_trace_synthetic_scene_branches():
+    """The checker on the synthetic case: finite image, every branch taken, deterministic."""
+    import rayaccel_b200 as rb
+    verts, indices, normals, tri_normals, tri_materials, materials, env, cam = synthetic_shading_case()
+    img = rb.HostImages(verts, indices)
+    images = oracle.SceneImages(img.nodes, img.pairs, img.remap, env)
+    sh = oracle.Shading(indices, normals, tri_normals, tri_materials, materials)
+    fb, waves = oracle.path_trace(images, sh, cam, 96, 64, 8, 6, seed=2)
+    assert np.isfinite(fb).all() and (fb >= 0).all() and fb[..., :3].max() > 0
+    assert waves[0] == 96 * 64 * 8 and waves[6] > 0, waves  # paths reach the depth limit
+    assert len({tuple(np.round(p[:3] / max(p[:3].max(), 1e-9), 2)) for p in fb.reshape(-1, 4)[::37]}) > 20  # coloured weights
+    again, _ = oracle.path_trace(images, sh, cam, 96, 64, 8, 6, seed=2, threads=3)
+    assert again.tobytes() == fb.tobytes()
+    # eta > 1 at grazing incidence: k < 0 -> Fresnel term 1 -> always the mirror direction with weight sum/3
+    wi, color = oracle.material_sample(materials[3], np.array([[0.3, 0.3, 0.3]], np.float32), np.array([[0, 0, 1]], np.float32),
+                                       np.array([[0.99, 0.0, 0.141]], np.float32) / np.float32(np.hypot(0.99, 0.141)))
+    assert np.allclose(color, (3.0 + materials[3][:3].sum()) / 3.0, rtol=1e-5)
+    assert wi[0, 2] > 0 and wi[0, 0] < 0
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
