@@ -328,3 +328,31 @@ def ref_material_sample(ke, rnd, normal, wo):
     wi, color = np.zeros_like(rnd), np.zeros_like(rnd)
     _shade.ref_material_sample(_p(ke), _p(rnd), _p(normal), _p(wo), ctypes.c_uint32(n), _p(wi), _p(color))
     return wi, color
+
+
+def _shade_lib() -> ctypes.CDLL:
+    global _shade
+    if _shade is None:
+        _shade = ctypes.CDLL(SHADE_SO)
+    return _shade
+
+
+def ref_camera_look_at(origin, target, up, fov: float, width: int, height: int) -> dict:
+    """The reference's Camera::lookAt (Renderer/Camera.cpp:13-25), executed: dict(origin, view, right, up)."""
+    o, t, u = (np.ascontiguousarray(a, dtype=np.float32).reshape(3) for a in (origin, target, up))
+    out = np.zeros(12, dtype=np.float32)
+    _shade_lib().ref_camera_look_at(_p(o), _p(t), _p(u), ctypes.c_float(fov), ctypes.c_int(width), ctypes.c_int(height), _p(out))
+    return dict(origin=out[0:3].copy(), view=out[3:6].copy(), right=out[6:9].copy(), up=out[9:12].copy())
+
+
+def ref_generate_tile(camera, tile_x: int, tile_y: int, tile_size: int, viewport_width: int):
+    """The reference's generateTileRays + generateTileLightPaths (Camera.cpp:55-114, LightPath.cpp:11-39) for one tile:
+    (rays as RAY_DTYPE, light paths as (n, 4) uint32 words: weight rgb bits, pixel)."""
+    c = _camera_struct(camera)
+    cam = np.array(list(c.origin) + list(c.view) + list(c.right) + list(c.up), dtype=np.float32)
+    n = tile_size * tile_size
+    rays = np.zeros(n, dtype=RAY_DTYPE)
+    paths = np.zeros((n, 4), dtype=np.uint32)
+    _shade_lib().ref_generate_tile(_p(cam), ctypes.c_uint(tile_x), ctypes.c_uint(tile_y), ctypes.c_uint(tile_size), ctypes.c_uint(viewport_width),
+                                   _p(rays), _p(paths))
+    return rays, paths

@@ -1,6 +1,7 @@
-// shade_host.cpp -- TEST INFRASTRUCTURE ONLY: calls the reference's UNMODIFIED ReflectiveDiffuseMaterial::sample8
-// (compiled from /root/reference/Renderer/Materials.cpp by oracle/Makefile, target `renderer`) for arrays of lanes, so
-// that oracle_material_sample (oracle/racc_oracle.c) can be pinned against it (tests/test_render_oracle.py).
+// shade_host.cpp -- TEST INFRASTRUCTURE ONLY: calls the reference's UNMODIFIED ReflectiveDiffuseMaterial::sample8,
+// Camera::lookAt, generateTileRays and generateTileLightPaths (compiled from /root/reference/Renderer/{Materials,Camera,
+// LightPath}.cpp by oracle/Makefile, target `renderer`) so that the checker's material, camera and primary rays can be
+// pinned against them (tests/test_render_oracle.py).
 #include "Materials.h"
 
 #include <cstdint>
@@ -33,4 +34,37 @@ extern "C" int ref_material_sample(const float* ke4, const float* rnd, const flo
 	material->~ReflectiveDiffuseMaterial();
 	_mm_free(memory);
 	return 0;
+}
+
+// ---- the reference's camera, from /root/reference/Renderer/Camera.cpp (linked in unmodified) ----
+#include "Camera.h"
+#include "LightPath.h"
+
+// camera12 out: origin, view, right, up of Camera::lookAt (Camera.cpp:13-25)
+extern "C" void ref_camera_look_at(const float* origin, const float* target, const float* up, float fov, int width, int height, float* camera12) {
+	Camera c = {};
+	c.lookAt(make_float3(origin[0], origin[1], origin[2]), make_float3(target[0], target[1], target[2]), make_float3(up[0], up[1], up[2]), fov,
+	         1e-3f, 1e+6f, width, height);
+	const float3 v[4] = {c.origin, c.view, c.right, c.up};
+	for (int k = 0; k < 4; ++k) { camera12[3 * k] = v[k].x; camera12[3 * k + 1] = v[k].y; camera12[3 * k + 2] = v[k].z; }
+}
+
+// generateTileRays (Camera.cpp:55-114) and generateTileLightPaths (LightPath.cpp:11-39) for one tile: tileSize^2 rays
+// (8 floats each) and light paths (weight rgb + pixel index, 4 words each). libc rand() seeds the jitter, as in the reference.
+extern "C" void ref_generate_tile(const float* camera12, unsigned tileX, unsigned tileY, unsigned tileSize, unsigned viewportWidth, float* rays8,
+                                  float* lightPaths4) {
+	Camera c = {};
+	c.origin = make_float3(camera12[0], camera12[1], camera12[2]);
+	c.view = make_float3(camera12[3], camera12[4], camera12[5]);
+	c.right = make_float3(camera12[6], camera12[7], camera12[8]);
+	c.up = make_float3(camera12[9], camera12[10], camera12[11]);
+	const size_t n = (size_t)tileSize * tileSize;
+	racc::Ray* rays = static_cast<racc::Ray*>(_mm_malloc(n * sizeof(racc::Ray), 64));
+	LightPath* paths = static_cast<LightPath*>(_mm_malloc(n * sizeof(LightPath), 64));
+	generateTileRays(rays, c, tileX, tileY, tileSize);
+	generateTileLightPaths(paths, viewportWidth, tileX, tileY, tileSize);
+	std::memcpy(rays8, rays, n * sizeof(racc::Ray));
+	std::memcpy(lightPaths4, paths, n * sizeof(LightPath));
+	_mm_free(rays);
+	_mm_free(paths);
 }

@@ -69,6 +69,57 @@ def test_material_matches_reference_sample8():
         assert np.isfinite(wi[~off]).all() and np.isfinite(color[~off]).all()
 
 
+@pytest.mark.skipif(not oracle.have_ref_shade(), reason="oracle/_ref/libshade_ref.so not built (needs /root/reference)")
+def test_camera_and_primary_rays_match_reference(battlefield, battlefield_images, shading):
+    """Camera::lookAt and generateTileRays / generateTileLightPaths executed from the reference's own source:
+    (1) our camera equals lookAt's up to its rsqrt approximation; (2) every reference ray of a tile starts at the camera, has
+    minT 0 / maxT 1e6, unit length, and passes through ITS pixel of the image plane (its jitter is rand()-seeded, so the
+    position inside the pixel is free); (3) the checker's and the engine's pixel-centre ray lies inside the same cell;
+    (4) light paths start with weight 1, depth bits 0 and name the pixel their ray goes through."""
+    w, h = 512, 384
+    ours = camera_for(battlefield, w, h)
+    ref = oracle.ref_camera_look_at(battlefield.cam_origin, battlefield.cam_target, battlefield.cam_up, battlefield.cam_fov, w, h)
+    # lookAt normalises with _mm_rsqrt_ss (VectorMath.h:77-79,446-448: 12-bit, and differs between CPU vendors); ours divides
+    # by the exact square root, hence 1e-3 and not float rounding
+    for k in ("origin", "view", "right", "up"):
+        assert np.allclose(getattr(ours, k), ref[k], rtol=1e-3, atol=1e-6), k
+    tile, tx, ty = 128, 256, 128
+    rays, paths = oracle.ref_generate_tile(ref, tx, ty, tile, w)
+    assert np.array_equal(rays["origin"], np.broadcast_to(ref["origin"], (tile * tile, 3)))
+    assert (rays["minT"] == 0).all() and (rays["maxT"] == np.float32(1e6)).all()
+    assert np.allclose(np.linalg.norm(rays["dir"].astype(np.float64), axis=1), 1.0, atol=5e-4)  # _mm256_rsqrt_ps
+    # invert d ~ view + up*py + right*px: solve the 3x3 system [right up -d] (px, py, s) = -view
+    d = rays["dir"].astype(np.float64)
+    a = np.zeros((tile * tile, 3, 3))
+    a[:, :, 0], a[:, :, 1], a[:, :, 2] = ref["right"].astype(np.float64), ref["up"].astype(np.float64), -d
+    sol = np.linalg.solve(a, np.broadcast_to(-ref["view"].astype(np.float64), (tile * tile, 3))[..., None])[..., 0]
+    # light paths: weight (1, 1, 1), depth bits 0, and the tile's pixels each exactly once (the AVX transposes store the
+    # eight rays of a group in the order 0 4 1 5 2 6 3 7; rays and light paths agree on it)
+    assert (paths[:, :3].view(np.float32) == 1.0).all()
+    assert (paths[:, 3] >> 24 == 0).all()
+    py_i, px_i = np.divmod(paths[:, 3].astype(np.int64), w)
+    ys, xs = np.divmod(np.arange(tile * tile), tile)
+    assert np.array_equal(np.sort(paths[:, 3]), np.sort(((ty + ys) * w + tx + xs).astype(np.uint32)))
+    eps = 2e-3
+    assert (sol[:, 0] >= px_i - eps).all() and (sol[:, 0] <= px_i + 1 + eps).all(), "a ray misses the pixel its light path names"
+    assert (sol[:, 1] >= py_i - eps).all() and (sol[:, 1] <= py_i + 1 + eps).all()
+    assert 0.3 < (sol[:, 0] - px_i).mean() < 0.7 and (sol[:, 0] - px_i).std() > 0.2  # jittered over the pixel
+    # the checker's primary rays (seed 0 = pixel centres) hit what the reference's pixel-centre rays would: compare through
+    # the radiance of a depth-0 frame against tracing the centre rays of the reference camera
+    from conftest import primary_rays_numpy
+    fb, _ = oracle.path_trace(battlefield_images, shading, camera_for(battlefield, 64, 48), 64, 48, 1, 0, seed=0)
+    cam_small = oracle.ref_camera_look_at(battlefield.cam_origin, battlefield.cam_target, battlefield.cam_up, battlefield.cam_fov, 64, 48)
+
+    class _C:  # primary_rays_numpy takes attributes
+        origin, view, right, up = cam_small["origin"], cam_small["view"], cam_small["right"], cam_small["up"]
+    res = oracle.traverse(battlefield_images, primary_rays_numpy(_C, 64, 48))
+    miss = res["triangle"] == oracle.INVALID
+    want = np.where(miss[:, None], np.stack([res["a"], res["b"], res["c"]], axis=1), 0.0)
+    # the two cameras differ by the rsqrt approximation (1e-4 of a pixel): silhouette pixels may flip, the rest agrees
+    off = np.abs(fb.reshape(-1, 4)[:, :3] - want).max(axis=1) > 2e-3
+    assert off.mean() < 0.01, f"{off.sum()} of {off.size} pixels differ"
+
+
 def test_material_known_answers():
     """Hand-checked lanes: normal incidence on eta = 1/1.4 -> F = ((1-eta)/(1+eta))^2 = 1/36; rnd.z above the
     reflection probability 3F/(3F+r+g+b) -> diffuse with weight k*(sum/s1), below -> mirror with weight sum/3 per channel."""
