@@ -74,6 +74,14 @@ def test_no_gpu_means_loud_failure_not_fallback(battlefield):
         rb.create_scene(battlefield.vertices, battlefield.indices)
     with pytest.raises(rb.EngineError):
         rb.create_environment(battlefield.environment)
+    with pytest.raises(rb.EngineError):  # the device-side renderer has no host path either
+        rb.create_shading(battlefield.normals, battlefield.triangle_normals, battlefield.materials)
+    assert lib.racc_cuda_path_trace(None, None, None, None, None, None, None, None) != 0
+    assert b"null argument" in lib.racc_cuda_last_error()
+    with pytest.raises(ValueError):
+        rb.create_shading(battlefield.normals[:, :3], battlefield.triangle_normals, battlefield.materials)
+    with pytest.raises(ValueError):
+        rb.create_shading(battlefield.normals, battlefield.triangle_normals[:10], battlefield.materials)
     rays = np.zeros(4, rb.RAY_DTYPE)
     assert lib.racc_cuda_trace(None, None, None, 0, None) != 0
     assert b"null scene" in lib.racc_cuda_last_error()
@@ -96,7 +104,7 @@ def test_product_never_touches_the_oracle():
             for fn in files:
                 if fn.endswith((".py", ".cu", ".cpp", ".h")):
                     text = open(os.path.join(dirpath, fn), errors="replace").read()
-                    if re.search(r"import\s+oracle|from\s+oracle|liboracle|racc_oracle\.h|oracle_traverse", text):
+                    if re.search(r"import\s+oracle|from\s+oracle|liboracle|racc_oracle\.h|oracle_traverse|oracle_path_trace\s*\(|oracle_material_sample\s*\(", text):
                         bad.append(os.path.join(dirpath, fn))
     assert not bad, bad
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
