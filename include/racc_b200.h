@@ -238,6 +238,15 @@ typedef struct {
 int racc_cuda_path_trace(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_shading* shading, const racc_cuda_camera* camera,
                          const racc_cuda_path_desc* desc, float* framebuffer4, uint64_t* wave_rays, void* cuda_stream);
 
+/* The reference's second example client, the Whitted renderer (Renderer/WhittedRenderer.cpp:136-676), with the shading on
+ * the device (rayaccel_b200/csrc/whitted.cu): same arguments and framebuffer meaning as racc_cuda_path_trace. Every hit
+ * adds direct light and spawns a reflection and a refraction ray; the ray tree is walked breadth-first, radiance is summed
+ * per pixel in 32.32 fixed point (integer atomics: order-independent), then added to framebuffer4. Uses the normals and
+ * triangle normals of `shading` (the renderer has one hard-wired material). desc->batch_spp 0 = about 4 M primary rays per
+ * batch. Results are bit-reproducible and equal oracle_whitted_trace's. 0 on success. */
+int racc_cuda_whitted_trace(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_shading* shading, const racc_cuda_camera* camera,
+                            const racc_cuda_path_desc* desc, float* framebuffer4, uint64_t* wave_rays, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -308,6 +308,21 @@ def path_trace(scene: SceneImages, shading: Shading, camera, width: int, height:
     return fb, waves
 
 
+def whitted_trace(scene: SceneImages, shading: Shading, camera, width: int, height: int, spp: int, max_depth: int, seed: int,
+                  sample_base: int = 0, framebuffer: np.ndarray | None = None, threads: int = 0):
+    """oracle_whitted_trace: returns (framebuffer (H, W, 4) float32 with the radiance sums added, rays traced per depth)."""
+    fb = np.zeros((height, width, 4), dtype=np.float32) if framebuffer is None else framebuffer
+    assert fb.dtype == np.float32 and fb.shape == (height, width, 4) and fb.flags.c_contiguous
+    waves = np.zeros(max_depth + 1, dtype=np.uint64)
+    s, sh, cam = scene.c_struct(), shading.c_struct(), _camera_struct(camera)
+    rc = lib().oracle_whitted_trace(ctypes.byref(s), ctypes.byref(sh), ctypes.byref(cam), ctypes.c_uint32(width), ctypes.c_uint32(height),
+                                    ctypes.c_uint32(sample_base), ctypes.c_uint32(spp), ctypes.c_uint32(max_depth), ctypes.c_uint32(seed),
+                                    _p(fb), _p(waves), ctypes.c_int(threads))
+    if rc:
+        raise RuntimeError("oracle_whitted_trace failed")
+    return fb, waves
+
+
 SHADE_SO = os.path.join(_HERE, "_ref", "libshade_ref.so")
 _shade = None
 

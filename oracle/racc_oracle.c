@@ -834,3 +834,137 @@ int oracle_path_trace(const oracle_scene* scene, const oracle_shading* shading, 
 	parallel_for(threads, ((int64_t)width * height + PT_CHUNK - 1) / PT_CHUNK, pt_body, &x);
 	return x.err;
 }
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* Whitted renderer (the reference's second example client, Renderer/WhittedRenderer.cpp:136-676):
+ * at every hit with depth < max_depth the path adds weight*0.3*max(n.L, 0) for the fixed light
+ * direction L = (0.57, 0.57, 0.57) (:343-372), scales its weight by 0.3 and, while a weight channel
+ * exceeds 0.01 (:404-413), continues as a mirror reflection AND a refraction (eta 1/1.1 entering,
+ * 1.1 leaving, :415-437), each subject to a side test against the geometric normal (:440-444) and a
+ * NaN test (:465-472); both children carry the parent's weight. Misses add probe radiance * weight
+ * (:578-660). The reference keeps the tree depth-first in a linked list to bound memory (:19-134);
+ * that is scheduling and is not restated -- the sum over the tree is. Contributions are summed in
+ * 32.32 fixed point so that the result does not depend on the order the tree is walked in (the CUDA
+ * renderer walks it breadth-first with atomics). */
+
+#define FIXED_ONE 4294967296.0f
+static inline uint64_t to_fixed(float c) {
+	if (!(c > 0.0f)) return 0; /* also NaN */
+	if (c > 1048576.0f) c = 1048576.0f;
+	return (uint64_t)llrintf(c * FIXED_ONE);
+}
+
+typedef struct { oracle_ray ray; float weight[3]; uint32_t depth; } whitted_item;
+
+typedef struct {
+	const oracle_scene* scene; const oracle_shading* sh; const oracle_camera* cam;
+	uint32_t width, height, sample_base, spp, max_depth, seed;
+	float* fb; uint64_t* waves; volatile int err;
+} wt_ctx;
+
+static void wt_body(void* p, int64_t c) {
+	wt_ctx* x = (wt_ctx*)p;
+	const oracle_shading* sh = x->sh;
+	const uint64_t pixels = (uint64_t)x->width * x->height;
+	uint64_t lo = (uint64_t)c * PT_CHUNK, hi = lo + PT_CHUNK < pixels ? lo + PT_CHUNK : pixels;
+	uint64_t waves[64] = { 0 };
+	whitted_item stack[72]; /* depth-first: at most one pending sibling per level */
+	for (uint64_t pixel = lo; pixel < hi; ++pixel) {
+		uint64_t acc[3] = { 0, 0, 0 };
+		for (uint32_t s = 0; s < x->spp; ++s) {
+			const uint32_t sample = x->sample_base + s;
+			float jx = 0.5f, jy = 0.5f;
+			if (x->seed) {
+				uint32_t h = pcg_hash((uint32_t)pixel ^ pcg_hash(sample ^ pcg_hash(x->seed)));
+				jx = unit_float(h);
+				jy = unit_float(pcg_hash(h));
+			}
+			const float fx = (float)(uint32_t)(pixel % x->width) + jx, fy = (float)(uint32_t)(pixel / x->width) + jy;
+			float d[3];
+			for (int k = 0; k < 3; ++k) d[k] = fmaf(x->cam->right[k], fx, fmaf(x->cam->up[k], fy, x->cam->view[k]));
+			const float scale = 1.0f / sqrtf(fmaf(d[2], d[2], fmaf(d[1], d[1], d[0] * d[0])));
+			int top = 0;
+			for (int k = 0; k < 3; ++k) { stack[0].ray.origin[k] = x->cam->origin[k]; stack[0].ray.dir[k] = d[k] * scale; stack[0].weight[k] = 1.0f; }
+			stack[0].ray.minT = 0.0f; stack[0].ray.maxT = 1e+6f; stack[0].depth = 0;
+			top = 1;
+			while (top) {
+				whitted_item it = stack[--top];
+				oracle_result res;
+				if (traverse_one(x->scene, &it.ray, &res, 0)) { x->err = -1; break; }
+				waves[it.depth < 64 ? it.depth : 63]++;
+				if (res.triangle == ORACLE_INVALID_TRIANGLE) {
+					acc[0] += to_fixed(res.a * it.weight[0]); acc[1] += to_fixed(res.b * it.weight[1]); acc[2] += to_fixed(res.c * it.weight[2]);
+					continue;
+				}
+				if (!(res.triangle < sh->triangle_count && it.depth < x->max_depth)) continue;
+				const uint32_t tri = res.triangle;
+				const float t = res.a, u = res.b, v = res.c;
+				const uint32_t* idx = sh->indices + 3 * (size_t)tri;
+				const float* n0 = sh->normals4 + 4 * (size_t)idx[0];
+				const float* n1 = sh->normals4 + 4 * (size_t)idx[1];
+				const float* n2 = sh->normals4 + 4 * (size_t)idx[2];
+				const float w = 1.0f - (u + v);
+				float n[3];
+				for (int k = 0; k < 3; ++k) n[k] = fmaf(n2[k], v, fmaf(n1[k], u, n0[k] * w));
+				const float fn = 1.0f / sqrtf(fmaf(n[2], n[2], fmaf(n[1], n[1], n[0] * n[0])));
+				const float* gn = sh->triangle_normals4 + 4 * (size_t)tri;
+				const float* rd = it.ray.dir;
+				const float rdgn = fmaf(rd[2], gn[2], fmaf(rd[1], gn[1], rd[0] * gn[0]));
+				const uint32_t sgn0 = f2u(rdgn) & 0x80000000u;
+				for (int k = 0; k < 3; ++k) n[k] = xor_sign(n[k] * fn, sgn0);
+				/* direct light, :349-372 */
+				float light = fmaf(n[2], 0.57f, fmaf(n[1], 0.57f, n[0] * 0.57f));
+				light = light > 0.0f ? light : 0.0f;
+				float weight[3];
+				for (int k = 0; k < 3; ++k) {
+					weight[k] = it.weight[k] * 0.3f;
+					acc[k] += to_fixed(weight[k] * light);
+				}
+				if (!(!(weight[0] <= 0.01f) || !(weight[1] <= 0.01f) || !(weight[2] <= 0.01f))) continue; /* _CMP_NLE_US */
+				/* reflection and refraction, :413-437 */
+				const float ddn = fmaf(rd[2], n[2], fmaf(rd[1], n[1], rd[0] * n[0]));
+				const float cosi = ddn * -2.0f;
+				const float eta = sgn0 ? 1.1f : 1.0f / 1.1f;
+				const float r = 1.0f - (eta * eta) * (1.0f - ddn * ddn);
+				const float mu = fmaf(eta, ddn, sqrtf(r));
+				float rl[3], rr[3], pos[3];
+				for (int k = 0; k < 3; ++k) {
+					rl[k] = fmaf(cosi, n[k], rd[k]);
+					rr[k] = fmaf(eta, rd[k], -(mu * n[k]));
+					pos[k] = fmaf(rd[k], t, it.ray.origin[k]);
+				}
+				const float sl = fmaf(rl[2], gn[2], fmaf(rl[1], gn[1], rl[0] * gn[0]));
+				const float sr = fmaf(rr[2], gn[2], fmaf(rr[1], gn[1], rr[0] * gn[0]));
+				int reflect = ((f2u(sl) ^ sgn0) >> 31) != 0;       /* back to the side it came from */
+				int refract = r > 0.0f && ((f2u(sr) ^ sgn0) >> 31) == 0; /* through the surface */
+				whitted_item a, b;
+				for (int k = 0; k < 3; ++k) {
+					a.ray.origin[k] = fmaf(xor_sign(gn[k], f2u(sl) & 0x80000000u), 1e-4f, pos[k]);
+					b.ray.origin[k] = fmaf(xor_sign(gn[k], f2u(sr) & 0x80000000u), 1e-4f, pos[k]);
+					a.ray.dir[k] = rl[k]; b.ray.dir[k] = rr[k];
+					reflect &= a.ray.origin[k] == a.ray.origin[k] && rl[k] == rl[k];
+					refract &= b.ray.origin[k] == b.ray.origin[k] && rr[k] == rr[k];
+					a.weight[k] = b.weight[k] = weight[k];
+				}
+				a.ray.minT = b.ray.minT = 1e-3f; a.ray.maxT = b.ray.maxT = 1e+6f;
+				a.depth = b.depth = it.depth + 1;
+				if (top + 2 > 72) { x->err = -1; break; }
+				if (refract) stack[top++] = b;
+				if (reflect) stack[top++] = a;
+			}
+		}
+		for (int k = 0; k < 3; ++k) x->fb[4 * pixel + k] += (float)acc[k] * (1.0f / FIXED_ONE);
+	}
+	if (x->waves)
+		for (uint32_t dpt = 0; dpt <= x->max_depth && dpt < 64; ++dpt) __sync_fetch_and_add(&x->waves[dpt], waves[dpt]);
+}
+
+int oracle_whitted_trace(const oracle_scene* scene, const oracle_shading* shading, const oracle_camera* camera, uint32_t width,
+                         uint32_t height, uint32_t sample_base, uint32_t spp, uint32_t max_depth, uint32_t seed, float* framebuffer4,
+                         uint64_t* wave_rays, int threads) {
+	if (max_depth > 62) return -1;
+	wt_ctx x = { scene, shading, camera, width, height, sample_base, spp, max_depth, seed, framebuffer4, wave_rays, 0 };
+	parallel_for(threads, ((int64_t)width * height + PT_CHUNK - 1) / PT_CHUNK, wt_body, &x);
+	return x.err;
+}

@@ -154,6 +154,15 @@ int oracle_path_trace(const oracle_scene* scene, const oracle_shading* shading, 
                       uint32_t height, uint32_t sample_base, uint32_t spp, uint32_t max_depth, uint32_t seed, float* framebuffer4,
                       uint64_t* wave_rays, int threads);
 
+/* The reference's Whitted renderer (Renderer/WhittedRenderer.cpp:136-676) per pixel sample: direct light from a
+ * fixed direction at every hit, weight * 0.3 per bounce, reflection + refraction children while a weight channel
+ * exceeds 0.01 and depth < max_depth, probe radiance on misses. Uses shading->indices / normals4 /
+ * triangle_normals4 only (the renderer has one hard-wired material). The radiance of a call is summed in 32.32
+ * fixed point per pixel (order-independent) and then ADDED to framebuffer4. wave_rays as oracle_path_trace. */
+int oracle_whitted_trace(const oracle_scene* scene, const oracle_shading* shading, const oracle_camera* camera, uint32_t width,
+                         uint32_t height, uint32_t sample_base, uint32_t spp, uint32_t max_depth, uint32_t seed, float* framebuffer4,
+                         uint64_t* wave_rays, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,6 @@ mirror of the reference's interface. There is no CPU fallback.
 """
 from .api import (BATTLEFIELD_MATERIALS, INVALID_TRIANGLE, RAY_DTYPE, RESULT_DTYPE, Environment, HostImages, Scene, Shading,  # noqa: F401
                   create_environment, create_scene, create_scene_from_images, create_shading, debug_warp_stats, device_count, generate_bounce, generate_primary, init,
-                  launch_count, pack_streams, path_trace, set_tuning, sync, trace_device, trace_host, trace_host_ptrs)
+                  launch_count, pack_streams, path_trace, set_tuning, sync, trace_device, trace_host, trace_host_ptrs, whitted_trace)
 from ._lib import EngineError  # noqa: F401
 from .scene_io import Camera, SceneFile, load_scene, synthetic_triangles  # noqa: F401

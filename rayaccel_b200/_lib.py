@@ -85,6 +85,8 @@ SYMBOLS = {
     "racc_cuda_shading_destroy": (None, [_P]),
     "racc_cuda_path_trace": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(CameraStruct), ctypes.POINTER(PathDesc), _P,
                                              ctypes.POINTER(ctypes.c_uint64), _P]),
+    "racc_cuda_whitted_trace": (ctypes.c_int, [_P, _P, _P, ctypes.POINTER(CameraStruct), ctypes.POINTER(PathDesc), _P,
+                                                ctypes.POINTER(ctypes.c_uint64), _P]),
 }
 
 _lib = None

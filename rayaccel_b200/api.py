@@ -314,6 +314,19 @@ def path_trace(scene: Scene, environment: Environment | None, shading: Shading, 
     """`spp` paths per pixel of the reference's path tracer (PathTracingRenderer.cpp) with the shading on the device.
     framebuffer_ptr: DEVICE pointer to width*height float4 radiance sums, added to in place; None = a fresh host array,
     returned as (H, W, 4) float32. Returns (framebuffer or None, rays traced per depth)."""
+    return _render("racc_cuda_path_trace", scene, environment, shading, camera, width, height, spp, max_depth, seed, framebuffer_ptr,
+                   sample_base, batch_spp, stream)
+
+
+def whitted_trace(scene: Scene, environment: Environment | None, shading: Shading, camera: Camera, width: int, height: int, spp: int,
+                  max_depth: int, seed: int, framebuffer_ptr: int | None = None, sample_base: int = 0, batch_spp: int = 0, stream=None):
+    """`spp` samples per pixel of the reference's Whitted renderer (WhittedRenderer.cpp) with the shading on the device; arguments
+    and return value as path_trace."""
+    return _render("racc_cuda_whitted_trace", scene, environment, shading, camera, width, height, spp, max_depth, seed, framebuffer_ptr,
+                   sample_base, batch_spp, stream)
+
+
+def _render(entry: str, scene, environment, shading, camera, width, height, spp, max_depth, seed, framebuffer_ptr, sample_base, batch_spp, stream):
     waves = (ctypes.c_uint64 * (max_depth + 1))()
     d = _lib.PathDesc(width, height, sample_base, spp, max_depth, seed, batch_spp, 0)
     fb = None
@@ -322,7 +335,6 @@ def path_trace(scene: Scene, environment: Environment | None, shading: Shading, 
         d.flags = _lib.FRAMEBUFFER_HOST
         framebuffer_ptr = fb.ctypes.data
     cam = _camera_struct(camera)
-    _lib.check(_lib.load().racc_cuda_path_trace(scene._h, environment._h if environment is not None else None, shading._h, ctypes.byref(cam),
-                                                 ctypes.byref(d), ctypes.c_void_p(framebuffer_ptr), waves, _cuda_stream_handle(stream)),
-               "racc_cuda_path_trace")
+    _lib.check(getattr(_lib.load(), entry)(scene._h, environment._h if environment is not None else None, shading._h, ctypes.byref(cam),
+                                           ctypes.byref(d), ctypes.c_void_p(framebuffer_ptr), waves, _cuda_stream_handle(stream)), entry)
     return fb, [int(x) for x in waves]

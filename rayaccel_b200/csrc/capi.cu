@@ -963,4 +963,109 @@ int racc_cuda_path_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda
 	return 0;
 }
 
+// The reference's Whitted renderer with the shading on the device (whitted.cu). Same descriptor and framebuffer
+// meaning as racc_cuda_path_trace; desc->batch_spp 0 = about 4 M primary rays per batch (a hit spawns up to two rays,
+// so waves grow before the 0.3-per-bounce weight ends them).
+int racc_cuda_whitted_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_shading* sh, const racc_cuda_camera* camera,
+                            const racc_cuda_path_desc* d, float* framebuffer4, uint64_t* wave_rays, void* cuda_stream) {
+	if (!s || !sh || !camera || !d || !framebuffer4) return fail("racc_cuda_whitted_trace: null argument");
+	if (!s->dIndices) return fail("racc_cuda_whitted_trace: scene was created from images and has no index data");
+	if (sh->triangleCount != s->triangleCount || sh->vertexCount < s->vertexCount)
+		return fail("racc_cuda_whitted_trace: shading data (%u triangles, %u vertices) does not match the scene (%u, %u)", sh->triangleCount,
+		            sh->vertexCount, s->triangleCount, s->vertexCount);
+	if (d->max_depth > 62) return fail("racc_cuda_whitted_trace: max_depth %u > 62", d->max_depth);
+	if (ensureInit()) return -1;
+	const uint64_t pixels = (uint64_t)d->width * d->height;
+	if (!pixels || !d->spp) return 0;
+	if (pixels > (1ull << 24)) return fail("racc_cuda_whitted_trace: viewport too large");
+	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+	uint32_t batchSpp = d->batch_spp ? d->batch_spp : (uint32_t)((4ull << 20) / pixels);
+	if (batchSpp < 1) batchSpp = 1;
+	if (batchSpp > d->spp) batchSpp = d->spp;
+	if (pixels * batchSpp > (1ull << 28)) return fail("racc_cuda_whitted_trace: batch of %u samples is too large", batchSpp);
+	const bool hostFb = (d->flags & RACC_CUDA_FRAMEBUFFER_HOST) != 0;
+
+	// stream-ordered scratch; everything still held is released on any return
+	struct Scratch {
+		cudaStream_t stream;
+		std::vector<void*> held;
+		int get(void** p, size_t bytes) {
+			RACC_CUDA_CHECK(cudaMallocAsync(p, bytes ? bytes : 16, stream));
+			held.push_back(*p);
+			return 0;
+		}
+		void release(void* p) {
+			for (size_t k = 0; k < held.size(); ++k)
+				if (held[k] == p) { held.erase(held.begin() + (long)k); cudaFreeAsync(p, stream); return; }
+		}
+		~Scratch() { for (void* q : held) cudaFreeAsync(q, stream); }
+	} scratch;
+	scratch.stream = stream;
+
+	unsigned long long* acc = nullptr;
+	uint32_t* counts = nullptr;
+	float4* fb = reinterpret_cast<float4*>(framebuffer4);
+	if (scratch.get(reinterpret_cast<void**>(&acc), (size_t)pixels * 3 * sizeof(unsigned long long))) return -1;
+	if (scratch.get(reinterpret_cast<void**>(&counts), 64 * sizeof(uint32_t))) return -1;
+	if (hostFb) {
+		if (scratch.get(reinterpret_cast<void**>(&fb), (size_t)pixels * 16)) return -1;
+		RACC_CUDA_CHECK(cudaMemcpyAsync(fb, framebuffer4, (size_t)pixels * 16, cudaMemcpyHostToDevice, stream));
+	}
+	RACC_CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)pixels * 3 * sizeof(unsigned long long), stream));
+
+	int launches = 0;
+	for (uint32_t done = 0; done < d->spp; done += batchSpp) {
+		const uint32_t spp = d->spp - done < batchSpp ? d->spp - done : batchSpp;
+		uint32_t count = (uint32_t)(pixels * spp);
+		RACC_CUDA_CHECK(cudaMemsetAsync(counts, 0, 64 * sizeof(uint32_t), stream));
+		DevRay* rays = nullptr;
+		float4* states = nullptr;
+		if (scratch.get(reinterpret_cast<void**>(&rays), (size_t)count * 32) || scratch.get(reinterpret_cast<void**>(&states), (size_t)count * 16)) return -1;
+		RACC_CUDA_CHECK(launchWhittedPrimary(camera->origin, d->width, d->height, d->sample_base + done, 0, count, d->seed, rays, states, stream, &launches));
+		for (uint32_t depth = 0; depth <= d->max_depth && count; ++depth) {
+			if (wave_rays) wave_rays[depth] += count;
+			if (count > 0x3fffffffu) return fail("racc_cuda_whitted_trace: a wave of %u rays is too large; lower batch_spp", count);
+			float4* results = nullptr;
+			DevRay* nextRays = nullptr;
+			float4* nextStates = nullptr;
+			const bool last = depth == d->max_depth; // nothing is extended past the last bounce
+			if (scratch.get(reinterpret_cast<void**>(&results), (size_t)count * 16)) return -1;
+			if (!last && (scratch.get(reinterpret_cast<void**>(&nextRays), (size_t)count * 2 * 32) ||
+			              scratch.get(reinterpret_cast<void**>(&nextStates), (size_t)count * 2 * 16))) return -1;
+			racc_cuda_stream_desc sd{};
+			sd.rays = rays;
+			sd.results = results;
+			sd.count = count;
+			sd.flags = 0;
+			if (traceImpl(s, env, &sd, 1, stream, nullptr, false)) return -1;
+			WhittedShadeParams p{};
+			p.rays = rays; p.results = results; p.states = states; p.count = count; p.depth = depth; p.maxDepth = d->max_depth;
+			p.indices = s->dIndices; p.normals = sh->dNormals; p.triangleNormals = sh->dTriangleNormals; p.triangleCount = sh->triangleCount;
+			p.outRays = nextRays; p.outStates = nextStates; p.outCount = counts + depth; p.accumulators = acc;
+			RACC_CUDA_CHECK(launchWhittedShade(p, stream, &launches));
+			uint32_t next = 0;
+			if (!last) {
+				// the size of the next wave decides its launch and its buffers: the one host round trip per bounce
+				RACC_CUDA_CHECK(cudaMemcpyAsync(&next, counts + depth, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+				RACC_CUDA_CHECK(cudaStreamSynchronize(stream));
+			}
+			scratch.release(results);
+			scratch.release(rays);
+			scratch.release(states);
+			rays = nextRays;
+			states = nextStates;
+			count = next;
+		}
+		if (rays) scratch.release(rays);
+		if (states) scratch.release(states);
+	}
+	RACC_CUDA_CHECK(launchWhittedFinish(acc, (uint32_t)pixels, fb, stream, &launches));
+	g_launches.fetch_add((uint64_t)launches);
+	if (hostFb) {
+		RACC_CUDA_CHECK(cudaMemcpyAsync(framebuffer4, fb, (size_t)pixels * 16, cudaMemcpyDeviceToHost, stream));
+		RACC_CUDA_CHECK(cudaStreamSynchronize(stream));
+	}
+	return 0;
+}
+
 } // extern "C"

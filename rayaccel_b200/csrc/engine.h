@@ -127,4 +127,25 @@ cudaError_t launchPathShade(const PathShadeParams& p, cudaStream_t stream, int* 
 cudaError_t launchPathAccumulate(const float4* radiance, uint32_t pixels, uint32_t spp, float4* framebuffer, cudaStream_t stream,
                                  int* launches);
 
+// device-side Whitted renderer (whitted.cu), see there
+struct WhittedShadeParams {
+	const DevRay* rays;       // the wave just traced: rays, results, states (weight rgb + pixel in .w)
+	const float4* results;
+	const float4* states;
+	uint32_t count, depth, maxDepth;
+	const uint32_t* indices;
+	const float4* normals;
+	const float4* triangleNormals;
+	uint32_t triangleCount;
+	DevRay* outRays;          // next wave (capacity 2 * count), its size in *outCount (zeroed by the caller)
+	float4* outStates;
+	uint32_t* outCount;
+	unsigned long long* accumulators; // 3 per pixel, 32.32 fixed-point radiance sums
+};
+
+cudaError_t launchWhittedPrimary(const float* camera12, uint32_t width, uint32_t height, uint32_t sampleBase, uint32_t firstPath, uint32_t count,
+                                 uint32_t seed, DevRay* rays, float4* states, cudaStream_t stream, int* launches);
+cudaError_t launchWhittedShade(const WhittedShadeParams& p, cudaStream_t stream, int* launches);
+cudaError_t launchWhittedFinish(const unsigned long long* accumulators, uint32_t pixels, float4* framebuffer, cudaStream_t stream, int* launches);
+
 } // namespace racc_b200
