@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--depth", type=int, default=3)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-api", action="store_true")
+    ap.add_argument("--whitted", action="store_true", help="the Whitted renderer (racc_cuda_whitted_trace) instead of the path tracer")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     rb.init(0)
@@ -45,8 +46,8 @@ def main():
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         a.record()
-        _, waves = rb.path_trace(scene, env, shading, cam, args.width, args.height, args.spp, args.depth, seed=1 + rep,
-                                 framebuffer_ptr=fb.data_ptr(), batch_spp=args.batch)
+        _, waves = (rb.whitted_trace if args.whitted else rb.path_trace)(scene, env, shading, cam, args.width, args.height, args.spp, args.depth,
+                                                                         seed=1 + rep, framebuffer_ptr=fb.data_ptr(), batch_spp=args.batch)
         b.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -55,7 +56,7 @@ def main():
     rays = sum(waves)
     best = min(t[0] for t in times)
     med = sorted(t[0] for t in times)[len(times) // 2]
-    line = {"what": "device-side wavefront path tracer, battlefield", "width": args.width, "height": args.height, "spp": args.spp,
+    line = {"what": "device-side Whitted renderer, battlefield" if args.whitted else "device-side wavefront path tracer, battlefield", "width": args.width, "height": args.height, "spp": args.spp,
             "batch_spp": args.batch, "max_depth": args.depth, "rays_per_frame_set": rays, "waves": waves,
             "ms_best": round(best * 1e3, 3), "ms_median": round(med * 1e3, 3), "wall_ms_best": round(min(t[1] for t in times) * 1e3, 3),
             "mrays_best": round(rays / best / 1e6, 1), "mrays_median": round(rays / med / 1e6, 1),
@@ -64,9 +65,10 @@ def main():
     if not args.no_api and os.path.exists(exe):
         try:
             out = subprocess.check_output([exe, "--width", str(args.width), "--height", str(args.height), "--frames", "6",
-                                           "--scene", os.path.join(ROOT, "data", "battlefield.bin")], cwd=ROOT, timeout=300)
+                                           "--scene", os.path.join(ROOT, "data", "battlefield.bin")] + (["--whitted"] if args.whitted else []),
+                                          cwd=ROOT, timeout=300)
             info = json.loads(out.decode().strip().splitlines()[-1])
-            line["api_host_shading"] = {"what": "reference PathTracingRenderer unchanged through racc::render (host callbacks)",
+            line["api_host_shading"] = {"what": "reference renderer unchanged through racc::render (host callbacks)",
                                         "mrps": info["mrps"], "mrps_best_frame": info["mrps_best_frame"],
                                         "callback_threads": info["callback_threads"], "mean_radiance": info["mean_luminance"] / 3}
         except Exception as e:  # noqa: BLE001
