@@ -74,6 +74,21 @@ def have_ref_kernel() -> bool:
     return os.path.exists(KERNEL_SO)
 
 
+KERNEL_RELAXED_SO = os.path.join(_HERE, "_ref", "libkernel_ref_relaxed.so")
+_kernel_relaxed = None
+
+
+def ref_kernel_traverse_relaxed(scene: "SceneImages", rays: np.ndarray, threads: int = 0) -> np.ndarray:
+    """The reference kernel source under the OTHER built-in model of oracle/ref_shim/opencl_c.h (RACC_SHIM_RELAXED: unfused
+    mad / dot, estimate-based native_recip / native_rsqrt): what a different, equally conforming OpenCL implementation
+    could return. Only for measuring the distance to the pinned results."""
+    global _kernel_relaxed
+    if _kernel_relaxed is None:
+        lib()
+        _kernel_relaxed = ctypes.CDLL(KERNEL_RELAXED_SO)
+    return _run_ref_kernel(_kernel_relaxed, scene, rays, threads)
+
+
 def ref_kernel_traverse(scene: "SceneImages", rays: np.ndarray, threads: int = 1) -> np.ndarray:
     """The reference's OpenCL `traversal` kernel, compiled from its own source text (Kernels.h) on top of
     oracle/ref_shim/opencl_c.h, run on the CPU one work-item per ray; threads > 1 hands batches of 1024
@@ -82,6 +97,10 @@ def ref_kernel_traverse(scene: "SceneImages", rays: np.ndarray, threads: int = 1
     if _kernel is None:
         lib()  # liboracle.so provides oracle_acosf
         _kernel = ctypes.CDLL(KERNEL_SO)
+    return _run_ref_kernel(_kernel, scene, rays, threads)
+
+
+def _run_ref_kernel(_kernel, scene: "SceneImages", rays: np.ndarray, threads: int) -> np.ndarray:
     rays = np.ascontiguousarray(rays)
     assert rays.dtype == RAY_DTYPE
     n = rays.shape[0]

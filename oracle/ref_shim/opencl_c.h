@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <xmmintrin.h>
 
 extern "C" float oracle_acosf(float x); // oracle/racc_oracle.c
 
@@ -154,17 +155,37 @@ inline float fmax(float a, float b) {
 }
 inline float3 fmin(const float3& a, const float3& b) { return float3(fmin(a.d[0], b.d[0]), fmin(a.d[1], b.d[1]), fmin(a.d[2], b.d[2])); }
 inline float3 fmax(const float3& a, const float3& b) { return float3(fmax(a.d[0], b.d[0]), fmax(a.d[1], b.d[1]), fmax(a.d[2], b.d[2])); }
+#ifndef RACC_SHIM_RELAXED
 inline float mad(float a, float b, float c) { return ::fmaf(a, b, c); }
-inline float3 mad(const float3& a, const float3& b, const float3& c) {
-	return float3(::fmaf(a.d[0], b.d[0], c.d[0]), ::fmaf(a.d[1], b.d[1], c.d[1]), ::fmaf(a.d[2], b.d[2], c.d[2]));
-}
 inline float dot(const float3& a, const float3& b) { return ::fmaf(a.d[2], b.d[2], ::fmaf(a.d[1], b.d[1], a.d[0] * b.d[0])); }
+#else
+// A second, equally legal reading of what -cl-fast-relaxed-math leaves open, used only to measure how far another
+// implementation's results can lie from the pinned ones (tests/test_oracle_kat.py::test_relaxed_builtin_model_*):
+// mad as a separately rounded multiply and add, dot summed left to right without fusion, native_recip / native_rsqrt
+// from the 12-bit hardware estimates refined by one Newton step (about 22 bits, not correctly rounded).
+inline float mad(float a, float b, float c) { return a * b + c; }
+inline float dot(const float3& a, const float3& b) { return (a.d[0] * b.d[0] + a.d[1] * b.d[1]) + a.d[2] * b.d[2]; }
+#endif
+inline float3 mad(const float3& a, const float3& b, const float3& c) {
+	return float3(mad(a.d[0], b.d[0], c.d[0]), mad(a.d[1], b.d[1], c.d[1]), mad(a.d[2], b.d[2], c.d[2]));
+}
 inline float fabs(float x) { return ::fabsf(x); }
 inline float copysign(float a, float b) { return ::copysignf(a, b); }
 inline int signbit(float x) { return as_int(x) < 0 ? 1 : 0; }
 inline int select(int a, int b, int c) { return c ? b : a; }
+#ifndef RACC_SHIM_RELAXED
 inline float native_recip(float x) { return 1.0f / x; }
 inline float native_rsqrt(float x) { return 1.0f / ::sqrtf(x); }
+#else
+inline float native_recip(float x) {
+	const float e = _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(x)));
+	return e * (2.0f - x * e);
+}
+inline float native_rsqrt(float x) {
+	const float e = _mm_cvtss_f32(_mm_rsqrt_ss(_mm_set_ss(x)));
+	return e * (1.5f - 0.5f * x * e * e);
+}
+#endif
 inline float acos(float x) { return oracle_acosf(x); }
 
 // ---- images ------------------------------------------------------------------------------------------
