@@ -164,9 +164,11 @@ int racc_cuda_set_variant(int variant);
  * Morton bits per axis of the re-binning key (origin / direction), 11 direction-major key, 12 scene build (0 host,
  * 1 SAH tree on the device + host packing, 2 all on the device, 3 auto), 13 traversal-stack entries kept in shared memory
  * (0, 8, 16, -1 auto: 16 for scenes far larger than L2), 14 HOST streams in pinned memory read by the kernel itself
- * instead of being staged (0 staged = default, 1 zero-copy). Returns the previous value. Also settable through
+ * instead of being staged (0 staged = default, 1 zero-copy), 15 / 16 racc_cuda_whitted_trace only, both 0 by default
+ * until measured on hardware: 15 wave buffers kept and grown per calling thread instead of allocated per wave,
+ * 16 a warp sums its rays' fixed-point radiance per pixel before the atomics (same bits). Returns the previous value. Also settable through
  * RACC_B200_VARIANT / _BLOCK / _CTAS_PER_SM / _SMEM_NODES / _FETCH_THRESHOLD / _LEAF_BAIL / _INNER_BAIL / _SORT /
- * _SORT_ORIGIN_BITS / _SORT_DIR_BITS / _SORT_DIR_MAJOR / _BUILD_DEVICE / _SMEM_STACK / _HOST_ZERO_COPY. Variant 3 (default) is the packed-format kernel;
+ * _SORT_ORIGIN_BITS / _SORT_DIR_BITS / _SORT_DIR_MAJOR / _BUILD_DEVICE / _SMEM_STACK / _HOST_ZERO_COPY / _WHITTED_ARENA / _WHITTED_COMBINE. Variant 3 (default) is the packed-format kernel;
  * 0-2 are the reference-format kernels kept for A/B. */
 int racc_cuda_set_tuning(int key, int value);
 

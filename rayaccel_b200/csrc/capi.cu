@@ -90,6 +90,8 @@ int ensureInit() {
 	g_tuning.buildDevice = envInt("RACC_B200_BUILD_DEVICE", g_tuning.buildDevice);
 	g_tuning.smemStack = envInt("RACC_B200_SMEM_STACK", g_tuning.smemStack);
 	g_tuning.hostZeroCopy = envInt("RACC_B200_HOST_ZERO_COPY", g_tuning.hostZeroCopy);
+	g_tuning.whittedArena = envInt("RACC_B200_WHITTED_ARENA", g_tuning.whittedArena);
+	g_tuning.whittedCombine = envInt("RACC_B200_WHITTED_COMBINE", g_tuning.whittedCombine);
 	g_initialised = true;
 	return 0;
 }
@@ -251,6 +253,8 @@ int racc_cuda_set_tuning(int key, int value) {
 	case 12: slot = &g_tuning.buildDevice; break;
 	case 13: slot = &g_tuning.smemStack; break;
 	case 14: slot = &g_tuning.hostZeroCopy; break;
+	case 15: slot = &g_tuning.whittedArena; break;
+	case 16: slot = &g_tuning.whittedCombine; break;
 	default: return fail("unknown tuning key %d", key);
 	}
 	const int previous = *slot;
@@ -528,6 +532,51 @@ struct PathLanes {
 };
 
 thread_local PathLanes t_pathLanes;
+
+// Wave buffers of racc_cuda_whitted_trace kept between waves, batches and calls (Tuning::whittedArena), one set per
+// calling host thread. A wave's size is only known after the previous one was shaded and differs from frame to frame, so
+// per-wave stream-ordered allocations keep asking the pool for sizes it has no block for; these buffers only ever grow
+// (by a quarter more than asked). Slots: 0/1 rays (ping-pong), 2/3 states, 4 results. A buffer is grown only while it
+// holds nothing live: the results before a wave is traced, the next wave's rays/states before they are written.
+struct WhittedArena {
+	static constexpr int kSlots = 5;
+	int device = -1;
+	void* p[kSlots] = {};
+	size_t cap[kSlots] = {};
+	cudaEvent_t idle = nullptr; // end of the previous call's work on these buffers
+	bool idleRecorded = false;
+
+	// a later call may come on another CUDA stream: it waits for the previous call's kernels before touching the buffers
+	int begin(cudaStream_t stream) {
+		if (device != g_device) {
+			for (int k = 0; k < kSlots; ++k) { p[k] = nullptr; cap[k] = 0; } // another device's pointers: dropped, not freed here
+			idle = nullptr;
+			idleRecorded = false;
+			device = g_device;
+		}
+		if (!idle) RACC_CUDA_CHECK(cudaEventCreateWithFlags(&idle, cudaEventDisableTiming));
+		if (idleRecorded) RACC_CUDA_CHECK(cudaStreamWaitEvent(stream, idle, 0));
+		return 0;
+	}
+	int end(cudaStream_t stream) {
+		RACC_CUDA_CHECK(cudaEventRecord(idle, stream));
+		idleRecorded = true;
+		return 0;
+	}
+	int ensure(int k, size_t bytes, cudaStream_t stream) {
+		if (cap[k] >= bytes && p[k]) return 0;
+		if (p[k]) RACC_CUDA_CHECK(cudaFreeAsync(p[k], stream));
+		p[k] = nullptr;
+		cap[k] = 0;
+		const size_t want = ((bytes + bytes / 4 + (2u << 20)) >> 21) << 21; // a quarter of headroom, whole 2 MiB pages
+		RACC_CUDA_CHECK(cudaMallocAsync(&p[k], want, stream));
+		cap[k] = want;
+		return 0;
+	}
+	~WhittedArena() { /* process teardown: the context may already be gone, leak on purpose */ }
+};
+
+thread_local WhittedArena t_whittedArena;
 
 void fillSceneParams(TraceParams& p, racc_cuda_scene* s, racc_cuda_env* env, void* device_counters) {
 	p.nodes = s->dNodes;
@@ -1013,6 +1062,13 @@ int racc_cuda_whitted_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_c
 	}
 	RACC_CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)pixels * 3 * sizeof(unsigned long long), stream));
 
+	// wave buffers: stream-ordered allocations per wave (default) or the calling thread's grow-only arena
+	const bool useArena = g_tuning.whittedArena != 0;
+	WhittedArena& arena = t_whittedArena;
+	if (useArena && arena.begin(stream)) return -1;
+	int cur = 0; // arena: which half of the ping-pong holds the current wave
+	enum { kRays = 0, kStates = 2, kResults = 4 };
+
 	int launches = 0;
 	for (uint32_t done = 0; done < d->spp; done += batchSpp) {
 		const uint32_t spp = d->spp - done < batchSpp ? d->spp - done : batchSpp;
@@ -1020,7 +1076,12 @@ int racc_cuda_whitted_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_c
 		RACC_CUDA_CHECK(cudaMemsetAsync(counts, 0, 64 * sizeof(uint32_t), stream));
 		DevRay* rays = nullptr;
 		float4* states = nullptr;
-		if (scratch.get(reinterpret_cast<void**>(&rays), (size_t)count * 32) || scratch.get(reinterpret_cast<void**>(&states), (size_t)count * 16)) return -1;
+		if (useArena) {
+			if (arena.ensure(kRays + cur, (size_t)count * 32, stream) || arena.ensure(kStates + cur, (size_t)count * 16, stream)) return -1;
+			rays = static_cast<DevRay*>(arena.p[kRays + cur]);
+			states = static_cast<float4*>(arena.p[kStates + cur]);
+		}
+		else if (scratch.get(reinterpret_cast<void**>(&rays), (size_t)count * 32) || scratch.get(reinterpret_cast<void**>(&states), (size_t)count * 16)) return -1;
 		RACC_CUDA_CHECK(launchWhittedPrimary(camera->origin, d->width, d->height, d->sample_base + done, 0, count, d->seed, rays, states, stream, &launches));
 		for (uint32_t depth = 0; depth <= d->max_depth && count; ++depth) {
 			if (wave_rays) wave_rays[depth] += count;
@@ -1029,9 +1090,20 @@ int racc_cuda_whitted_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_c
 			DevRay* nextRays = nullptr;
 			float4* nextStates = nullptr;
 			const bool last = depth == d->max_depth; // nothing is extended past the last bounce
-			if (scratch.get(reinterpret_cast<void**>(&results), (size_t)count * 16)) return -1;
-			if (!last && (scratch.get(reinterpret_cast<void**>(&nextRays), (size_t)count * 2 * 32) ||
-			              scratch.get(reinterpret_cast<void**>(&nextStates), (size_t)count * 2 * 16))) return -1;
+			if (useArena) {
+				if (arena.ensure(kResults, (size_t)count * 16, stream)) return -1;
+				results = static_cast<float4*>(arena.p[kResults]);
+				if (!last) {
+					if (arena.ensure(kRays + (cur ^ 1), (size_t)count * 2 * 32, stream) || arena.ensure(kStates + (cur ^ 1), (size_t)count * 2 * 16, stream)) return -1;
+					nextRays = static_cast<DevRay*>(arena.p[kRays + (cur ^ 1)]);
+					nextStates = static_cast<float4*>(arena.p[kStates + (cur ^ 1)]);
+				}
+			}
+			else {
+				if (scratch.get(reinterpret_cast<void**>(&results), (size_t)count * 16)) return -1;
+				if (!last && (scratch.get(reinterpret_cast<void**>(&nextRays), (size_t)count * 2 * 32) ||
+				              scratch.get(reinterpret_cast<void**>(&nextStates), (size_t)count * 2 * 16))) return -1;
+			}
 			racc_cuda_stream_desc sd{};
 			sd.rays = rays;
 			sd.results = results;
@@ -1042,6 +1114,7 @@ int racc_cuda_whitted_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_c
 			p.rays = rays; p.results = results; p.states = states; p.count = count; p.depth = depth; p.maxDepth = d->max_depth;
 			p.indices = s->dIndices; p.normals = sh->dNormals; p.triangleNormals = sh->dTriangleNormals; p.triangleCount = sh->triangleCount;
 			p.outRays = nextRays; p.outStates = nextStates; p.outCount = counts + depth; p.accumulators = acc;
+			p.combine = g_tuning.whittedCombine != 0;
 			RACC_CUDA_CHECK(launchWhittedShade(p, stream, &launches));
 			uint32_t next = 0;
 			if (!last) {
@@ -1049,16 +1122,22 @@ int racc_cuda_whitted_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_c
 				RACC_CUDA_CHECK(cudaMemcpyAsync(&next, counts + depth, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 				RACC_CUDA_CHECK(cudaStreamSynchronize(stream));
 			}
-			scratch.release(results);
-			scratch.release(rays);
-			scratch.release(states);
+			if (useArena) cur ^= 1;
+			else {
+				scratch.release(results);
+				scratch.release(rays);
+				scratch.release(states);
+			}
 			rays = nextRays;
 			states = nextStates;
 			count = next;
 		}
-		if (rays) scratch.release(rays);
-		if (states) scratch.release(states);
+		if (!useArena) {
+			if (rays) scratch.release(rays);
+			if (states) scratch.release(states);
+		}
 	}
+	if (useArena && arena.end(stream)) return -1;
 	RACC_CUDA_CHECK(launchWhittedFinish(acc, (uint32_t)pixels, fb, stream, &launches));
 	g_launches.fetch_add((uint64_t)launches);
 	if (hostFb) {

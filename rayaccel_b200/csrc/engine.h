@@ -65,6 +65,9 @@ struct Tuning {
 	                         // itself (one launch, no staging copies), 0 = staged H2D / trace / D2H pipeline
 	int buildDevice = 3;     // scene build (same images either way): 0 host threads; 1 SAH tree on the GPU, packing on the
 	                         // host; 2 everything on the GPU (bvh_build.cu); 3 auto = 2 from kAutoDeviceBuildTriangles up
+	// device-side Whitted renderer (whitted.cu); both written after the round's last GPU call, hence off until measured
+	int whittedArena = 0;    // 1 = wave buffers kept and grown per calling thread instead of stream-ordered allocations per wave
+	int whittedCombine = 0;  // 1 = a warp sums its rays' fixed-point radiance per pixel run before the atomics (same bits)
 };
 
 // counterMode: 0 none, 1 rays+hits only, 2 rays, hits, inner-node and pair visits
@@ -141,6 +144,7 @@ struct WhittedShadeParams {
 	float4* outStates;
 	uint32_t* outCount;
 	unsigned long long* accumulators; // 3 per pixel, 32.32 fixed-point radiance sums
+	bool combine;             // Tuning::whittedCombine
 };
 
 cudaError_t launchWhittedPrimary(const float* camera12, uint32_t width, uint32_t height, uint32_t sampleBase, uint32_t firstPath, uint32_t count,

@@ -63,6 +63,13 @@ struct WhittedArgs {
 	unsigned long long* accumulators; // 3 per pixel, 32.32 fixed point
 };
 
+// kCombine (Tuning::whittedCombine): the rays of a pixel's tree stay adjacent through the order-preserving compaction, so
+// a warp holds runs of lanes with the same pixel. Each lane turns its contribution into fixed point as before; the runs
+// are then summed with a segmented shuffle reduction and only the first lane of a run issues the (up to three) atomics.
+// Integer sums are associative and cannot overflow here (32 terms < 2^52 each), so the accumulators receive the same
+// totals bit for bit. Runs are told apart by a run number, not by the pixel, so two separate runs of one pixel inside a
+// warp are simply two atomics.
+template <bool kCombine>
 __global__ void __launch_bounds__(kBlock) whittedShadeKernel(const WhittedArgs a) {
 	__shared__ uint32_t warpBase[kBlock / 32];
 	__shared__ uint32_t ctaBase;
@@ -70,13 +77,17 @@ __global__ void __launch_bounds__(kBlock) whittedShadeKernel(const WhittedArgs a
 	bool reflect = false, refract = false;
 	DevRay rl, rr;
 	float4 state = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	uint32_t runKey = 0xffffffffu;                // kCombine: the lane's pixel
+	unsigned long long qr = 0ull, qg = 0ull, qb = 0ull; // kCombine: the lane's contribution, fixed point
 	if (i < a.count) {
 		const float4 res = a.results[i];
 		state = a.states[i];
 		const uint32_t pixel = __float_as_uint(state.w);
 		const uint32_t tri = __float_as_uint(res.x);
+		runKey = pixel;
 		if (tri == 0xffffffffu) {
-			addRadiance(a.accumulators, pixel, res.y * state.x, res.z * state.y, res.w * state.z);
+			if (kCombine) { qr = toFixed(res.y * state.x); qg = toFixed(res.z * state.y); qb = toFixed(res.w * state.z); }
+			else addRadiance(a.accumulators, pixel, res.y * state.x, res.z * state.y, res.w * state.z);
 		}
 		else if (tri < a.triangleCount && a.depth < a.maxDepth) {
 			const DevRay ray = a.rays[i];
@@ -98,7 +109,8 @@ __global__ void __launch_bounds__(kBlock) whittedShadeKernel(const WhittedArgs a
 			float light = fmaf(n[2], 0.57f, fmaf(n[1], 0.57f, n[0] * 0.57f));
 			light = light > 0.0f ? light : 0.0f;
 			state.x *= 0.3f; state.y *= 0.3f; state.z *= 0.3f;
-			addRadiance(a.accumulators, pixel, state.x * light, state.y * light, state.z * light);
+			if (kCombine) { qr = toFixed(state.x * light); qg = toFixed(state.y * light); qb = toFixed(state.z * light); }
+			else addRadiance(a.accumulators, pixel, state.x * light, state.y * light, state.z * light);
 			if (!(state.x <= 0.01f) || !(state.y <= 0.01f) || !(state.z <= 0.01f)) {
 				// reflection and refraction
 				const float ddn = fmaf(rd[2], n[2], fmaf(rd[1], n[1], rd[0] * n[0]));
@@ -132,8 +144,28 @@ __global__ void __launch_bounds__(kBlock) whittedShadeKernel(const WhittedArgs a
 			}
 		}
 	}
-	// compaction of 0..2 rays per thread: warp scan, one atomic per CTA; reflection before refraction
 	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (kCombine) {
+		// every lane of the warp is here (no early exits above); lanes past the end carry key 0xffffffff and zeros
+		const uint32_t before = __shfl_up_sync(0xffffffffu, runKey, 1);
+		const bool head = lane == 0 || before != runKey;
+		const uint32_t run = __popc(__ballot_sync(0xffffffffu, head) & (0xffffffffu >> (31 - lane))); // heads at or below this lane
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t otherRun = __shfl_down_sync(0xffffffffu, run, o);
+			const unsigned long long ur = __shfl_down_sync(0xffffffffu, qr, o);
+			const unsigned long long ug = __shfl_down_sync(0xffffffffu, qg, o);
+			const unsigned long long ub = __shfl_down_sync(0xffffffffu, qb, o);
+			if (lane + o < 32 && otherRun == run) { qr += ur; qg += ug; qb += ub; }
+		}
+		if (head && runKey != 0xffffffffu) {
+			unsigned long long* p = a.accumulators + 3 * (size_t)runKey;
+			if (qr) atomicAdd(p, qr);
+			if (qg) atomicAdd(p + 1, qg);
+			if (qb) atomicAdd(p + 2, qb);
+		}
+	}
+	// compaction of 0..2 rays per thread: warp scan, one atomic per CTA; reflection before refraction
 	const uint32_t mine = (reflect ? 1u : 0u) + (refract ? 1u : 0u);
 	uint32_t incl = mine;
 #pragma unroll
@@ -193,7 +225,8 @@ cudaError_t launchWhittedShade(const WhittedShadeParams& p, cudaStream_t stream,
 	a.rays = p.rays; a.results = p.results; a.states = p.states; a.count = p.count; a.depth = p.depth; a.maxDepth = p.maxDepth;
 	a.indices = p.indices; a.normals = p.normals; a.triangleNormals = p.triangleNormals; a.triangleCount = p.triangleCount;
 	a.outRays = p.outRays; a.outStates = p.outStates; a.outCount = p.outCount; a.accumulators = p.accumulators;
-	whittedShadeKernel<<<(p.count + kBlock - 1) / kBlock, kBlock, 0, stream>>>(a);
+	if (p.combine) whittedShadeKernel<true><<<(p.count + kBlock - 1) / kBlock, kBlock, 0, stream>>>(a);
+	else whittedShadeKernel<false><<<(p.count + kBlock - 1) / kBlock, kBlock, 0, stream>>>(a);
 	if (launches) *launches += 1;
 	return cudaGetLastError();
 }

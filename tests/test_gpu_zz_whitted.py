@@ -81,3 +81,24 @@ def test_device_whitted_matches_reference_renderer_image_and_device_framebuffer(
     _, waves2 = rb.whitted_trace(scene, env, shading, cam, w, h, spp, depth, seed=11, framebuffer_ptr=dev.data_ptr(), batch_spp=5)
     rb.sync()
     assert waves2 == waves and dev.cpu().numpy().tobytes() == fb.tobytes(), "device framebuffer / other batch split differs"
+
+
+@pytest.mark.skipif(os.environ.get("RACC_B200_TEST_UNMEASURED") != "1",
+                    reason="tuning keys 15/16 were written after the round's last GPU call; opt in with RACC_B200_TEST_UNMEASURED=1")
+@pytest.mark.parametrize("arena,combine", [(1, 0), (0, 1), (1, 1)])
+def test_device_whitted_options_keep_the_bits(world, battlefield, arena, combine):
+    """Grow-only wave buffers (key 15) and per-warp radiance sums before the atomics (key 16) change scheduling only:
+    same framebuffer bytes and wave sizes as the checker, over several frames of different sizes so the buffers grow,
+    get reused while too large, and are handed over between calls."""
+    scene, env, shading, images, sh = world
+    rb.set_tuning(whitted_arena=arena, whitted_combine=combine)
+    try:
+        for width, height, spp, depth, seed, batch in [(64, 48, 1, 8, 3, 0), (256, 128, 3, 8, 11, 1), (200, 96, 2, 2, 3, 0),
+                                                       (33, 17, 1, 1, 9, 0), (256, 128, 2, 8, 12, 0)]:
+            cam = camera_for(battlefield, width, height)
+            want, want_waves = oracle.whitted_trace(images, sh, cam, width, height, spp, depth, seed)
+            got, waves = rb.whitted_trace(scene, env, shading, cam, width, height, spp, depth, seed, batch_spp=batch)
+            assert waves == [int(x) for x in want_waves], "rays traced per bounce differ"
+            assert got.tobytes() == want.tobytes(), f"{width}x{height}x{spp} depth {depth}: framebuffer differs"
+    finally:
+        rb.set_tuning(whitted_arena=0, whitted_combine=0)

@@ -1,13 +1,17 @@
 // Micro-benchmark: L1 data-pipe wavefronts of divergent read-only loads by width and sharing pattern.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o l1wf l1_wavefronts.cu ; run under
-// ncu --metrics l1tex__data_pipe_lsu_wavefronts.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum,gpu__time_duration.sum
+// ncu --metrics l1tex__data_pipe_lsu_wavefronts.sum,l1tex__data_pipe_tex_wavefronts.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum,gpu__time_duration.sum
+// Modes 8-10 (added after round 1's last GPU call, not yet run): the same 64-byte node fetched through the TEXTURE path
+// (tex1Dfetch, 16 bytes per lane per instruction), alone and mixed with LDG.256 -- the question for round 2 is whether
+// texture fetches draw on a wavefront budget of their own (then the pair fetches of the traversal kernel could move there)
+// or on the same data pipe as LSU loads (then nothing is gained).
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
 
 // Each lane reads `BYTES` bytes at idx[lane-th]*64 (a 64-byte "node"); pattern decides how many lanes share a node.
 template <int MODE>
-__global__ void k(const float4* __restrict__ data, const uint32_t* __restrict__ idx, int iters, float* out) {
+__global__ void k(const float4* __restrict__ data, const uint32_t* __restrict__ idx, int iters, float* out, cudaTextureObject_t tex) {
 	const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
 	float acc = 0.f;
 	uint32_t n = idx[gid];
@@ -57,6 +61,25 @@ __global__ void k(const float4* __restrict__ data, const uint32_t* __restrict__ 
 			acc += v[0] + v[5] + v[10] + v[15];
 			n = (__float_as_uint(v[15]) + n * 1664525u + 1013904223u) & 0xffffu;
 		}
+		else if (MODE == 8) { // 4 x TEX (tex1Dfetch float4), every lane its own node
+			const int e = 4 * (int)n;
+			float4 a = tex1Dfetch<float4>(tex, e), b = tex1Dfetch<float4>(tex, e + 1), c = tex1Dfetch<float4>(tex, e + 2), d = tex1Dfetch<float4>(tex, e + 3);
+			acc += a.x + b.y + c.z + d.w;
+			n = (__float_as_uint(d.w) + n * 1664525u + 1013904223u) & 0xffffu;
+		}
+		else if (MODE == 9) { // 1 x LDG.256 (first half) + 2 x TEX (second half): a node split over both paths
+			float v[8];
+			asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+			const int e = 4 * (int)n;
+			float4 c = tex1Dfetch<float4>(tex, e + 2), d = tex1Dfetch<float4>(tex, e + 3);
+			acc += v[0] + v[5] + c.z + d.w;
+			n = (__float_as_uint(d.w) + n * 1664525u + 1013904223u) & 0xffffu;
+		}
+		else if (MODE == 10) { // 1 x TEX (16 bytes)
+			float4 a = tex1Dfetch<float4>(tex, 4 * (int)n);
+			acc += a.x;
+			n = (__float_as_uint(a.w) + n * 1664525u + 1013904223u) & 0xffffu;
+		}
 		else if (MODE == 7) { // 1 x LDG.64
 			float2 a = __ldg(reinterpret_cast<const float2*>(p));
 			acc += a.x;
@@ -74,9 +97,15 @@ int main() {
 	uint32_t* h = new uint32_t[threads];
 	uint32_t s = 1; for (int i = 0; i < threads; ++i) { s = s * 1664525u + 1013904223u; h[i] = (s >> 8) & 0xffffu; }
 	cudaMemcpy(idx, h, threads * 4, cudaMemcpyHostToDevice);
+	cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = data;
+	rd.res.linear.desc = cudaCreateChannelDesc<float4>(); rd.res.linear.sizeInBytes = (size_t)nodes * 64;
+	cudaTextureDesc td = {}; td.readMode = cudaReadModeElementType;
+	cudaTextureObject_t tex = 0;
+	if (cudaCreateTextureObject(&tex, &rd, &td, nullptr) != cudaSuccess) { printf("texture object failed\n"); return 1; }
 	cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-#define RUN(M) { k<M><<<threads / 256, 256>>>(data, idx, iters, out); cudaEventRecord(a); k<M><<<threads / 256, 256>>>(data, idx, iters, out); cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms, a, b); \
+#define RUN(M) { k<M><<<threads / 256, 256>>>(data, idx, iters, out, tex); cudaEventRecord(a); k<M><<<threads / 256, 256>>>(data, idx, iters, out, tex); cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms, a, b); \
 	printf("mode %d: %.3f ms, %.2f G lane-loads(of a node)/s\n", M, ms, (double)threads * iters / ms / 1e6); }
-	RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7)
+	RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(10)
+	if (cudaDeviceSynchronize() != cudaSuccess) { printf("kernel error\n"); return 1; }
 	return 0;
 }

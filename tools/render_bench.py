@@ -30,9 +30,14 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-api", action="store_true")
     ap.add_argument("--whitted", action="store_true", help="the Whitted renderer (racc_cuda_whitted_trace) instead of the path tracer")
+    ap.add_argument("--tuning", default="", help="rb.set_tuning keys, e.g. whitted_arena=1,whitted_combine=1")
+    ap.add_argument("--same-seed", action="store_true", help="every repetition renders the same frame (same wave sizes)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     rb.init(0)
+    tuning = {k: int(v) for k, v in (kv.split("=") for kv in args.tuning.split(",") if kv)}
+    if tuning:
+        rb.set_tuning(**tuning)
     sf = rb.load_scene()
     scene = rb.create_scene(sf.vertices, sf.indices)
     env = rb.create_environment(sf.environment)
@@ -47,7 +52,7 @@ def main():
         t0 = time.perf_counter()
         a.record()
         _, waves = (rb.whitted_trace if args.whitted else rb.path_trace)(scene, env, shading, cam, args.width, args.height, args.spp, args.depth,
-                                                                         seed=1 + rep, framebuffer_ptr=fb.data_ptr(), batch_spp=args.batch)
+                                                                         seed=1 if args.same_seed else 1 + rep, framebuffer_ptr=fb.data_ptr(), batch_spp=args.batch)
         b.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -57,7 +62,8 @@ def main():
     best = min(t[0] for t in times)
     med = sorted(t[0] for t in times)[len(times) // 2]
     line = {"what": "device-side Whitted renderer, battlefield" if args.whitted else "device-side wavefront path tracer, battlefield", "width": args.width, "height": args.height, "spp": args.spp,
-            "batch_spp": args.batch, "max_depth": args.depth, "rays_per_frame_set": rays, "waves": waves,
+            "batch_spp": args.batch, "max_depth": args.depth, "tuning": tuning, "same_seed": args.same_seed, "rays_per_frame_set": rays, "waves": waves,
+            "ms_all": [round(t[0] * 1e3, 3) for t in times],
             "ms_best": round(best * 1e3, 3), "ms_median": round(med * 1e3, 3), "wall_ms_best": round(min(t[1] for t in times) * 1e3, 3),
             "mrays_best": round(rays / best / 1e6, 1), "mrays_median": round(rays / med / 1e6, 1),
             "mean_radiance": float(fb.view(-1, 4)[:, :3].double().mean().item() / args.spp)}
