@@ -166,9 +166,10 @@ int racc_cuda_set_variant(int variant);
  * (0, 8, 16, -1 auto: 16 for scenes far larger than L2), 14 HOST streams in pinned memory read by the kernel itself
  * instead of being staged (0 staged = default, 1 zero-copy), 15 / 16 racc_cuda_whitted_trace only, both 0 by default
  * until measured on hardware: 15 wave buffers kept and grown per calling thread instead of allocated per wave,
- * 16 a warp sums its rays' fixed-point radiance per pixel before the atomics (same bits). Returns the previous value. Also settable through
+ * 16 a warp sums its rays' fixed-point radiance per pixel before the atomics (same bits); 17 staged HOST streams: the
+ * last chunks of a call shrink geometrically down to this many K rays (0 = off, the default until measured). Returns the previous value. Also settable through
  * RACC_B200_VARIANT / _BLOCK / _CTAS_PER_SM / _SMEM_NODES / _FETCH_THRESHOLD / _LEAF_BAIL / _INNER_BAIL / _SORT /
- * _SORT_ORIGIN_BITS / _SORT_DIR_BITS / _SORT_DIR_MAJOR / _BUILD_DEVICE / _SMEM_STACK / _HOST_ZERO_COPY / _WHITTED_ARENA / _WHITTED_COMBINE. Variant 3 (default) is the packed-format kernel;
+ * _SORT_ORIGIN_BITS / _SORT_DIR_BITS / _SORT_DIR_MAJOR / _BUILD_DEVICE / _SMEM_STACK / _HOST_ZERO_COPY / _WHITTED_ARENA / _WHITTED_COMBINE / _HOST_TAPER. Variant 3 (default) is the packed-format kernel;
  * 0-2 are the reference-format kernels kept for A/B. */
 int racc_cuda_set_tuning(int key, int value);
 

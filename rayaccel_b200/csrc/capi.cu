@@ -90,6 +90,7 @@ int ensureInit() {
 	g_tuning.buildDevice = envInt("RACC_B200_BUILD_DEVICE", g_tuning.buildDevice);
 	g_tuning.smemStack = envInt("RACC_B200_SMEM_STACK", g_tuning.smemStack);
 	g_tuning.hostZeroCopy = envInt("RACC_B200_HOST_ZERO_COPY", g_tuning.hostZeroCopy);
+	g_tuning.hostTaper = envInt("RACC_B200_HOST_TAPER", g_tuning.hostTaper);
 	g_tuning.whittedArena = envInt("RACC_B200_WHITTED_ARENA", g_tuning.whittedArena);
 	g_tuning.whittedCombine = envInt("RACC_B200_WHITTED_COMBINE", g_tuning.whittedCombine);
 	g_initialised = true;
@@ -255,6 +256,7 @@ int racc_cuda_set_tuning(int key, int value) {
 	case 14: slot = &g_tuning.hostZeroCopy; break;
 	case 15: slot = &g_tuning.whittedArena; break;
 	case 16: slot = &g_tuning.whittedCombine; break;
+	case 17: slot = &g_tuning.hostTaper; break;
 	default: return fail("unknown tuning key %d", key);
 	}
 	const int previous = *slot;
@@ -703,22 +705,34 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 		unsigned chunk = 0;
 		size_t si = 0;
 		uint32_t sBegin = 0;
+		// Tuning::hostTaper: what follows the call's last H2D copy -- one traversal and one D2H copy -- overlaps nothing,
+		// so the last chunks halve (remaining / 2, never below hostTaper K rays) instead of ending on a full-size one.
+		uint64_t remaining = 0;
+		for (const racc_cuda_stream_desc* d : hostStreams) remaining += d->count;
+		const uint64_t taperFloor = g_tuning.hostTaper > 0 ? (uint64_t)g_tuning.hostTaper << 10 : 0;
 		while (si < hostStreams.size()) {
 			const int l = (int)(chunk % HostPipeline::kLanes);
 			struct Segment { char* hResults; uint32_t offset, n; };
 			Segment segs[64];
 			int nsegs = 0;
 			uint32_t filled = 0;
-			while (si < hostStreams.size() && filled < pipe.chunkRays && nsegs < 64) {
+			uint32_t capacity = pipe.chunkRays;
+			if (taperFloor && remaining < 2ull * pipe.chunkRays) {
+				uint64_t half = (remaining + 1) / 2;
+				if (half < taperFloor) half = taperFloor;
+				if (half < capacity) capacity = (uint32_t)half;
+			}
+			while (si < hostStreams.size() && filled < capacity && nsegs < 64) {
 				const racc_cuda_stream_desc* d = hostStreams[si];
 				const uint32_t left = d->count - sBegin;
-				const uint32_t room = pipe.chunkRays - filled;
+				const uint32_t room = capacity - filled;
 				const uint32_t n = left < room ? left : room;
 				RACC_CUDA_CHECK(cudaMemcpyAsync(pipe.dRays[l] + filled, static_cast<const char*>(d->rays) + (size_t)sBegin * 32, (size_t)n * 32,
 				                                cudaMemcpyHostToDevice, pipe.lane[l]));
 				segs[nsegs++] = Segment{static_cast<char*>(d->results) + (size_t)sBegin * 16, filled, n};
 				filled += n;
 				sBegin += n;
+				remaining -= n;
 				if (sBegin == d->count) { ++si; sBegin = 0; }
 			}
 			TraceParams p{};

@@ -65,6 +65,9 @@ struct Tuning {
 	                         // itself (one launch, no staging copies), 0 = staged H2D / trace / D2H pipeline
 	int buildDevice = 3;     // scene build (same images either way): 0 host threads; 1 SAH tree on the GPU, packing on the
 	                         // host; 2 everything on the GPU (bvh_build.cu); 3 auto = 2 from kAutoDeviceBuildTriangles up
+	int hostTaper = 0;       // staged HOST streams: > 0 = the last chunks of a call shrink geometrically down to this many K rays,
+	                         // so that the traversal and D2H copy left exposed after the last H2D copy are short (written after
+	                         // the round's last GPU call: off until measured)
 	// device-side Whitted renderer (whitted.cu); both written after the round's last GPU call, hence off until measured
 	int whittedArena = 0;    // 1 = wave buffers kept and grown per calling thread instead of stream-ordered allocations per wave
 	int whittedCombine = 0;  // 1 = a warp sums its rays' fixed-point radiance per pixel run before the atomics (same bits)

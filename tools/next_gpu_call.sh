@@ -23,3 +23,9 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/micro/l1wf.bin tools/m
   timeout 300 ncu --metrics l1tex__data_pipe_lsu_wavefronts.sum,l1tex__data_pipe_tex_wavefronts.sum,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed,gpu__time_duration.sum \
     --clock-control none --csv --log-file gpurun_out/next_l1wf_ncu.csv ./tools/micro/l1wf.bin > /dev/null 2>&1
 }
+# 5. tapered tail of the HOST staging pipeline (tuning key 17): e2e of the bench batch with the floor at 0 (off) / 64 / 128 / 256 K rays;
+#    every line carries results_match_device_run
+for t in 0 64 128 256; do
+  RACC_B200_HOST_TAPER=$t timeout 300 python bench.py --steps 20 --warmup 3 2> /dev/null | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(json.dumps({'host_taper_k': $t, 'e2e': d['e2e']}))" >> gpurun_out/next_host_taper.jsonl
+done
+cat gpurun_out/next_host_taper.jsonl | cut -c1-300
