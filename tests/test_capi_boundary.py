@@ -96,6 +96,23 @@ def test_host_only_entry_points_work_without_gpu(battlefield):
     assert np.allclose(h.info["bounds_max"], battlefield.vertices[:, :3].max(0), atol=1e-3)
 
 
+def test_tuning_keys_documented_and_settable_without_gpu():
+    """racc_cuda_set_tuning is host-only: every key the header documents is accepted and returns the previous value, the
+    options written after the last GPU call (15-17) default to off, an unknown key is an error with a message."""
+    lib = _lib.load()
+    lib.racc_cuda_set_tuning.restype = ctypes.c_int
+    header = open(os.path.join(ROOT, "include", "racc_b200.h")).read()
+    for env in ["_WHITTED_ARENA", "_WHITTED_COMBINE", "_HOST_TAPER", "_SMEM_STACK", "_HOST_ZERO_COPY"]:
+        assert env in header
+    for key in range(18):
+        prev = lib.racc_cuda_set_tuning(key, 1)
+        assert lib.racc_cuda_set_tuning(key, prev) == 1, f"key {key} did not keep the value"
+        if key in (15, 16, 17):
+            assert prev == 0, f"key {key} must be off by default until it has been measured on hardware"
+    assert lib.racc_cuda_set_tuning(18, 1) == -1
+    assert b"unknown tuning key" in lib.racc_cuda_last_error()
+
+
 def test_product_never_touches_the_oracle():
     """Static check: nothing under rayaccel_b200/, include/ imports, links or loads oracle/."""
     bad = []
