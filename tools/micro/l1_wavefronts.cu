@@ -9,6 +9,11 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// Mode 11 (same status): the node read from __constant__ memory with a per-lane index -- the constant path serialises
+// distinct addresses, but it is a pipe of its own; if it sustains a useful rate beside LDG traffic, the top of the tree
+// (512 nodes = 32 KB take roughly half of all visits) could be served from it.
+__constant__ float4 cnodes[2048];
+
 // Each lane reads `BYTES` bytes at idx[lane-th]*64 (a 64-byte "node"); pattern decides how many lanes share a node.
 template <int MODE>
 __global__ void k(const float4* __restrict__ data, const uint32_t* __restrict__ idx, int iters, float* out, cudaTextureObject_t tex) {
@@ -80,6 +85,27 @@ __global__ void k(const float4* __restrict__ data, const uint32_t* __restrict__ 
 			acc += a.x;
 			n = (__float_as_uint(a.w) + n * 1664525u + 1013904223u) & 0xffffu;
 		}
+		else if (MODE == 11) { // 4 x LDC.128 with a divergent index (512 nodes in constant memory)
+			const int e = 4 * (int)(n & 511u);
+			float4 a = cnodes[e], b = cnodes[e + 1], c = cnodes[e + 2], d = cnodes[e + 3];
+			acc += (a.x + a.y + a.z + a.w) + (b.x + b.y + b.z + b.w) + (c.x + c.y + c.z + c.w) + (d.x + d.y + d.z + d.w); // all 64 bytes are needed
+			n = (__float_as_uint(d.w) + n * 1664525u + 1013904223u) & 0xffffu;
+		}
+		else if (MODE == 12) { // every other visit from constant memory, the others 2 x LDG.256: do the two paths overlap?
+			if (it & 1) {
+				const int e = 4 * (int)(n & 511u);
+				float4 a = cnodes[e], b = cnodes[e + 1], c = cnodes[e + 2], d = cnodes[e + 3];
+				acc += (a.x + a.y + a.z + a.w) + (b.x + b.y + b.z + b.w) + (c.x + c.y + c.z + c.w) + (d.x + d.y + d.z + d.w); // all 64 bytes are needed
+				n = (__float_as_uint(d.w) + n * 1664525u + 1013904223u) & 0xffffu;
+			}
+			else {
+				float v[16];
+				asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+				asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+32];" : "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]) : "l"(p));
+				acc += v[0] + v[5] + v[10] + v[15];
+				n = (__float_as_uint(v[15]) + n * 1664525u + 1013904223u) & 0xffffu;
+			}
+		}
 		else if (MODE == 7) { // 1 x LDG.64
 			float2 a = __ldg(reinterpret_cast<const float2*>(p));
 			acc += a.x;
@@ -105,7 +131,7 @@ int main() {
 	cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
 #define RUN(M) { k<M><<<threads / 256, 256>>>(data, idx, iters, out, tex); cudaEventRecord(a); k<M><<<threads / 256, 256>>>(data, idx, iters, out, tex); cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms, a, b); \
 	printf("mode %d: %.3f ms, %.2f G lane-loads(of a node)/s\n", M, ms, (double)threads * iters / ms / 1e6); }
-	RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(10)
+	RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(10) RUN(11) RUN(12)
 	if (cudaDeviceSynchronize() != cudaSuccess) { printf("kernel error\n"); return 1; }
 	return 0;
 }
