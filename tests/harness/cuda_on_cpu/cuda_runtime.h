@@ -11,6 +11,7 @@
 #pragma once
 
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -193,3 +194,98 @@ template <typename T> static inline T __ldg(const T* p) { return *p; }
 // one OS thread runs every fiber, and fibers only switch inside collectives: plain read-modify-write is atomic here
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { const uint32_t old = *p; *p = old + v; return old; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long old = *p; *p = old + v; return old; }
+
+// ---- what the traversal kernels need on top of the shading kernels ------------------------------------------------
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+template <typename T> static inline T __shfl_xor_sync(unsigned mask, T v, int laneMask) {
+	if (mask != 0xffffffffu) abort();
+	const int lane = (int)(threadIdx.x % 32);
+	const uint64_t* s = ::cuda_on_cpu::exchange(::cuda_on_cpu::to_bits(v));
+	return ::cuda_on_cpu::from_bits<T>(s[(lane ^ laneMask) & 31]);
+}
+// IEEE round-to-nearest reciprocal, square root and division (the process runs FTZ/DAZ like the device code)
+static inline float __frcp_rn(float x) { return 1.0f / x; }
+static inline float __fsqrt_rn(float x) { return sqrtf(x); }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned v) { const unsigned long long old = *p; *p = old + v; return old; }
+template <typename T> static inline T min(T a, T b) { return b < a ? b : a; }
+template <typename T> static inline T max(T a, T b) { return a < b ? b : a; }
+
+namespace cuda_on_cpu {
+// FMNMX: minNum / maxNum, subnormal inputs flushed, -0 < +0 (what fminf/fmaxf compile to under -ftz=true)
+inline float flush_subnormal(float x) {
+	uint32_t u; memcpy(&u, &x, 4);
+	if (u & 0x7f800000u) return x;
+	u &= 0x80000000u; memcpy(&x, &u, 4);
+	return x;
+}
+inline float device_fminf(float a, float b) {
+	a = flush_subnormal(a); b = flush_subnormal(b);
+	if (a != a) return b;
+	if (b != b) return a;
+	if (a < b) return a;
+	if (b < a) return b;
+	uint32_t ua, ub; memcpy(&ua, &a, 4); memcpy(&ub, &b, 4); ua |= ub; memcpy(&a, &ua, 4);
+	return a;
+}
+inline float device_fmaxf(float a, float b) {
+	a = flush_subnormal(a); b = flush_subnormal(b);
+	if (a != a) return b;
+	if (b != b) return a;
+	if (a > b) return a;
+	if (b > a) return b;
+	uint32_t ua, ub; memcpy(&ua, &a, 4); memcpy(&ub, &b, 4); ua &= ub; memcpy(&a, &ua, 4);
+	return a;
+}
+
+// Address windows. Kernel-local arrays live on the fibers' stacks, __shared__ arrays are statics of this library:
+// a 32-bit "local" / "shared" address is the distance from a fixed anchor of that region.
+inline char shared_anchor;
+inline uint32_t local_address(const void* p) { return (uint32_t)((uintptr_t)p - (uintptr_t)g.stacks.data()); }
+inline uint32_t shared_address(const void* p) { return (uint32_t)((intptr_t)p - (intptr_t)&shared_anchor); }
+
+namespace ptx {
+inline uint32_t* local_word(unsigned long long address) { return reinterpret_cast<uint32_t*>(g.stacks.data() + (uint32_t)address); }
+inline uint32_t* shared_word(unsigned long long address) { return reinterpret_cast<uint32_t*>(&shared_anchor + (int32_t)(uint32_t)address); }
+inline void pack2(unsigned long long& out, float lo, float hi) {
+	uint32_t a, b; memcpy(&a, &lo, 4); memcpy(&b, &hi, 4);
+	out = (unsigned long long)a | ((unsigned long long)b << 32);
+}
+inline void unpack2(float& lo, float& hi, unsigned long long v) {
+	const uint32_t a = (uint32_t)v, b = (uint32_t)(v >> 32); memcpy(&lo, &a, 4); memcpy(&hi, &b, 4);
+}
+inline void unpack2(uint32_t& lo, uint32_t& hi, unsigned long long v) { lo = (uint32_t)v; hi = (uint32_t)(v >> 32); }
+// fma.rn.ftz.f32x2: one IEEE fma per half, inputs and results flushed (MXCSR FTZ/DAZ does that to fmaf here)
+inline void fma2(unsigned long long& out, unsigned long long a, unsigned long long b, unsigned long long c) {
+	float al, ah, bl, bh, cl, ch;
+	unpack2(al, ah, a); unpack2(bl, bh, b); unpack2(cl, ch, c);
+	pack2(out, fmaf(al, bl, cl), fmaf(ah, bh, ch));
+}
+inline void ld8f(unsigned long long address, float& a, float& b, float& c, float& d, float& e, float& f, float& g_, float& h) {
+	if (address & 31) abort(); // a 256-bit load must be 32-byte aligned
+	float v[8]; memcpy(v, reinterpret_cast<const void*>((uintptr_t)address), 32);
+	a = v[0]; b = v[1]; c = v[2]; d = v[3]; e = v[4]; f = v[5]; g_ = v[6]; h = v[7];
+}
+inline void ld4q(unsigned long long address, unsigned long long& a, unsigned long long& b, unsigned long long& c, unsigned long long& d) {
+	if (address & 31) abort();
+	unsigned long long v[4]; memcpy(v, reinterpret_cast<const void*>((uintptr_t)address), 32);
+	a = v[0]; b = v[1]; c = v[2]; d = v[3];
+}
+[[noreturn]] inline void unsupported(const char* what) { fprintf(stderr, "cuda_on_cpu: PTX not available on the CPU: %s\n", what); abort(); }
+} // namespace ptx
+} // namespace cuda_on_cpu
+
+#define fminf(a, b) ::cuda_on_cpu::device_fminf((a), (b))
+#define fmaxf(a, b) ::cuda_on_cpu::device_fmaxf((a), (b))
+static inline size_t __cvta_generic_to_local(const void* p) { return ::cuda_on_cpu::local_address(p); }
+static inline size_t __cvta_generic_to_shared(const void* p) { return ::cuda_on_cpu::shared_address(p); }
+
+// the few runtime calls the launchers make
+enum cudaDeviceAttr { cudaDevAttrMaxSharedMemoryPerMultiprocessor = 81, cudaDevAttrMultiProcessorCount = 16 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
+static inline cudaError_t cudaGetDevice(int* device) { *device = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetAttribute(int* value, cudaDeviceAttr attr, int) { *value = attr == cudaDevAttrMultiProcessorCount ? 2 : 233472; return cudaSuccess; }
+template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* blocks, F, int, size_t) { *blocks = 2; return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t) { memset(p, value, bytes); return cudaSuccess; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "cuda_on_cpu"; }
