@@ -47,12 +47,21 @@ struct Fiber {
 	ucontext_t context;
 	Dim tid = {0, 0, 0};
 	bool done = false;
-	int parity = 0; // which half of the warp's exchange slots the next collective uses
+};
+
+// One warp-level rendezvous per distinct member mask (a kernel may have lanes inside `if (valid) __match_any_sync(mask, ..)`
+// while the others already wait in a full-mask __syncwarp()). Values are exchanged through two slot sets that alternate
+// with the generation, so one rendezvous per collective is enough.
+struct Collective {
+	unsigned mask = 0, arrived = 0, generation = 0;
+	unsigned participants[2] = {0, 0}; // who took part in the generation that used this slot set
+	uint64_t slot[2][32];
 };
 
 struct Warp {
-	Rendezvous rendezvous;
-	uint64_t slot[2][32];
+	unsigned alive = 0xffffffffu; // lanes that have not left the kernel
+	unsigned used = 0;
+	Collective collective[16];
 };
 
 struct State {
@@ -60,13 +69,15 @@ struct State {
 	std::vector<Fiber> fibers;
 	std::vector<char> stacks;
 	std::vector<Warp> warps;
+	std::vector<char> dynamicShared;
 	Rendezvous block;
 	Fiber* current = nullptr;
 	Dim blockIdx_ = {0, 0, 0}, blockDim_ = {1, 1, 1}, gridDim_ = {1, 1, 1};
 	const std::function<void()>* body = nullptr;
 };
 
-inline State g;
+// per OS thread: host threads (the API's submitters) may launch concurrently, each runs its own fibers
+inline thread_local State g;
 
 inline void yield() { swapcontext(&g.current->context, &g.scheduler); }
 
@@ -81,24 +92,35 @@ inline void rendezvous(Rendezvous& r) {
 	while (r.generation == generation) yield();
 }
 
+inline void release_if_complete(const Warp& w, Collective& c) {
+	const unsigned expected = c.mask & w.alive;
+	if (c.arrived && (c.arrived & w.alive) == expected) {
+		c.participants[c.generation & 1] = expected;
+		c.arrived = 0;
+		++c.generation;
+	}
+}
+
 inline void fiber_main() {
 	Fiber* self = g.current;
 	(*g.body)();
 	self->done = true;
 	// a thread that has left the kernel no longer takes part in barriers (CUDA: exited threads count as arrived)
-	Rendezvous& w = g.warps[self->tid.x / 32].rendezvous;
-	--w.alive; release_if_complete(w);
+	Warp& w = g.warps[self->tid.x / 32];
+	w.alive &= ~(1u << (self->tid.x % 32));
+	for (unsigned k = 0; k < w.used; ++k) release_if_complete(w, w.collective[k]);
 	--g.block.alive; release_if_complete(g.block);
 	swapcontext(&self->context, &g.scheduler);
 }
 
 // kernel<<<grid, block>>>(args) -> launch(grid, block, [=] { kernel(args); })
-inline void launch(unsigned grid, unsigned block, const std::function<void()>& body) {
+inline void launch(unsigned grid, unsigned block, const std::function<void()>& body, size_t dynamicSharedBytes = 0) {
 	const size_t kStack = 256 * 1024;
 	if (block == 0 || block % 32 != 0 || block > 1024) abort();
 	g.fibers.assign(block, Fiber());
 	g.stacks.resize(kStack * block);
-	g.warps.assign(block / 32, Warp());
+	g.warps.resize(block / 32);
+	g.dynamicShared.assign(dynamicSharedBytes + 128, 0);
 	g.body = &body;
 	g.blockDim_ = {block, 1, 1};
 	g.gridDim_ = {grid, 1, 1};
@@ -106,12 +128,11 @@ inline void launch(unsigned grid, unsigned block, const std::function<void()>& b
 		g.blockIdx_ = {b, 0, 0};
 		g.block = Rendezvous();
 		g.block.alive = block;
-		for (Warp& w : g.warps) { w.rendezvous = Rendezvous(); w.rendezvous.alive = 32; }
+		for (Warp& w : g.warps) { w.alive = 0xffffffffu; w.used = 0; }
 		for (unsigned t = 0; t < block; ++t) {
 			Fiber& f = g.fibers[t];
 			f.tid = {t, 0, 0};
 			f.done = false;
-			f.parity = 0;
 			getcontext(&f.context);
 			f.context.uc_stack.ss_sp = g.stacks.data() + kStack * t;
 			f.context.uc_stack.ss_size = kStack;
@@ -133,16 +154,31 @@ inline void launch(unsigned grid, unsigned block, const std::function<void()>& b
 	g.body = nullptr;
 }
 
-// every lane of the warp deposits a value, then reads any lane's; one rendezvous per collective (slots alternate)
-inline const uint64_t* exchange(uint64_t mine) {
+// every lane named in `mask` deposits a value, then reads any member's; returns the slot set and who took part
+struct Exchanged { const uint64_t* slot; unsigned participants; };
+inline Exchanged exchange(unsigned mask, uint64_t mine) {
 	Fiber* self = g.current;
 	Warp& w = g.warps[self->tid.x / 32];
-	const int parity = self->parity;
-	self->parity ^= 1;
-	w.slot[parity][self->tid.x % 32] = mine;
-	rendezvous(w.rendezvous);
-	return w.slot[parity];
+	const unsigned lane = self->tid.x % 32;
+	if (!(mask >> lane & 1u)) abort(); // a lane must name itself
+	unsigned k = 0;
+	while (k < w.used && w.collective[k].mask != mask) ++k;
+	if (k == w.used) {
+		if (w.used == 16) abort();
+		w.collective[k] = Collective();
+		w.collective[k].mask = mask;
+		++w.used;
+	}
+	Collective& c = w.collective[k];
+	const unsigned generation = c.generation;
+	c.slot[generation & 1][lane] = mine;
+	c.arrived |= 1u << lane;
+	release_if_complete(w, c);
+	while (c.generation == generation) yield();
+	return Exchanged{c.slot[generation & 1], c.participants[generation & 1]};
 }
+
+inline void* dynamic_shared() { return reinterpret_cast<void*>(((uintptr_t)g.dynamicShared.data() + 127) & ~(uintptr_t)127); }
 
 template <typename T> inline uint64_t to_bits(T v) { static_assert(sizeof(T) <= 8, ""); uint64_t b = 0; memcpy(&b, &v, sizeof(T)); return b; }
 template <typename T> inline T from_bits(uint64_t b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
@@ -156,30 +192,34 @@ template <typename T> inline T from_bits(uint64_t b) { T v; memcpy(&v, &b, sizeo
 
 static inline void __syncthreads() { ::cuda_on_cpu::rendezvous(::cuda_on_cpu::g.block); }
 
-// Only full-mask collectives are supported (all the two files use); anything else aborts instead of guessing.
+static inline unsigned __activemask() { return ::cuda_on_cpu::g.warps[threadIdx.x / 32].alive; } // lanes still in the kernel
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { ::cuda_on_cpu::exchange(mask, 0); }
 static inline unsigned __ballot_sync(unsigned mask, bool predicate) {
-	if (mask != 0xffffffffu) abort();
-	const uint64_t* s = ::cuda_on_cpu::exchange(predicate ? 1u : 0u);
+	const ::cuda_on_cpu::Exchanged e = ::cuda_on_cpu::exchange(mask, predicate ? 1u : 0u);
 	unsigned r = 0;
-	for (int l = 0; l < 32; ++l) r |= (unsigned)(s[l] & 1u) << l;
+	for (int l = 0; l < 32; ++l) if (e.participants >> l & 1u) r |= (unsigned)(e.slot[l] & 1u) << l;
+	return r;
+}
+template <typename T> static inline unsigned __match_any_sync(unsigned mask, T v) {
+	const uint64_t mine = ::cuda_on_cpu::to_bits(v);
+	const ::cuda_on_cpu::Exchanged e = ::cuda_on_cpu::exchange(mask, mine);
+	unsigned r = 0;
+	for (int l = 0; l < 32; ++l) if ((e.participants >> l & 1u) && e.slot[l] == mine) r |= 1u << l;
 	return r;
 }
 template <typename T> static inline T __shfl_sync(unsigned mask, T v, int src) {
-	if (mask != 0xffffffffu) abort();
-	const uint64_t* s = ::cuda_on_cpu::exchange(::cuda_on_cpu::to_bits(v));
-	return ::cuda_on_cpu::from_bits<T>(s[src & 31]);
+	const ::cuda_on_cpu::Exchanged e = ::cuda_on_cpu::exchange(mask, ::cuda_on_cpu::to_bits(v));
+	return ::cuda_on_cpu::from_bits<T>(e.slot[src & 31]);
 }
 template <typename T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
-	if (mask != 0xffffffffu) abort();
 	const int lane = (int)(threadIdx.x % 32);
-	const uint64_t* s = ::cuda_on_cpu::exchange(::cuda_on_cpu::to_bits(v));
-	return lane - (int)delta >= 0 ? ::cuda_on_cpu::from_bits<T>(s[lane - (int)delta]) : v;
+	const ::cuda_on_cpu::Exchanged e = ::cuda_on_cpu::exchange(mask, ::cuda_on_cpu::to_bits(v));
+	return lane - (int)delta >= 0 ? ::cuda_on_cpu::from_bits<T>(e.slot[lane - (int)delta]) : v;
 }
 template <typename T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta) {
-	if (mask != 0xffffffffu) abort();
 	const int lane = (int)(threadIdx.x % 32);
-	const uint64_t* s = ::cuda_on_cpu::exchange(::cuda_on_cpu::to_bits(v));
-	return lane + (int)delta < 32 ? ::cuda_on_cpu::from_bits<T>(s[lane + (int)delta]) : v;
+	const ::cuda_on_cpu::Exchanged e = ::cuda_on_cpu::exchange(mask, ::cuda_on_cpu::to_bits(v));
+	return lane + (int)delta < 32 ? ::cuda_on_cpu::from_bits<T>(e.slot[lane + (int)delta]) : v;
 }
 
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
@@ -198,10 +238,9 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
 // ---- what the traversal kernels need on top of the shading kernels ------------------------------------------------
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 template <typename T> static inline T __shfl_xor_sync(unsigned mask, T v, int laneMask) {
-	if (mask != 0xffffffffu) abort();
 	const int lane = (int)(threadIdx.x % 32);
-	const uint64_t* s = ::cuda_on_cpu::exchange(::cuda_on_cpu::to_bits(v));
-	return ::cuda_on_cpu::from_bits<T>(s[(lane ^ laneMask) & 31]);
+	const ::cuda_on_cpu::Exchanged e = ::cuda_on_cpu::exchange(mask, ::cuda_on_cpu::to_bits(v));
+	return ::cuda_on_cpu::from_bits<T>(e.slot[(lane ^ laneMask) & 31]);
 }
 // IEEE round-to-nearest reciprocal, square root and division (the process runs FTZ/DAZ like the device code)
 static inline float __frcp_rn(float x) { return 1.0f / x; }
