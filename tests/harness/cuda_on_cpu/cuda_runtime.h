@@ -160,11 +160,11 @@ inline Exchanged exchange(unsigned mask, uint64_t mine) {
 	Fiber* self = g.current;
 	Warp& w = g.warps[self->tid.x / 32];
 	const unsigned lane = self->tid.x % 32;
-	if (!(mask >> lane & 1u)) abort(); // a lane must name itself
+	if (!(mask >> lane & 1u)) { fprintf(stderr, "cuda_on_cpu: lane %u calls a collective with mask %08x that does not name it\n", lane, mask); abort(); }
 	unsigned k = 0;
 	while (k < w.used && w.collective[k].mask != mask) ++k;
 	if (k == w.used) {
-		if (w.used == 16) abort();
+		if (w.used == 16) { fprintf(stderr, "cuda_on_cpu: more than 16 distinct member masks in one warp\n"); abort(); }
 		w.collective[k] = Collective();
 		w.collective[k].mask = mask;
 		++w.used;
@@ -192,7 +192,9 @@ template <typename T> inline T from_bits(uint64_t b) { T v; memcpy(&v, &b, sizeo
 
 static inline void __syncthreads() { ::cuda_on_cpu::rendezvous(::cuda_on_cpu::g.block); }
 
-static inline unsigned __activemask() { return ::cuda_on_cpu::g.warps[threadIdx.x / 32].alive; } // lanes still in the kernel
+// lanes still in the kernel. The other fibers get one turn first, so lanes that leave the kernel without waiting for
+// anybody (`if (i >= n) return;`) have left -- as they have on hardware by the time a working lane asks.
+static inline unsigned __activemask() { ::cuda_on_cpu::yield(); return ::cuda_on_cpu::g.warps[threadIdx.x / 32].alive; }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { ::cuda_on_cpu::exchange(mask, 0); }
 static inline unsigned __ballot_sync(unsigned mask, bool predicate) {
 	const ::cuda_on_cpu::Exchanged e = ::cuda_on_cpu::exchange(mask, predicate ? 1u : 0u);
@@ -279,13 +281,35 @@ inline float device_fmaxf(float a, float b) {
 
 // Address windows. Kernel-local arrays live on the fibers' stacks, __shared__ arrays are statics of this library:
 // a 32-bit "local" / "shared" address is the distance from a fixed anchor of that region.
-inline char shared_anchor;
 inline uint32_t local_address(const void* p) { return (uint32_t)((uintptr_t)p - (uintptr_t)g.stacks.data()); }
-inline uint32_t shared_address(const void* p) { return (uint32_t)((intptr_t)p - (intptr_t)&shared_anchor); }
+// shared window: a 32-bit "shared address" is (segment << 28 | offset). Segment 8 and up is the launch's dynamic block;
+// segments 1-7 are 256 MB regions of this process registered the first time a __shared__ static inside them is converted
+// (the statics of the libraries built over this header may lie anywhere in the address space).
+inline thread_local uintptr_t shared_segment[7];
+inline thread_local unsigned shared_segments = 0;
+inline uint32_t shared_address(const void* p) {
+	const char* c = static_cast<const char*>(p);
+	const char* dyn = static_cast<const char*>(dynamic_shared());
+	if (c >= dyn && c < dyn + g.dynamicShared.size()) return 0x80000000u + (uint32_t)(c - dyn);
+	const uintptr_t a = (uintptr_t)c;
+	for (unsigned k = 0; k < shared_segments; ++k)
+		if (a >= shared_segment[k] + 0x00100000u && a < shared_segment[k] + 0x0ff00000u) return ((k + 1) << 28) | (uint32_t)(a - shared_segment[k]);
+	if (shared_segments == 7) { fprintf(stderr, "cuda_on_cpu: too many shared-memory regions\n"); abort(); }
+	shared_segment[shared_segments] = (a - 0x04000000u) & ~(uintptr_t)0xfffff;
+	++shared_segments;
+	return (shared_segments << 28) | (uint32_t)(a - shared_segment[shared_segments - 1]);
+}
 
 namespace ptx {
 inline uint32_t* local_word(unsigned long long address) { return reinterpret_cast<uint32_t*>(g.stacks.data() + (uint32_t)address); }
-inline uint32_t* shared_word(unsigned long long address) { return reinterpret_cast<uint32_t*>(&shared_anchor + (int32_t)(uint32_t)address); }
+inline char* shared_pointer(unsigned long long address) {
+	const uint32_t a = (uint32_t)address;
+	if (a & 0x80000000u) return static_cast<char*>(dynamic_shared()) + (a & 0x7fffffffu);
+	const unsigned segment = a >> 28;
+	if (segment == 0 || segment > shared_segments) { fprintf(stderr, "cuda_on_cpu: %08x is not a shared address\n", a); abort(); }
+	return reinterpret_cast<char*>(shared_segment[segment - 1] + (a & 0x0fffffffu));
+}
+inline uint32_t* shared_word(unsigned long long address) { return reinterpret_cast<uint32_t*>(shared_pointer(address)); }
 inline void pack2(unsigned long long& out, float lo, float hi) {
 	uint32_t a, b; memcpy(&a, &lo, 4); memcpy(&b, &hi, 4);
 	out = (unsigned long long)a | ((unsigned long long)b << 32);
@@ -301,12 +325,17 @@ inline void fma2(unsigned long long& out, unsigned long long a, unsigned long lo
 	pack2(out, fmaf(al, bl, cl), fmaf(ah, bh, ch));
 }
 inline void ld8f(unsigned long long address, float& a, float& b, float& c, float& d, float& e, float& f, float& g_, float& h) {
-	if (address & 31) abort(); // a 256-bit load must be 32-byte aligned
+	if (address & 31) { fprintf(stderr, "cuda_on_cpu: misaligned 256-bit load\n"); abort(); }
 	float v[8]; memcpy(v, reinterpret_cast<const void*>((uintptr_t)address), 32);
 	a = v[0]; b = v[1]; c = v[2]; d = v[3]; e = v[4]; f = v[5]; g_ = v[6]; h = v[7];
 }
+inline void ld4f(unsigned long long address, float& a, float& b, float& c, float& d) {
+	if (address & 15) { fprintf(stderr, "cuda_on_cpu: misaligned 128-bit load\n"); abort(); }
+	float v[4]; memcpy(v, reinterpret_cast<const void*>((uintptr_t)address), 16);
+	a = v[0]; b = v[1]; c = v[2]; d = v[3];
+}
 inline void ld4q(unsigned long long address, unsigned long long& a, unsigned long long& b, unsigned long long& c, unsigned long long& d) {
-	if (address & 31) abort();
+	if (address & 31) { fprintf(stderr, "cuda_on_cpu: misaligned 256-bit load\n"); abort(); }
 	unsigned long long v[4]; memcpy(v, reinterpret_cast<const void*>((uintptr_t)address), 32);
 	a = v[0]; b = v[1]; c = v[2]; d = v[3];
 }
@@ -320,7 +349,7 @@ static inline size_t __cvta_generic_to_local(const void* p) { return ::cuda_on_c
 static inline size_t __cvta_generic_to_shared(const void* p) { return ::cuda_on_cpu::shared_address(p); }
 
 // the few runtime calls the launchers make
-enum cudaDeviceAttr { cudaDevAttrMaxSharedMemoryPerMultiprocessor = 81, cudaDevAttrMultiProcessorCount = 16 };
+enum cudaDeviceAttr { cudaDevAttrMaxSharedMemoryPerMultiprocessor = 81, cudaDevAttrMultiProcessorCount = 16, cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 static inline cudaError_t cudaGetDevice(int* device) { *device = 0; return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int* value, cudaDeviceAttr attr, int) { *value = attr == cudaDevAttrMultiProcessorCount ? 2 : 233472; return cudaSuccess; }
@@ -328,3 +357,52 @@ template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFunc
 template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* blocks, F, int, size_t) { *blocks = 2; return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t) { memset(p, value, bytes); return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "cuda_on_cpu"; }
+
+// ---- a synchronous stand-in for the runtime calls capi.cu makes (device memory is host memory, streams run in order
+// because every call completes before it returns) -- enough to compile the WHOLE engine library for the CPU test build
+#define __constant__
+#define __align__(n) __attribute__((aligned(n)))
+typedef void* cudaEvent_t;
+typedef void* cudaMemPool_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocPortable = 1, cudaHostAllocMapped = 2 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void* devicePointer; void* hostPointer; };
+
+namespace cuda_on_cpu {
+inline cudaError_t allocate(void** p, size_t bytes) {
+	*p = aligned_alloc(256, (bytes + 255) & ~(size_t)255);
+	return *p ? cudaSuccess : 2;
+}
+} // namespace cuda_on_cpu
+static inline cudaError_t cudaMalloc(void** p, size_t bytes) { return ::cuda_on_cpu::allocate(p, bytes ? bytes : 1); }
+template <typename T> static inline cudaError_t cudaMalloc(T** p, size_t bytes) { return cudaMalloc(reinterpret_cast<void**>(p), bytes); }
+static inline cudaError_t cudaMallocAsync(void** p, size_t bytes, cudaStream_t) { return cudaMalloc(p, bytes); }
+template <typename T> static inline cudaError_t cudaMallocAsync(T** p, size_t bytes, cudaStream_t s) { return cudaMallocAsync(reinterpret_cast<void**>(p), bytes, s); }
+static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { return ::cuda_on_cpu::allocate(p, bytes ? bytes : 1); }
+static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { if (bytes) memmove(dst, src, bytes); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy(dst, src, bytes, k); }
+static inline cudaError_t cudaMemset(void* p, int value, size_t bytes) { memset(p, value, bytes); return cudaSuccess; }
+template <typename T> static inline cudaError_t cudaMemcpyToSymbol(T& symbol, const void* src, size_t bytes) { memcpy(&symbol, src, bytes); return cudaSuccess; }
+template <typename T> static inline cudaError_t cudaMemcpyFromSymbol(void* dst, const T& symbol, size_t bytes) { memcpy(dst, &symbol, bytes); return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = malloc(8); return cudaSuccess; }
+static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { return cudaStreamCreateWithFlags(s, 0); }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = malloc(8); return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int device) { return device == 0 ? cudaSuccess : 101; }
+static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) { *pool = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+	a->type = cudaMemoryTypeHost; a->device = 0; a->devicePointer = const_cast<void*>(p); a->hostPointer = const_cast<void*>(p);
+	return cudaSuccess;
+}

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import re
 
+DYNAMIC_SHARED = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([A-Za-z_][\w ]*?)\s+(\w+)\[\];")
 LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<\w+>)?)<<<(.*?)>>>\((.*?)\);", re.S)
 
 
@@ -42,8 +43,12 @@ def rewrite_launches(source: str) -> tuple[str, int]:
     def repl(m):
         cfg = split_top_level(m.group(2))
         assert len(cfg) in (2, 3, 4), m.group(0)
-        return f"::cuda_on_cpu::launch(({cfg[0]}), ({cfg[1]}), [=]() {{ {m.group(1)}({m.group(3)}); }});"
-    return LAUNCH.subn(repl, source)
+        dynamic = f", ({cfg[2]})" if len(cfg) >= 3 and cfg[2] != "0" else ""
+        return f"::cuda_on_cpu::launch(({cfg[0]}), ({cfg[1]}), [=]() {{ {m.group(1)}({m.group(3)}); }}{dynamic});"
+    text, n = LAUNCH.subn(repl, source)
+    # dynamic shared memory: `extern __shared__ [__align__(n)] T name[];` -> a pointer to the launch's dynamic block
+    text = DYNAMIC_SHARED.sub(lambda m: f"{m.group(1)}* {m.group(2)} = static_cast<{m.group(1)}*>(::cuda_on_cpu::dynamic_shared());", text)
+    return text, n
 
 
 # normalised PTX template -> C++ (operands substituted for %N)
@@ -55,11 +60,13 @@ PTX_FORMS: list[tuple[re.Pattern, str]] = [
     (re.compile(r"^fma\.rn\.ftz\.f32x2 %(\d+), %(\d+), %(\d+), %(\d+);$"), "::cuda_on_cpu::ptx::fma2({0}, {1}, {2}, {3});"),
     (re.compile(r"^mad\.wide\.u32 %(\d+), %(\d+), (\d+), %(\d+);$"), "{0} = (unsigned long long)(uint32_t)({1}) * {imm}ull + (unsigned long long)({3});"),
     (re.compile(r"^ld\.global\.nc\.v8\.f32 \{%0,%1,%2,%3,%4,%5,%6,%7\}, " + _MEM + r";$"), "LD8F"),
+    (re.compile(r"^ld\.v4\.f32 \{%0,%1,%2,%3\}, " + _MEM + r";$"), "LD4F"),
     (re.compile(r"^ld\.global\.nc\.v4\.b64 \{%0,%1,%2,%3\}, " + _MEM + r";$"), "LD4Q"),
     (re.compile(r"^st\.local\.u32 \[%(\d+)\], %(\d+);$"), "*::cuda_on_cpu::ptx::local_word({0}) = {1};"),
     (re.compile(r"^ld\.local\.u32 %(\d+), \[%(\d+)\];$"), "{0} = *::cuda_on_cpu::ptx::local_word({1});"),
     (re.compile(r"^st\.shared\.u32 \[%(\d+)\], %(\d+);$"), "*::cuda_on_cpu::ptx::shared_word({0}) = {1};"),
     (re.compile(r"^ld\.shared\.u32 %(\d+), \[%(\d+)\];$"), "{0} = *::cuda_on_cpu::ptx::shared_word({1});"),
+    (re.compile(r"^cvta\.shared\.u64 %(\d+), %(\d+);$"), "{0} = (unsigned long long)(uintptr_t)::cuda_on_cpu::ptx::shared_pointer({1});"),
     # PlainStack::pushIf: a predicated store + bump
     (re.compile(r"^\{ \.reg \.pred pu; setp\.ne\.u32 pu, %2, 0; @pu st\.local\.u32 \[%1\], %3; @pu add\.u32 %0, %0, 4; \}$"),
      "if ({2}) {{ *::cuda_on_cpu::ptx::local_word({1}) = {3}; {0} += 4; }}"),
@@ -112,10 +119,10 @@ def translate_asm(inner: str) -> tuple[str, bool]:
         m = pattern.match(template)
         if not m:
             continue
-        if code in ("LD8F", "LD4Q"):
+        if code in ("LD8F", "LD4Q", "LD4F"):
             n = 8 if code == "LD8F" else 4
             addr, off = ops[int(m.group(1))], m.group(2) or "0"
-            fn = "ld8f" if code == "LD8F" else "ld4q"
+            fn = code.lower()
             return f"::cuda_on_cpu::ptx::{fn}((unsigned long long){addr} + {off}ull, " + ", ".join(ops[:n]) + ");", True
         if "{imm}" in code:
             return code.format(ops[int(m.group(1))], ops[int(m.group(2))], None, ops[int(m.group(4))], imm=m.group(3)), True
