@@ -33,7 +33,8 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__ static
+// per host thread: the API's submitters launch concurrently, each must see its own block's shared memory
+#define __shared__ static thread_local
 
 namespace cuda_on_cpu {
 
