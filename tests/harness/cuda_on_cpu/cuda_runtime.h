@@ -356,7 +356,7 @@ static inline cudaError_t cudaGetDevice(int* device) { *device = 0; return cudaS
 static inline cudaError_t cudaDeviceGetAttribute(int* value, cudaDeviceAttr attr, int) { *value = attr == cudaDevAttrMultiProcessorCount ? 2 : 233472; return cudaSuccess; }
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* blocks, F, int, size_t) { *blocks = 2; return cudaSuccess; }
-static inline cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t) { memset(p, value, bytes); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t = nullptr) { memset(p, value, bytes); return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "cuda_on_cpu"; }
 
 // ---- a synchronous stand-in for the runtime calls capi.cu makes (device memory is host memory, streams run in order
@@ -386,7 +386,7 @@ static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return
 static inline cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { return ::cuda_on_cpu::allocate(p, bytes ? bytes : 1); }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { if (bytes) memmove(dst, src, bytes); return cudaSuccess; }
-static inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy(dst, src, bytes, k); }
+static inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(dst, src, bytes, k); }
 static inline cudaError_t cudaMemset(void* p, int value, size_t bytes) { memset(p, value, bytes); return cudaSuccess; }
 template <typename T> static inline cudaError_t cudaMemcpyToSymbol(T& symbol, const void* src, size_t bytes) { memcpy(&symbol, src, bytes); return cudaSuccess; }
 template <typename T> static inline cudaError_t cudaMemcpyFromSymbol(void* dst, const T& symbol, size_t bytes) { memcpy(dst, &symbol, bytes); return cudaSuccess; }
@@ -407,3 +407,14 @@ static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, con
 	a->type = cudaMemoryTypeHost; a->device = 0; a->devicePointer = const_cast<void*>(p); a->hostPointer = const_cast<void*>(p);
 	return cudaSuccess;
 }
+
+// ---- what bvh_build.cu needs on top ---------------------------------------------------------------------------------
+struct dim3 { unsigned x, y, z; dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {} };
+static inline cudaError_t cudaLaunchCooperativeKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) { return 720; } // cooperative launch too large
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline uint32_t atomicMin(uint32_t* p, uint32_t v) { const uint32_t old = *p; if (v < old) *p = v; return old; }
+static inline uint32_t atomicMax(uint32_t* p, uint32_t v) { const uint32_t old = *p; if (v > old) *p = v; return old; }
+static inline int atomicAdd(int* p, int v) { const int old = *p; *p = old + v; return old; }

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY: the two mechanical source rewrites that let g++ compile the engine's .cu files over
 tests/harness/cuda_on_cpu/cuda_runtime.h.
 
-1. `kernel<<<grid, block, smem, stream>>>(args);`  ->  `::cuda_on_cpu::launch((grid), (block), [=]() { kernel(args); });`
+1. `kernel<<<grid, block, smem, stream>>>(args);`  ->  `::cuda_on_cpu::launch((grid), (block), [&]() { kernel(args); });`
 2. every inline-PTX statement `asm [volatile]("..." : outputs : inputs : clobbers);` -> a call of the C++ function in
    cuda_runtime.h (namespace cuda_on_cpu::ptx) that states what that PTX instruction does. Only the handful of
    instruction forms the traversal kernels use are known; anything else becomes `::cuda_on_cpu::ptx::unsupported("...")`,
@@ -14,7 +14,7 @@ from __future__ import annotations
 import re
 
 DYNAMIC_SHARED = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([A-Za-z_][\w ]*?)\s+(\w+)\[\];")
-LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<\w+>)?)<<<(.*?)>>>\((.*?)\);", re.S)
+LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)<<<(.*?)>>>\((.*?)\);", re.S)
 
 
 def split_top_level(text: str, sep: str = ",") -> list[str]:
@@ -44,7 +44,7 @@ def rewrite_launches(source: str) -> tuple[str, int]:
         cfg = split_top_level(m.group(2))
         assert len(cfg) in (2, 3, 4), m.group(0)
         dynamic = f", ({cfg[2]})" if len(cfg) >= 3 and cfg[2] != "0" else ""
-        return f"::cuda_on_cpu::launch(({cfg[0]}), ({cfg[1]}), [=]() {{ {m.group(1)}({m.group(3)}); }}{dynamic});"
+        return f"::cuda_on_cpu::launch(({cfg[0]}), ({cfg[1]}), [&]() {{ {m.group(1)}({m.group(3)}); }}{dynamic});"
     text, n = LAUNCH.subn(repl, source)
     # dynamic shared memory: `extern __shared__ [__align__(n)] T name[];` -> a pointer to the launch's dynamic block
     text = DYNAMIC_SHARED.sub(lambda m: f"{m.group(1)}* {m.group(2)} = static_cast<{m.group(1)}*>(::cuda_on_cpu::dynamic_shared());", text)
