@@ -48,7 +48,14 @@ struct Fiber {
 	ucontext_t context;
 	Dim tid = {0, 0, 0};
 	bool done = false;
+	uint32_t collectives = 0; // warp collectives this lane has taken part in: lanes of a warp between the same two votes agree
 };
+
+// Optional load tracing for the L1 gather model (tools/l1_model.py): every 256-bit gather of a kernel is reported with the
+// warp, the lane's collective count (lanes between the same two warp votes execute the same instruction instance) and
+// its address. Off unless a sink is installed.
+typedef void (*LoadSink)(uint32_t block, uint32_t warp, uint32_t epoch, uint32_t lane, unsigned long long address, uint32_t bytes);
+inline LoadSink load_sink = nullptr;
 
 // One warp-level rendezvous per distinct member mask (a kernel may have lanes inside `if (valid) __match_any_sync(mask, ..)`
 // while the others already wait in a full-mask __syncwarp()). Values are exchanged through two slot sets that alternate
@@ -134,6 +141,7 @@ inline void launch(unsigned grid, unsigned block, const std::function<void()>& b
 			Fiber& f = g.fibers[t];
 			f.tid = {t, 0, 0};
 			f.done = false;
+			f.collectives = 0;
 			getcontext(&f.context);
 			f.context.uc_stack.ss_sp = g.stacks.data() + kStack * t;
 			f.context.uc_stack.ss_size = kStack;
@@ -171,6 +179,7 @@ inline Exchanged exchange(unsigned mask, uint64_t mine) {
 		++w.used;
 	}
 	Collective& c = w.collective[k];
+	++self->collectives;
 	const unsigned generation = c.generation;
 	c.slot[generation & 1][lane] = mine;
 	c.arrived |= 1u << lane;
@@ -327,6 +336,7 @@ inline void fma2(unsigned long long& out, unsigned long long a, unsigned long lo
 }
 inline void ld8f(unsigned long long address, float& a, float& b, float& c, float& d, float& e, float& f, float& g_, float& h) {
 	if (address & 31) { fprintf(stderr, "cuda_on_cpu: misaligned 256-bit load\n"); abort(); }
+	if (load_sink) load_sink(g.blockIdx_.x, g.current->tid.x / 32, g.current->collectives, g.current->tid.x % 32, address, 32);
 	float v[8]; memcpy(v, reinterpret_cast<const void*>((uintptr_t)address), 32);
 	a = v[0]; b = v[1]; c = v[2]; d = v[3]; e = v[4]; f = v[5]; g_ = v[6]; h = v[7];
 }
@@ -337,6 +347,7 @@ inline void ld4f(unsigned long long address, float& a, float& b, float& c, float
 }
 inline void ld4q(unsigned long long address, unsigned long long& a, unsigned long long& b, unsigned long long& c, unsigned long long& d) {
 	if (address & 31) { fprintf(stderr, "cuda_on_cpu: misaligned 256-bit load\n"); abort(); }
+	if (load_sink) load_sink(g.blockIdx_.x, g.current->tid.x / 32, g.current->collectives, g.current->tid.x % 32, address, 32);
 	unsigned long long v[4]; memcpy(v, reinterpret_cast<const void*>((uintptr_t)address), 32);
 	a = v[0]; b = v[1]; c = v[2]; d = v[3];
 }

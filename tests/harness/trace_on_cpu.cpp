@@ -7,9 +7,78 @@
 #include <pmmintrin.h>
 #include <xmmintrin.h>
 
+#include <algorithm>
+#include <map>
+#include <tuple>
 #include <vector>
 
 using namespace racc_b200;
+
+// ---- L1 gather model (tools/l1_model.py) -------------------------------------------------------------------------------
+// profiles/r01_l1_wavefront_microbench.md: a divergent 256-bit load costs the L1 data pipe about 1.07 wavefronts per
+// DISTINCT 32-byte sector it touches and never less than 0.27 per participating lane (register write-back), one
+// wavefront per clock per SM. The sink below groups the traced loads of a launch into warp-level instruction instances
+// (same block, warp, vote epoch and load ordinal within the epoch) and sums that cost.
+namespace {
+struct L1Model {
+	std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t>, std::vector<unsigned long long>> instances; // address | lane in the low 5 bits
+	uint32_t epochOf[32][32];
+	uint32_t ordinal[32][32];
+	uint32_t block = 0xffffffffu;
+	double wavefronts = 0, laneLoads = 0, count = 0, wavefrontsByQuarter = 0, wavefrontsByFour = 0, wavefrontsByPair = 0;
+	static double price(std::vector<unsigned long long>& a) {
+		if (a.empty()) return 0.0;
+		const double lanes = (double)a.size();
+		std::sort(a.begin(), a.end());
+		const double d = (double)(std::unique(a.begin(), a.end()) - a.begin());
+		return std::max(0.266 * lanes, 1.065 * d);
+	}
+	void flush() {
+		for (auto& kv : instances) {
+			std::vector<unsigned long long> all, quarter[4];
+			for (unsigned long long v : kv.second) {
+				all.push_back(v & ~31ull);
+				quarter[(v & 31u) / 8].push_back(v & ~31ull);
+			}
+			laneLoads += (double)all.size();
+			wavefronts += price(all);
+			for (int q = 0; q < 4; ++q) wavefrontsByQuarter += price(quarter[q]);
+			std::vector<unsigned long long> four[8], pair[16];
+			for (unsigned long long v : kv.second) {
+				four[(v & 31u) / 4].push_back(v & ~31ull);
+				pair[(v & 31u) / 2].push_back(v & ~31ull);
+			}
+			for (int q = 0; q < 8; ++q) wavefrontsByFour += price(four[q]);
+			for (int q = 0; q < 16; ++q) wavefrontsByPair += price(pair[q]);
+			count += 1;
+		}
+		instances.clear();
+	}
+} g_model;
+
+void modelSink(uint32_t block, uint32_t warp, uint32_t epoch, uint32_t lane, unsigned long long address, uint32_t) {
+	if (block != g_model.block) {
+		g_model.flush();
+		g_model.block = block;
+		memset(g_model.epochOf, 0xff, sizeof(g_model.epochOf));
+	}
+	if (g_model.epochOf[warp][lane] != epoch) { g_model.epochOf[warp][lane] = epoch; g_model.ordinal[warp][lane] = 0; }
+	g_model.instances[std::make_tuple(warp, epoch, g_model.ordinal[warp][lane]++, 0u)].push_back((address & ~31ull) | lane);
+	if (g_model.instances.size() > (1u << 20)) g_model.flush(); // epochs only grow: old instances are complete
+}
+} // namespace
+
+extern "C" void cpu_l1_model_begin() {
+	g_model = L1Model();
+	::cuda_on_cpu::load_sink = modelSink;
+}
+// out = {modelled wavefronts (sharing across the whole warp), lane-level loads, warp-level instruction instances,
+//        modelled wavefronts when only lanes of the same quarter-warp can share a sector}
+extern "C" void cpu_l1_model_end(double* out4) { // out4 has room for 6 values: ..., sharing within 4 lanes, within 2 lanes
+	::cuda_on_cpu::load_sink = nullptr;
+	g_model.flush();
+	out4[0] = g_model.wavefronts; out4[1] = g_model.laneLoads; out4[2] = g_model.count; out4[3] = g_model.wavefrontsByQuarter; out4[4] = g_model.wavefrontsByFour; out4[5] = g_model.wavefrontsByPair;
+}
 
 namespace {
 struct FlushToZero {

@@ -9,6 +9,12 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// Modes 13-15 (same status): WHICH lanes may share a sector for free? tools/l1_model.py (the traversal kernel's own source
+// run on the CPU with its gathers traced) reproduces the measured bounce-stream throughput only if sharing is exploited
+// among very few neighbouring lanes. 13: lanes with equal (lane & 7) share (8 nodes per warp, every quarter-warp all
+// distinct): 8.5 wavefronts per instruction if the whole warp coalesces, 34 if only a quarter-warp does. 14: lanes l and
+// l^4 share (16 nodes per warp, 4 per quarter-warp, every aligned group of 4 all distinct): 17 if groups of 8 or more
+// coalesce, 34 if only groups of 4. 15: lanes l and l^2 share: 17 if groups of 4 coalesce, 34 if only pairs.
 // Mode 11 (same status): the node read from __constant__ memory with a per-lane index -- the constant path serialises
 // distinct addresses, but it is a pipe of its own; if it sustains a useful rate beside LDG traffic, the top of the tree
 // (512 nodes = 32 KB take roughly half of all visits) could be served from it.
@@ -106,6 +112,15 @@ __global__ void k(const float4* __restrict__ data, const uint32_t* __restrict__ 
 				n = (__float_as_uint(v[15]) + n * 1664525u + 1013904223u) & 0xffffu;
 			}
 		}
+		else if (MODE == 13 || MODE == 14 || MODE == 15) { // 2 x LDG.256, sharing lanes far apart / 4 apart / 2 apart
+			const int src = MODE == 13 ? (threadIdx.x & 7) : MODE == 14 ? (threadIdx.x & 27) : (threadIdx.x & 29);
+			const float4* q = data + 4 * (size_t)__shfl_sync(0xffffffffu, n, src);
+			float v[16];
+			asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(q));
+			asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+32];" : "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]) : "l"(q));
+			acc += v[0] + v[5] + v[10] + v[15];
+			n = (__float_as_uint(v[15]) + n * 1664525u + 1013904223u) & 0xffffu;
+		}
 		else if (MODE == 7) { // 1 x LDG.64
 			float2 a = __ldg(reinterpret_cast<const float2*>(p));
 			acc += a.x;
@@ -131,7 +146,7 @@ int main() {
 	cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
 #define RUN(M) { k<M><<<threads / 256, 256>>>(data, idx, iters, out, tex); cudaEventRecord(a); k<M><<<threads / 256, 256>>>(data, idx, iters, out, tex); cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms, a, b); \
 	printf("mode %d: %.3f ms, %.2f G lane-loads(of a node)/s\n", M, ms, (double)threads * iters / ms / 1e6); }
-	RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(10) RUN(11) RUN(12)
+	RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(10) RUN(11) RUN(12) RUN(13) RUN(14) RUN(15)
 	if (cudaDeviceSynchronize() != cudaSuccess) { printf("kernel error\n"); return 1; }
 	return 0;
 }
