@@ -51,7 +51,7 @@ struct Fiber {
 	uint32_t collectives = 0; // warp collectives this lane has taken part in: lanes of a warp between the same two votes agree
 };
 
-// Optional load tracing for the L1 gather model (tools/l1_model.py): every 256-bit gather of a kernel is reported with the
+// Optional load tracing for the L1 gather model (tests/harness/l1_model.py): every 256-bit gather of a kernel is reported with the
 // warp, the lane's collective count (lanes between the same two warp votes execute the same instruction instance) and
 // its address. Off unless a sink is installed.
 typedef void (*LoadSink)(uint32_t block, uint32_t warp, uint32_t epoch, uint32_t lane, unsigned long long address, uint32_t bytes);

@@ -14,7 +14,9 @@ One thing differs from the device: there 148 x 5 x 8 = 5920 warps pull from the 
 ONE warp are ~95 K rays apart; here one CTA runs at a time. `--spread` (default) visits the rays through a permutation
 that hands consecutive 16-ray chunks out 5920 chunks apart, which reproduces that; `--no-spread` is arrival order.
 
-    python tools/l1_model.py --width 480 --height 270 --spp 1
+    python tests/harness/l1_model.py --width 480 --height 270 --spp 1
+
+Test infrastructure (it lives under tests/ because it builds on tests/harness/cuda_on_cpu and uses the checker).
 """
 import argparse
 import ctypes
@@ -25,11 +27,11 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-import oracle  # noqa: E402  (analysis tool: the checker supplies the hits the bounce generator needs)
+import oracle  # noqa: E402  (test infrastructure: the checker supplies the hits the bounce generator needs)
 import rayaccel_b200 as rb  # noqa: E402
 from oracle import raygen  # noqa: E402
 from test_kernels_on_cpu import build_tracer, trace_on_cpu  # noqa: E402

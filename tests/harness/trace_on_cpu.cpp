@@ -14,7 +14,7 @@
 
 using namespace racc_b200;
 
-// ---- L1 gather model (tools/l1_model.py) -------------------------------------------------------------------------------
+// ---- L1 gather model (tests/harness/l1_model.py) -------------------------------------------------------------------------------
 // profiles/r01_l1_wavefront_microbench.md: a divergent 256-bit load costs the L1 data pipe about 1.07 wavefronts per
 // DISTINCT 32-byte sector it touches and never less than 0.27 per participating lane (register write-back), one
 // wavefront per clock per SM. The sink below groups the traced loads of a launch into warp-level instruction instances

@@ -9,7 +9,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-// Modes 13-15 (same status): WHICH lanes may share a sector for free? tools/l1_model.py (the traversal kernel's own source
+// Modes 13-15 (same status): WHICH lanes may share a sector for free? tests/harness/l1_model.py (the traversal kernel's own source
 // run on the CPU with its gathers traced) reproduces the measured bounce-stream throughput only if sharing is exploited
 // among very few neighbouring lanes. 13: lanes with equal (lane & 7) share (8 nodes per warp, every quarter-warp all
 // distinct): 8.5 wavefronts per instruction if the whole warp coalesces, 34 if only a quarter-warp does. 14: lanes l and
