@@ -15,6 +15,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <ucontext.h>
 
 #include <functional>
@@ -36,6 +37,25 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 // per host thread: the API's submitters launch concurrently, each must see its own block's shared memory
 #define __shared__ static thread_local
 
+// Fiber switch. By default a dozen instructions of x86-64 assembly (callee-saved registers + stack pointer; every fiber
+// runs with the same MXCSR / x87 control words, so those are not switched): barrier-heavy kernels spend their time here,
+// and swapcontext() costs two system calls per switch. -DCUDA_ON_CPU_UCONTEXT selects swapcontext (what the sanitizer build
+// uses: AddressSanitizer understands it).
+#if !defined(CUDA_ON_CPU_UCONTEXT) && defined(__x86_64__)
+#define CUDA_ON_CPU_ASM_SWITCH 1
+extern "C" void cuda_on_cpu_switch(void** saveStackPointer, void* loadStackPointer);
+__asm__(".text\n"
+        ".weak cuda_on_cpu_switch\n"
+        ".type cuda_on_cpu_switch,@function\n"
+        "cuda_on_cpu_switch:\n"
+        "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+        "  movq %rsp, (%rdi)\n"
+        "  movq %rsi, %rsp\n"
+        "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n"
+        "  ret\n"
+        ".size cuda_on_cpu_switch,.-cuda_on_cpu_switch\n");
+#endif
+
 namespace cuda_on_cpu {
 
 struct Dim { unsigned x, y, z; };
@@ -45,7 +65,11 @@ struct Rendezvous {
 };
 
 struct Fiber {
+#ifdef CUDA_ON_CPU_ASM_SWITCH
+	void* stackPointer = nullptr;
+#else
 	ucontext_t context;
+#endif
 	Dim tid = {0, 0, 0};
 	bool done = false;
 	uint32_t collectives = 0; // warp collectives this lane has taken part in: lanes of a warp between the same two votes agree
@@ -73,7 +97,11 @@ struct Warp {
 };
 
 struct State {
+#ifdef CUDA_ON_CPU_ASM_SWITCH
+	void* scheduler = nullptr; // the scheduler's saved stack pointer while a fiber runs
+#else
 	ucontext_t scheduler;
+#endif
 	std::vector<Fiber> fibers;
 	std::vector<char> stacks;
 	std::vector<Warp> warps;
@@ -87,7 +115,11 @@ struct State {
 // per OS thread: host threads (the API's submitters) may launch concurrently, each runs its own fibers
 inline thread_local State g;
 
+#ifdef CUDA_ON_CPU_ASM_SWITCH
+inline void yield() { cuda_on_cpu_switch(&g.current->stackPointer, g.scheduler); }
+#else
 inline void yield() { swapcontext(&g.current->context, &g.scheduler); }
+#endif
 
 inline void release_if_complete(Rendezvous& r) {
 	if (r.alive && r.arrived == r.alive) { r.arrived = 0; ++r.generation; }
@@ -118,11 +150,13 @@ inline void fiber_main() {
 	w.alive &= ~(1u << (self->tid.x % 32));
 	for (unsigned k = 0; k < w.used; ++k) release_if_complete(w, w.collective[k]);
 	--g.block.alive; release_if_complete(g.block);
-	swapcontext(&self->context, &g.scheduler);
+	for (;;) yield(); // never resumed: the scheduler skips fibers that are done
 }
 
 // kernel<<<grid, block>>>(args) -> launch(grid, block, [=] { kernel(args); })
+inline bool trace_launches() { static const bool on = getenv("CUDA_ON_CPU_TRACE") != nullptr; return on; } // per-launch wall time on stderr
 inline void launch(unsigned grid, unsigned block, const std::function<void()>& body, size_t dynamicSharedBytes = 0) {
+	timespec t0; clock_gettime(CLOCK_MONOTONIC, &t0);
 	const size_t kStack = 256 * 1024;
 	if (block == 0 || block % 32 != 0 || block > 1024) abort();
 	g.fibers.assign(block, Fiber());
@@ -142,11 +176,22 @@ inline void launch(unsigned grid, unsigned block, const std::function<void()>& b
 			f.tid = {t, 0, 0};
 			f.done = false;
 			f.collectives = 0;
+#ifdef CUDA_ON_CPU_ASM_SWITCH
+			// first switch "returns" into fiber_main: [top-16] = return address (16-byte aligned slot, so that the stack is
+			// aligned as after a call), six zeroed callee-saved registers below it
+			char* top = g.stacks.data() + kStack * (t + 1);
+			top -= (uintptr_t)top & 15;
+			void** slot = reinterpret_cast<void**>(top - 16);
+			slot[0] = reinterpret_cast<void*>(&fiber_main);
+			for (int r = 1; r <= 6; ++r) slot[-r] = nullptr;
+			f.stackPointer = slot - 6;
+#else
 			getcontext(&f.context);
 			f.context.uc_stack.ss_sp = g.stacks.data() + kStack * t;
 			f.context.uc_stack.ss_size = kStack;
 			f.context.uc_link = &g.scheduler;
 			makecontext(&f.context, fiber_main, 0);
+#endif
 		}
 		unsigned remaining = block;
 		while (remaining) {
@@ -154,13 +199,21 @@ inline void launch(unsigned grid, unsigned block, const std::function<void()>& b
 				Fiber& f = g.fibers[t];
 				if (f.done) continue;
 				g.current = &f;
+#ifdef CUDA_ON_CPU_ASM_SWITCH
+				cuda_on_cpu_switch(&g.scheduler, f.stackPointer);
+#else
 				swapcontext(&g.scheduler, &f.context);
+#endif
 				if (f.done) --remaining;
 			}
 		}
 	}
 	g.current = nullptr;
 	g.body = nullptr;
+	if (trace_launches()) {
+		timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1);
+		fprintf(stderr, "cuda_on_cpu: launch %u x %u: %.1f ms\n", grid, block, (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+	}
 }
 
 // every lane named in `mask` deposits a value, then reads any member's; returns the slot set and who took part

@@ -14,7 +14,7 @@ if __import__("os").environ.get("RACC_SANITIZE_CHILD") != "1":
     import glob, os, sys
     srcs = sorted(glob.glob(LIBDIR + "/*_on_cpu.cpp")) + ["/root/repo/rayaccel_b200/csrc/scene_build.cpp", "/root/repo/rayaccel_b200/csrc/racc_api.cpp"]
     subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fno-omit-frame-pointer", "-mavx2", "-mfma", "-ffp-contract=off", "-fno-fast-math", "-fPIC",
-                    "-shared", "-w", "-pthread"] + FLAGS + ["-I", "/root/repo/tests/harness/cuda_on_cpu", "-I", LIBDIR, "-I", "/root/repo/rayaccel_b200/csrc"] +
+                    "-shared", "-w", "-pthread", "-DCUDA_ON_CPU_UCONTEXT"] + FLAGS + ["-I", "/root/repo/tests/harness/cuda_on_cpu", "-I", LIBDIR, "-I", "/root/repo/rayaccel_b200/csrc"] +
                    srcs + ["-o", OUT], check=True)
     rt = subprocess.check_output(["gcc", "-print-file-name=" + ("libasan.so" if SAN == "address" else "libubsan.so")], text=True).strip()
     env = dict(os.environ, RACC_SANITIZE_CHILD="1", LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1")
