@@ -1,13 +1,18 @@
-// cuda_runtime.h -- TEST INFRASTRUCTURE ONLY: a stand-in for the CUDA runtime header that lets g++ compile the
-// engine's *shading* kernels (rayaccel_b200/csrc/pathtrace.cu, whitted.cu) unchanged and run them on the CPU, so that
-// the CPU-only test suite executes the kernels' own source against the checker (tests/test_kernels_on_cpu.py) -- the
-// same idea as oracle/ref_shim/opencl_c.h for the reference's OpenCL kernel. Nothing in the product includes this.
+// cuda_runtime.h -- TEST INFRASTRUCTURE ONLY: a stand-in for the CUDA runtime header that lets g++ compile the engine's
+// .cu files (rayaccel_b200/csrc: the traversal kernels, the shading kernels, the radix sort, the device scene builder and
+// capi.cu itself) as they are and run them on the CPU, so that the CPU-only test suite executes the kernels' OWN SOURCE
+// against the checker (tests/test_kernels_on_cpu.py, tests/test_library_on_cpu.py) -- the same idea
+// as oracle/ref_shim/opencl_c.h for the reference's OpenCL kernel. Nothing in the product includes this.
 //
-// Execution model: a launch runs its blocks one after the other; the threads of a block are user-level fibers
-// (ucontext) scheduled round-robin on the calling OS thread, so warp collectives (__ballot_sync, __shfl_*_sync) and
-// __syncthreads are real rendezvous points and divergence is whatever the kernel's control flow makes it. Only what the
-// two files use is provided. Floating point: the harness is compiled -ffp-contract=off -mfma and runs with FTZ/DAZ set,
-// which is the arithmetic nvcc is held to by -fmad=false -ftz=true -prec-div=true -prec-sqrt=true.
+// Execution model: a launch runs its blocks one after the other; the threads of a block are user-level fibers scheduled
+// round-robin on the calling OS thread, so warp collectives (__ballot_sync, __shfl_*_sync, __match_any_sync,
+// __syncwarp(mask): one rendezvous per member mask) and __syncthreads are real rendezvous points and divergence is
+// whatever the kernel's control flow makes it. __shared__ is a per-host-thread static; 32-bit local / shared "window"
+// addresses map onto the fibers' stacks and those statics. The runtime API is a synchronous host equivalent (device
+// memory is host memory). Inline PTX and <<<...>>> launches are rewritten by rewrite.py into the functions of namespace
+// cuda_on_cpu(::ptx) below. Only what the engine's files use is provided; anything else aborts loudly.
+// Floating point: built -ffp-contract=off -mfma and run with FTZ/DAZ set, fminf/fmaxf = FMNMX -- the arithmetic nvcc is
+// held to by -fmad=false -ftz=true -prec-div=true -prec-sqrt=true.
 #pragma once
 
 #include <math.h>
