@@ -2,6 +2,9 @@
 # First GPU call after round 1: everything that was written after that round's GPU budget ran out, measured in one go.
 # Outputs -> gpurun_out/next_*. Run as: gpurun --timeout 1500 -- 'bash tools/next_gpu_call.sh'
 mkdir -p gpurun_out
+# 0. the standing check first: all GPU tests, smoke, bench, reference arm (defaults are what was validated in round 1;
+#    their SASS / control flow did not change since, and the CPU test build says the same -- confirm on hardware)
+bash tools/gpu_check.sh
 # 1. tuning keys 15 (grow-only wave buffers) and 16 (per-warp radiance sums) of the device Whitted renderer: parity first
 RACC_B200_TEST_UNMEASURED=1 timeout 600 python -m pytest tests/test_gpu_zz_whitted.py -m gpu -x -q > gpurun_out/next_pytest_whitted.log 2>&1
 echo "whitted pytest rc=$?" | tee -a gpurun_out/next_pytest_whitted.log; tail -5 gpurun_out/next_pytest_whitted.log
