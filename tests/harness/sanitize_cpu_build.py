@@ -3,7 +3,7 @@
 host code's own source, compiled by g++ with -fsanitize=..., driven through the C-ABI -- host staging (both tail
 policies), every traversal variant, re-binning, both device renderers (with and without tuning keys 15/16) and the device
 scene builder. compute-sanitizer does this on the B200 (tools/sanitize.sh); this is the same question asked where there is
-no GPU.   python tools/sanitize_cpu_build.py address|undefined
+no GPU.   python tests/harness/sanitize_cpu_build.py address|undefined
 First run `python -m pytest tests/test_library_on_cpu.py -k builds` so that the rewritten sources exist."""
 import subprocess
 SAN = (__import__("sys").argv[1:] or ["address"])[0]
