@@ -153,6 +153,15 @@ namespace racc {
 	inline cl_context cudaDevice(int ordinal = 0) {
 		return reinterpret_cast<cl_context>(static_cast<uintptr_t>(ordinal) + 1);
 	}
+
+	// A token for `count` consecutive CUDA devices starting at `firstOrdinal` (at most 255 each): the context then drives
+	// all of them -- scene and environment replicated on each, gpuSubmissionThreads submitters per device, ready ray
+	// streams dealt over the devices, Stats.raysTraced summed over them with NCCL at the end of every frame. Ray
+	// streams shard by index and need nothing from another GPU, so this is the reference's gpuSubmissionThreads idea
+	// (RayAccelerator.cpp:711-717) taken from "several queues of one device" to "several devices".
+	inline cl_context cudaDevices(int firstOrdinal, int count) {
+		return reinterpret_cast<cl_context>((static_cast<uintptr_t>(firstOrdinal) + 1) | (static_cast<uintptr_t>(count) << 8));
+	}
 }
 
 #endif

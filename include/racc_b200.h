@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define RACC_CUDA_ABI_VERSION 1
+#define RACC_CUDA_ABI_VERSION 2
 
 typedef struct racc_cuda_scene racc_cuda_scene;   /* replaces racc::Scene        (Scene.h:15-21) */
 typedef struct racc_cuda_env racc_cuda_env;       /* replaces racc::Environment  (Environment.h:16-24) */
@@ -60,9 +60,23 @@ typedef struct {
 } racc_cuda_counters;
 
 /* replaces racc::init() + the OpenCL device pick (RayAccelerator.cpp:417-423,463-478;
- * Renderer/main.cpp:68-115). devices == NULL or n == 0: use the current CUDA device.
- * Only devices[0] is bound to the calling process (one process per GPU). */
+ * Renderer/main.cpp:68-115). Sets the calling THREAD's device set to the n CUDA devices named (devices == NULL or
+ * n == 0: the current CUDA device), initialising each on first use. The first device is the one the thread is bound to:
+ * its DEVICE streams, cudaStream_t handles and renderer calls live there. Scenes, environments and shading data created
+ * by the thread are replicated on every device of its set (built once, copied peer to peer), and the HOST streams of
+ * one racc_cuda_trace call are dealt over all of them. A thread that never calls this is bound to the current CUDA
+ * device. Nothing is process-global: threads (and racc::Contexts) on different devices do not disturb each other; a
+ * scene can be traced on any device it has a copy on. */
 int racc_cuda_init(const int* devices, int n);
+
+/* The calling thread's device set (bound device first): writes up to `capacity` CUDA ordinals, returns the set's size. */
+int racc_cuda_current_devices(int* devices, int capacity);
+
+/* Releases the calling thread's per-device scratch (staging pipelines of HOST streams: three lanes of device buffers and
+ * streams per device; renderer lanes and wave buffers). Call it when a thread that traced HOST streams or rendered ends --
+ * racc::destroy(Context*) does for its submitter threads; the counterpart of clReleaseCommandQueue at
+ * RayAccelerator.cpp:774-779. */
+void racc_cuda_thread_release(void);
 
 /* CUDA devices visible, or -1 if the runtime cannot be initialised (no fallback exists). */
 int racc_cuda_device_count(void);
@@ -122,6 +136,21 @@ int racc_cuda_trace(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_
 int racc_cuda_trace_counted(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_stream_desc* streams,
                             uint32_t nstreams, void* cuda_stream, void* device_counters, int detail);
 
+/* The per-frame hit reduction -- the one collective on the path. Every traversal launch without a
+ * caller-supplied counter record adds its rays and hits to its device's frame record. This call sums the records over
+ * the calling thread's device set (ncclAllReduce, one communicator per device, this process) and, when the process has
+ * joined a rank communicator (below), over all ranks; zeroes them for the next frame; and returns the totals -- what
+ * racc::Stats.raysTraced is on the reference's single host (RayAccelerator.cpp:200,372,755-758). totals == NULL: no
+ * wait, the sums stay on the device, ordered on cuda_stream. Launches to be counted must have completed or have been
+ * enqueued on cuda_stream. NCCL is bound at run time (dlopen) and only when more than one GPU takes part. */
+int racc_cuda_frame_reduce(racc_cuda_counters* totals, void* cuda_stream);
+
+/* Multi-process jobs (one process per GPU, e.g. under torchrun): rank 0 makes an id (128 bytes, ncclGetUniqueId), the
+ * application hands it to every rank, every rank joins. racc_cuda_frame_reduce then spans all ranks. */
+int racc_cuda_comm_unique_id(void* id128);
+int racc_cuda_comm_init_rank(const void* id128, int rank, int nranks);
+void racc_cuda_comm_destroy(void);
+
 /* Pinned (page-locked) host memory for ray streams: replaces the 4 KiB-aligned stream slab that the
  * reference wraps in zero-copy CL_MEM_USE_HOST_PTR buffers (RayAccelerator.cpp:532-568,636-645).
  * A discrete GPU has no zero-copy path; pinned memory is what lets HOST streams move at PCIe rate.
@@ -164,12 +193,13 @@ int racc_cuda_set_variant(int variant);
  * Morton bits per axis of the re-binning key (origin / direction), 11 direction-major key, 12 scene build (0 host,
  * 1 SAH tree on the device + host packing, 2 all on the device, 3 auto), 13 traversal-stack entries kept in shared memory
  * (0, 8, 16, -1 auto: 16 for scenes far larger than L2), 14 HOST streams in pinned memory read by the kernel itself
- * instead of being staged (0 staged = default, 1 zero-copy), 15 / 16 racc_cuda_whitted_trace only, both 0 by default
- * until measured on hardware: 15 wave buffers kept and grown per calling thread instead of allocated per wave,
- * 16 a warp sums its rays' fixed-point radiance per pixel before the atomics (same bits); 17 staged HOST streams: the
- * last chunks of a call shrink geometrically down to this many K rays (0 = off, the default until measured). Returns the previous value. Also settable through
+ * instead of being staged (0 staged = default, 1 zero-copy), 15 / 16 racc_cuda_whitted_trace only: 15 wave buffers kept
+ * and grown per calling thread instead of allocated per wave (default 1: 11 ms instead of 24-31 ms per 1080p x 4 spp frame),
+ * 16 a warp sums its rays' fixed-point radiance per pixel before the atomics (same bits; default 0: neutral); 17 staged HOST streams: the
+ * last chunks of a call shrink geometrically down to this many K rays (0 = off, default 256); 18 racc_cuda_path_trace waits
+ * for every wave's size on the host (1) instead of leaving the sizes on the device (0, default). Returns the previous value. Also settable through
  * RACC_B200_VARIANT / _BLOCK / _CTAS_PER_SM / _SMEM_NODES / _FETCH_THRESHOLD / _LEAF_BAIL / _INNER_BAIL / _SORT /
- * _SORT_ORIGIN_BITS / _SORT_DIR_BITS / _SORT_DIR_MAJOR / _BUILD_DEVICE / _SMEM_STACK / _HOST_ZERO_COPY / _WHITTED_ARENA / _WHITTED_COMBINE / _HOST_TAPER. Variant 3 (default) is the packed-format kernel;
+ * _SORT_ORIGIN_BITS / _SORT_DIR_BITS / _SORT_DIR_MAJOR / _BUILD_DEVICE / _SMEM_STACK / _HOST_ZERO_COPY / _WHITTED_ARENA / _WHITTED_COMBINE / _HOST_TAPER / _PATH_SYNC. Variant 3 (default) is the packed-format kernel;
  * 0-2 are the reference-format kernels kept for A/B. */
 int racc_cuda_set_tuning(int key, int value);
 
@@ -236,8 +266,8 @@ typedef struct {
  * pointer unless RACC_CUDA_FRAMEBUFFER_HOST), like the reference's frameBuffer (PathTracingRenderer.cpp:540-543): sums,
  * not means. wave_rays (host, may be NULL): [max_depth+1] counters, += rays traced at each depth; their total is
  * Stats::raysTraced of the equivalent render() calls. The scene must have been created from triangles (not from images).
- * Work is enqueued on cuda_stream; the call waits for each bounce's ray count, and a device framebuffer is complete once
- * the stream has been synchronised. Results are bit-reproducible and equal oracle_path_trace's. 0 on success. */
+ * Work is enqueued on cuda_stream without a host round trip (wave sizes stay on the device); the call waits -- once per
+ * batch -- only when wave_rays is given, and a device framebuffer is complete once the stream has been synchronised. Results are bit-reproducible and equal oracle_path_trace's. 0 on success. */
 int racc_cuda_path_trace(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_shading* shading, const racc_cuda_camera* camera,
                          const racc_cuda_path_desc* desc, float* framebuffer4, uint64_t* wave_rays, void* cuda_stream);
 

@@ -54,6 +54,12 @@ _U32 = ctypes.c_uint32
 SYMBOLS = {
     "racc_cuda_init": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "racc_cuda_device_count": (ctypes.c_int, []),
+    "racc_cuda_current_devices": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "racc_cuda_thread_release": (None, []),
+    "racc_cuda_frame_reduce": (ctypes.c_int, [ctypes.POINTER(Counters), _P]),
+    "racc_cuda_comm_unique_id": (ctypes.c_int, [_P]),
+    "racc_cuda_comm_init_rank": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int]),
+    "racc_cuda_comm_destroy": (None, []),
     "racc_cuda_abi_version": (ctypes.c_int, []),
     "racc_cuda_last_error": (ctypes.c_char_p, []),
     "racc_cuda_scene_create": (_P, [_P, _U32, _P, _U32]),

@@ -24,14 +24,56 @@ RESULT_DTYPE = np.dtype([("triangle", "<u4"), ("a", "<f4"), ("b", "<f4"), ("c", 
 NODE_BYTES, PAIR_BYTES = 64, 48
 
 
-def init(device: int | None = None) -> None:
-    """racc::init(): binds the calling process to one CUDA device."""
+def init(device=None) -> None:
+    """racc::init(): sets the calling thread's device set -- one CUDA ordinal, a list of them (the first is the device the
+    thread is bound to; scenes are replicated on all, HOST streams dealt over all), or None for the current device."""
     lib = _lib.load()
     if device is None:
         _lib.check(lib.racc_cuda_init(None, 0), "racc_cuda_init")
     else:
-        arr = (ctypes.c_int * 1)(device)
-        _lib.check(lib.racc_cuda_init(arr, 1), "racc_cuda_init")
+        devices = [int(device)] if isinstance(device, (int, np.integer)) else [int(d) for d in device]
+        arr = (ctypes.c_int * len(devices))(*devices)
+        _lib.check(lib.racc_cuda_init(arr, len(devices)), "racc_cuda_init")
+
+
+def current_devices() -> list[int]:
+    arr = (ctypes.c_int * 64)()
+    n = _lib.load().racc_cuda_current_devices(arr, 64)
+    if n < 0:
+        raise EngineError(_lib.last_error())
+    return [int(arr[k]) for k in range(n)]
+
+
+def thread_release() -> None:
+    """Frees the calling thread's staging pipelines and renderer scratch (racc_cuda_thread_release)."""
+    _lib.load().racc_cuda_thread_release()
+
+
+def frame_reduce(stream=None, wait: bool = True):
+    """The per-frame hit reduction (racc_cuda_frame_reduce): sums and zeroes the frame records of the thread's device set and,
+    after comm_init_rank, of all ranks. wait=True returns {rays, hits, inner_nodes, pairs_tested}; wait=False only enqueues."""
+    lib = _lib.load()
+    if not wait:
+        _lib.check(lib.racc_cuda_frame_reduce(None, _cuda_stream_handle(stream)), "racc_cuda_frame_reduce")
+        return None
+    c = Counters()
+    _lib.check(lib.racc_cuda_frame_reduce(ctypes.byref(c), _cuda_stream_handle(stream)), "racc_cuda_frame_reduce")
+    return {"rays": int(c.rays), "hits": int(c.hits), "inner_nodes": int(c.inner_nodes), "pairs_tested": int(c.pairs_tested)}
+
+
+def comm_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    _lib.check(_lib.load().racc_cuda_comm_unique_id(buf), "racc_cuda_comm_unique_id")
+    return buf.raw
+
+
+def comm_init_rank(unique_id: bytes, rank: int, nranks: int) -> None:
+    buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+    _lib.check(_lib.load().racc_cuda_comm_init_rank(buf, rank, nranks), "racc_cuda_comm_init_rank")
+
+
+def comm_destroy() -> None:
+    _lib.load().racc_cuda_comm_destroy()
 
 
 def device_count() -> int:
@@ -180,6 +222,9 @@ def trace_host(scene: Scene, environment: Environment | None, rays: np.ndarray, 
         raise ValueError("rays must have RAY_DTYPE")
     if results is None:
         results = np.zeros(rays.shape[0], dtype=RESULT_DTYPE)
+    elif results.dtype != RESULT_DTYPE or results.ndim != 1 or results.shape[0] < rays.shape[0] or not results.flags["C_CONTIGUOUS"]:
+        raise ValueError("results must be a C-contiguous RESULT_DTYPE array with at least one record per ray "
+                         "(the engine writes 16 bytes per ray into it)")
     desc = StreamDesc(rays.ctypes.data, results.ctypes.data, rays.shape[0], _lib.STREAM_HOST)
     lib = _lib.load()
     h = _cuda_stream_handle(stream)
@@ -239,10 +284,13 @@ def debug_warp_stats(reset: bool = True) -> list[int]:
 def set_tuning(**kw) -> None:
     keys = {"variant": 0, "block": 1, "ctas_per_sm": 2, "smem_nodes": 3, "fetch_threshold": 4, "leaf_bail": 5, "carveout": 6, "inner_bail": 7,
             "sort": 8, "sort_origin_bits": 9, "sort_dir_bits": 10, "sort_dir_major": 11, "build_device": 12, "smem_stack": 13, "host_zero_copy": 14,
-            "whitted_arena": 15, "whitted_combine": 16, "host_taper": 17}
+            "whitted_arena": 15, "whitted_combine": 16, "host_taper": 17, "path_sync": 18}
     lib = _lib.load()
+    unknown = [k for k in kw if k not in keys]
+    if unknown:
+        raise ValueError(f"unknown tuning key(s) {unknown}; known: {sorted(keys)}")
     for k, v in kw.items():
-        lib.racc_cuda_set_tuning(keys[k], int(v))
+        lib.racc_cuda_set_tuning(keys[k], int(v))  # returns the previous value (which may itself be -1)
 
 
 def generate_primary(camera: Camera, width: int, height: int, spp: int, jitter_seed: int, rays_ptr: int, stream=None) -> int:

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libracc_b200.so")
 
-SOURCES = ["capi.cu", "traverse.cu", "traverse_packed.cu", "raysort.cu", "bvh_build.cu", "raygen.cu", "pathtrace.cu", "whitted.cu", "scene_build.cpp", "racc_api.cpp"]
+SOURCES = ["capi.cu", "capi_render.cu", "comm.cu", "traverse.cu", "traverse_packed.cu", "raysort.cu", "bvh_build.cu", "raygen.cu", "pathtrace.cu", "whitted.cu", "scene_build.cpp", "racc_api.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + srcs + ["-lpthread"]
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + srcs + ["-lpthread", "-ldl"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode:
         sys.stderr.write(proc.stdout + proc.stderr)

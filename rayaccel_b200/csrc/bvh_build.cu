@@ -1505,7 +1505,7 @@ bool buildSceneImagesDevice(const float* vertices4, uint32_t vertexCount, const 
 	static const char* kEmpty = "scene has no triangles";
 	static const char* kIndex = "triangle index out of range";
 	static const char* kTooBig = "scene exceeds 2^30 triangles (remap word holds 30 index bits)";
-	static const char* kTiny = "scene needs at least 3 triangles (root must be an inner node)";
+	static const char* kTiny = "the root is a leaf (tiny scene): the host builder makes the synthetic root";
 	static const char* kPairs = "scene exceeds 2^24 triangle pairs (leaf reference holds 24 index bits)";
 	if (indexCount % 3) { if (error) *error = kMod3; return false; }
 	const uint32_t n = indexCount / 3;

@@ -1,145 +1,140 @@
-// capi.cu -- implementation of the C-ABI declared in include/racc_b200.h.
-// Device management, scene/environment upload, stream staging and kernel launch. No CPU fallback:
-// every compute entry point fails with an error string when CUDA is unavailable.
-#include "../../include/racc_b200.h"
+// capi.cu -- implementation of the C-ABI declared in include/racc_b200.h: devices, scene / environment upload and
+// replication, ray-stream staging and kernel launch. (The device-side renderers live in capi_render.cu, the per-frame
+// hit reduction in comm.cu.) No CPU fallback: every compute entry point fails with an error string when CUDA is
+// unavailable.
+#include "capi_internal.h"
 
-#include "engine.h"
-#include "scene_build.h"
-
-#include <atomic>
-#include <cstdarg>
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
-#include <vector>
+#include <utility>
 
 using namespace racc_b200;
 
+namespace racc_b200 {
+
 namespace {
 
-thread_local char g_error[512] = "";
-std::mutex g_initMutex;
-bool g_initialised = false;
-int g_device = 0;
-int g_smCount = 0;
+thread_local char t_error[512] = "";
+thread_local std::vector<int> t_deviceSet; // CUDA ordinals, bound device first
+
+std::mutex g_mutex; // device table, tuning
+DeviceState g_devices[kMaxDevices];
 Tuning g_tuning;
+bool g_tuningFromEnv = false;
 std::atomic<uint64_t> g_launches{0};
-
-int fail(const char* fmt, ...) {
-	va_list ap;
-	va_start(ap, fmt);
-	vsnprintf(g_error, sizeof(g_error), fmt, ap);
-	va_end(ap);
-	return -1;
-}
-
-#define RACC_CUDA_CHECK(call)                                                                              \
-	do {                                                                                                   \
-		cudaError_t e_ = (call);                                                                           \
-		if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-	} while (0)
-
-#define RACC_CUDA_CHECK_NULL(call)                                                                         \
-	do {                                                                                                   \
-		cudaError_t e_ = (call);                                                                           \
-		if (e_ != cudaSuccess) {                                                                           \
-			fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);              \
-			return nullptr;                                                                                \
-		}                                                                                                  \
-	} while (0)
 
 int envInt(const char* name, int fallback) {
 	const char* v = getenv(name);
 	return v && *v ? atoi(v) : fallback;
 }
 
-int ensureInit() {
-	std::lock_guard<std::mutex> lock(g_initMutex);
-	if (g_initialised) {
-		cudaError_t e = cudaSetDevice(g_device);
-		return e == cudaSuccess ? 0 : fail("cudaSetDevice(%d) failed: %s", g_device, cudaGetErrorString(e));
+// caller holds g_mutex
+void readTuningFromEnvironment() {
+	if (g_tuningFromEnv) return;
+	g_tuningFromEnv = true;
+	Tuning& t = g_tuning;
+	t.variant = envInt("RACC_B200_VARIANT", t.variant);
+	t.blockThreads = envInt("RACC_B200_BLOCK", t.blockThreads);
+	t.ctasPerSm = envInt("RACC_B200_CTAS_PER_SM", t.ctasPerSm);
+	t.smemNodes = envInt("RACC_B200_SMEM_NODES", t.smemNodes);
+	t.fetchThreshold = envInt("RACC_B200_FETCH_THRESHOLD", t.fetchThreshold);
+	t.leafBail = envInt("RACC_B200_LEAF_BAIL", t.leafBail);
+	t.innerBail = envInt("RACC_B200_INNER_BAIL", t.innerBail);
+	t.carveout = envInt("RACC_B200_CARVEOUT", t.carveout);
+	t.sortMode = envInt("RACC_B200_SORT", t.sortMode);
+	t.sortOriginBits = envInt("RACC_B200_SORT_ORIGIN_BITS", t.sortOriginBits);
+	t.sortDirBits = envInt("RACC_B200_SORT_DIR_BITS", t.sortDirBits);
+	t.sortDirMajor = envInt("RACC_B200_SORT_DIR_MAJOR", t.sortDirMajor);
+	t.buildDevice = envInt("RACC_B200_BUILD_DEVICE", t.buildDevice);
+	t.smemStack = envInt("RACC_B200_SMEM_STACK", t.smemStack);
+	t.hostZeroCopy = envInt("RACC_B200_HOST_ZERO_COPY", t.hostZeroCopy);
+	t.hostTaper = envInt("RACC_B200_HOST_TAPER", t.hostTaper);
+	t.whittedArena = envInt("RACC_B200_WHITTED_ARENA", t.whittedArena);
+	t.whittedCombine = envInt("RACC_B200_WHITTED_COMBINE", t.whittedCombine);
+	t.pathSync = envInt("RACC_B200_PATH_SYNC", t.pathSync);
+}
+
+} // namespace
+
+int fail(const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(t_error, sizeof(t_error), fmt, ap);
+	va_end(ap);
+	return -1;
+}
+
+Tuning tuningSnapshot() {
+	std::lock_guard<std::mutex> lock(g_mutex);
+	readTuningFromEnvironment();
+	return g_tuning;
+}
+
+void countLaunches(int launches) { g_launches.fetch_add((uint64_t)launches); }
+
+DeviceState* useDevice(int ordinal) {
+	if (ordinal < 0 || ordinal >= kMaxDevices) {
+		fail("CUDA device %d out of range", ordinal);
+		return nullptr;
 	}
-	int count = 0;
-	cudaError_t e = cudaGetDeviceCount(&count);
-	if (e != cudaSuccess || count <= 0)
-		return fail("no CUDA device available (%s); the engine has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-	RACC_CUDA_CHECK(cudaGetDevice(&g_device));
-	RACC_CUDA_CHECK(cudaDeviceGetAttribute(&g_smCount, cudaDevAttrMultiProcessorCount, g_device));
+	cudaError_t e = cudaSetDevice(ordinal);
+	if (e != cudaSuccess) {
+		fail("cudaSetDevice(%d) failed: %s; the engine has no CPU fallback", ordinal, cudaGetErrorString(e));
+		return nullptr;
+	}
+	DeviceState& d = g_devices[ordinal];
+	std::lock_guard<std::mutex> lock(g_mutex);
+	if (d.ready) return &d;
+	readTuningFromEnvironment();
+	d.ordinal = ordinal;
+	if ((e = cudaDeviceGetAttribute(&d.smCount, cudaDevAttrMultiProcessorCount, ordinal)) != cudaSuccess) {
+		fail("cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
+		return nullptr;
+	}
 	{
-		// stream-ordered scratch (stream tables, re-binning buffers) is recycled instead of being handed
+		// stream-ordered scratch (stream tables, re-binning buffers, renderer waves) is recycled instead of being handed
 		// back to the driver at every synchronisation
 		cudaMemPool_t pool = nullptr;
-		if (cudaDeviceGetDefaultMemPool(&pool, g_device) == cudaSuccess && pool) {
+		if (cudaDeviceGetDefaultMemPool(&pool, ordinal) == cudaSuccess && pool) {
 			unsigned long long keep = ~0ull;
 			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
 		}
 	}
-	g_tuning.variant = envInt("RACC_B200_VARIANT", g_tuning.variant);
-	g_tuning.blockThreads = envInt("RACC_B200_BLOCK", g_tuning.blockThreads);
-	g_tuning.ctasPerSm = envInt("RACC_B200_CTAS_PER_SM", g_tuning.ctasPerSm);
-	g_tuning.smemNodes = envInt("RACC_B200_SMEM_NODES", g_tuning.smemNodes);
-	g_tuning.fetchThreshold = envInt("RACC_B200_FETCH_THRESHOLD", g_tuning.fetchThreshold);
-	g_tuning.leafBail = envInt("RACC_B200_LEAF_BAIL", g_tuning.leafBail);
-	g_tuning.innerBail = envInt("RACC_B200_INNER_BAIL", g_tuning.innerBail);
-	g_tuning.carveout = envInt("RACC_B200_CARVEOUT", g_tuning.carveout);
-	g_tuning.sortMode = envInt("RACC_B200_SORT", g_tuning.sortMode);
-	g_tuning.sortOriginBits = envInt("RACC_B200_SORT_ORIGIN_BITS", g_tuning.sortOriginBits);
-	g_tuning.sortDirBits = envInt("RACC_B200_SORT_DIR_BITS", g_tuning.sortDirBits);
-	g_tuning.sortDirMajor = envInt("RACC_B200_SORT_DIR_MAJOR", g_tuning.sortDirMajor);
-	g_tuning.buildDevice = envInt("RACC_B200_BUILD_DEVICE", g_tuning.buildDevice);
-	g_tuning.smemStack = envInt("RACC_B200_SMEM_STACK", g_tuning.smemStack);
-	g_tuning.hostZeroCopy = envInt("RACC_B200_HOST_ZERO_COPY", g_tuning.hostZeroCopy);
-	g_tuning.hostTaper = envInt("RACC_B200_HOST_TAPER", g_tuning.hostTaper);
-	g_tuning.whittedArena = envInt("RACC_B200_WHITTED_ARENA", g_tuning.whittedArena);
-	g_tuning.whittedCombine = envInt("RACC_B200_WHITTED_COMBINE", g_tuning.whittedCombine);
-	g_initialised = true;
-	return 0;
+	if ((e = cudaMalloc(reinterpret_cast<void**>(&d.dFrame), 8 * sizeof(unsigned long long))) != cudaSuccess ||
+	    (e = cudaMemset(d.dFrame, 0, 8 * sizeof(unsigned long long))) != cudaSuccess ||
+	    (e = cudaStreamCreateWithFlags(&d.reduceStream, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaEventCreateWithFlags(&d.reduceReady, cudaEventDisableTiming)) != cudaSuccess ||
+	    (e = cudaEventCreateWithFlags(&d.reduceDone, cudaEventDisableTiming)) != cudaSuccess) {
+		fail("device %d: frame counters: %s", ordinal, cudaGetErrorString(e));
+		return nullptr;
+	}
+	d.dFrameTotal = d.dFrame + 4;
+	d.ready = true;
+	return &d;
 }
 
-constexpr int kCursorRing = 256;
-constexpr size_t kAutoSortSceneBytes = 256u << 20; // twice the 126 MB L2
-constexpr uint32_t kAutoDeviceBuildTriangles = 4096; // tiny scenes: not worth a dozen kernel launches
+DeviceState* currentDevice() {
+	if (t_deviceSet.empty()) {
+		int count = 0;
+		cudaError_t e = cudaGetDeviceCount(&count);
+		if (e != cudaSuccess || count <= 0) {
+			fail("no CUDA device available (%s); the engine has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+			return nullptr;
+		}
+		int ordinal = 0;
+		if ((e = cudaGetDevice(&ordinal)) != cudaSuccess) {
+			fail("cudaGetDevice failed: %s", cudaGetErrorString(e));
+			return nullptr;
+		}
+		DeviceState* d = useDevice(ordinal);
+		if (d) t_deviceSet.assign(1, ordinal);
+		return d;
+	}
+	return useDevice(t_deviceSet[0]);
+}
 
-} // namespace
-
-struct racc_cuda_scene {
-	SceneImages host;            // host images; left empty when the scene was built on the device
-	racc_cuda_scene_info info{}; // counts, depth and bounds of what is on the device
-	uint32_t triangleCount = 0;
-	uint32_t vertexCount = 0;    // of dVerts (0 when the scene was created from images)
-	float4* dNodes = nullptr;
-	float4* dPairs = nullptr;
-	uint32_t* dRemap = nullptr;
-	float4* dTNodes = nullptr;   // packed images walked by the default kernel (traverse_packed.cu)
-	float4* dTPairs = nullptr;
-	float4* dVerts = nullptr;    // for the synthetic bounce generator and the device-side renderer (indices)
-	uint32_t* dIndices = nullptr;
-	uint32_t* dCursors = nullptr;
-	std::atomic<uint32_t> nextCursor{0};
-	uint32_t* dBounceScratch = nullptr;
-	size_t bounceScratchWords = 0;
-};
-
-struct racc_cuda_host_images {
-	SceneImages images;
-	uint32_t triangleCount = 0;
-};
-
-struct racc_cuda_env {
-	float4* dTexels = nullptr;
-	float4* dTexelPairs = nullptr; // (width+1) x height pairs of horizontally adjacent texels (traverse_packed.cu)
-	uint32_t width = 0, height = 0;
-};
-
-// What the reference's example path tracer shades with (Renderer/SceneData.h), resident on the device.
-struct racc_cuda_shading {
-	float4* dNormals = nullptr;
-	float4* dTriangleNormals = nullptr;
-	uint16_t* dTriangleMaterials = nullptr;
-	float4* dMaterials = nullptr;
-	uint32_t vertexCount = 0, triangleCount = 0, materialCount = 0;
-};
+const std::vector<int>& currentDeviceSet() { return t_deviceSet; }
 
 namespace {
 
@@ -156,55 +151,153 @@ void fillInfo(const SceneImages& h, uint32_t triangleCount, racc_cuda_scene_info
 	}
 }
 
-// device-private packed copies of the node and pair images, derived on the device
-racc_cuda_scene* packScene(racc_cuda_scene* s) {
+// Every traversal kernel keeps the reference's 64-entry stack (Kernels.h:166). A ray pushes at most one far child per inner
+// level, so a tree of `depth` levels (leaves included) needs depth-1 entries; the reference overruns its private array
+// silently on a deeper tree, here such a scene is refused when it is created.
+constexpr uint32_t kTraversalStackEntries = 64;
+
+bool depthFitsStack(uint32_t depth) {
+	if (depth <= kTraversalStackEntries + 1) return true;
+	fail("scene tree is %u levels deep; the traversal stack holds %u entries (Kernels.h:166), i.e. trees up to %u levels", depth,
+	     kTraversalStackEntries, kTraversalStackEntries + 1);
+	return false;
+}
+
+// Levels of a node image (leaves included), or 0 when the image is not a tree (a reference cycle or a shared node).
+uint32_t imageDepth(const std::vector<GpuNode>& nodes) {
+	std::vector<std::pair<uint32_t, uint32_t>> todo;
+	todo.emplace_back(0u, 1u);
+	size_t visited = 0;
+	uint32_t depth = 0;
+	while (!todo.empty()) {
+		const auto [index, level] = todo.back();
+		todo.pop_back();
+		if (++visited > nodes.size()) return 0;
+		const uint32_t refs[2] = {nodes[index].first, nodes[index].last};
+		for (uint32_t r : refs) {
+			if (r & 0x80000000u) todo.emplace_back(r & 0x7fffffffu, level + 1);
+			else if (level + 1 > depth) depth = level + 1;
+		}
+	}
+	return depth;
+}
+
+void freeReplica(SceneReplica& r) {
+	if (r.device >= 0) cudaSetDevice(r.device);
+	cudaFree(r.dNodes);
+	cudaFree(r.dPairs);
+	cudaFree(r.dRemap);
+	cudaFree(r.dTNodes);
+	cudaFree(r.dTPairs);
+	cudaFree(r.dQNodes);
+	cudaFree(r.dVerts);
+	cudaFree(r.dIndices);
+	cudaFree(r.dCursors);
+	cudaFree(r.dBounceScratch);
+}
+
+// device-private packed copies of the node and pair images, derived on the device the replica lives on (current)
+bool packReplica(racc_cuda_scene* s, SceneReplica* r) {
 	cudaError_t e;
 	int launches = 0;
-	if ((e = cudaMalloc(reinterpret_cast<void**>(&s->dTNodes), (size_t)s->info.node_count * 64 + 64)) != cudaSuccess ||
-	    (e = cudaMalloc(reinterpret_cast<void**>(&s->dTPairs), (size_t)s->info.pair_count * 64 + 64)) != cudaSuccess ||
-	    (e = launchPackImages(s->dNodes, s->info.node_count, s->dPairs, s->info.pair_count, s->dTNodes, s->dTPairs, nullptr, &launches)) != cudaSuccess ||
+	if ((e = cudaMalloc(reinterpret_cast<void**>(&r->dCursors), kCursorRing * sizeof(uint32_t))) != cudaSuccess ||
+	    (e = cudaMalloc(reinterpret_cast<void**>(&r->dTNodes), (size_t)s->info.node_count * 64 + 64)) != cudaSuccess ||
+	    (e = cudaMalloc(reinterpret_cast<void**>(&r->dTPairs), (size_t)s->info.pair_count * 64 + 64)) != cudaSuccess ||
+	    (e = launchPackImages(r->dNodes, s->info.node_count, r->dPairs, s->info.pair_count, r->dTNodes, r->dTPairs, nullptr, &launches)) != cudaSuccess ||
 	    (e = cudaDeviceSynchronize()) != cudaSuccess) {
 		fail("scene packing failed: %s", cudaGetErrorString(e));
-		racc_cuda_scene_destroy(s);
-		return nullptr;
+		return false;
 	}
-	g_launches.fetch_add((uint64_t)launches);
+	countLaunches(launches);
+	return true;
+}
+
+// dst (on device `to`, allocated here) = src (on device `from`)
+template <typename T>
+bool cloneBuffer(T** dst, int to, const T* src, int from, size_t bytes) {
+	*dst = nullptr;
+	if (!src) return true;
+	cudaError_t e;
+	if ((e = cudaSetDevice(to)) != cudaSuccess || (e = cudaMalloc(reinterpret_cast<void**>(dst), bytes ? bytes : 16)) != cudaSuccess ||
+	    (bytes && (e = cudaMemcpyPeer(*dst, to, src, from, bytes)) != cudaSuccess)) {
+		fail("replicating to CUDA device %d failed: %s", to, cudaGetErrorString(e));
+		return false;
+	}
+	return true;
+}
+
+// The scene exists on the first device of the calling thread's set; copy it to the others (peer copies over NVLink: the
+// build, the pair merge and the packing run once).
+racc_cuda_scene* finishScene(racc_cuda_scene* s) {
+	const std::vector<int> set = currentDeviceSet();
+	SceneReplica* first = s->replicas[0].get();
+	const racc_cuda_scene_info& in = s->info;
+	for (size_t k = 1; k < set.size(); ++k) {
+		if (!useDevice(set[k])) { racc_cuda_scene_destroy(s); return nullptr; }
+		std::unique_ptr<SceneReplica> r(new SceneReplica());
+		r->device = set[k];
+		const bool ok = cloneBuffer(&r->dNodes, r->device, first->dNodes, first->device, (size_t)in.node_count * 64) &&
+		                cloneBuffer(&r->dPairs, r->device, first->dPairs, first->device, (size_t)in.pair_count * 48) &&
+		                cloneBuffer(&r->dRemap, r->device, first->dRemap, first->device, (size_t)in.remap_count * 4) &&
+		                cloneBuffer(&r->dTNodes, r->device, first->dTNodes, first->device, (size_t)in.node_count * 64 + 64) &&
+		                cloneBuffer(&r->dTPairs, r->device, first->dTPairs, first->device, (size_t)in.pair_count * 64 + 64) &&
+		                cloneBuffer(&r->dVerts, r->device, first->dVerts, first->device, (size_t)s->vertexCount * 16) &&
+		                cloneBuffer(&r->dIndices, r->device, first->dIndices, first->device, (size_t)s->triangleCount * 12);
+		cudaError_t e = cudaSuccess;
+		if (ok) e = cudaMalloc(reinterpret_cast<void**>(&r->dCursors), kCursorRing * sizeof(uint32_t));
+		s->replicas.push_back(std::move(r));
+		if (!ok || e != cudaSuccess) {
+			if (ok) fail("replicating to CUDA device %d failed: %s", set[k], cudaGetErrorString(e));
+			racc_cuda_scene_destroy(s);
+			return nullptr;
+		}
+	}
+	cudaSetDevice(set[0]);
 	return s;
 }
 
 racc_cuda_scene* uploadScene(racc_cuda_scene* s, const float* verts4, uint32_t nverts, const uint32_t* indices, uint32_t nindices) {
 	const SceneImages& h = s->host;
+	DeviceState* dev = currentDevice();
+	if (!dev) { delete s; return nullptr; }
 	auto bail = [&]() -> racc_cuda_scene* { racc_cuda_scene_destroy(s); return nullptr; };
 	cudaError_t e;
 	fillInfo(h, s->triangleCount, &s->info);
+	if (!depthFitsStack(s->info.depth)) return bail();
+	s->replicas.emplace_back(new SceneReplica());
+	SceneReplica* r = s->replicas[0].get();
+	r->device = dev->ordinal;
 #define UP(dst, src, bytes)                                                                  \
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&dst), (bytes) != 0 ? (bytes) : 16)) != cudaSuccess || \
 	    (e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {            \
 		fail("scene upload failed: %s", cudaGetErrorString(e));                               \
 		return bail();                                                                        \
 	}
-	UP(s->dNodes, h.nodes.data(), h.nodes.size() * sizeof(GpuNode))
-	UP(s->dPairs, h.pairs.data(), h.pairs.size() * sizeof(GpuPair))
-	UP(s->dRemap, h.remap.data(), h.remap.size() * sizeof(uint32_t))
+	UP(r->dNodes, h.nodes.data(), h.nodes.size() * sizeof(GpuNode))
+	UP(r->dPairs, h.pairs.data(), h.pairs.size() * sizeof(GpuPair))
+	UP(r->dRemap, h.remap.data(), h.remap.size() * sizeof(uint32_t))
 	if (verts4 && indices) {
-		UP(s->dVerts, verts4, (size_t)nverts * 16)
-		UP(s->dIndices, indices, (size_t)nindices * 4)
+		UP(r->dVerts, verts4, (size_t)nverts * 16)
+		UP(r->dIndices, indices, (size_t)nindices * 4)
 	}
 #undef UP
-	if ((e = cudaMalloc(reinterpret_cast<void**>(&s->dCursors), kCursorRing * sizeof(uint32_t))) != cudaSuccess) {
-		fail("scene upload failed: %s", cudaGetErrorString(e));
-		return bail();
-	}
-	return packScene(s);
+	if (!packReplica(s, r)) return bail();
+	return finishScene(s);
 }
 
 } // namespace
+
+bool sceneExceedsL2(const racc_cuda_scene* s) {
+	return ((size_t)s->info.node_count + s->info.pair_count) * 64 > kAutoSortSceneBytes;
+}
+
+} // namespace racc_b200
 
 extern "C" {
 
 int racc_cuda_abi_version(void) { return RACC_CUDA_ABI_VERSION; }
 
-const char* racc_cuda_last_error(void) { return g_error; }
+const char* racc_cuda_last_error(void) { return t_error; }
 
 int racc_cuda_device_count(void) {
 	int count = 0;
@@ -217,26 +310,35 @@ int racc_cuda_device_count(void) {
 }
 
 int racc_cuda_init(const int* devices, int n) {
-	if (devices && n > 0) {
-		cudaError_t e = cudaSetDevice(devices[0]);
-		if (e != cudaSuccess)
-			return fail("cudaSetDevice(%d) failed: %s; the engine has no CPU fallback", devices[0], cudaGetErrorString(e));
-		std::lock_guard<std::mutex> lock(g_initMutex);
-		if (g_initialised && g_device != devices[0])
-			g_initialised = false; // re-bind the process (tuning is re-read from the environment)
+	if (!devices || n <= 0) {
+		t_deviceSet.clear();
+		return currentDevice() ? 0 : -1;
 	}
-	return ensureInit();
+	std::vector<int> set;
+	for (int k = 0; k < n; ++k) {
+		for (int seen : set)
+			if (seen == devices[k]) return fail("racc_cuda_init: CUDA device %d named twice", devices[k]);
+		if (!useDevice(devices[k])) return -1;
+		set.push_back(devices[k]);
+	}
+	t_deviceSet = set;
+	return currentDevice() ? 0 : -1;
 }
 
-int racc_cuda_set_variant(int variant) {
-	const int previous = g_tuning.variant;
-	g_tuning.variant = variant;
-	return previous;
+int racc_cuda_current_devices(int* devices, int capacity) {
+	if (!currentDevice()) return -1;
+	const std::vector<int>& set = currentDeviceSet();
+	for (int k = 0; k < (int)set.size() && k < capacity; ++k)
+		if (devices) devices[k] = set[k];
+	return (int)set.size();
 }
 
-// Extended tuning access for the benchmark sweeps: key 0 variant, 1 block threads, 2 CTAs/SM,
-// 3 staged nodes, 4 fetch threshold. Returns the previous value.
+int racc_cuda_set_variant(int variant) { return racc_cuda_set_tuning(0, variant); }
+
+// Extended tuning access for the benchmark sweeps (keys in include/racc_b200.h). Returns the previous value.
 int racc_cuda_set_tuning(int key, int value) {
+	std::lock_guard<std::mutex> lock(g_mutex);
+	readTuningFromEnvironment();
 	int* slot = nullptr;
 	switch (key) {
 	case 0: slot = &g_tuning.variant; break;
@@ -257,6 +359,7 @@ int racc_cuda_set_tuning(int key, int value) {
 	case 15: slot = &g_tuning.whittedArena; break;
 	case 16: slot = &g_tuning.whittedCombine; break;
 	case 17: slot = &g_tuning.hostTaper; break;
+	case 18: slot = &g_tuning.pathSync; break;
 	default: return fail("unknown tuning key %d", key);
 	}
 	const int previous = *slot;
@@ -273,7 +376,7 @@ int racc_cuda_debug_rcp_table(float* out2048) {
 
 int racc_cuda_debug_warp_stats(uint64_t* out8, int reset) {
 	if (!out8) return fail("racc_cuda_debug_warp_stats: null argument");
-	if (ensureInit()) return -1;
+	if (!currentDevice()) return -1;
 	RACC_CUDA_CHECK(cudaDeviceSynchronize());
 	RACC_CUDA_CHECK(readWarpStats(reinterpret_cast<unsigned long long*>(out8), reset != 0));
 	return 0;
@@ -281,19 +384,26 @@ int racc_cuda_debug_warp_stats(uint64_t* out8, int reset) {
 
 racc_cuda_scene* racc_cuda_scene_create(const float* verts4, uint32_t nverts, const uint32_t* indices, uint32_t nindices) {
 	if (!verts4 || !indices) { fail("racc_cuda_scene_create: null input"); return nullptr; }
-	if (ensureInit()) return nullptr;
+	DeviceState* dev = currentDevice();
+	if (!dev) return nullptr;
+	const Tuning tuning = tuningSnapshot();
 	racc_cuda_scene* s = new racc_cuda_scene();
 	const char* why = "";
 	bool built = false;
 	s->triangleCount = nindices / 3;
 	s->vertexCount = nverts;
-	if (g_tuning.buildDevice == 2 || (g_tuning.buildDevice == 3 && nindices / 3 >= kAutoDeviceBuildTriangles)) {
+	if (tuning.buildDevice == 2 || (tuning.buildDevice == 3 && nindices / 3 >= kAutoDeviceBuildTriangles)) {
 		// the whole build on the device: the images never exist on the host
 		DeviceSceneImages img;
 		if (buildSceneImagesDevice(verts4, nverts, indices, nindices, &img, &why)) {
-			s->dNodes = static_cast<float4*>(img.nodes);
-			s->dPairs = static_cast<float4*>(img.pairs);
-			s->dRemap = img.remap;
+			s->replicas.emplace_back(new SceneReplica());
+			SceneReplica* r = s->replicas[0].get();
+			r->device = dev->ordinal;
+			r->dNodes = static_cast<float4*>(img.nodes);
+			r->dPairs = static_cast<float4*>(img.pairs);
+			r->dRemap = img.remap;
+			r->dVerts = static_cast<float4*>(img.verts);
+			r->dIndices = img.indices;
 			s->info.node_count = img.nodeCount;
 			s->info.pair_count = img.pairCount;
 			s->info.real_pair_count = img.realPairs;
@@ -301,19 +411,15 @@ racc_cuda_scene* racc_cuda_scene_create(const float* verts4, uint32_t nverts, co
 			s->info.depth = img.depth;
 			s->info.triangle_count = s->triangleCount;
 			for (int k = 0; k < 3; ++k) { s->info.bounds_min[k] = img.boundsMin[k]; s->info.bounds_max[k] = img.boundsMax[k]; }
-			s->dVerts = static_cast<float4*>(img.verts);
-			s->dIndices = img.indices;
-			cudaError_t e;
-			if ((e = cudaMalloc(reinterpret_cast<void**>(&s->dCursors), kCursorRing * sizeof(uint32_t))) != cudaSuccess) {
-				fail("scene upload failed: %s", cudaGetErrorString(e));
+			if (!depthFitsStack(s->info.depth) || !packReplica(s, r)) {
 				racc_cuda_scene_destroy(s);
 				return nullptr;
 			}
-			return packScene(s);
+			return finishScene(s);
 		}
-		fprintf(stderr, "RayAccelerator: device scene build declined (%s); building on the host\n", why);
+		if (tuning.buildDevice == 2) fprintf(stderr, "RayAccelerator: device scene build declined (%s); building on the host\n", why);
 	}
-	else if (g_tuning.buildDevice == 1) {
+	else if (tuning.buildDevice == 1) {
 		built = buildSceneImages(verts4, nverts, indices, nindices, 0, &s->host, &why, buildBvh2Device);
 		if (!built) fprintf(stderr, "RayAccelerator: device SAH build declined (%s); building on the host\n", why);
 	}
@@ -357,18 +463,20 @@ void racc_cuda_host_images_destroy(racc_cuda_host_images* img) { delete img; }
 racc_cuda_scene* racc_cuda_scene_create_from_images(const void* nodes, uint32_t node_count, const void* pairs,
                                                     uint32_t pair_count, const uint32_t* remap, uint32_t remap_count) {
 	if (!nodes || !pairs || !remap || !node_count || !pair_count) { fail("racc_cuda_scene_create_from_images: null or empty image"); return nullptr; }
-	if (ensureInit()) return nullptr;
+	if (!currentDevice()) return nullptr;
 	racc_cuda_scene* s = new racc_cuda_scene();
 	s->host.nodes.assign(static_cast<const GpuNode*>(nodes), static_cast<const GpuNode*>(nodes) + node_count);
 	s->host.pairs.assign(static_cast<const GpuPair*>(pairs), static_cast<const GpuPair*>(pairs) + pair_count);
 	s->host.remap.assign(remap, remap + remap_count);
 	s->host.realPairs = remap_count / 2;
 	{
-		// scene bounds = union of the root's two child boxes (used only by the ray re-binning keys)
+		// scene bounds = union of the root's two child boxes (used only by the ray re-binning keys); a synthetic root's
+		// second box sits at +infinity (scene_build.cpp) and is left out
 		const GpuNode& root = s->host.nodes[0];
 		for (int k = 0; k < 3; ++k) {
-			s->host.boundsMin[k] = root.leftMin[k] < root.rightMin[k] ? root.leftMin[k] : root.rightMin[k];
-			s->host.boundsMax[k] = root.leftMax[k] > root.rightMax[k] ? root.leftMax[k] : root.rightMax[k];
+			const bool both = root.rightMin[k] <= root.rightMax[k] && root.rightMin[k] < 3.0e38f;
+			s->host.boundsMin[k] = both && root.rightMin[k] < root.leftMin[k] ? root.rightMin[k] : root.leftMin[k];
+			s->host.boundsMax[k] = both && root.rightMax[k] > root.leftMax[k] ? root.rightMax[k] : root.leftMax[k];
 		}
 	}
 	// validate references so a malformed image cannot send the kernel out of bounds
@@ -384,20 +492,21 @@ racc_cuda_scene* racc_cuda_scene_create_from_images(const void* nodes, uint32_t 
 			}
 		}
 	}
+	s->host.depth = imageDepth(s->host.nodes);
+	if (!s->host.depth) {
+		fail("racc_cuda_scene_create_from_images: the node image is not a tree (a node is referenced twice or lies on a cycle)");
+		delete s;
+		return nullptr;
+	}
 	return uploadScene(s, nullptr, 0, nullptr, 0);
 }
 
 void racc_cuda_scene_destroy(racc_cuda_scene* s) {
 	if (!s) return;
-	cudaFree(s->dNodes);
-	cudaFree(s->dPairs);
-	cudaFree(s->dRemap);
-	cudaFree(s->dTNodes);
-	cudaFree(s->dTPairs);
-	cudaFree(s->dVerts);
-	cudaFree(s->dIndices);
-	cudaFree(s->dCursors);
-	cudaFree(s->dBounceScratch);
+	int before = -1;
+	cudaGetDevice(&before);
+	for (auto& r : s->replicas) freeReplica(*r);
+	if (before >= 0) cudaSetDevice(before);
 	delete s;
 }
 
@@ -409,54 +518,76 @@ int racc_cuda_scene_get_info(const racc_cuda_scene* s, racc_cuda_scene_info* inf
 
 int racc_cuda_scene_download(const racc_cuda_scene* s, void* nodes, void* pairs, uint32_t* remap) {
 	if (!s) return fail("racc_cuda_scene_download: null scene");
+	DeviceState* dev = currentDevice();
+	if (!dev) return -1;
 	// read back from the device so the test sees what the kernel sees
-	if (nodes) RACC_CUDA_CHECK(cudaMemcpy(nodes, s->dNodes, (size_t)s->info.node_count * sizeof(GpuNode), cudaMemcpyDeviceToHost));
-	if (pairs) RACC_CUDA_CHECK(cudaMemcpy(pairs, s->dPairs, (size_t)s->info.pair_count * sizeof(GpuPair), cudaMemcpyDeviceToHost));
-	if (remap) RACC_CUDA_CHECK(cudaMemcpy(remap, s->dRemap, (size_t)s->info.remap_count * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	const SceneReplica* r = s->on(dev->ordinal);
+	if (!r) {
+		r = s->replicas[0].get();
+		RACC_CUDA_CHECK(cudaSetDevice(r->device));
+	}
+	if (nodes) RACC_CUDA_CHECK(cudaMemcpy(nodes, r->dNodes, (size_t)s->info.node_count * sizeof(GpuNode), cudaMemcpyDeviceToHost));
+	if (pairs) RACC_CUDA_CHECK(cudaMemcpy(pairs, r->dPairs, (size_t)s->info.pair_count * sizeof(GpuPair), cudaMemcpyDeviceToHost));
+	if (remap) RACC_CUDA_CHECK(cudaMemcpy(remap, r->dRemap, (size_t)s->info.remap_count * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	RACC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
 	return 0;
 }
 
 racc_cuda_env* racc_cuda_env_create(const float* rgba, uint32_t width, uint32_t height) {
 	if (!rgba || !width || !height) { fail("racc_cuda_env_create: null or empty image"); return nullptr; }
-	if (ensureInit()) return nullptr;
+	if (!currentDevice()) return nullptr;
+	const std::vector<int> set = currentDeviceSet();
 	racc_cuda_env* env = new racc_cuda_env();
 	env->width = width;
 	env->height = height;
 	const size_t bytes = (size_t)width * height * 16;
-	cudaError_t e;
-	if ((e = cudaMalloc(reinterpret_cast<void**>(&env->dTexels), bytes)) != cudaSuccess ||
-	    (e = cudaMemcpy(env->dTexels, rgba, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {
-		fail("environment upload failed: %s", cudaGetErrorString(e));
-		cudaFree(env->dTexels);
-		delete env;
-		return nullptr;
+	for (int ordinal : set) {
+		if (!useDevice(ordinal)) { racc_cuda_env_destroy(env); return nullptr; }
+		env->replicas.emplace_back(new EnvReplica());
+		EnvReplica* r = env->replicas.back().get();
+		r->device = ordinal;
+		cudaError_t e;
+		int launches = 0;
+		if ((e = cudaMalloc(reinterpret_cast<void**>(&r->dTexels), bytes)) != cudaSuccess ||
+		    (e = cudaMemcpy(r->dTexels, rgba, bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+		    (e = cudaMalloc(reinterpret_cast<void**>(&r->dTexelPairs), ((size_t)width + 1) * height * 32)) != cudaSuccess ||
+		    (e = launchPackEnv(r->dTexels, width, height, r->dTexelPairs, nullptr, &launches)) != cudaSuccess ||
+		    (e = cudaDeviceSynchronize()) != cudaSuccess) {
+			fail("environment upload failed: %s", cudaGetErrorString(e));
+			racc_cuda_env_destroy(env);
+			cudaSetDevice(set[0]);
+			return nullptr;
+		}
+		countLaunches(launches);
 	}
-	int launches = 0;
-	if ((e = cudaMalloc(reinterpret_cast<void**>(&env->dTexelPairs), ((size_t)width + 1) * height * 32)) != cudaSuccess ||
-	    (e = launchPackEnv(env->dTexels, width, height, env->dTexelPairs, nullptr, &launches)) != cudaSuccess ||
-	    (e = cudaDeviceSynchronize()) != cudaSuccess) {
-		fail("environment packing failed: %s", cudaGetErrorString(e));
-		racc_cuda_env_destroy(env);
-		return nullptr;
-	}
-	g_launches.fetch_add((uint64_t)launches);
+	cudaSetDevice(set[0]);
 	return env;
 }
 
 void racc_cuda_env_destroy(racc_cuda_env* env) {
 	if (!env) return;
-	cudaFree(env->dTexels);
-	cudaFree(env->dTexelPairs);
+	int before = -1;
+	cudaGetDevice(&before);
+	for (auto& r : env->replicas) {
+		cudaSetDevice(r->device);
+		cudaFree(r->dTexels);
+		cudaFree(r->dTexelPairs);
+	}
+	if (before >= 0) cudaSetDevice(before);
 	delete env;
 }
 
+} // extern "C"
+
+namespace racc_b200 {
 namespace {
 
 // Staging pipeline for HOST ray streams: chunks alternate over a few internal CUDA streams so that
 // the H2D copy of chunk k+1, the traversal of chunk k and the D2H copy of chunk k-1 overlap (PCIe
-// is full duplex). One pipeline per calling host thread, so concurrent submitters never share
+// is full duplex). One pipeline per calling host thread and device, so concurrent submitters never share
 // staging buffers. Replaces the reference's zero-copy CL_MEM_USE_HOST_PTR streams
-// (RayAccelerator.cpp:643-644), which a discrete GPU does not have.
+// (RayAccelerator.cpp:643-644), which a discrete GPU does not have. Released by racc_cuda_thread_release
+// (racc_api.cpp calls it when a submitter thread ends).
 struct HostPipeline {
 	static constexpr int kLanes = 3;
 	bool ready = false;
@@ -468,10 +599,11 @@ struct HostPipeline {
 	DevRay* dRays[kLanes] = {};
 	float4* dResults[kLanes] = {};
 
-	int init() {
-		if (ready && device == g_device) return 0;
-		release();
-		device = g_device;
+	// the device is current
+	int init(int ordinal) {
+		if (ready) return 0;
+		release(); // whatever an earlier, failed init left behind
+		device = ordinal;
 		chunkRays = (uint32_t)envInt("RACC_B200_HOST_CHUNK", 1 << 20); // 32 MB of rays per H2D copy: best of 256K..4M (profiles/r01_e2e_chunk_sweep.txt)
 		if (chunkRays < 1024) chunkRays = 1024;
 		RACC_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
@@ -485,13 +617,14 @@ struct HostPipeline {
 		return 0;
 	}
 
+	// frees whatever exists, also after an init() that failed part-way
 	void release() {
-		if (!ready) return;
+		if (device >= 0) cudaSetDevice(device);
 		for (int l = 0; l < kLanes; ++l) {
 			if (lane[l]) { cudaStreamSynchronize(lane[l]); cudaStreamDestroy(lane[l]); }
 			if (done[l]) cudaEventDestroy(done[l]);
-			cudaFree(dRays[l]);
-			cudaFree(dResults[l]);
+			if (dRays[l]) cudaFree(dRays[l]);
+			if (dResults[l]) cudaFree(dResults[l]);
 			lane[l] = nullptr; done[l] = nullptr; dRays[l] = nullptr; dResults[l] = nullptr;
 		}
 		if (fork) cudaEventDestroy(fork);
@@ -499,120 +632,61 @@ struct HostPipeline {
 		ready = false;
 	}
 
-	~HostPipeline() { /* process teardown: the context may already be gone, leak on purpose */ }
+	~HostPipeline() { /* thread exit without racc_cuda_thread_release, or process teardown (the context may be gone): leak on purpose */ }
 };
 
-thread_local HostPipeline t_pipeline;
+thread_local std::vector<std::unique_ptr<HostPipeline>> t_pipelines;
 
-// Internal streams of racc_cuda_path_trace (one set per calling host thread), see there.
-struct PathLanes {
-	static constexpr int kMax = 4;
-	bool ready = false;
-	int device = -1;
-	int count = 2;
-	cudaStream_t stream[kMax] = {};
-	cudaEvent_t done[kMax] = {};
-	cudaEvent_t fork = nullptr;
-	uint32_t* hostCounts = nullptr; // pinned: the next wave's size of each lane
+HostPipeline* pipelineOn(int ordinal) {
+	for (auto& p : t_pipelines)
+		if (p->device == ordinal) return p.get();
+	t_pipelines.emplace_back(new HostPipeline());
+	t_pipelines.back()->device = ordinal;
+	return t_pipelines.back().get();
+}
 
-	int init() {
-		if (ready && device == g_device) return 0;
-		device = g_device;
-		count = envInt("RACC_B200_PATH_LANES", 2);
-		if (count < 1) count = 1;
-		if (count > kMax) count = kMax;
-		RACC_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-		RACC_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&hostCounts), kMax * sizeof(uint32_t), cudaHostAllocPortable));
-		for (int l = 0; l < kMax; ++l) {
-			RACC_CUDA_CHECK(cudaStreamCreateWithFlags(&stream[l], cudaStreamNonBlocking));
-			RACC_CUDA_CHECK(cudaEventCreateWithFlags(&done[l], cudaEventDisableTiming));
-		}
-		ready = true;
-		return 0;
-	}
-	~PathLanes() { /* process teardown: the context may already be gone, leak on purpose */ }
-};
-
-thread_local PathLanes t_pathLanes;
-
-// Wave buffers of racc_cuda_whitted_trace kept between waves, batches and calls (Tuning::whittedArena), one set per
-// calling host thread. A wave's size is only known after the previous one was shaded and differs from frame to frame, so
-// per-wave stream-ordered allocations keep asking the pool for sizes it has no block for; these buffers only ever grow
-// (by a quarter more than asked). Slots: 0/1 rays (ping-pong), 2/3 states, 4 results. A buffer is grown only while it
-// holds nothing live: the results before a wave is traced, the next wave's rays/states before they are written.
-struct WhittedArena {
-	static constexpr int kSlots = 5;
-	int device = -1;
-	void* p[kSlots] = {};
-	size_t cap[kSlots] = {};
-	cudaEvent_t idle = nullptr; // end of the previous call's work on these buffers
-	bool idleRecorded = false;
-
-	// a later call may come on another CUDA stream: it waits for the previous call's kernels before touching the buffers
-	int begin(cudaStream_t stream) {
-		if (device != g_device) {
-			for (int k = 0; k < kSlots; ++k) { p[k] = nullptr; cap[k] = 0; } // another device's pointers: dropped, not freed here
-			idle = nullptr;
-			idleRecorded = false;
-			device = g_device;
-		}
-		if (!idle) RACC_CUDA_CHECK(cudaEventCreateWithFlags(&idle, cudaEventDisableTiming));
-		if (idleRecorded) RACC_CUDA_CHECK(cudaStreamWaitEvent(stream, idle, 0));
-		return 0;
-	}
-	int end(cudaStream_t stream) {
-		RACC_CUDA_CHECK(cudaEventRecord(idle, stream));
-		idleRecorded = true;
-		return 0;
-	}
-	int ensure(int k, size_t bytes, cudaStream_t stream) {
-		if (cap[k] >= bytes && p[k]) return 0;
-		if (p[k]) RACC_CUDA_CHECK(cudaFreeAsync(p[k], stream));
-		p[k] = nullptr;
-		cap[k] = 0;
-		const size_t want = ((bytes + bytes / 4 + (2u << 20)) >> 21) << 21; // a quarter of headroom, whole 2 MiB pages
-		RACC_CUDA_CHECK(cudaMallocAsync(&p[k], want, stream));
-		cap[k] = want;
-		return 0;
-	}
-	~WhittedArena() { /* process teardown: the context may already be gone, leak on purpose */ }
-};
-
-thread_local WhittedArena t_whittedArena;
-
-void fillSceneParams(TraceParams& p, racc_cuda_scene* s, racc_cuda_env* env, void* device_counters) {
-	p.nodes = s->dNodes;
-	p.pairs = s->dPairs;
-	p.remap = s->dRemap;
-	p.env = env ? env->dTexels : nullptr;
+void fillSceneParams(TraceParams& p, const racc_cuda_scene* s, const SceneReplica* r, const racc_cuda_env* env, const EnvReplica* er,
+                     unsigned long long* counters) {
+	p.nodes = r->dNodes;
+	p.pairs = r->dPairs;
+	p.remap = r->dRemap;
+	p.env = er ? er->dTexels : nullptr;
 	p.envWidth = env ? env->width : 0;
 	p.envHeight = env ? env->height : 0;
 	p.nodeCount = s->info.node_count;
-	p.counters = static_cast<unsigned long long*>(device_counters);
-	p.tnodes = s->dTNodes;
-	p.tpairs = s->dTPairs;
+	p.counters = counters;
+	p.tnodes = r->dTNodes;
+	p.tpairs = r->dTPairs;
 	p.perm = nullptr;
-	p.envPairs = env ? env->dTexelPairs : nullptr;
+	p.envPairs = er ? er->dTexelPairs : nullptr;
+	p.totalPtr = nullptr;
 }
 
-bool sceneExceedsL2(const racc_cuda_scene* s) {
-	return ((size_t)s->info.node_count + s->info.pair_count) * 64 > kAutoSortSceneBytes;
-}
-
-cudaError_t launchAny(const racc_cuda_scene* s, const TraceParams& p, int counterMode, cudaStream_t stream, int* launches) {
-	if (g_tuning.variant != 3)
-		return launchTrace(p, g_tuning, counterMode, g_smCount, stream, launches);
-	Tuning t = g_tuning;
+cudaError_t launchAny(const racc_cuda_scene* s, const Tuning& tuning, const DeviceState* dev, const TraceParams& p, int counterMode,
+                      cudaStream_t stream, int* launches) {
+	if (tuning.variant != 3)
+		return launchTrace(p, tuning, counterMode, dev->smCount, stream, launches);
+	Tuning t = tuning;
 	if (t.smemStack < 0) t.smemStack = sceneExceedsL2(s) ? 16 : 0;
-	return launchTracePacked(p, t, counterMode, g_smCount, stream, launches);
+	return launchTracePacked(p, t, counterMode, dev->smCount, stream, launches);
 }
 
-int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams,
-              void* cuda_stream, void* device_counters, bool fullCounters) {
+} // namespace
+
+int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams, void* cuda_stream,
+              void* device_counters, bool fullCounters, const uint32_t* deviceTotal) {
 	if (!s) return fail("racc_cuda_trace: null scene");
 	if (!streams && nstreams) return fail("racc_cuda_trace: null stream list");
-	if (ensureInit()) return -1;
+	DeviceState* dev = currentDevice();
+	if (!dev) return -1;
+	const Tuning tuning = tuningSnapshot();
 	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+	SceneReplica* rep = s->on(dev->ordinal);
+	if (!rep) return fail("racc_cuda_trace: the scene has no copy on CUDA device %d (it was created for another device set)", dev->ordinal);
+	EnvReplica* erep = env ? env->on(dev->ordinal) : nullptr;
+	if (env && !erep) return fail("racc_cuda_trace: the environment has no copy on CUDA device %d", dev->ordinal);
+	// Without a caller's record every launch adds rays + hits to its device's frame record (racc_cuda_frame_reduce)
+	const int counterMode = device_counters ? (fullCounters ? 2 : 1) : 1;
 
 	std::vector<StreamRef> refs; // device-resident streams: one launch for all of them
 	std::vector<const racc_cuda_stream_desc*> hostStreams;
@@ -629,7 +703,7 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 			// written by the kernel itself over PCIe: no staging copies, one launch, H2D and D2H traffic interleaved
 			// ray by ray. Anything else goes through the staging pipeline below.
 			bool direct = false;
-			if (g_tuning.hostZeroCopy && !((reinterpret_cast<uintptr_t>(d.rays) | reinterpret_cast<uintptr_t>(d.results)) & 15)) {
+			if (tuning.hostZeroCopy && !((reinterpret_cast<uintptr_t>(d.rays) | reinterpret_cast<uintptr_t>(d.results)) & 15)) {
 				cudaPointerAttributes ar{}, ao{};
 				if (cudaPointerGetAttributes(&ar, d.rays) == cudaSuccess && cudaPointerGetAttributes(&ao, d.results) == cudaSuccess &&
 				    ar.type == cudaMemoryTypeHost && ao.type == cudaMemoryTypeHost && ar.devicePointer && ao.devicePointer) {
@@ -658,15 +732,17 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 		total += d.count;
 		if (total > 0x7fffffffull) return fail("racc_cuda_trace: more than 2^31-1 rays in one launch");
 	}
+	if (deviceTotal && (refs.size() != 1 || !hostStreams.empty())) return fail("racc_cuda_trace: a device-side ray count needs exactly one DEVICE stream");
 
 	int launches = 0;
 	if (total) {
 		TraceParams p{};
-		fillSceneParams(p, s, env, device_counters);
+		fillSceneParams(p, s, rep, env, erep, device_counters ? static_cast<unsigned long long*>(device_counters) : dev->dFrame);
 		p.nstreams = (uint32_t)refs.size();
 		p.total = (uint32_t)total;
+		p.totalPtr = deviceTotal;
 		p.single = refs[0];
-		p.cursor = s->dCursors + (s->nextCursor.fetch_add(1) % kCursorRing);
+		p.cursor = rep->dCursors + (rep->nextCursor.fetch_add(1) % kCursorRing);
 		void* dRefs = nullptr;
 		if (refs.size() > 1) {
 			RACC_CUDA_CHECK(cudaMallocAsync(&dRefs, refs.size() * sizeof(StreamRef), stream));
@@ -674,8 +750,8 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 			p.streams = static_cast<const StreamRef*>(dRefs);
 		}
 		void* sortScratch = nullptr;
-		const bool rebin = g_tuning.variant == 3 && total >= 4096 && !zeroCopy &&
-		                   (g_tuning.sortMode == 1 || (g_tuning.sortMode == 2 && sceneExceedsL2(s) && total >= (1u << 18)));
+		const bool rebin = tuning.variant == 3 && total >= 4096 && !zeroCopy && !deviceTotal &&
+		                   (tuning.sortMode == 1 || (tuning.sortMode == 2 && sceneExceedsL2(s) && total >= (1u << 18)));
 		if (rebin) {
 			// re-bin the launch: visiting order by origin/direction key, results stay index-parallel
 			// an optimisation only: when the scratch does not fit, trace in arrival order
@@ -684,21 +760,37 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 				sortScratch = nullptr;
 			}
 			else {
-				RACC_CUDA_CHECK(launchRaySort(p, s->info.bounds_min, s->info.bounds_max, g_tuning.sortOriginBits, g_tuning.sortDirBits,
-				                              g_tuning.sortDirMajor, sortScratch, g_smCount, stream, &p.perm, &launches));
+				RACC_CUDA_CHECK(launchRaySort(p, s->info.bounds_min, s->info.bounds_max, tuning.sortOriginBits, tuning.sortDirBits,
+				                              tuning.sortDirMajor, sortScratch, dev->smCount, stream, &p.perm, &launches));
 			}
 		}
-		RACC_CUDA_CHECK(launchAny(s, p, device_counters ? (fullCounters ? 2 : 1) : 0, stream, &launches));
+		RACC_CUDA_CHECK(launchAny(s, tuning, dev, p, counterMode, stream, &launches));
 		if (sortScratch) RACC_CUDA_CHECK(cudaFreeAsync(sortScratch, stream));
 		if (dRefs) RACC_CUDA_CHECK(cudaFreeAsync(dRefs, stream));
 	}
 
 	if (!hostStreams.empty()) {
-		HostPipeline& pipe = t_pipeline;
-		if (pipe.init()) return -1;
-		RACC_CUDA_CHECK(cudaEventRecord(pipe.fork, stream));
-		for (int l = 0; l < HostPipeline::kLanes; ++l)
-			RACC_CUDA_CHECK(cudaStreamWaitEvent(pipe.lane[l], pipe.fork, 0));
+		// Devices of this call: the calling thread's whole set, on which the scene (and environment) have a copy. Chunks
+		// are dealt round-robin over them -- the analogue of the reference's gpuSubmissionThreads sharing one device's
+		// queue (RayAccelerator.cpp:335-414), for a box where every GPU hangs off its own PCIe link.
+		struct Target { DeviceState* dev; SceneReplica* rep; EnvReplica* erep; HostPipeline* pipe; unsigned chunks; };
+		std::vector<Target> targets;
+		for (int ordinal : currentDeviceSet()) {
+			SceneReplica* r = s->on(ordinal);
+			EnvReplica* er = env ? env->on(ordinal) : nullptr;
+			if (!r || (env && !er)) continue;
+			DeviceState* d = useDevice(ordinal);
+			if (!d) return -1;
+			HostPipeline* pipe = pipelineOn(ordinal);
+			if (pipe->init(ordinal)) return -1;
+			targets.push_back(Target{d, r, er, pipe, 0u});
+		}
+		RACC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
+		HostPipeline& first = *targets[0].pipe;
+		RACC_CUDA_CHECK(cudaEventRecord(first.fork, stream));
+		for (Target& t : targets)
+			for (int l = 0; l < HostPipeline::kLanes; ++l)
+				RACC_CUDA_CHECK(cudaStreamWaitEvent(t.pipe->lane[l], first.fork, 0));
 		// Pack host streams into staging chunks: a chunk takes whole streams or slices of them until it
 		// holds chunkRays rays, so that many small API streams (<= 65 535 rays each under the
 		// RayAccelerator.h Configuration) still become ONE launch that fills the machine.
@@ -709,57 +801,72 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 		// so the last chunks halve (remaining / 2, never below hostTaper K rays) instead of ending on a full-size one.
 		uint64_t remaining = 0;
 		for (const racc_cuda_stream_desc* d : hostStreams) remaining += d->count;
-		const uint64_t taperFloor = g_tuning.hostTaper > 0 ? (uint64_t)g_tuning.hostTaper << 10 : 0;
+		const uint64_t taperFloor = tuning.hostTaper > 0 ? (uint64_t)tuning.hostTaper << 10 : 0;
+		struct Segment { char* hResults; uint32_t offset, n; };
+		std::vector<Segment> segs; // a chunk of many tiny streams has as many segments as it needs
 		while (si < hostStreams.size()) {
-			const int l = (int)(chunk % HostPipeline::kLanes);
-			struct Segment { char* hResults; uint32_t offset, n; };
-			Segment segs[64];
-			int nsegs = 0;
+			Target& t = targets[chunk % targets.size()];
+			HostPipeline& pipe = *t.pipe;
+			const int l = (int)(t.chunks % HostPipeline::kLanes);
+			if (targets.size() > 1) RACC_CUDA_CHECK(cudaSetDevice(t.dev->ordinal));
+			segs.clear();
 			uint32_t filled = 0;
 			uint32_t capacity = pipe.chunkRays;
-			if (taperFloor && remaining < 2ull * pipe.chunkRays) {
-				uint64_t half = (remaining + 1) / 2;
+			if (taperFloor && remaining < 2ull * pipe.chunkRays * targets.size()) {
+				uint64_t half = (remaining / targets.size() + 1) / 2;
 				if (half < taperFloor) half = taperFloor;
 				if (half < capacity) capacity = (uint32_t)half;
 			}
-			while (si < hostStreams.size() && filled < capacity && nsegs < 64) {
+			while (si < hostStreams.size() && filled < capacity) {
 				const racc_cuda_stream_desc* d = hostStreams[si];
 				const uint32_t left = d->count - sBegin;
 				const uint32_t room = capacity - filled;
 				const uint32_t n = left < room ? left : room;
 				RACC_CUDA_CHECK(cudaMemcpyAsync(pipe.dRays[l] + filled, static_cast<const char*>(d->rays) + (size_t)sBegin * 32, (size_t)n * 32,
 				                                cudaMemcpyHostToDevice, pipe.lane[l]));
-				segs[nsegs++] = Segment{static_cast<char*>(d->results) + (size_t)sBegin * 16, filled, n};
+				segs.push_back(Segment{static_cast<char*>(d->results) + (size_t)sBegin * 16, filled, n});
 				filled += n;
 				sBegin += n;
 				remaining -= n;
 				if (sBegin == d->count) { ++si; sBegin = 0; }
 			}
 			TraceParams p{};
-			fillSceneParams(p, s, env, device_counters);
+			fillSceneParams(p, s, t.rep, env, t.erep, device_counters && t.dev == dev ? static_cast<unsigned long long*>(device_counters) : t.dev->dFrame);
 			p.nstreams = 1;
 			p.total = filled;
 			p.single.rays = pipe.dRays[l];
 			p.single.results = pipe.dResults[l];
 			p.single.begin = 0;
 			p.single.count = filled;
-			p.cursor = s->dCursors + (s->nextCursor.fetch_add(1) % kCursorRing);
-			RACC_CUDA_CHECK(launchAny(s, p, device_counters ? (fullCounters ? 2 : 1) : 0, pipe.lane[l], &launches));
-			for (int k = 0; k < nsegs; ++k)
-				RACC_CUDA_CHECK(cudaMemcpyAsync(segs[k].hResults, pipe.dResults[l] + segs[k].offset, (size_t)segs[k].n * 16, cudaMemcpyDeviceToHost, pipe.lane[l]));
+			p.cursor = t.rep->dCursors + (t.rep->nextCursor.fetch_add(1) % kCursorRing);
+			RACC_CUDA_CHECK(launchAny(s, tuning, t.dev, p, device_counters && t.dev == dev ? counterMode : 1, pipe.lane[l], &launches));
+			// results go home: adjacent segments of one host buffer (a stream cut by nothing) are already one copy;
+			// segments of different streams are separate copies of at least one stream each
+			for (const Segment& g : segs)
+				RACC_CUDA_CHECK(cudaMemcpyAsync(g.hResults, pipe.dResults[l] + g.offset, (size_t)g.n * 16, cudaMemcpyDeviceToHost, pipe.lane[l]));
+			++t.chunks;
 			++chunk;
 		}
-		const int used = chunk < (unsigned)HostPipeline::kLanes ? (int)chunk : HostPipeline::kLanes;
-		for (int l = 0; l < used; ++l) {
-			RACC_CUDA_CHECK(cudaEventRecord(pipe.done[l], pipe.lane[l]));
-			RACC_CUDA_CHECK(cudaStreamWaitEvent(stream, pipe.done[l], 0));
+		for (Target& t : targets) {
+			const int used = t.chunks < (unsigned)HostPipeline::kLanes ? (int)t.chunks : HostPipeline::kLanes;
+			if (targets.size() > 1) RACC_CUDA_CHECK(cudaSetDevice(t.dev->ordinal));
+			for (int l = 0; l < used; ++l)
+				RACC_CUDA_CHECK(cudaEventRecord(t.pipe->done[l], t.pipe->lane[l]));
+		}
+		RACC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
+		for (Target& t : targets) {
+			const int used = t.chunks < (unsigned)HostPipeline::kLanes ? (int)t.chunks : HostPipeline::kLanes;
+			for (int l = 0; l < used; ++l)
+				RACC_CUDA_CHECK(cudaStreamWaitEvent(stream, t.pipe->done[l], 0));
 		}
 	}
-	g_launches.fetch_add((uint64_t)launches);
+	countLaunches(launches);
 	return 0;
 }
 
-} // namespace
+} // namespace racc_b200
+
+extern "C" {
 
 int racc_cuda_trace(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams, void* cuda_stream) {
 	return traceImpl(scene, env, streams, nstreams, cuda_stream, nullptr, false);
@@ -771,10 +878,15 @@ int racc_cuda_trace_counted(racc_cuda_scene* scene, racc_cuda_env* env, const ra
 	return traceImpl(scene, env, streams, nstreams, cuda_stream, device_counters, detail != 0);
 }
 
+int racc_cuda_frame_reduce(racc_cuda_counters* totals, void* cuda_stream) {
+	if (!currentDevice()) return -1;
+	return commFrameReduce(totals, static_cast<cudaStream_t>(cuda_stream));
+}
+
 // Pinned host memory for ray streams (replaces the 4 KiB-aligned slab of RayAccelerator.cpp:532-568
 // that the reference wraps in CL_MEM_USE_HOST_PTR buffers, :643-644).
 void* racc_cuda_host_alloc(size_t bytes) {
-	if (ensureInit()) return nullptr;
+	if (!currentDevice()) return nullptr;
 	void* p = nullptr;
 	cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
 	if (e != cudaSuccess) {
@@ -790,7 +902,7 @@ void racc_cuda_host_free(void* p) {
 
 // One CUDA stream per submitter (replaces the per-thread cl_command_queue, RayAccelerator.cpp:711-717).
 void* racc_cuda_stream_create(void) {
-	if (ensureInit()) return nullptr;
+	if (!currentDevice()) return nullptr;
 	cudaStream_t s = nullptr;
 	cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
 	if (e != cudaSuccess) {
@@ -805,20 +917,29 @@ void racc_cuda_stream_destroy(void* cuda_stream) {
 }
 
 int racc_cuda_sync(void* cuda_stream) {
-	if (ensureInit()) return -1;
+	if (!currentDevice()) return -1;
 	RACC_CUDA_CHECK(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
 	return 0;
+}
+
+void racc_cuda_thread_release(void) {
+	int before = -1;
+	cudaGetDevice(&before);
+	for (auto& p : t_pipelines) p->release();
+	t_pipelines.clear();
+	releaseRenderScratch();
+	if (before >= 0) cudaSetDevice(before);
 }
 
 int racc_cuda_generate_primary(const racc_cuda_camera* camera, uint32_t width, uint32_t height, uint32_t spp,
                                uint32_t jitter_seed, void* device_rays, void* cuda_stream) {
 	if (!camera || !device_rays) return fail("racc_cuda_generate_primary: null argument");
-	if (ensureInit()) return -1;
+	if (!currentDevice()) return -1;
 	if ((uint64_t)width * height * spp > 0x7fffffffull) return fail("racc_cuda_generate_primary: too many rays");
 	int launches = 0;
 	RACC_CUDA_CHECK(launchGeneratePrimary(camera->origin, width, height, spp, jitter_seed, static_cast<DevRay*>(device_rays),
 	                                      static_cast<cudaStream_t>(cuda_stream), &launches));
-	g_launches.fetch_add((uint64_t)launches);
+	countLaunches(launches);
 	return 0;
 }
 
@@ -826,338 +947,24 @@ int racc_cuda_generate_bounce(const racc_cuda_scene* scene_, const void* device_
                               uint32_t seed, void* device_out_rays, uint32_t* device_out_count, void* cuda_stream) {
 	racc_cuda_scene* s = const_cast<racc_cuda_scene*>(scene_);
 	if (!s || !device_rays || !device_results || !device_out_rays || !device_out_count) return fail("racc_cuda_generate_bounce: null argument");
-	if (!s->dVerts) return fail("racc_cuda_generate_bounce: scene was created from images and has no vertex data");
-	if (ensureInit()) return -1;
+	DeviceState* dev = currentDevice();
+	if (!dev) return -1;
+	SceneReplica* r = s->on(dev->ordinal);
+	if (!r) return fail("racc_cuda_generate_bounce: the scene has no copy on CUDA device %d", dev->ordinal);
+	if (!r->dVerts) return fail("racc_cuda_generate_bounce: scene was created from images and has no vertex data");
 	const size_t words = bounceScratchWords(count);
-	if (words > s->bounceScratchWords) {
+	if (words > r->bounceScratchWords) {
 		RACC_CUDA_CHECK(cudaDeviceSynchronize());
-		cudaFree(s->dBounceScratch);
-		s->dBounceScratch = nullptr;
-		RACC_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->dBounceScratch), words * sizeof(uint32_t)));
-		s->bounceScratchWords = words;
+		cudaFree(r->dBounceScratch);
+		r->dBounceScratch = nullptr;
+		RACC_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&r->dBounceScratch), words * sizeof(uint32_t)));
+		r->bounceScratchWords = words;
 	}
 	int launches = 0;
-	RACC_CUDA_CHECK(launchGenerateBounce(s->dVerts, s->dIndices, static_cast<const DevRay*>(device_rays),
+	RACC_CUDA_CHECK(launchGenerateBounce(r->dVerts, r->dIndices, static_cast<const DevRay*>(device_rays),
 	                                     static_cast<const float4*>(device_results), count, seed, static_cast<DevRay*>(device_out_rays),
-	                                     device_out_count, s->dBounceScratch, static_cast<cudaStream_t>(cuda_stream), &launches));
-	g_launches.fetch_add((uint64_t)launches);
-	return 0;
-}
-
-// ---- device-side wavefront path tracer (pathtrace.cu) ----
-
-racc_cuda_shading* racc_cuda_shading_create(const racc_cuda_shading_desc* d) {
-	if (!d || !d->normals4 || !d->triangle_normals4 || !d->triangle_materials || !d->materials_ke4) {
-		fail("racc_cuda_shading_create: null input");
-		return nullptr;
-	}
-	if (!d->material_count) { fail("racc_cuda_shading_create: no materials"); return nullptr; }
-	if (ensureInit()) return nullptr;
-	racc_cuda_shading* sh = new racc_cuda_shading();
-	sh->vertexCount = d->vertex_count;
-	sh->triangleCount = d->triangle_count;
-	sh->materialCount = d->material_count;
-	cudaError_t e;
-#define UP(dst, src, bytes)                                                                                 \
-	if ((e = cudaMalloc(reinterpret_cast<void**>(&dst), (bytes) != 0 ? (bytes) : 16)) != cudaSuccess ||     \
-	    (e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {                         \
-		fail("racc_cuda_shading_create: upload failed: %s", cudaGetErrorString(e));                         \
-		racc_cuda_shading_destroy(sh);                                                                      \
-		return nullptr;                                                                                     \
-	}
-	UP(sh->dNormals, d->normals4, (size_t)d->vertex_count * 16)
-	UP(sh->dTriangleNormals, d->triangle_normals4, (size_t)d->triangle_count * 16)
-	UP(sh->dTriangleMaterials, d->triangle_materials, (size_t)d->triangle_count * 2)
-	UP(sh->dMaterials, d->materials_ke4, (size_t)d->material_count * 16)
-#undef UP
-	return sh;
-}
-
-void racc_cuda_shading_destroy(racc_cuda_shading* sh) {
-	if (!sh) return;
-	cudaFree(sh->dNormals);
-	cudaFree(sh->dTriangleNormals);
-	cudaFree(sh->dTriangleMaterials);
-	cudaFree(sh->dMaterials);
-	delete sh;
-}
-
-int racc_cuda_path_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_shading* sh, const racc_cuda_camera* camera,
-                         const racc_cuda_path_desc* d, float* framebuffer4, uint64_t* wave_rays, void* cuda_stream) {
-	if (!s || !sh || !camera || !d || !framebuffer4) return fail("racc_cuda_path_trace: null argument");
-	if (!s->dIndices) return fail("racc_cuda_path_trace: scene was created from images and has no index data");
-	if (sh->triangleCount != s->triangleCount || sh->vertexCount < s->vertexCount)
-		return fail("racc_cuda_path_trace: shading data (%u triangles, %u vertices) does not match the scene (%u, %u)", sh->triangleCount,
-		            sh->vertexCount, s->triangleCount, s->vertexCount);
-	if (d->max_depth > 62) return fail("racc_cuda_path_trace: max_depth %u > 62", d->max_depth);
-	if (ensureInit()) return -1;
-	const uint64_t pixels = (uint64_t)d->width * d->height;
-	if (!pixels || !d->spp) return 0;
-	if (pixels > (1ull << 28)) return fail("racc_cuda_path_trace: viewport too large");
-	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-	// paths per batch: whole samples, about 32 M paths (128 B of device memory each, 4 GB) unless the caller says otherwise:
-	// the deeper waves of a batch are a tenth of its size, and a persistent launch over < 1 M rays is mostly tail
-	// (1920x1080, 16 spp: 4.4 / 5.8 / 6.3 Gray/s at 2 M / 8 M / 33 M paths per batch, profiles/r01_render_device.md)
-	uint32_t batchSpp = d->batch_spp ? d->batch_spp : (uint32_t)((32ull << 20) / pixels);
-	if (batchSpp < 1) batchSpp = 1;
-	if (batchSpp > d->spp) batchSpp = d->spp;
-	if (pixels * batchSpp > 0x7fffffffull) return fail("racc_cuda_path_trace: batch of %u samples is too large", batchSpp);
-	const size_t paths = (size_t)pixels * batchSpp;
-	const bool hostFb = (d->flags & RACC_CUDA_FRAMEBUFFER_HOST) != 0;
-
-	// Lanes: a batch is cut into contiguous path ranges that advance bounce by bounce on their own streams. While the host
-	// waits for one lane's wave size, the other lane's launches are queued, and the tail of a traversal launch (few long
-	// paths left, most SMs idle) is filled by the other lane's kernels.
-	PathLanes& lanes = t_pathLanes;
-	if (lanes.init()) return -1;
-	const int nlanes = paths >= (size_t)lanes.count * 65536 ? lanes.count : 1;
-	const size_t lanePaths = (paths + nlanes - 1) / nlanes;
-
-	struct Buffers {
-		cudaStream_t stream;
-		void* p[8] = {};
-		bool joined = false; // every lane's work is ordered before `stream`; false on an error return
-		~Buffers() {
-			if (!joined) cudaDeviceSynchronize(); // lanes may still be using the buffers
-			for (void* q : p) if (q) cudaFreeAsync(q, stream);
-		}
-	} buf;
-	buf.stream = stream;
-	const size_t sizes[8] = {lanePaths * nlanes * 32, lanePaths * nlanes * 32, lanePaths * nlanes * 16, lanePaths * nlanes * 16,
-	                         lanePaths * nlanes * 16, paths * 16, (size_t)PathLanes::kMax * 64 * sizeof(uint32_t), hostFb ? (size_t)pixels * 16 : 0};
-	for (int k = 0; k < 8; ++k)
-		if (sizes[k]) RACC_CUDA_CHECK(cudaMallocAsync(&buf.p[k], sizes[k], stream));
-	float4* radiance = static_cast<float4*>(buf.p[5]);
-	uint32_t* counts = static_cast<uint32_t*>(buf.p[6]);
-	float4* fb = hostFb ? static_cast<float4*>(buf.p[7]) : reinterpret_cast<float4*>(framebuffer4);
-	if (hostFb) RACC_CUDA_CHECK(cudaMemcpyAsync(fb, framebuffer4, (size_t)pixels * 16, cudaMemcpyHostToDevice, stream));
-
-	struct Lane {
-		DevRay* rays[2];
-		float4* states[2];
-		float4* results;
-		uint32_t* counts; // device, one per depth
-		cudaStream_t stream;
-		uint32_t count, depth;
-		int cur;
-		bool busy;
-	} lane[PathLanes::kMax];
-	for (int l = 0; l < nlanes; ++l) {
-		lane[l].rays[0] = static_cast<DevRay*>(buf.p[0]) + (size_t)l * lanePaths;
-		lane[l].rays[1] = static_cast<DevRay*>(buf.p[1]) + (size_t)l * lanePaths;
-		lane[l].states[0] = static_cast<float4*>(buf.p[2]) + (size_t)l * lanePaths;
-		lane[l].states[1] = static_cast<float4*>(buf.p[3]) + (size_t)l * lanePaths;
-		lane[l].results = static_cast<float4*>(buf.p[4]) + (size_t)l * lanePaths;
-		lane[l].counts = counts + (size_t)l * 64;
-		lane[l].stream = nlanes > 1 ? lanes.stream[l] : stream;
-	}
-
-	int launches = 0;
-	for (uint32_t done = 0; done < d->spp; done += batchSpp) {
-		const uint32_t spp = d->spp - done < batchSpp ? d->spp - done : batchSpp;
-		const uint32_t sampleBase = d->sample_base + done;
-		const uint32_t batchPaths = (uint32_t)(pixels * spp);
-		RACC_CUDA_CHECK(cudaMemsetAsync(radiance, 0, (size_t)batchPaths * 16, stream));
-		RACC_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)PathLanes::kMax * 64 * sizeof(uint32_t), stream));
-		if (nlanes > 1) {
-			RACC_CUDA_CHECK(cudaEventRecord(lanes.fork, stream));
-			for (int l = 0; l < nlanes; ++l) RACC_CUDA_CHECK(cudaStreamWaitEvent(lane[l].stream, lanes.fork, 0));
-		}
-		// one wave of one lane: trace, shade + compact, and (unless it was the last bounce) ask for the next wave's size
-		auto enqueue = [&](Lane& ln, int l) -> int {
-			if (wave_rays) wave_rays[ln.depth] += ln.count;
-			racc_cuda_stream_desc sd{};
-			sd.rays = ln.rays[ln.cur];
-			sd.results = ln.results;
-			sd.count = ln.count;
-			sd.flags = 0;
-			if (traceImpl(s, env, &sd, 1, ln.stream, nullptr, false)) return -1;
-			PathShadeParams p{};
-			p.rays = ln.rays[ln.cur]; p.results = ln.results; p.states = ln.states[ln.cur]; p.count = ln.count;
-			p.depth = ln.depth; p.maxDepth = d->max_depth; p.seed = d->seed; p.pixels = (uint32_t)pixels; p.sampleBase = sampleBase;
-			p.indices = s->dIndices; p.normals = sh->dNormals; p.triangleNormals = sh->dTriangleNormals;
-			p.triangleMaterials = sh->dTriangleMaterials; p.materials = sh->dMaterials;
-			p.triangleCount = sh->triangleCount; p.materialCount = sh->materialCount;
-			p.outRays = ln.rays[ln.cur ^ 1]; p.outStates = ln.states[ln.cur ^ 1]; p.outCount = ln.counts + ln.depth; p.radiance = radiance;
-			RACC_CUDA_CHECK(launchPathShade(p, ln.stream, &launches));
-			if (ln.depth == d->max_depth) { ln.busy = false; return 0; } // nothing is extended past the last bounce
-			RACC_CUDA_CHECK(cudaMemcpyAsync(lanes.hostCounts + l, ln.counts + ln.depth, sizeof(uint32_t), cudaMemcpyDeviceToHost, ln.stream));
-			return 0;
-		};
-		int active = 0;
-		for (int l = 0; l < nlanes; ++l) {
-			Lane& ln = lane[l];
-			const size_t first = (size_t)l * lanePaths;
-			ln.count = first < batchPaths ? (uint32_t)(batchPaths - first < lanePaths ? batchPaths - first : lanePaths) : 0;
-			ln.depth = 0;
-			ln.cur = 0;
-			ln.busy = ln.count != 0;
-			if (!ln.busy) continue;
-			RACC_CUDA_CHECK(launchPathPrimary(camera->origin, d->width, d->height, sampleBase, (uint32_t)first, ln.count, d->seed, ln.rays[0],
-			                                  ln.states[0], ln.stream, &launches));
-			if (enqueue(ln, l)) return -1;
-			active += ln.busy;
-		}
-		// round robin: the size of a lane's next wave decides its launch -- the one host round trip per bounce and lane
-		for (int l = 0; active; l = (l + 1) % nlanes) {
-			Lane& ln = lane[l];
-			if (!ln.busy) continue;
-			RACC_CUDA_CHECK(cudaStreamSynchronize(ln.stream));
-			ln.count = lanes.hostCounts[l];
-			ln.depth += 1;
-			ln.cur ^= 1;
-			if (!ln.count) { ln.busy = false; --active; continue; }
-			if (enqueue(ln, l)) return -1;
-			if (!ln.busy) --active;
-		}
-		if (nlanes > 1)
-			for (int l = 0; l < nlanes; ++l) {
-				RACC_CUDA_CHECK(cudaEventRecord(lanes.done[l], lane[l].stream));
-				RACC_CUDA_CHECK(cudaStreamWaitEvent(stream, lanes.done[l], 0));
-			}
-		RACC_CUDA_CHECK(launchPathAccumulate(radiance, (uint32_t)pixels, spp, fb, stream, &launches));
-	}
-	buf.joined = true;
-	g_launches.fetch_add((uint64_t)launches);
-	if (hostFb) {
-		RACC_CUDA_CHECK(cudaMemcpyAsync(framebuffer4, fb, (size_t)pixels * 16, cudaMemcpyDeviceToHost, stream));
-		RACC_CUDA_CHECK(cudaStreamSynchronize(stream));
-	}
-	return 0;
-}
-
-// The reference's Whitted renderer with the shading on the device (whitted.cu). Same descriptor and framebuffer
-// meaning as racc_cuda_path_trace; desc->batch_spp 0 = about 4 M primary rays per batch (a hit spawns up to two rays,
-// so waves grow before the 0.3-per-bounce weight ends them).
-int racc_cuda_whitted_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_shading* sh, const racc_cuda_camera* camera,
-                            const racc_cuda_path_desc* d, float* framebuffer4, uint64_t* wave_rays, void* cuda_stream) {
-	if (!s || !sh || !camera || !d || !framebuffer4) return fail("racc_cuda_whitted_trace: null argument");
-	if (!s->dIndices) return fail("racc_cuda_whitted_trace: scene was created from images and has no index data");
-	if (sh->triangleCount != s->triangleCount || sh->vertexCount < s->vertexCount)
-		return fail("racc_cuda_whitted_trace: shading data (%u triangles, %u vertices) does not match the scene (%u, %u)", sh->triangleCount,
-		            sh->vertexCount, s->triangleCount, s->vertexCount);
-	if (d->max_depth > 62) return fail("racc_cuda_whitted_trace: max_depth %u > 62", d->max_depth);
-	if (ensureInit()) return -1;
-	const uint64_t pixels = (uint64_t)d->width * d->height;
-	if (!pixels || !d->spp) return 0;
-	if (pixels > (1ull << 24)) return fail("racc_cuda_whitted_trace: viewport too large");
-	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-	uint32_t batchSpp = d->batch_spp ? d->batch_spp : (uint32_t)((4ull << 20) / pixels);
-	if (batchSpp < 1) batchSpp = 1;
-	if (batchSpp > d->spp) batchSpp = d->spp;
-	if (pixels * batchSpp > (1ull << 28)) return fail("racc_cuda_whitted_trace: batch of %u samples is too large", batchSpp);
-	const bool hostFb = (d->flags & RACC_CUDA_FRAMEBUFFER_HOST) != 0;
-
-	// stream-ordered scratch; everything still held is released on any return
-	struct Scratch {
-		cudaStream_t stream;
-		std::vector<void*> held;
-		int get(void** p, size_t bytes) {
-			RACC_CUDA_CHECK(cudaMallocAsync(p, bytes ? bytes : 16, stream));
-			held.push_back(*p);
-			return 0;
-		}
-		void release(void* p) {
-			for (size_t k = 0; k < held.size(); ++k)
-				if (held[k] == p) { held.erase(held.begin() + (long)k); cudaFreeAsync(p, stream); return; }
-		}
-		~Scratch() { for (void* q : held) cudaFreeAsync(q, stream); }
-	} scratch;
-	scratch.stream = stream;
-
-	unsigned long long* acc = nullptr;
-	uint32_t* counts = nullptr;
-	float4* fb = reinterpret_cast<float4*>(framebuffer4);
-	if (scratch.get(reinterpret_cast<void**>(&acc), (size_t)pixels * 3 * sizeof(unsigned long long))) return -1;
-	if (scratch.get(reinterpret_cast<void**>(&counts), 64 * sizeof(uint32_t))) return -1;
-	if (hostFb) {
-		if (scratch.get(reinterpret_cast<void**>(&fb), (size_t)pixels * 16)) return -1;
-		RACC_CUDA_CHECK(cudaMemcpyAsync(fb, framebuffer4, (size_t)pixels * 16, cudaMemcpyHostToDevice, stream));
-	}
-	RACC_CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)pixels * 3 * sizeof(unsigned long long), stream));
-
-	// wave buffers: stream-ordered allocations per wave (default) or the calling thread's grow-only arena
-	const bool useArena = g_tuning.whittedArena != 0;
-	WhittedArena& arena = t_whittedArena;
-	if (useArena && arena.begin(stream)) return -1;
-	int cur = 0; // arena: which half of the ping-pong holds the current wave
-	enum { kRays = 0, kStates = 2, kResults = 4 };
-
-	int launches = 0;
-	for (uint32_t done = 0; done < d->spp; done += batchSpp) {
-		const uint32_t spp = d->spp - done < batchSpp ? d->spp - done : batchSpp;
-		uint32_t count = (uint32_t)(pixels * spp);
-		RACC_CUDA_CHECK(cudaMemsetAsync(counts, 0, 64 * sizeof(uint32_t), stream));
-		DevRay* rays = nullptr;
-		float4* states = nullptr;
-		if (useArena) {
-			if (arena.ensure(kRays + cur, (size_t)count * 32, stream) || arena.ensure(kStates + cur, (size_t)count * 16, stream)) return -1;
-			rays = static_cast<DevRay*>(arena.p[kRays + cur]);
-			states = static_cast<float4*>(arena.p[kStates + cur]);
-		}
-		else if (scratch.get(reinterpret_cast<void**>(&rays), (size_t)count * 32) || scratch.get(reinterpret_cast<void**>(&states), (size_t)count * 16)) return -1;
-		RACC_CUDA_CHECK(launchWhittedPrimary(camera->origin, d->width, d->height, d->sample_base + done, 0, count, d->seed, rays, states, stream, &launches));
-		for (uint32_t depth = 0; depth <= d->max_depth && count; ++depth) {
-			if (wave_rays) wave_rays[depth] += count;
-			if (count > 0x3fffffffu) return fail("racc_cuda_whitted_trace: a wave of %u rays is too large; lower batch_spp", count);
-			float4* results = nullptr;
-			DevRay* nextRays = nullptr;
-			float4* nextStates = nullptr;
-			const bool last = depth == d->max_depth; // nothing is extended past the last bounce
-			if (useArena) {
-				if (arena.ensure(kResults, (size_t)count * 16, stream)) return -1;
-				results = static_cast<float4*>(arena.p[kResults]);
-				if (!last) {
-					if (arena.ensure(kRays + (cur ^ 1), (size_t)count * 2 * 32, stream) || arena.ensure(kStates + (cur ^ 1), (size_t)count * 2 * 16, stream)) return -1;
-					nextRays = static_cast<DevRay*>(arena.p[kRays + (cur ^ 1)]);
-					nextStates = static_cast<float4*>(arena.p[kStates + (cur ^ 1)]);
-				}
-			}
-			else {
-				if (scratch.get(reinterpret_cast<void**>(&results), (size_t)count * 16)) return -1;
-				if (!last && (scratch.get(reinterpret_cast<void**>(&nextRays), (size_t)count * 2 * 32) ||
-				              scratch.get(reinterpret_cast<void**>(&nextStates), (size_t)count * 2 * 16))) return -1;
-			}
-			racc_cuda_stream_desc sd{};
-			sd.rays = rays;
-			sd.results = results;
-			sd.count = count;
-			sd.flags = 0;
-			if (traceImpl(s, env, &sd, 1, stream, nullptr, false)) return -1;
-			WhittedShadeParams p{};
-			p.rays = rays; p.results = results; p.states = states; p.count = count; p.depth = depth; p.maxDepth = d->max_depth;
-			p.indices = s->dIndices; p.normals = sh->dNormals; p.triangleNormals = sh->dTriangleNormals; p.triangleCount = sh->triangleCount;
-			p.outRays = nextRays; p.outStates = nextStates; p.outCount = counts + depth; p.accumulators = acc;
-			p.combine = g_tuning.whittedCombine != 0;
-			RACC_CUDA_CHECK(launchWhittedShade(p, stream, &launches));
-			uint32_t next = 0;
-			if (!last) {
-				// the size of the next wave decides its launch and its buffers: the one host round trip per bounce
-				RACC_CUDA_CHECK(cudaMemcpyAsync(&next, counts + depth, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-				RACC_CUDA_CHECK(cudaStreamSynchronize(stream));
-			}
-			if (useArena) cur ^= 1;
-			else {
-				scratch.release(results);
-				scratch.release(rays);
-				scratch.release(states);
-			}
-			rays = nextRays;
-			states = nextStates;
-			count = next;
-		}
-		if (!useArena) {
-			if (rays) scratch.release(rays);
-			if (states) scratch.release(states);
-		}
-	}
-	if (useArena && arena.end(stream)) return -1;
-	RACC_CUDA_CHECK(launchWhittedFinish(acc, (uint32_t)pixels, fb, stream, &launches));
-	g_launches.fetch_add((uint64_t)launches);
-	if (hostFb) {
-		RACC_CUDA_CHECK(cudaMemcpyAsync(framebuffer4, fb, (size_t)pixels * 16, cudaMemcpyDeviceToHost, stream));
-		RACC_CUDA_CHECK(cudaStreamSynchronize(stream));
-	}
+	                                     device_out_count, r->dBounceScratch, static_cast<cudaStream_t>(cuda_stream), &launches));
+	countLaunches(launches);
 	return 0;
 }
 

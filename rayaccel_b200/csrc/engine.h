@@ -36,6 +36,8 @@ struct TraceParams {
 	const float4* tpairs;     //   4 x float4 per triangle pair
 	const uint32_t* perm;     // optional visiting order (launch-wide ray indices), null = arrival order
 	const float4* envPairs;   // light probe as horizontally adjacent texel PAIRS: (envWidth+1) x envHeight x 32 B, or null
+	const uint32_t* totalPtr; // non-null: the number of rays is read from DEVICE memory at kernel start (<= total, which then
+	                          // only sizes the grid); lets a wavefront renderer enqueue wave k+1 before wave k's size is known
 };
 
 // Tunables (racc_cuda_set_variant / RACC_B200_* environment variables), see DESIGN.md section 5.
@@ -65,12 +67,16 @@ struct Tuning {
 	                         // itself (one launch, no staging copies), 0 = staged H2D / trace / D2H pipeline
 	int buildDevice = 3;     // scene build (same images either way): 0 host threads; 1 SAH tree on the GPU, packing on the
 	                         // host; 2 everything on the GPU (bvh_build.cu); 3 auto = 2 from kAutoDeviceBuildTriangles up
-	int hostTaper = 0;       // staged HOST streams: > 0 = the last chunks of a call shrink geometrically down to this many K rays,
-	                         // so that the traversal and D2H copy left exposed after the last H2D copy are short (written after
-	                         // the round's last GPU call: off until measured)
-	// device-side Whitted renderer (whitted.cu); both written after the round's last GPU call, hence off until measured
-	int whittedArena = 0;    // 1 = wave buffers kept and grown per calling thread instead of stream-ordered allocations per wave
-	int whittedCombine = 0;  // 1 = a warp sums its rays' fixed-point radiance per pixel run before the atomics (same bits)
+	int hostTaper = 256;     // staged HOST streams: > 0 = the last chunks of a call shrink geometrically down to this many K rays,
+	                         // so that the traversal and D2H copy left exposed after the last H2D copy are short; measured on the
+	                         // bench batch: e2e 1498 (off) / 1582 (64 K) / 1596 (256 K) Mrays/s (profiles/r02_call1_open_questions.md)
+	// device-side Whitted renderer (whitted.cu)
+	int whittedArena = 1;    // 1 = wave buffers kept and grown per calling thread instead of stream-ordered allocations per wave:
+	                         // 1920x1080x4spp depth 8 in 11.2 ms instead of 24-31 ms (same file)
+	int whittedCombine = 0;  // 1 = a warp sums its rays' fixed-point radiance per pixel run before the atomics (same bits);
+	                         // measured neutral with the arena (11.13 vs 11.16 ms) and erratic without it: stays off
+	int pathSync = 0;        // racc_cuda_path_trace: 1 = the host waits for every wave's size (round 1's scheme); 0 = wave sizes stay on
+	                         // the device and the whole batch is enqueued without a host round trip
 };
 
 // counterMode: 0 none, 1 rays+hits only, 2 rays, hits, inner-node and pair visits
@@ -113,6 +119,8 @@ struct PathShadeParams {
 	const float4* results;
 	const float4* states;
 	uint32_t count;
+	const uint32_t* countPtr; // non-null: the wave's size is read from device memory (<= count, which then sizes the grid)
+	uint32_t gridLimit;       // 0 = one CTA per 256 rays of `count`; else at most this many CTAs, each looping over tiles
 	uint32_t depth, maxDepth; // bounce number of this wave; hits are extended while depth < maxDepth
 	uint32_t seed, pixels, sampleBase;
 	const uint32_t* indices;

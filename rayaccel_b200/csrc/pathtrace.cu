@@ -108,6 +108,7 @@ struct ShadeArgs {
 	const float4* results;
 	const float4* states;    // weight rgb, path index (within the batch) in .w
 	uint32_t count;
+	const uint32_t* countPtr; // non-null: the wave's size lives on the device (<= count); see TraceParams::totalPtr
 	uint32_t depth, maxDepth; // this wave's bounce number; paths are extended while depth < maxDepth
 	uint32_t seed, pixels, sampleBase;
 	const uint32_t* indices;  // scene data of Renderer/SceneData.h
@@ -125,11 +126,15 @@ struct ShadeArgs {
 __global__ void __launch_bounds__(kShadeBlock) pathShadeKernel(const ShadeArgs a) {
 	__shared__ uint32_t warpCount[kShadeBlock / 32];
 	__shared__ uint32_t ctaBase;
-	const uint32_t i = blockIdx.x * kShadeBlock + threadIdx.x;
+	// tiles of kShadeBlock rays dealt round-robin to the CTAs: the grid is sized on the host from an upper bound of the
+	// wave's size, the size itself may still be on the device
+	const uint32_t count = a.countPtr ? min(__ldg(a.countPtr), a.count) : a.count;
+	for (uint32_t tile = blockIdx.x; (size_t)tile * kShadeBlock < count; tile += gridDim.x) {
+	const uint32_t i = tile * kShadeBlock + threadIdx.x;
 	bool go = false;
 	DevRay next;
 	float4 state = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-	if (i < a.count) {
+	if (i < count) {
 		const float4 res = a.results[i];
 		state = a.states[i];
 		const uint32_t tri = __float_as_uint(res.x);
@@ -204,6 +209,8 @@ __global__ void __launch_bounds__(kShadeBlock) pathShadeKernel(const ShadeArgs a
 		a.outRays[slot] = next;
 		a.outStates[slot] = state;
 	}
+	__syncthreads(); // warpCount / ctaBase are reused by the next tile
+	}
 }
 
 // framebuffer[p] += radiance of sample 0, 1, ... of the batch, in that order (PathTracingRenderer.cpp:540-543 adds one
@@ -233,12 +240,14 @@ cudaError_t launchPathPrimary(const float* camera12, uint32_t width, uint32_t he
 cudaError_t launchPathShade(const PathShadeParams& p, cudaStream_t stream, int* launches) {
 	if (!p.count) return cudaSuccess;
 	ShadeArgs a;
-	a.rays = p.rays; a.results = p.results; a.states = p.states; a.count = p.count;
+	a.rays = p.rays; a.results = p.results; a.states = p.states; a.count = p.count; a.countPtr = p.countPtr;
 	a.depth = p.depth; a.maxDepth = p.maxDepth; a.seed = p.seed; a.pixels = p.pixels; a.sampleBase = p.sampleBase;
 	a.indices = p.indices; a.normals = p.normals; a.triangleNormals = p.triangleNormals; a.triangleMaterials = p.triangleMaterials;
 	a.materials = p.materials; a.triangleCount = p.triangleCount; a.materialCount = p.materialCount;
 	a.outRays = p.outRays; a.outStates = p.outStates; a.outCount = p.outCount; a.radiance = p.radiance;
-	pathShadeKernel<<<(p.count + kShadeBlock - 1) / kShadeBlock, kShadeBlock, 0, stream>>>(a);
+	uint32_t grid = (p.count + kShadeBlock - 1) / kShadeBlock;
+	if (p.gridLimit && grid > p.gridLimit) grid = p.gridLimit;
+	pathShadeKernel<<<grid, kShadeBlock, 0, stream>>>(a);
 	if (launches) *launches += 1;
 	return cudaGetLastError();
 }

@@ -18,6 +18,10 @@
 //     threads idle, nothing being tested), instead of whenever a submitter is idle (:360-363).
 //   * there is no CPU tester (:158-244): no CpuTestJob slots, no cpuThreadsTesting.
 //   * stream memory is one pinned slab (racc_cuda_host_alloc) instead of CL_MEM_USE_HOST_PTR.
+//   * a context may own SEVERAL B200s (racc::cudaDevices): scene and environment are replicated on each, every device
+//     gets its own `gpuSubmissionThreads` submitters (one CUDA stream each), ready streams are dealt over the devices
+//     that have an idle submitter, and Stats.raysTraced of a frame is the NCCL sum of the devices' frame records
+//     (racc_cuda_frame_reduce) -- the "per-frame hit reduction". No ray, node or result crosses between GPUs.
 #include "../../include/RayAccelerator.h"
 #include "../../include/racc_b200.h"
 
@@ -43,7 +47,8 @@ struct Environment {
 
 struct Context {
 	Configuration configuration{};
-	int device = 0;
+	std::vector<int> devices;      // CUDA ordinals this context drives; scenes are replicated on all of them
+	uint32_t idleSubmitters = 0;   // submitters asleep on `work`
 
 	// stream pool
 	std::vector<RayStream> streams;
@@ -208,10 +213,17 @@ void callbackThread(Context* c, unsigned thread) {
 	}
 }
 
-// The device boundary (replaces gpuWorkerThread, RayAccelerator.cpp:335-414).
-void submitterThread(Context* c) {
+// How many of `ready` full streams one submitter takes: with several devices a burst is split so that every device
+// with a sleeping submitter gets a share, but never into pieces too small to fill 148 SMs (four streams ~ 200 K rays).
+size_t submitterShare(const Context* c, size_t ready) {
+	const size_t others = std::min<size_t>(c->idleSubmitters, c->devices.size() - 1);
+	const size_t share = std::max<size_t>(4, (ready + others) / (others + 1));
+	return std::min(ready, share);
+}
+
+// The device boundary (replaces gpuWorkerThread, RayAccelerator.cpp:335-414). One or more per device of the context.
+void submitterThread(Context* c, int device) {
 	setFlushToZero();
-	int device = c->device;
 	if (racc_cuda_init(&device, 1)) {
 		fprintf(stderr, "RayAccelerator: %s\n", racc_cuda_last_error());
 		abort();
@@ -228,13 +240,18 @@ void submitterThread(Context* c) {
 	while (!c->quit) {
 		batch.clear();
 		if (!c->ready.empty()) {
-			batch.swap(c->ready); // every full stream goes into one aggregated launch
+			// full streams go into one aggregated launch; with several devices, this one's share of them
+			const size_t take = c->devices.size() > 1 ? submitterShare(c, c->ready.size()) : c->ready.size();
+			batch.assign(c->ready.end() - (std::ptrdiff_t)take, c->ready.end());
+			c->ready.resize(c->ready.size() - take);
 		}
 		else if (!c->partial.empty() && c->busyCallbacks == 0 && c->tested.empty() && c->launchesInFlight == 0) {
 			batch.swap(c->partial); // nothing else can make progress: flush the stragglers
 		}
 		else {
+			++c->idleSubmitters;
 			c->work.wait(lock);
+			--c->idleSubmitters;
 			continue;
 		}
 
@@ -264,9 +281,20 @@ void submitterThread(Context* c) {
 	}
 	lock.unlock();
 	racc_cuda_stream_destroy(cudaStream);
+	racc_cuda_thread_release(); // this thread's staging pipeline: three lanes of device buffers (clReleaseCommandQueue, :774-779)
 }
 
-int deviceOf(cl_context token) { return (int)(reinterpret_cast<uintptr_t>(token) - 1); }
+// racc::cudaDevice / racc::cudaDevices tokens: bits 0-7 first ordinal + 1, bits 8-15 device count (0 = one)
+std::vector<int> devicesOf(cl_context token) {
+	const uintptr_t v = reinterpret_cast<uintptr_t>(token);
+	const int first = (int)(v & 0xff) - 1;
+	const int count = (int)((v >> 8) & 0xff);
+	std::vector<int> out;
+	for (int k = 0; k < (count ? count : 1); ++k) out.push_back(first + k);
+	return out;
+}
+
+int bindAll(const Context* c) { return racc_cuda_init(c->devices.data(), (int)c->devices.size()); }
 
 } // namespace
 
@@ -306,13 +334,14 @@ racc::Context* racc::createContext(Configuration cfg) {
 		fprintf(stderr, "RayAccelerator: invalid configuration.\n");
 		return nullptr;
 	}
-	int device = deviceOf(cfg.gpuContext);
-	const int devices = racc_cuda_device_count();
-	if (devices <= 0 || device < 0 || device >= devices) {
-		fprintf(stderr, "RayAccelerator: CUDA device %d is not available (%s).\n", device, devices < 0 ? racc_cuda_last_error() : "no such device");
+	const std::vector<int> devices = devicesOf(cfg.gpuContext);
+	const int available = racc_cuda_device_count();
+	if (available <= 0 || devices.front() < 0 || devices.back() >= available) {
+		fprintf(stderr, "RayAccelerator: CUDA device %d is not available (%s).\n", devices.front() < 0 ? devices.front() : devices.back(),
+		        available < 0 ? racc_cuda_last_error() : "no such device");
 		return nullptr;
 	}
-	if (racc_cuda_init(&device, 1)) {
+	if (racc_cuda_init(devices.data(), (int)devices.size())) {
 		fprintf(stderr, "RayAccelerator: %s\n", racc_cuda_last_error());
 		return nullptr;
 	}
@@ -321,7 +350,7 @@ racc::Context* racc::createContext(Configuration cfg) {
 	// full batch plus whatever one more callback may add; enough streams that every thread can hold
 	// two (one in, one out) on top of the rays-in-flight budget.
 	const uint32_t capacity = (uint32_t)cfg.rayStreamBatchSize + std::max<uint32_t>(cfg.maxRaysPerSpawn, cfg.cpuShadeBatch);
-	const uint32_t held = (uint32_t)cfg.gpuSubmissionThreads + 2u * cfg.cpuThreads;
+	const uint32_t held = (uint32_t)cfg.gpuSubmissionThreads * (uint32_t)devices.size() + 2u * cfg.cpuThreads;
 	const uint32_t count = held + (cfg.maxRaysInFlight + cfg.rayStreamBatchSize - 1u) / cfg.rayStreamBatchSize;
 	if (count > 65535u) {
 		fprintf(stderr, "RayAccelerator: configuration needs %u ray streams (limit 65535).\n", count);
@@ -338,7 +367,7 @@ racc::Context* racc::createContext(Configuration cfg) {
 
 	Context* c = new Context();
 	c->configuration = cfg;
-	c->device = device;
+	c->devices = devices;
 	c->slab = slab;
 	c->streamCapacity = capacity;
 	c->streams.resize(count);
@@ -355,8 +384,9 @@ racc::Context* racc::createContext(Configuration cfg) {
 	}
 	for (unsigned i = 0; i < cfg.cpuThreads; ++i)
 		c->threads.emplace_back(callbackThread, c, i);
-	for (unsigned i = 0; i < cfg.gpuSubmissionThreads; ++i)
-		c->threads.emplace_back(submitterThread, c);
+	for (int device : devices)
+		for (unsigned i = 0; i < cfg.gpuSubmissionThreads; ++i)
+			c->threads.emplace_back(submitterThread, c, device);
 	return c;
 }
 
@@ -387,8 +417,7 @@ racc::Scene* racc::createScene(Context* context, const Vertex* vertices, unsigne
 		fprintf(stderr, "RayAccelerator: Invalid scene input.\n"); // the reference asserts (Scene.cpp:186-187)
 		return nullptr;
 	}
-	int device = context->device;
-	racc_cuda_init(&device, 1);
+	bindAll(context); // the scene is replicated on every device of the context
 	racc_cuda_scene* handle = racc_cuda_scene_create(&vertices->x, vertexCount, indices, indexCount);
 	if (!handle) {
 		fprintf(stderr, "RayAccelerator: Unable to create scene (%s).\n", racc_cuda_last_error());
@@ -408,8 +437,7 @@ racc::Environment* racc::createEnvironment(Context* context, const Color* colors
 		fprintf(stderr, "RayAccelerator: Invalid environment input.\n");
 		return nullptr;
 	}
-	int device = context->device;
-	racc_cuda_init(&device, 1);
+	bindAll(context);
 	racc_cuda_env* handle = racc_cuda_env_create(&colors->r, width, height);
 	if (!handle) {
 		fprintf(stderr, "RayAccelerator: Unable to create environment image (%s).\n", racc_cuda_last_error());
@@ -434,6 +462,19 @@ racc::Stats racc::render(Context* c, Scene* scene, Environment* environment, Ren
 	c->work.notify_all();
 	c->done.wait(lock, [c] { return frameFinished(c); });
 	Stats stats = {};
-	stats.raysTraced = c->raysTraced;
+	stats.raysTraced = c->raysTraced; // what the submitters handed to the device (RayAccelerator.cpp:372)
+	lock.unlock();
+	// The per-frame hit reduction: every device counted the rays its launches traced; their NCCL sum is the frame's total.
+	// All launches have completed (a submitter files its streams as tested only after racc_cuda_sync). The frame records
+	// are per device, not per context: when another context traced on the same devices meanwhile the sum is larger, and
+	// the host count above stands.
+	racc_cuda_counters totals = {};
+	if (c->devices.size() > 1 && bindAll(c) == 0 && racc_cuda_frame_reduce(&totals, nullptr) == 0) {
+		if (totals.rays != stats.raysTraced)
+			fprintf(stderr, "RayAccelerator: devices counted %llu rays, submitters %llu (another context on the same devices?)\n",
+			        (unsigned long long)totals.rays, (unsigned long long)stats.raysTraced);
+		else
+			stats.raysTraced = totals.rays;
+	}
 	return stats;
 }

@@ -471,7 +471,7 @@ inline float boxArea(const Bvh2::Node& n) {
 bool buildSceneImages(const float* vertices4, uint32_t vertexCount, const uint32_t* indices, uint32_t indexCount,
                       int threads, SceneImages* out, const char** error, DeviceBvhBuilder deviceBuilder) {
 	static const char* kMod3 = "index count is not a multiple of 3";
-	static const char* kTiny = "scene needs at least 3 triangles (root must be an inner node)";
+	static const char* kEmpty = "scene has no triangles";
 	static const char* kPairs = "scene exceeds 2^24 triangle pairs (leaf reference holds 24 index bits)";
 	if (indexCount % 3) { if (error) *error = kMod3; return false; }
 	const bool verbose = getenv("RACC_B200_BUILD_VERBOSE") != nullptr;
@@ -480,7 +480,36 @@ bool buildSceneImages(const float* vertices4, uint32_t vertexCount, const uint32
 	Bvh2 bvh;
 	if (!buildBvh2(vertices4, vertexCount, indices, indexCount / 3, threads, &bvh, error, deviceBuilder))
 		return false;
-	if (!bvh.nodes[0].kind) { if (error) *error = kTiny; return false; }
+	if (bvh.nodes.empty() || indexCount == 0) { if (error) *error = kEmpty; return false; }
+	if (!bvh.nodes[0].kind) {
+		// The SAH test left the root a leaf (it may for 1..126 triangles). The traversal starts at inner node 0
+		// (Kernels.h:168; the reference uploads an EMPTY node image in this case, Scene.cpp:274-342, and cannot trace
+		// the scene at all), so the image gets one synthetic inner root: first child = that leaf, last child = a box
+		// at +infinity that no finite ray enters (every slab distance is +-inf, so t0 > t1). Its reference names the
+		// same leaf, so even a ray with maxT = inf that "enters" it only re-tests pairs it has already tested.
+		const Bvh2::Node& leaf = bvh.nodes[0];
+		out->nodes.assign(1, GpuNode{});
+		out->pairs.clear();
+		out->remap.clear();
+		packLeaf(bvh.triangles.data() + leaf.first, leaf.last - leaf.first, vertices4, indices, out->pairs, out->remap);
+		GpuNode& g = out->nodes[0];
+		g.kind = 1;
+		g.parent = kNone;
+		g.first = g.last = ((uint32_t)out->pairs.size() << 24) | 0u;
+		for (int k = 0; k < 3; ++k) {
+			g.leftMin[k] = leaf.bbMin[k];
+			g.leftMax[k] = leaf.bbMax[k];
+			g.rightMin[k] = g.rightMax[k] = std::numeric_limits<float>::infinity();
+			out->boundsMin[k] = leaf.bbMin[k];
+			out->boundsMax[k] = leaf.bbMax[k];
+		}
+		out->realPairs = (uint32_t)out->pairs.size();
+		do {
+			out->pairs.push_back(out->pairs[0]);
+		} while ((out->pairs.size() * 3) % 32 != 0);
+		out->depth = 2;
+		return true;
+	}
 
 	const uint32_t nodeCount = (uint32_t)bvh.nodes.size();
 	const double t1 = now();

@@ -80,7 +80,7 @@ __device__ __forceinline__ uint32_t innerStep(const float4* np, const RayState& 
 template <bool kCount>
 __global__ void __launch_bounds__(256) traceSimpleKernel(const TraceParams p) {
 	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= p.total)
+	if (idx >= (p.totalPtr ? min(__ldg(p.totalPtr), p.total) : p.total))
 		return;
 	const DevRay* rays; float4* out; uint32_t local;
 	locate(p, idx, rays, out, local);
@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(cons
 
 	enum { kEmpty = 0, kTraversing = 1, kFinished = 2 };
 	int state = kEmpty;
+	const uint32_t total = p.totalPtr ? min(__ldg(p.totalPtr), p.total) : p.total;
 	bool exhausted = false; // warp-uniform: the cursor has run past the last ray
 
 	RayState r; HitState h;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(cons
 				base = __shfl_sync(kFullMask, base, leader);
 				if (state == kEmpty) {
 					const uint32_t idx = base + __popc(idle & ltMask);
-					if (idx < p.total) {
+					if (idx < total) {
 						const DevRay* rays; uint32_t local;
 						locate(p, idx, rays, outPtr, local);
 						outPtr += local;
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePersistentKernel(cons
 						state = kTraversing;
 					}
 				}
-				exhausted = base + (uint32_t)want >= p.total;
+				exhausted = base + (uint32_t)want >= total;
 			}
 			if (!__ballot_sync(kFullMask, state == kTraversing))
 				break;

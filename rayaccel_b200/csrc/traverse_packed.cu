@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const Tr
 	asm volatile("mov.b64 %0, %1;" : "=l"(nodeBase) : "l"(reinterpret_cast<u64>(p.tnodes) - (0x80000000ull << 6)));
 	asm volatile("mov.b64 %0, %1;" : "=l"(pairBase) : "l"(reinterpret_cast<u64>(p.tpairs)));
 
+	const uint32_t total = p.totalPtr ? min(__ldg(p.totalPtr), p.total) : p.total;
 	bool exhausted = false; // warp-uniform: the cursor has run past the last ray
 	RayState r; HitState h;
 	__shared__ uint32_t smStack[kSmStack ? kSmStack : 1][kSmStack ? kBlock : 1];
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const Tr
 				base = __shfl_sync(kFullMask, base, leader);
 				if (node == 0) {
 					uint32_t idx = base + __popc(idle & ltMask);
-					if (idx < p.total) {
+					if (idx < total) {
 						if (p.perm) idx = __ldg(p.perm + idx);
 						const DevRay* rays; uint32_t local;
 						locate(p, idx, rays, outPtr, local);
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const Tr
 						node = kInnerBit;
 					}
 				}
-				exhausted = base + (uint32_t)want >= p.total;
+				exhausted = base + (uint32_t)want >= total;
 			}
 			idle = __ballot_sync(kFullMask, node == 0);
 			if (idle == kFullMask)

@@ -421,7 +421,13 @@ static inline size_t __cvta_generic_to_shared(const void* p) { return ::cuda_on_
 // the few runtime calls the launchers make
 enum cudaDeviceAttr { cudaDevAttrMaxSharedMemoryPerMultiprocessor = 81, cudaDevAttrMultiProcessorCount = 16, cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
-static inline cudaError_t cudaGetDevice(int* device) { *device = 0; return cudaSuccess; }
+// Several "devices" on request (CUDA_ON_CPU_DEVICES=n): they share the host's memory, which is all the multi-device host
+// logic of capi.cu needs (replicas, dealing HOST streams over a device set, the frame reduction over a stand-in NCCL).
+namespace cuda_on_cpu {
+inline int deviceCount() { const char* v = getenv("CUDA_ON_CPU_DEVICES"); const int n = v ? atoi(v) : 1; return n < 1 ? 1 : n; }
+inline int& currentDevice() { static thread_local int d = 0; return d; }
+} // namespace cuda_on_cpu
+static inline cudaError_t cudaGetDevice(int* device) { *device = ::cuda_on_cpu::currentDevice(); return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int* value, cudaDeviceAttr attr, int) { *value = attr == cudaDevAttrMultiProcessorCount ? 2 : 233472; return cudaSuccess; }
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* blocks, F, int, size_t) { *blocks = 2; return cudaSuccess; }
@@ -468,8 +474,14 @@ static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-static inline cudaError_t cudaSetDevice(int device) { return device == 0 ? cudaSuccess : 101; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = ::cuda_on_cpu::deviceCount(); return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int device) {
+	if (device < 0 || device >= ::cuda_on_cpu::deviceCount()) return 101;
+	::cuda_on_cpu::currentDevice() = device;
+	return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpyPeer(void* dst, int, const void* src, int, size_t bytes) { if (bytes) memmove(dst, src, bytes); return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) { *pool = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
 static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {

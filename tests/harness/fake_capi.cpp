@@ -29,6 +29,17 @@ static std::atomic<uint64_t> g_calls{0};
 static std::atomic<uint64_t> g_streams{0};
 static std::atomic<uint64_t> g_rays{0};
 static std::atomic<uint64_t> g_maxRaysPerCall{0};
+// several pretend devices (FAKE_CAPI_DEVICES=n): which thread is bound to which, what each traced, per-device frame records
+static constexpr int kFakeDevices = 16;
+static std::atomic<uint64_t> g_deviceCalls[kFakeDevices];
+static std::atomic<uint64_t> g_deviceRays[kFakeDevices];
+static std::atomic<uint64_t> g_frameRays[kFakeDevices];
+static std::atomic<uint64_t> g_reduces{0};
+static std::atomic<uint64_t> g_threadReleases{0};
+static thread_local int t_bound = 0;
+static thread_local int t_setSize = 1;
+static thread_local int t_set[kFakeDevices] = {0};
+static int fakeDeviceCount() { const char* v = getenv("FAKE_CAPI_DEVICES"); const int n = v ? atoi(v) : 1; return n < 1 ? 1 : (n > kFakeDevices ? kFakeDevices : n); }
 
 extern "C" {
 
@@ -38,8 +49,30 @@ uint64_t fake_capi_streams(void) { return g_streams.load(); }
 uint64_t fake_capi_rays(void) { return g_rays.load(); }
 uint64_t fake_capi_max_rays_per_call(void) { return g_maxRaysPerCall.load(); }
 
-int racc_cuda_init(const int*, int) { return 0; }
-int racc_cuda_device_count(void) { return 1; }
+uint64_t fake_capi_device_calls(int d) { return g_deviceCalls[d].load(); }
+uint64_t fake_capi_device_rays(int d) { return g_deviceRays[d].load(); }
+uint64_t fake_capi_reduces(void) { return g_reduces.load(); }
+uint64_t fake_capi_thread_releases(void) { return g_threadReleases.load(); }
+
+int racc_cuda_init(const int* devices, int n) {
+	if (!devices || n <= 0) { t_bound = 0; t_setSize = 1; t_set[0] = 0; return 0; }
+	for (int k = 0; k < n; ++k) {
+		if (devices[k] < 0 || devices[k] >= fakeDeviceCount()) return -1;
+		t_set[k] = devices[k];
+	}
+	t_setSize = n;
+	t_bound = devices[0];
+	return 0;
+}
+int racc_cuda_device_count(void) { return fakeDeviceCount(); }
+void racc_cuda_thread_release(void) { g_threadReleases.fetch_add(1); }
+int racc_cuda_frame_reduce(racc_cuda_counters* totals, void*) {
+	uint64_t rays = 0;
+	for (int k = 0; k < t_setSize; ++k) rays += g_frameRays[t_set[k]].exchange(0);
+	if (totals) { totals->rays = rays; totals->hits = 0; totals->inner_nodes = 0; totals->pairs_tested = 0; }
+	g_reduces.fetch_add(1);
+	return 0;
+}
 int racc_cuda_abi_version(void) { return RACC_CUDA_ABI_VERSION; }
 const char* racc_cuda_last_error(void) { return "fake C-ABI"; }
 
@@ -98,6 +131,9 @@ int racc_cuda_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stre
 		rays += streams[i].count;
 	}
 	g_calls.fetch_add(1);
+	g_deviceCalls[t_bound].fetch_add(1);
+	g_deviceRays[t_bound].fetch_add(rays);
+	g_frameRays[t_bound].fetch_add(rays);
 	g_streams.fetch_add(nstreams);
 	g_rays.fetch_add(rays);
 	uint64_t prev = g_maxRaysPerCall.load();

@@ -20,6 +20,15 @@
 #include <cstring>
 #include <vector>
 
+#ifdef RACC_FAKE_CAPI
+extern "C" {
+uint64_t fake_capi_device_calls(int d);
+uint64_t fake_capi_device_rays(int d);
+uint64_t fake_capi_reduces(void);
+uint64_t fake_capi_thread_releases(void);
+}
+#endif
+
 namespace {
 
 struct Tag {
@@ -135,7 +144,7 @@ void shadeCb(void* data, unsigned thread, const racc::RayStream* in, unsigned st
 } // namespace
 
 int main(int argc, char** argv) {
-	uint32_t totalPrimary = 200000, grid = 96, frames = 2;
+	uint32_t totalPrimary = 200000, grid = 96, frames = 2, devices = 1;
 	racc::init();
 	racc::Configuration cfg = racc::defaultConfiguration(racc::cudaDevice(0));
 	cfg.cpuThreads = 4;
@@ -155,7 +164,9 @@ int main(int argc, char** argv) {
 		else if (!strcmp(argv[i], "--shade")) cfg.cpuShadeBatch = (uint16_t)v;
 		else if (!strcmp(argv[i], "--batch")) cfg.rayStreamBatchSize = (uint16_t)v;
 		else if (!strcmp(argv[i], "--inflight")) cfg.maxRaysInFlight = (uint32_t)v;
+		else if (!strcmp(argv[i], "--devices")) devices = (uint32_t)v;
 	}
+	if (devices > 1) cfg.gpuContext = racc::cudaDevices(0, (int)devices); // one context over several GPUs
 
 	// a bumpy height field of 2*grid*grid triangles
 	std::vector<racc::Vertex> verts((size_t)(grid + 1) * (grid + 1));
@@ -248,6 +259,15 @@ int main(int argc, char** argv) {
 	racc::deinit();
 
 	const bool ok = !mismatches && !missing && !client.violations.load() && tracedTotal == expectedTotal;
+#ifdef RACC_FAKE_CAPI
+	// the test double's bookkeeping: what every pretend device traced, frame reductions, submitter teardown
+	printf("{\"fake\": true, \"reduces\": %llu, \"thread_releases\": %llu, \"device_rays\": [", (unsigned long long)fake_capi_reduces(),
+	       (unsigned long long)fake_capi_thread_releases());
+	for (uint32_t d = 0; d < devices; ++d) printf("%s%llu", d ? ", " : "", (unsigned long long)fake_capi_device_rays((int)d));
+	printf("], \"device_calls\": [");
+	for (uint32_t d = 0; d < devices; ++d) printf("%s%llu", d ? ", " : "", (unsigned long long)fake_capi_device_calls((int)d));
+	printf("]}\n");
+#endif
 	printf("{\"ok\": %s, \"frames\": %u, \"rays_traced\": %llu, \"rays_expected\": %llu, \"primary_hits\": %llu, \"mismatches\": %llu, "
 	       "\"missing\": %llu, \"violations\": %llu, \"stream_count\": %u, \"stream_size\": %u, \"thread_count\": %u}\n",
 	       ok ? "true" : "false", frames, (unsigned long long)tracedTotal, (unsigned long long)expectedTotal, (unsigned long long)hitsTotal,

@@ -31,7 +31,7 @@ def plumbing_cpu():
     src = [os.path.join(HARNESS, "plumbing_client.cpp"), os.path.join(HARNESS, "fake_capi.cpp"),
            os.path.join(ROOT, "rayaccel_b200", "csrc", "racc_api.cpp"), os.path.join(ROOT, "rayaccel_b200", "csrc", "scene_build.cpp")]
     if _stale(exe, src + [oracle.ORACLE_SO]):
-        subprocess.run(CXX + src + ["-L", os.path.dirname(oracle.ORACLE_SO), "-loracle", "-Wl,-rpath," + os.path.dirname(oracle.ORACLE_SO), "-o", exe], check=True)
+        subprocess.run(CXX + ["-DRACC_FAKE_CAPI"] + src + ["-L", os.path.dirname(oracle.ORACLE_SO), "-loracle", "-Wl,-rpath," + os.path.dirname(oracle.ORACLE_SO), "-o", exe], check=True)
     return exe
 
 
@@ -70,6 +70,26 @@ def test_scheduler_contract_cpu(plumbing_cpu, args):
     rc, out = run_json([plumbing_cpu] + args)
     assert rc == 0 and out["ok"], out
     assert out["rays_traced"] == out["rays_expected"] and out["mismatches"] == 0 and out["missing"] == 0 and out["violations"] == 0
+
+
+@pytest.mark.parametrize("devices", [2, 4])
+def test_one_context_over_several_devices_deals_streams_and_reduces_cpu(plumbing_cpu, devices):
+    """racc::cudaDevices(0, n): one context, n pretend devices behind the test double. Every device gets its own submitters
+    and a share of the ready streams, every result still comes back to the right ray (checked against the oracle by the
+    client), and Stats.raysTraced of each frame is the sum of the devices' frame records (one reduction per frame). The
+    submitters release their per-thread device scratch when the context is destroyed."""
+    frames, submitters = 3, 2
+    p = subprocess.run([plumbing_cpu, "--devices", str(devices), "--threads", "8", "--submitters", str(submitters), "--rays", "400000",
+                        "--frames", str(frames), "--inflight", "1048576", "--batch", "8192"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env={**os.environ, "FAKE_CAPI_DEVICES": str(devices)})
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert p.returncode == 0 and len(lines) == 2, p.stdout + p.stderr
+    fake, out = lines
+    assert out["ok"] and out["rays_traced"] == out["rays_expected"] and out["mismatches"] == 0 and out["missing"] == 0
+    assert fake["reduces"] == frames and fake["thread_releases"] == devices * submitters
+    assert sum(fake["device_rays"]) == out["rays_traced"]
+    assert all(r > 0.02 * out["rays_traced"] for r in fake["device_rays"]), f"a device was starved: {fake}"
+    assert "devices counted" not in p.stderr
 
 
 def test_reference_whitted_renderer_unchanged_cpu_plumbing():

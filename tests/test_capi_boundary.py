@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libracc_b200.so does not export {n}"
     assert sorted(_lib.SYMBOLS) == names, "rayaccel_b200/_lib.py SYMBOLS out of sync with include/racc_b200.h"
-    assert lib.racc_cuda_abi_version() == 1
+    assert lib.racc_cuda_abi_version() == 2
 
 
 def test_cpp_api_is_exported():
@@ -98,18 +98,20 @@ def test_host_only_entry_points_work_without_gpu(battlefield):
 
 def test_tuning_keys_documented_and_settable_without_gpu():
     """racc_cuda_set_tuning is host-only: every key the header documents is accepted and returns the previous value, the
-    options written after the last GPU call (15-17) default to off, an unknown key is an error with a message."""
+    defaults are the measured ones (profiles/r02_call1_open_questions.md: 15 on, 16 off, 17 = 256 K rays), an unknown key is an
+    error with a message."""
     lib = _lib.load()
     lib.racc_cuda_set_tuning.restype = ctypes.c_int
     header = open(os.path.join(ROOT, "include", "racc_b200.h")).read()
     for env in ["_WHITTED_ARENA", "_WHITTED_COMBINE", "_HOST_TAPER", "_SMEM_STACK", "_HOST_ZERO_COPY"]:
         assert env in header
-    for key in range(18):
+    defaults = {15: 1, 16: 0, 17: 256, 18: 0}
+    for key in range(19):
         prev = lib.racc_cuda_set_tuning(key, 1)
         assert lib.racc_cuda_set_tuning(key, prev) == 1, f"key {key} did not keep the value"
-        if key in (15, 16, 17):
-            assert prev == 0, f"key {key} must be off by default until it has been measured on hardware"
-    assert lib.racc_cuda_set_tuning(18, 1) == -1
+        if key in defaults and not os.environ.get("RACC_B200_HOST_TAPER"):
+            assert prev == defaults[key], f"key {key}: default {prev}, documented {defaults[key]}"
+    assert lib.racc_cuda_set_tuning(99, 1) == -1
     assert b"unknown tuning key" in lib.racc_cuda_last_error()
 
 
