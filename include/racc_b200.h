@@ -57,6 +57,9 @@ typedef struct {
 	uint64_t hits;
 	uint64_t inner_nodes;
 	uint64_t pairs_tested;
+	uint64_t stack_pushes;  /* far children pushed (= entries popped): with the two above, the gather instructions a ray costs */
+	uint64_t leaf_visits;
+	uint64_t reserved[2];   /* 64 bytes in all: what a caller of racc_cuda_trace_counted allocates and zeroes */
 } racc_cuda_counters;
 
 /* replaces racc::init() + the OpenCL device pick (RayAccelerator.cpp:417-423,463-478;
@@ -132,7 +135,8 @@ int racc_cuda_trace(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_
 /* Same, additionally accumulating into *device_counters (a device pointer to a racc_cuda_counters
  * that the caller zeroed). detail == 0: rays and hits only (free: one atomic per warp; this is the
  * per-frame hit count the multi-GPU reduction sums, and what racc::Stats reports). detail != 0:
- * also inner-node and pair visits (slower; used for the roofline accounting only). */
+ * also inner-node and pair visits (slower; used for the roofline accounting only) and, from the default
+ * kernel (variant 3), stack pushes and leaf visits. */
 int racc_cuda_trace_counted(racc_cuda_scene* scene, racc_cuda_env* env, const racc_cuda_stream_desc* streams,
                             uint32_t nstreams, void* cuda_stream, void* device_counters, int detail);
 

@@ -22,7 +22,7 @@ INVALID = 0xFFFFFFFF
 
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("minT", "<f4"), ("dir", "<f4", 3), ("maxT", "<f4")])
 RESULT_DTYPE = np.dtype([("triangle", "<u4"), ("a", "<f4"), ("b", "<f4"), ("c", "<f4")])
-COUNTER_DTYPE = np.dtype([("inner", "<u2"), ("pairs", "<u2"), ("max_stack", "<u2"), ("hit", "<u2")])
+COUNTER_DTYPE = np.dtype([("inner", "<u2"), ("pairs", "<u2"), ("max_stack", "<u2"), ("hit", "<u2"), ("pushes", "<u2"), ("leaves", "<u2")])
 
 
 def build(ref: bool = True) -> None:

@@ -308,7 +308,7 @@ static int traverse_one(const oracle_scene* sc, const oracle_ray* in, oracle_res
 	uint32_t node = 0x80000000u; /* Kernels.h:164 */
 	uint32_t stack[ORACLE_STACK];
 	unsigned stackHead = 0;
-	unsigned nInner = 0, nPairs = 0, maxStack = 0;
+	unsigned nInner = 0, nPairs = 0, maxStack = 0, nPushes = 0, nLeaves = 0;
 	const uint32_t* nodesU = (const uint32_t*)sc->nodes;
 
 	for (;;) {
@@ -336,6 +336,7 @@ static int traverse_one(const oracle_scene* sc, const oracle_ray* in, oracle_res
 				if (pmax(tFirst, tLast) != tRay) { /* both hit: push the far one, Kernels.h:194-195 */
 					if (stackHead >= ORACLE_STACK) return -1;
 					stack[stackHead++] = sgn ? childFirst : childLast;
+					++nPushes;
 					if (stackHead > maxStack) maxStack = stackHead;
 				}
 				node = sgn ? childLast : childFirst; /* Kernels.h:196 */
@@ -346,6 +347,7 @@ static int traverse_one(const oracle_scene* sc, const oracle_ray* in, oracle_res
 			uint32_t first = node & 0xffffffu; /* Kernels.h:201-204 */
 			uint32_t last = first + (node >> 24);
 			if (last > sc->pair_count) return -1;
+			++nLeaves;
 			for (uint32_t i = first; i < last; ++i) {
 				ray.tFar = pair_intersect(sc->pairs, i, &ray, &hit);
 				++nPairs;
@@ -363,6 +365,8 @@ static int traverse_one(const oracle_scene* sc, const oracle_ray* in, oracle_res
 		cnt->pairs = (uint16_t)(nPairs > 65535 ? 65535 : nPairs);
 		cnt->max_stack = (uint16_t)maxStack;
 		cnt->hit = hit.index != 0xffffffffu;
+		cnt->pushes = (uint16_t)(nPushes > 65535 ? 65535 : nPushes);
+		cnt->leaves = (uint16_t)(nLeaves > 65535 ? 65535 : nLeaves);
 	}
 	return 0;
 }

@@ -88,6 +88,8 @@ typedef struct {
 	uint16_t pairs;     /* triangle pairs tested */
 	uint16_t max_stack; /* deepest stack head reached */
 	uint16_t hit;       /* 1 = hit, 0 = miss */
+	uint16_t pushes;    /* far children pushed (= entries popped): the stack traffic of the ray */
+	uint16_t leaves;    /* leaves visited */
 } oracle_counters;
 
 /* Kernels.h:141-242 for rays[0..count). counters may be NULL. threads<=0 -> all cores. */

@@ -28,7 +28,8 @@ class SceneInfo(ctypes.Structure):
 
 
 class Counters(ctypes.Structure):
-    _fields_ = [("rays", ctypes.c_uint64), ("hits", ctypes.c_uint64), ("inner_nodes", ctypes.c_uint64), ("pairs_tested", ctypes.c_uint64)]
+    _fields_ = [("rays", ctypes.c_uint64), ("hits", ctypes.c_uint64), ("inner_nodes", ctypes.c_uint64), ("pairs_tested", ctypes.c_uint64),
+                ("stack_pushes", ctypes.c_uint64), ("leaf_visits", ctypes.c_uint64), ("reserved", ctypes.c_uint64 * 2)]
 
 
 class CameraStruct(ctypes.Structure):

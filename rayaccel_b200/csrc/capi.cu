@@ -101,15 +101,15 @@ DeviceState* useDevice(int ordinal) {
 			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
 		}
 	}
-	if ((e = cudaMalloc(reinterpret_cast<void**>(&d.dFrame), 8 * sizeof(unsigned long long))) != cudaSuccess ||
-	    (e = cudaMemset(d.dFrame, 0, 8 * sizeof(unsigned long long))) != cudaSuccess ||
+	if ((e = cudaMalloc(reinterpret_cast<void**>(&d.dFrame), 16 * sizeof(unsigned long long))) != cudaSuccess ||
+	    (e = cudaMemset(d.dFrame, 0, 16 * sizeof(unsigned long long))) != cudaSuccess ||
 	    (e = cudaStreamCreateWithFlags(&d.reduceStream, cudaStreamNonBlocking)) != cudaSuccess ||
 	    (e = cudaEventCreateWithFlags(&d.reduceReady, cudaEventDisableTiming)) != cudaSuccess ||
 	    (e = cudaEventCreateWithFlags(&d.reduceDone, cudaEventDisableTiming)) != cudaSuccess) {
 		fail("device %d: frame counters: %s", ordinal, cudaGetErrorString(e));
 		return nullptr;
 	}
-	d.dFrameTotal = d.dFrame + 4;
+	d.dFrameTotal = d.dFrame + 8;
 	d.ready = true;
 	return &d;
 }
@@ -204,6 +204,9 @@ bool packReplica(racc_cuda_scene* s, SceneReplica* r) {
 	    (e = cudaMalloc(reinterpret_cast<void**>(&r->dTNodes), (size_t)s->info.node_count * 64 + 64)) != cudaSuccess ||
 	    (e = cudaMalloc(reinterpret_cast<void**>(&r->dTPairs), (size_t)s->info.pair_count * 64 + 64)) != cudaSuccess ||
 	    (e = launchPackImages(r->dNodes, s->info.node_count, r->dPairs, s->info.pair_count, r->dTNodes, r->dTPairs, nullptr, &launches)) != cudaSuccess ||
+	    (e = cudaMalloc(&r->dQNodes, (size_t)s->info.node_count * 32 + 32)) != cudaSuccess ||
+	    (e = launchQuantiseNodes(r->dNodes, s->info.node_count, s->info.bounds_min, s->info.bounds_max, r->dQNodes, s->qOrigin, s->qCell, nullptr,
+	                             &launches)) != cudaSuccess ||
 	    (e = cudaDeviceSynchronize()) != cudaSuccess) {
 		fail("scene packing failed: %s", cudaGetErrorString(e));
 		return false;
@@ -241,6 +244,7 @@ racc_cuda_scene* finishScene(racc_cuda_scene* s) {
 		                cloneBuffer(&r->dRemap, r->device, first->dRemap, first->device, (size_t)in.remap_count * 4) &&
 		                cloneBuffer(&r->dTNodes, r->device, first->dTNodes, first->device, (size_t)in.node_count * 64 + 64) &&
 		                cloneBuffer(&r->dTPairs, r->device, first->dTPairs, first->device, (size_t)in.pair_count * 64 + 64) &&
+		                cloneBuffer(reinterpret_cast<char**>(&r->dQNodes), r->device, static_cast<const char*>(first->dQNodes), first->device, (size_t)in.node_count * 32 + 32) &&
 		                cloneBuffer(&r->dVerts, r->device, first->dVerts, first->device, (size_t)s->vertexCount * 16) &&
 		                cloneBuffer(&r->dIndices, r->device, first->dIndices, first->device, (size_t)s->triangleCount * 12);
 		cudaError_t e = cudaSuccess;
@@ -660,11 +664,13 @@ void fillSceneParams(TraceParams& p, const racc_cuda_scene* s, const SceneReplic
 	p.perm = nullptr;
 	p.envPairs = er ? er->dTexelPairs : nullptr;
 	p.totalPtr = nullptr;
+	p.qnodes = r->dQNodes;
+	for (int a = 0; a < 3; ++a) { p.qOrigin[a] = s->qOrigin[a]; p.qCell[a] = s->qCell[a]; }
 }
 
 cudaError_t launchAny(const racc_cuda_scene* s, const Tuning& tuning, const DeviceState* dev, const TraceParams& p, int counterMode,
                       cudaStream_t stream, int* launches) {
-	if (tuning.variant != 3)
+	if (tuning.variant != 3 && tuning.variant != 4)
 		return launchTrace(p, tuning, counterMode, dev->smCount, stream, launches);
 	Tuning t = tuning;
 	if (t.smemStack < 0) t.smemStack = sceneExceedsL2(s) ? 16 : 0;
@@ -750,7 +756,7 @@ int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_des
 			p.streams = static_cast<const StreamRef*>(dRefs);
 		}
 		void* sortScratch = nullptr;
-		const bool rebin = tuning.variant == 3 && total >= 4096 && !zeroCopy && !deviceTotal &&
+		const bool rebin = (tuning.variant == 3 || tuning.variant == 4) && total >= 4096 && !zeroCopy && !deviceTotal &&
 		                   (tuning.sortMode == 1 || (tuning.sortMode == 2 && sceneExceedsL2(s) && total >= (1u << 18)));
 		if (rebin) {
 			// re-bin the launch: visiting order by origin/direction key, results stay index-parallel

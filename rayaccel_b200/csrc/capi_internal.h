@@ -77,7 +77,7 @@ struct SceneReplica {
 	uint32_t* dRemap = nullptr;
 	float4* dTNodes = nullptr;   // packed images walked by the default kernel (traverse_packed.cu)
 	float4* dTPairs = nullptr;
-	void* dQNodes = nullptr;     // 32-byte quantised nodes (traverse_quant.cu), built on first use
+	void* dQNodes = nullptr;     // 32-byte quantised nodes (traverse_packed.cu, variant 4)
 	float4* dVerts = nullptr;    // for the synthetic bounce generator and the device-side renderers
 	uint32_t* dIndices = nullptr;
 	uint32_t* dCursors = nullptr;
@@ -114,6 +114,7 @@ struct racc_cuda_scene {
 	racc_cuda_scene_info info{};  // counts, depth and bounds of what is on the devices
 	uint32_t triangleCount = 0;
 	uint32_t vertexCount = 0;     // of dVerts (0 when the scene was created from images)
+	float qOrigin[3] = {0, 0, 0}, qCell[3] = {0, 0, 0}; // grid of the quantised node image
 	std::vector<std::unique_ptr<racc_b200::SceneReplica>> replicas;
 	racc_b200::SceneReplica* on(int device) const { return racc_b200::replicaOn(replicas, device); }
 };

@@ -183,6 +183,7 @@ void racc_cuda_shading_destroy(racc_cuda_shading* sh) {
 int racc_cuda_path_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_shading* sh, const racc_cuda_camera* camera,
                          const racc_cuda_path_desc* d, float* framebuffer4, uint64_t* wave_rays, void* cuda_stream) {
 	if (!s || !sh || !camera || !d || !framebuffer4) return fail("racc_cuda_path_trace: null argument");
+	if (!s->vertexCount) return fail("racc_cuda_path_trace: scene was created from images and has no index data");
 	if (sh->triangleCount != s->triangleCount || sh->vertexCount < s->vertexCount)
 		return fail("racc_cuda_path_trace: shading data (%u triangles, %u vertices) does not match the scene (%u, %u)", sh->triangleCount,
 		            sh->vertexCount, s->triangleCount, s->vertexCount);
@@ -213,7 +214,7 @@ int racc_cuda_path_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda
 	// whole batch is enqueued without one host round trip. The host-synchronised scheme of round 1 (wait for each wave's
 	// size, launch exactly that) remains for launches that need the size on the host: re-binned traversal (scenes far
 	// larger than L2) and tuning key 18.
-	const bool rebinned = tuning.variant == 3 && (tuning.sortMode == 1 || (tuning.sortMode == 2 && sceneExceedsL2(s)));
+	const bool rebinned = (tuning.variant == 3 || tuning.variant == 4) && (tuning.sortMode == 1 || (tuning.sortMode == 2 && sceneExceedsL2(s)));
 	const bool hostSizes = tuning.pathSync != 0 || rebinned;
 
 	// Lanes: a batch is cut into contiguous path ranges that advance bounce by bounce on their own streams, so that the
@@ -365,6 +366,7 @@ int racc_cuda_path_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda
 int racc_cuda_whitted_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_shading* sh, const racc_cuda_camera* camera,
                             const racc_cuda_path_desc* d, float* framebuffer4, uint64_t* wave_rays, void* cuda_stream) {
 	if (!s || !sh || !camera || !d || !framebuffer4) return fail("racc_cuda_whitted_trace: null argument");
+	if (!s->vertexCount) return fail("racc_cuda_whitted_trace: scene was created from images and has no index data");
 	if (sh->triangleCount != s->triangleCount || sh->vertexCount < s->vertexCount)
 		return fail("racc_cuda_whitted_trace: shading data (%u triangles, %u vertices) does not match the scene (%u, %u)", sh->triangleCount,
 		            sh->vertexCount, s->triangleCount, s->vertexCount);

@@ -116,13 +116,13 @@ int commFrameReduce(racc_cuda_counters* totals, cudaStream_t stream) {
 		for (size_t k = 0; k < set.size(); ++k) {
 			DeviceState* d = useDevice(set[k]);
 			if (!d) { g_nccl.GroupEnd(); return -1; }
-			RACC_NCCL_CHECK(g_nccl.AllReduce(d->dFrame, d->dFrameTotal, 4, kNcclUint64, kNcclSum, g_setComms[k], d->reduceStream));
+			RACC_NCCL_CHECK(g_nccl.AllReduce(d->dFrame, d->dFrameTotal, 8, kNcclUint64, kNcclSum, g_setComms[k], d->reduceStream));
 		}
 		RACC_NCCL_CHECK(g_nccl.GroupEnd());
 		for (size_t k = 0; k < set.size(); ++k) {
 			DeviceState* d = useDevice(set[k]);
 			if (!d) return -1;
-			RACC_CUDA_CHECK(cudaMemsetAsync(d->dFrame, 0, 4 * sizeof(unsigned long long), d->reduceStream));
+			RACC_CUDA_CHECK(cudaMemsetAsync(d->dFrame, 0, 8 * sizeof(unsigned long long), d->reduceStream));
 			if (k) RACC_CUDA_CHECK(cudaStreamSynchronize(d->reduceStream)); // later launches there start from a zeroed record
 		}
 		RACC_CUDA_CHECK(cudaSetDevice(dev->ordinal));
@@ -130,19 +130,15 @@ int commFrameReduce(racc_cuda_counters* totals, cudaStream_t stream) {
 		RACC_CUDA_CHECK(cudaStreamWaitEvent(stream, dev->reduceDone, 0));
 	}
 	else {
-		RACC_CUDA_CHECK(cudaMemcpyAsync(dev->dFrameTotal, dev->dFrame, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
-		RACC_CUDA_CHECK(cudaMemsetAsync(dev->dFrame, 0, 4 * sizeof(unsigned long long), stream));
+		RACC_CUDA_CHECK(cudaMemcpyAsync(dev->dFrameTotal, dev->dFrame, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
+		RACC_CUDA_CHECK(cudaMemsetAsync(dev->dFrame, 0, 8 * sizeof(unsigned long long), stream));
 	}
 	if (ranks) // the sum over this process' devices, summed over the processes
-		RACC_NCCL_CHECK(g_nccl.AllReduce(dev->dFrameTotal, dev->dFrameTotal, 4, kNcclUint64, kNcclSum, g_rankComm, stream));
+		RACC_NCCL_CHECK(g_nccl.AllReduce(dev->dFrameTotal, dev->dFrameTotal, 8, kNcclUint64, kNcclSum, g_rankComm, stream));
 	if (totals) {
-		unsigned long long host[4];
-		RACC_CUDA_CHECK(cudaMemcpyAsync(host, dev->dFrameTotal, sizeof(host), cudaMemcpyDeviceToHost, stream));
+		static_assert(sizeof(racc_cuda_counters) == 8 * sizeof(unsigned long long), "counter record is 8 x u64");
+		RACC_CUDA_CHECK(cudaMemcpyAsync(totals, dev->dFrameTotal, sizeof(*totals), cudaMemcpyDeviceToHost, stream));
 		RACC_CUDA_CHECK(cudaStreamSynchronize(stream));
-		totals->rays = host[0];
-		totals->hits = host[1];
-		totals->inner_nodes = host[2];
-		totals->pairs_tested = host[3];
 	}
 	return 0;
 }

@@ -30,19 +30,22 @@ struct TraceParams {
 	uint32_t total;           // rays in the launch
 	StreamRef single;         // the stream when nstreams == 1 (no indirection)
 	uint32_t* cursor;         // work cursor for the persistent kernels (zeroed before launch)
-	unsigned long long* counters; // 4 x u64 {rays,hits,inner,pairs} or null
+	unsigned long long* counters; // racc_cuda_counters (8 x u64: rays, hits, inner, pairs, pushes, leaves, -, -) or null
 	uint32_t smemNodes;       // inner nodes staged in shared memory by the persistent kernel
 	const float4* tnodes;     // packed images (traverse_packed.cu): 4 x float4 per inner node,
 	const float4* tpairs;     //   4 x float4 per triangle pair
 	const uint32_t* perm;     // optional visiting order (launch-wide ray indices), null = arrival order
 	const float4* envPairs;   // light probe as horizontally adjacent texel PAIRS: (envWidth+1) x envHeight x 32 B, or null
+	const void* qnodes;       // quantised node image (variant 4): 32 B per inner node, see traverse_packed.cu
+	float qOrigin[3], qCell[3]; //   its grid: plane = qOrigin + q * qCell
 	const uint32_t* totalPtr; // non-null: the number of rays is read from DEVICE memory at kernel start (<= total, which then
 	                          // only sizes the grid); lets a wavefront renderer enqueue wave k+1 before wave k's size is known
 };
 
 // Tunables (racc_cuda_set_variant / RACC_B200_* environment variables), see DESIGN.md section 5.
 struct Tuning {
-	int variant = 3;        // 3 packed-format persistent while-while with bail-out (default, traverse_packed.cu);
+	int variant = 3;        // 3 packed-format persistent while-while with bail-out (default, traverse_packed.cu); 4 the same
+	                        // kernel on 32-byte quantised nodes (one gather per node; not bit-exact at ties, opt-in);
 	                        // reference-format kernels of traverse.cu kept for A/B: 0 persistent while-while,
 	                        // 1 one-thread-per-ray, 2 persistent while-while with bail-out
 	int blockThreads = 256; // threads per CTA
@@ -87,6 +90,10 @@ cudaError_t launchTracePacked(const TraceParams& p, const Tuning& t, int counter
 
 // light probe -> texel-pair table for the packed kernel (once per environment)
 cudaError_t launchPackEnv(const float4* texels, uint32_t width, uint32_t height, float4* pairsOut, cudaStream_t stream, int* launches);
+
+// reference-format node image -> 32-byte quantised nodes on a 16-bit grid over the scene bounds (once per scene)
+cudaError_t launchQuantiseNodes(const float4* nodes, uint32_t nodeCount, const float boundsMin[3], const float boundsMax[3], void* qnodes,
+                                float qOrigin[3], float qCell[3], cudaStream_t stream, int* launches);
 
 // reference-format images -> packed images, on the device (once per scene)
 cudaError_t launchPackImages(const float4* nodes, uint32_t nodeCount, const float4* pairs, uint32_t pairCount,

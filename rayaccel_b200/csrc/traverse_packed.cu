@@ -21,6 +21,17 @@
 //
 // An optional permutation (TraceParams::perm, built by raysort.cu) makes the kernel visit the rays
 // in a coherence-improving order; results are still written index-parallel to the rays.
+//
+// kQuant (tuning variant 4; SURVEY.md section 8f rank 4, "compressed node format"): the same kernel walking 32-byte
+// QUANTISED inner nodes -- the same BVH2, child references and visiting rule, but both child boxes as 12 16-bit
+// coordinates on a global grid over the scene bounds, rounded outwards with a quarter cell of margin. A node visit is then ONE
+// 256-bit gather instead of two (the L1 data pipe, not HBM, bounds this kernel: DESIGN.md section 5.1) and the node
+// image is half as large. The boxes are conservative, so a ray visits a superset of the leaves the exact boxes would
+// let it into and finds the same closest hit with the same t, u, v (the pair test is unchanged); what can differ from
+// the reference's result is only which of two triangles wins an EXACT tie in t (the visiting order of near-equal
+// children may flip) and rays that graze a box the fp32 slab test of the reference misses by rounding. That is
+// north_star's bar (ids equal except fp ties, |dt|/t <= 1e-4), not the bit-exact bar of the default format, so the
+// exact format stays the default and this one is opt-in.
 #include "traverse_common.cuh"
 
 #include <type_traits>
@@ -73,6 +84,39 @@ __global__ void packPairsKernel(const float4* __restrict__ pairs, uint32_t count
 	out[4 * (size_t)i + 1] = t1;
 	out[4 * (size_t)i + 2] = t2;
 	out[4 * (size_t)i + 3] = make_float4(n1x, n1y, n1z, 0.0f);
+}
+
+// Packed node image -> 32-byte quantised nodes: {Lx Ly Lz Rx Ry Rz | first last}, every box word = (min | max << 16) in
+// cells of a 16-bit grid over the scene bounds. min rounds down and max rounds up after moving a quarter cell outwards:
+// the quantised box contains the fp32 box with a margin of at least 0.25 cell, ~15x what the kernel's grid-space slab
+// arithmetic can differ from the reference's (both err by about 2^-22 of the scene extent = 0.016 cell). A whole extra
+// cell of padding was measured and dropped: rays that START on flat, axis-aligned geometry (battlefield's ground: its
+// exact boxes have zero thickness, so a bounce ray leaving the ground never enters them) would then begin inside every
+// such box on their way -- +23 % node visits and +82 % pair tests on the first bounce (profiles/r02_quantised_nodes.md).
+// Arithmetic in double: done once per scene.
+struct QuantGrid { float origin[3]; float cell[3]; double inverse[3]; };
+
+__global__ void quantiseNodesKernel(const float4* __restrict__ nodes, uint32_t count, QuantGrid g, uint4* __restrict__ out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count)
+		return;
+	const float4 d0 = nodes[4 * (size_t)i], d1 = nodes[4 * (size_t)i + 1], d2 = nodes[4 * (size_t)i + 2], d3 = nodes[4 * (size_t)i + 3];
+	// reference layout (Scene.cpp:73-78): left min (d1.x,d1.y,d1.z) max (d1.w,d2.x,d2.y); right min (d2.z,d2.w,d3.x) max (d3.y,d3.z,d3.w)
+	const float mn[6] = {d1.x, d1.y, d1.z, d2.z, d2.w, d3.x};
+	const float mx[6] = {d1.w, d2.x, d2.y, d3.y, d3.z, d3.w};
+	uint32_t w[6];
+	for (int k = 0; k < 6; ++k) {
+		const int a = k % 3;
+		double lo = floor(((double)mn[k] - (double)g.origin[a]) * g.inverse[a] - 0.25);
+		double hi = ceil(((double)mx[k] - (double)g.origin[a]) * g.inverse[a] + 0.25);
+		if (!(lo > 0.0)) lo = 0.0;          // also NaN
+		if (lo > 65535.0) lo = 65535.0;     // +inf: the synthetic root's unreachable child (scene_build.cpp)
+		if (!(hi > 0.0)) hi = 0.0;
+		if (hi > 65535.0) hi = 65535.0;
+		w[k] = (uint32_t)lo | ((uint32_t)hi << 16);
+	}
+	out[2 * (size_t)i + 0] = make_uint4(w[0], w[1], w[2], w[3]);
+	out[2 * (size_t)i + 1] = make_uint4(w[4], w[5], __float_as_uint(d0.z), __float_as_uint(d0.w));
 }
 
 // Light probe as texel pairs: entry k of row j holds {texel(clamp(k-1)), texel(clamp(k))}, k in [0, width], so the two
@@ -236,8 +280,8 @@ struct PlainStack : LocalStack {
 
 // One inner-node step (Kernels.h:170-199) on a packed node. `node` has bit 31 set. Returns the next
 // reference: the nearer hit child, else the popped entry, else 0.
-template <typename Stack>
-__device__ __forceinline__ uint32_t innerStepPacked(u64 nodeBase, uint32_t node, const RayState& r, Stack& stack) {
+template <bool kCount, typename Stack>
+__device__ __forceinline__ uint32_t innerStepPacked(u64 nodeBase, uint32_t node, const RayState& r, Stack& stack, unsigned& pushes) {
 	u64 a;
 	asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(a) : "r"(node), "l"(nodeBase)); // nodeBase is biased by -(2^31 * 64)
 	u64 lx, ly, lz, rx, ry, rz, refs, unused;
@@ -273,19 +317,72 @@ __device__ __forceinline__ uint32_t innerStepPacked(u64 nodeBase, uint32_t node,
 	// most or all lanes off still sits in the load pipeline behind the warp's outstanding misses.
 	uint32_t next = any ? nearRef : 0u;
 	stack.pushIf(both, farRef);
+	if (kCount) pushes += both;
 	if (!any && !stack.empty())
 		next = stack.pop();
 	return next;
 }
 
-template <bool kCount, int kBlock, int kMinBlocks, int kSmStack>
+// The same step on a 32-byte quantised node (kQuant). The ray was moved into grid space once (quantRay): r.ix = cell *
+// invDir, r.px = (gridOrigin - origin) * invDir, so a plane's distance is fma(q, r.ix, r.px) with q the plane's 16-bit
+// cell index as a float (I2F.U16 with a half-word selector: the conversions run on the otherwise idle XU pipe).
+template <bool kCount, typename Stack>
+__device__ __forceinline__ uint32_t innerStepQuant(u64 nodeBase, uint32_t node, const RayState& r, Stack& stack, unsigned& pushes) {
+	u64 a;
+	asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(a) : "r"(node), "l"(nodeBase)); // nodeBase is biased by -(2^31 * 32)
+	uint32_t w0, w1, w2, w3, w4, w5, cf, cl;
+	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3), "=r"(w4), "=r"(w5), "=r"(cf), "=r"(cl) : "l"(a));
+	const float tRay = r.tFar;
+	float n0x, f0x, n0y, f0y, n0z, f0z, n1x, f1x, n1y, f1y, n1z, f1z;
+#define RACC_QPLANES(w, i, p, lo, hi)                                                                                  \
+	{                                                                                                                  \
+		u64 q;                                                                                                         \
+		asm("mov.b64 %0, {%1,%2};" : "=l"(q) : "f"((float)(unsigned short)(w)), "f"((float)(unsigned short)((w) >> 16))); \
+		unpack2(fma2(q, splat2(i), splat2(p)), lo, hi);                                                                \
+	}
+	RACC_QPLANES(w0, r.ix, r.px, n0x, f0x)
+	RACC_QPLANES(w1, r.iy, r.py, n0y, f0y)
+	RACC_QPLANES(w2, r.iz, r.pz, n0z, f0z)
+	RACC_QPLANES(w3, r.ix, r.px, n1x, f1x)
+	RACC_QPLANES(w4, r.iy, r.py, n1y, f1y)
+	RACC_QPLANES(w5, r.iz, r.pz, n1z, f1z)
+#undef RACC_QPLANES
+	const float a0 = fmaxf(fmaxf(r.tNear, fminf(n0x, f0x)), fmaxf(fminf(n0y, f0y), fminf(n0z, f0z)));
+	const float b0 = fminf(fminf(tRay, fmaxf(n0x, f0x)), fminf(fmaxf(n0y, f0y), fmaxf(n0z, f0z)));
+	const float a1 = fmaxf(fmaxf(r.tNear, fminf(n1x, f1x)), fmaxf(fminf(n1y, f1y), fminf(n1z, f1z)));
+	const float b1 = fminf(fminf(tRay, fmaxf(n1x, f1x)), fminf(fmaxf(n1y, f1y), fmaxf(n1z, f1z)));
+	const float tFirst = a0 > b0 ? tRay : a0;
+	const float tLast = a1 > b1 ? tRay : a1;
+	const float firstDiff = tRay - tFirst;
+	const float lastDiff = tRay - tLast;
+	const bool any = firstDiff + lastDiff != 0.0f;
+	const bool sgn = (int)__float_as_uint(tLast - tFirst) < 0;
+	const bool both = any && fmaxf(tFirst, tLast) != tRay;
+	const uint32_t nearRef = sgn ? cl : cf, farRef = sgn ? cf : cl;
+	uint32_t next = any ? nearRef : 0u;
+	stack.pushIf(both, farRef);
+	if (kCount) pushes += both;
+	if (!any && !stack.empty())
+		next = stack.pop();
+	return next;
+}
+
+// Moves a freshly initialised ray into the quantisation grid (see innerStepQuant). Only ix..pz change; the pair test uses
+// the origin and the direction, the miss epilogue the direction.
+__device__ __forceinline__ void quantRay(const TraceParams& p, RayState& r) {
+	r.px = (p.qOrigin[0] - r.ox) * r.ix; r.py = (p.qOrigin[1] - r.oy) * r.iy; r.pz = (p.qOrigin[2] - r.oz) * r.iz;
+	r.ix = p.qCell[0] * r.ix; r.iy = p.qCell[1] * r.iy; r.iz = p.qCell[2] * r.iz;
+}
+
+template <bool kCount, int kBlock, int kMinBlocks, int kSmStack, bool kQuant>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const TraceParams p, const int fetchThreshold, const int innerBail, const int leafBail) {
 	const unsigned lane = threadIdx.x & 31;
 	const unsigned ltMask = (1u << lane) - 1u;
 	// both bases are made opaque so that they stay in registers (otherwise they are re-derived from
 	// the constant bank, several instructions, at every step)
 	u64 nodeBase, pairBase;
-	asm volatile("mov.b64 %0, %1;" : "=l"(nodeBase) : "l"(reinterpret_cast<u64>(p.tnodes) - (0x80000000ull << 6)));
+	asm volatile("mov.b64 %0, %1;" : "=l"(nodeBase) : "l"(kQuant ? reinterpret_cast<u64>(p.qnodes) - (0x80000000ull << 5)
+	                                                                    : reinterpret_cast<u64>(p.tnodes) - (0x80000000ull << 6)));
 	asm volatile("mov.b64 %0, %1;" : "=l"(pairBase) : "l"(reinterpret_cast<u64>(p.tpairs)));
 
 	const uint32_t total = p.totalPtr ? min(__ldg(p.totalPtr), p.total) : p.total;
@@ -299,7 +396,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const Tr
 	uint32_t node = 0;         // 0: no ray in flight on this lane; bit 31: at an inner node; else at a leaf
 	float4* outPtr = nullptr;  // non-null: the lane holds a ray (in flight, or finished and not yet written)
 	unsigned long long cInner = 0, cPairs = 0;
-	unsigned cRays = 0, cHits = 0;
+	unsigned cRays = 0, cHits = 0, cPushes = 0, cLeaves = 0; // the last two only in the kCount build
 
 	for (;;) {
 		// ---- retire finished lanes and refill idle ones, warp-wide -----------------------------
@@ -325,6 +422,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const Tr
 						locate(p, idx, rays, outPtr, local);
 						outPtr += local;
 						initRay(rays, local, r, h);
+						if (kQuant) quantRay(p, r);
 						stack.reset();
 						node = kInnerBit;
 					}
@@ -346,7 +444,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const Tr
 			while (go) {
 				if ((int)node < 0) {
 					if (kCount) ++cInner;
-					node = innerStepPacked(nodeBase, node, r, stack);
+					node = kQuant ? innerStepQuant<kCount>(nodeBase, node, r, stack, cPushes) : innerStepPacked<kCount>(nodeBase, node, r, stack, cPushes);
+					if (kCount) cLeaves += (int)node > 0;
 				}
 				innerMask = __ballot_sync(kFullMask, (int)node < 0);
 				go = innerMask == liveMask || __popc(innerMask) >= innerBail;
@@ -361,7 +460,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const Tr
 					pairTestPacked(pairBase, node & 0xffffffu, r, h);
 					if (kCount) ++cPairs;
 					// one pair of this leaf done: (count << 24 | first) -> (count-1 << 24 | first+1)
-					node = node >= 0x2000000u ? node + 1u - 0x1000000u : (stack.empty() ? 0u : stack.pop());
+					const bool lastPair = node < 0x2000000u;
+					node = !lastPair ? node + 1u - 0x1000000u : (stack.empty() ? 0u : stack.pop());
+					if (kCount) cLeaves += lastPair && (int)node > 0; // the popped entry is another leaf
 				}
 				const unsigned leafMask = __ballot_sync(kFullMask, (int)node > 0);
 				go = leafMask != 0;
@@ -374,13 +475,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const Tr
 	// Frame statistics (rays, hits): one atomic per warp, always on when a counter record is given;
 	// this is the value the multi-GPU hit reduction sums. Visit counters only in the kCount build.
 	if (p.counters) {
-		unsigned long long rays = cRays, hits = cHits;
+		unsigned long long rays = cRays, hits = cHits, pushes = cPushes, leaves = cLeaves;
 		for (int o = 16; o; o >>= 1) {
 			rays += __shfl_xor_sync(kFullMask, rays, o);
 			hits += __shfl_xor_sync(kFullMask, hits, o);
 			if (kCount) {
 				cInner += __shfl_xor_sync(kFullMask, cInner, o);
 				cPairs += __shfl_xor_sync(kFullMask, cPairs, o);
+				pushes += __shfl_xor_sync(kFullMask, pushes, o);
+				leaves += __shfl_xor_sync(kFullMask, leaves, o);
 			}
 		}
 		if (lane == 0) {
@@ -389,14 +492,16 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) tracePackedKernel(const Tr
 			if (kCount) {
 				atomicAdd(p.counters + 2, cInner);
 				atomicAdd(p.counters + 3, cPairs);
+				atomicAdd(p.counters + 4, pushes);
+				atomicAdd(p.counters + 5, leaves);
 			}
 		}
 	}
 }
 
-template <bool kCount, int kBlock, int kMinBlocks, int kSmStack = 0>
+template <bool kCount, int kBlock, int kMinBlocks, int kSmStack = 0, bool kQuant = false>
 cudaError_t launchPacked(const TraceParams& p, const Tuning& t, int smCount, cudaStream_t stream) {
-	auto kernel = tracePackedKernel<kCount, kBlock, kMinBlocks, kSmStack>;
+	auto kernel = tracePackedKernel<kCount, kBlock, kMinBlocks, kSmStack, kQuant>;
 	static thread_local int plannedDevice = -1, plannedCarveout = -2, resident = 1;
 	int device = 0;
 	cudaGetDevice(&device);
@@ -432,6 +537,10 @@ cudaError_t launchPacked(const TraceParams& p, const Tuning& t, int smCount, cud
 
 template <bool kCount>
 cudaError_t dispatchPacked(const TraceParams& p, const Tuning& t, int smCount, cudaStream_t stream) {
+	if (t.variant == 4) { // quantised nodes: the default launch shape, stack all-local or its tops in shared memory
+		if (t.smemStack > 0) return launchPacked<kCount, 256, 5, 16, true>(p, t, smCount, stream);
+		return launchPacked<kCount, 256, 5, 0, true>(p, t, smCount, stream);
+	}
 	if (t.smemStack > 0 && t.blockThreads == 256) { // stack tops in shared memory: 256 x 5 only
 		if (t.smemStack <= 8) return launchPacked<kCount, 256, 5, 8>(p, t, smCount, stream);
 		return launchPacked<kCount, 256, 5, 16>(p, t, smCount, stream);
@@ -458,6 +567,25 @@ cudaError_t launchPackImages(const float4* nodes, uint32_t nodeCount, const floa
 	}
 	if (pairCount) {
 		packPairsKernel<<<(pairCount + 255u) / 256u, 256, 0, stream>>>(pairs, pairCount, tpairs);
+		if (launches) *launches += 1;
+	}
+	return cudaGetLastError();
+}
+
+cudaError_t launchQuantiseNodes(const float4* nodes, uint32_t nodeCount, const float boundsMin[3], const float boundsMax[3], void* qnodes,
+                                float qOrigin[3], float qCell[3], cudaStream_t stream, int* launches) {
+	QuantGrid g;
+	for (int a = 0; a < 3; ++a) {
+		const double extent = (double)boundsMax[a] - (double)boundsMin[a];
+		const bool usable = extent > 0.0 && extent < 3.0e38;
+		g.origin[a] = boundsMin[a];
+		g.cell[a] = usable ? (float)(extent / 65533.0) : 0.0f;   // head room for the outward rounding
+		g.inverse[a] = usable ? 65533.0 / extent : 0.0;
+		qOrigin[a] = g.origin[a];
+		qCell[a] = g.cell[a];
+	}
+	if (nodeCount) {
+		quantiseNodesKernel<<<(nodeCount + 255u) / 256u, 256, 0, stream>>>(nodes, nodeCount, g, static_cast<uint4*>(qnodes));
 		if (launches) *launches += 1;
 	}
 	return cudaGetLastError();

@@ -64,3 +64,37 @@ def primary_rays_numpy(cam, width, height):
     d = cam.view[None, None, :] + cam.up[None, None, :] * ys[..., None] + cam.right[None, None, :] * xs[..., None]
     d = d / np.linalg.norm(d, axis=2, keepdims=True)
     return make_rays(np.broadcast_to(cam.origin, (width * height, 3)), d.reshape(-1, 3).astype(np.float32))
+
+
+def assert_tolerance_parity(got_u32, want_struct, rays, vertices, indices, what, max_id_mismatch=2e-5):
+    """north_star's bar for a scene encoding that is NOT bit-exact by design (quantised nodes): hit/miss and triangle id
+    equal to the oracle's except at fp ties, |dt|/t <= 1e-4; every ray whose id differs is taken to the independent fp64
+    brute force over the ORIGINAL triangles, where the returned triangle must lie in the tie set (t within 1e-6 of the
+    closest hit) -- or, for a ray the oracle calls a miss, must be a genuine hit the reference's non-watertight fp32 box
+    test skipped. Returns the number of differing rays."""
+    import oracle
+    want = want_struct.view(np.uint32).reshape(-1, 4)
+    got = np.ascontiguousarray(got_u32).reshape(-1, 4)
+    n = want.shape[0]
+    same_id = got[:, 0] == want[:, 0]
+    bad = np.nonzero(~same_id)[0]
+    assert bad.size <= max(3, max_id_mismatch * n), f"{what}: {bad.size}/{n} triangle ids differ from the oracle"
+    hit = same_id & (want[:, 0] != 0xFFFFFFFF)
+    t_got, t_want = got[:, 1].copy().view(np.float32), want[:, 1].copy().view(np.float32)
+    assert np.all(np.abs(t_got[hit] - t_want[hit]) <= 1e-4 * np.abs(t_want[hit])), f"{what}: t differs by more than 1e-4 relative"
+    # in fact the pair test is unchanged, so equal ids mean equal bits
+    assert np.array_equal(got[hit], want[hit]), f"{what}: same triangle, different t/u/v bits"
+    miss = same_id & (want[:, 0] == 0xFFFFFFFF)
+    assert np.array_equal(got[miss], want[miss]), f"{what}: a miss returned different radiance"
+    if bad.size and vertices is not None:
+        sub = np.ascontiguousarray(rays[bad])
+        t64, _ = oracle.brute_f64(vertices, indices, sub)
+        ids = got[bad, 0]
+        got_hit = ids != 0xFFFFFFFF
+        t_of = oracle.tri_t_f64(vertices, indices, sub, np.where(got_hit, ids, 0xFFFFFFFF).astype(np.uint32))
+        ok_hit = got_hit & np.isfinite(t_of) & (t_of <= t64 * (1 + 1e-5) + 1e-7)
+        # a returned miss where fp64 sees a hit would be a real error of the conservative boxes: never allowed
+        ok_miss = ~got_hit & ~np.isfinite(t64)
+        wrong = ~(ok_hit | ok_miss)
+        assert not wrong.any(), f"{what}: {int(wrong.sum())} differing rays are outside the fp64 tie set (first: ray {bad[np.nonzero(wrong)[0][0]]})"
+    return int(bad.size)

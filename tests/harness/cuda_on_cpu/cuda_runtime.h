@@ -28,6 +28,8 @@
 
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 v = {x, y, z, w}; return v; }
+struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v = {x, y, z, w}; return v; }
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
@@ -396,6 +398,12 @@ inline void ld8f(unsigned long long address, float& a, float& b, float& c, float
 	if (address & 31) { fprintf(stderr, "cuda_on_cpu: misaligned 256-bit load\n"); abort(); }
 	if (load_sink) load_sink(g.blockIdx_.x, g.current->tid.x / 32, g.current->collectives, g.current->tid.x % 32, address, 32);
 	float v[8]; memcpy(v, reinterpret_cast<const void*>((uintptr_t)address), 32);
+	a = v[0]; b = v[1]; c = v[2]; d = v[3]; e = v[4]; f = v[5]; g_ = v[6]; h = v[7];
+}
+inline void ld8u(unsigned long long address, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d, uint32_t& e, uint32_t& f, uint32_t& g_, uint32_t& h) {
+	if (address & 31) { fprintf(stderr, "cuda_on_cpu: misaligned 256-bit load\n"); abort(); }
+	if (load_sink) load_sink(g.blockIdx_.x, g.current->tid.x / 32, g.current->collectives, g.current->tid.x % 32, address, 32);
+	uint32_t v[8]; memcpy(v, reinterpret_cast<const void*>((uintptr_t)address), 32);
 	a = v[0]; b = v[1]; c = v[2]; d = v[3]; e = v[4]; f = v[5]; g_ = v[6]; h = v[7];
 }
 inline void ld4f(unsigned long long address, float& a, float& b, float& c, float& d) {

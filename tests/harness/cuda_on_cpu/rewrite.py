@@ -60,6 +60,7 @@ PTX_FORMS: list[tuple[re.Pattern, str]] = [
     (re.compile(r"^fma\.rn\.ftz\.f32x2 %(\d+), %(\d+), %(\d+), %(\d+);$"), "::cuda_on_cpu::ptx::fma2({0}, {1}, {2}, {3});"),
     (re.compile(r"^mad\.wide\.u32 %(\d+), %(\d+), (\d+), %(\d+);$"), "{0} = (unsigned long long)(uint32_t)({1}) * {imm}ull + (unsigned long long)({3});"),
     (re.compile(r"^ld\.global\.nc\.v8\.f32 \{%0,%1,%2,%3,%4,%5,%6,%7\}, " + _MEM + r";$"), "LD8F"),
+    (re.compile(r"^ld\.global\.nc\.v8\.u32 \{%0,%1,%2,%3,%4,%5,%6,%7\}, " + _MEM + r";$"), "LD8U"),
     (re.compile(r"^ld\.v4\.f32 \{%0,%1,%2,%3\}, " + _MEM + r";$"), "LD4F"),
     (re.compile(r"^ld\.global\.nc\.v4\.b64 \{%0,%1,%2,%3\}, " + _MEM + r";$"), "LD4Q"),
     (re.compile(r"^st\.local\.u32 \[%(\d+)\], %(\d+);$"), "*::cuda_on_cpu::ptx::local_word({0}) = {1};"),
@@ -119,8 +120,8 @@ def translate_asm(inner: str) -> tuple[str, bool]:
         m = pattern.match(template)
         if not m:
             continue
-        if code in ("LD8F", "LD4Q", "LD4F"):
-            n = 8 if code == "LD8F" else 4
+        if code in ("LD8F", "LD8U", "LD4Q", "LD4F"):
+            n = 8 if code in ("LD8F", "LD8U") else 4
             addr, off = ops[int(m.group(1))], m.group(2) or "0"
             fn = code.lower()
             return f"::cuda_on_cpu::ptx::{fn}((unsigned long long){addr} + {off}ull, " + ", ".join(ops[:n]) + ");", True

@@ -97,3 +97,57 @@ KAT_CASES = [
 
 def build_kat_scene(case):
     return case["scene"](), case["rays"]()
+
+
+def deep_stack_scene(levels=60, n_rays=4096, seed=17):
+    """A chain of `levels` inner nodes built so that a ray travelling along +z pushes one stack entry per level: at level
+    k the FIRST child is a far leaf (one triangle at z = 100 + k) and the LAST child is the next inner node, whose box
+    starts at z = 0 -- nearer, so the ray descends into the chain and the far leaf goes onto the stack (Kernels.h:192-197).
+    The chain's boxes narrow in x with k, so rays with different |x| leave the chain at different levels (lanes of a warp
+    hold stacks of different depths), and each triangle covers only y < its own threshold, so some popped leaves hit and
+    some miss. With levels > 17 the stack outgrows the 16 entries the packed kernel may keep in shared memory
+    (HybridStack's spill branch), with 60 it comes close to the reference's 64 (Kernels.h:166). Leaves come off the stack
+    farthest first, so every hit replaces the previous one: the answer is the triangle of the lowest level whose
+    threshold the ray is under. Returns (SceneImages, rays, expected triangle per ray)."""
+    rng = np.random.default_rng(seed)
+    half = float(levels + 4)
+    nodes, pairs, remap = [], [], []
+    thresholds = rng.uniform(-0.8 * half, 0.8 * half, size=levels + 1)
+    for k in range(levels + 1):  # leaf k: one triangle in the plane z = 100 + k covering y < thresholds[k]
+        z = 100.0 + k
+        pairs.append(pair([-4 * half, thresholds[k], z], [4 * half, thresholds[k], z], [0.0, thresholds[k] - 8 * half, z]))
+        remap += [1000 + k, 0]
+    for k in range(levels):
+        w = half - k * (half - 2.0) / levels  # chain box half-width at level k
+        leaf_box = ([-half, -half, 100.0 + k], [half, half, 100.0 + k])
+        if k + 1 < levels:
+            w_next = half - (k + 1) * (half - 2.0) / levels
+            nodes.append(node(leaf(k, 1), INNER | (k + 1), leaf_box[0], leaf_box[1], [-w_next, -half, 0.0], [w_next, half, 50.0]))
+        else:  # the end of the chain: two leaves
+            nodes.append(node(leaf(k, 1), leaf(k + 1, 1), leaf_box[0], leaf_box[1], [-w, -half, 100.0 + k + 1], [w, half, 100.0 + k + 1]))
+    pairs = np.stack(pairs)
+    pairs = np.concatenate([pairs, np.repeat(pairs[:1], (-pairs.shape[0]) % 32 or 32, axis=0)])  # tail padding (Scene.cpp:335-338)
+    images = oracle.SceneImages(np.stack(nodes), pairs, np.asarray(remap, np.uint32))
+    x = rng.uniform(-half, half, size=n_rays)
+    y = rng.uniform(-half, half, size=n_rays)
+    rays = make_rays(np.stack([x, y, np.full(n_rays, -1.0)], axis=1), [[0.0, 0.0, 1.0]] * n_rays)
+    # reachable leaves for |x|: 0..m where m = number of chain boxes entered; the last node adds leaf `levels` within its box
+    expect = np.full(n_rays, 0xFFFFFFFF, np.uint32)
+    for r in range(n_rays):
+        reach = [0]
+        for k in range(1, levels):
+            if abs(x[r]) <= half - k * (half - 2.0) / levels:
+                reach.append(k)
+            else:
+                break
+        else:
+            if abs(x[r]) <= half - (levels - 1) * (half - 2.0) / levels:
+                reach.append(levels)
+        for k in reach:
+            if y[r] < thresholds[k] - 1e-3 and abs(x[r]) < 4 * half * (1 - (thresholds[k] - y[r]) / (8 * half)) - 1e-3:
+                expect[r] = 1000 + k
+                break
+            if abs(y[r] - thresholds[k]) <= 1e-3:
+                expect[r] = 0xFFFFFFFE  # too close to an edge to call by hand
+                break
+    return images, rays, expect

@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 import rayaccel_b200 as rb
-from conftest import make_rays, random_rays
+from conftest import assert_tolerance_parity, make_rays, random_rays
 
 pytestmark = pytest.mark.gpu
 
@@ -166,7 +166,7 @@ def test_counters_match_oracle(scene, env, images, battlefield):
         rb.set_tuning(**{**DEFAULT, "variant": variant})
         d_rays = to_device(rays)
         d_res = torch.empty(rays.shape[0] * 4, dtype=torch.float32, device="cuda")
-        d_cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+        d_cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
         rb.trace_device(scene, env, [(d_rays.data_ptr(), d_res.data_ptr(), rays.shape[0])], counters_ptr=d_cnt.data_ptr())
         torch.cuda.synchronize()
         c = d_cnt.cpu().numpy()
@@ -174,6 +174,8 @@ def test_counters_match_oracle(scene, env, images, battlefield):
         assert c[1] == int(cnt["hit"].sum())
         assert c[2] == int(cnt["inner"].astype(np.int64).sum())
         assert c[3] == int(cnt["pairs"].astype(np.int64).sum())
+        if variant == 3:
+            assert c[4] == int(cnt["pushes"].astype(np.int64).sum()) and c[5] == int(cnt["leaves"].astype(np.int64).sum())
     rb.set_tuning(**DEFAULT)
 
 
@@ -375,6 +377,220 @@ def test_synthetic_soup_scene_bit_exact(gpu):
     assert_bit_exact(got, oracle.traverse(img, rays), "soup")
     assert 0.001 < (got[:, 0] != rb.INVALID_TRIANGLE).mean() < 0.9
     s.destroy()
+
+
+@pytest.mark.parametrize("tuning", VARIANTS, ids=lambda t: "-".join(f"{k}{v}" for k, v in t.items()))
+def test_deep_stack_scene_bit_exact(tuning, gpu):
+    """tests/kat_scenes.py::deep_stack_scene on every launch shape: traversal stacks of up to 60 entries (Kernels.h:166
+    allows 64), lanes of one warp at different depths. For `smem_stack` 16 / 8 everything past the shared-memory entries
+    goes through HybridStack's spill branch (traverse_packed.cu) -- no battlefield ray gets there (deepest stack 12)."""
+    from kat_scenes import deep_stack_scene
+    images, rays, expect = deep_stack_scene(n_rays=40_000)
+    s = rb.create_scene_from_images(images.nodes, images.pairs, images.remap)
+    rb.set_tuning(**{**DEFAULT, **tuning})
+    try:
+        got = trace_dev(s, None, rays)
+        want, cnt = oracle.traverse(images, rays, counters=True)
+        assert int(cnt["max_stack"].max()) == 60
+        assert_bit_exact(got, want, "deep stack")
+        sure = expect != 0xFFFFFFFE
+        assert np.array_equal(got[sure, 0], expect[sure])
+    finally:
+        rb.set_tuning(**DEFAULT)
+        s.destroy()
+
+
+def test_scene_larger_than_l2_auto_path_bit_exact(gpu):
+    """BASELINE.json configs[4] at a size where the AUTO path engages (3 M triangles: node + pair images 279 MB > 2 x L2):
+    rays re-binned by origin (raysort.cu) and stack tops in shared memory -- what the config-5 numbers are measured with --
+    against the oracle on the downloaded images, 1 M uniform random rays, every bit. Then the same rays with each of the
+    two features alone and with neither."""
+    v, i = rb.synthetic_triangles(3_000_000, seed=7, extent=1000.0, edge=2.0)
+    s = rb.create_scene(v, i)
+    assert (s.info["node_count"] + s.info["pair_count"]) * 64 > 256 << 20, "the scene no longer exceeds the auto threshold"
+    assert s.info["depth"] > 16
+    nodes, pairs, remap = s.download()
+    img = oracle.SceneImages(nodes, pairs, remap)
+    rays = random_rays(1_000_000, np.zeros(3), np.full(3, 1000.0), seed=8)
+    want, cnt = oracle.traverse(img, rays, counters=True)
+    assert 0.3 < (want["triangle"] != oracle.INVALID).mean() < 0.95
+    try:
+        for tuning in (dict(sort=2, smem_stack=-1), dict(sort=1, smem_stack=0), dict(sort=0, smem_stack=16), dict(sort=0, smem_stack=0),
+                       dict(sort=1, smem_stack=8, sort_origin_bits=8, sort_dir_bits=2)):
+            rb.set_tuning(**{**DEFAULT, **tuning})
+            d_rays = to_device(rays)
+            d_res = torch.full((rays.shape[0] * 4,), 7.0, dtype=torch.float32, device="cuda")
+            d_cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
+            rb.trace_device(s, None, [(d_rays.data_ptr(), d_res.data_ptr(), rays.shape[0])], counters_ptr=d_cnt.data_ptr())
+            torch.cuda.synchronize()
+            assert_bit_exact(d_res.cpu().numpy().view(np.uint32).reshape(-1, 4), want, f"3 M-triangle soup {tuning}")
+            c = d_cnt.cpu().numpy()
+            assert c[2] == int(cnt["inner"].astype(np.int64).sum()) and c[3] == int(cnt["pairs"].astype(np.int64).sum())
+    finally:
+        rb.set_tuning(**{**DEFAULT, "sort": 2, "smem_stack": -1})
+        s.destroy()
+
+
+# ---------------------------------------------------------------------------------------------
+# variant 4: 32-byte quantised nodes (SURVEY 8f rank 4). NOT bit-exact by design: north_star's bar, arbitrated by fp64.
+
+@pytest.mark.parametrize("tuning", [dict(variant=4), dict(variant=4, smem_stack=16), dict(variant=4, sort=1, smem_stack=16)],
+                         ids=["quantised", "quantised_smem16", "quantised_rebinned_smem16"])
+def test_quantised_nodes_battlefield_tolerance_parity(tuning, scene, env, images, battlefield):
+    """480x270 primaries + 3 bounces through the quantised-node kernel: every result equal to the oracle's except rays whose
+    id the fp64 brute force confirms as a tie; same id => same bits (the pair test is the exact one)."""
+    rb.set_tuning(**{**DEFAULT, **tuning})
+    try:
+        w, h = 480, 270
+        d_rays = device_primary(battlefield, w, h, 1, seed=1)
+        n = w * h
+        differing = 0
+        for bounce in range(4):
+            rays_np = d_rays[: n * 8].cpu().numpy().view(oracle.RAY_DTYPE)
+            d_res = torch.empty(n * 4, dtype=torch.float32, device="cuda")
+            rb.trace_device(scene, env, [(d_rays.data_ptr(), d_res.data_ptr(), n)])
+            torch.cuda.synchronize()
+            got = d_res.cpu().numpy().view(np.uint32).reshape(-1, 4)
+            differing += assert_tolerance_parity(got, oracle.traverse(images, rays_np), rays_np, battlefield.vertices, battlefield.indices, f"bounce {bounce}")
+            d_rays, n = device_bounce(scene, d_rays, d_res, n, seed=2 + bounce)
+        print(f"quantised nodes {tuning}: {differing} rays differ from the oracle over 4 waves")
+    finally:
+        rb.set_tuning(**DEFAULT)
+
+
+def test_quantised_nodes_full_size_and_soup(scene, env, battlefield):
+    """Variant 4 at size, against variant 3 on the same rays (which the tests above pin to the oracle): the full 8.3 M-ray
+    primary stream of the bench and 1 M random rays in a 3 M-triangle soup (the config the format is meant for). Ids may
+    differ only for a vanishing fraction of rays, and where they agree every bit agrees."""
+    w, h, spp = 1920, 1080, 4
+    n = w * h * spp
+    d_rays = device_primary(battlefield, w, h, spp, seed=1)
+    cases = [("battlefield primaries", scene, env, d_rays, n, battlefield.vertices, battlefield.indices)]
+    v, i = rb.synthetic_triangles(3_000_000, seed=7, extent=1000.0, edge=2.0)
+    soup = rb.create_scene(v, i)
+    soup_rays = to_device(random_rays(1_000_000, np.zeros(3), np.full(3, 1000.0), seed=8))
+    cases.append(("3 M-triangle soup", soup, None, soup_rays, 1_000_000, v, i))
+    try:
+        for name, sc, en, rays, count, verts, idx in cases:
+            out = []
+            for variant in (3, 4):
+                rb.set_tuning(**{**DEFAULT, "variant": variant, "sort": 2, "smem_stack": -1})
+                d_res = torch.empty(count * 4, dtype=torch.float32, device="cuda")
+                rb.trace_device(sc, en, [(rays.data_ptr(), d_res.data_ptr(), count)])
+                torch.cuda.synchronize()
+                out.append(d_res.view(-1, 4).view(torch.int32))
+            exact, quant = out
+            same = (exact[:, 0] == quant[:, 0])
+            differing = int((~same).sum())
+            assert differing <= 2e-5 * count + 3, f"{name}: {differing} of {count} ids differ"
+            assert torch.equal(exact[same], quant[same]), f"{name}: same triangle, different bits"
+            if differing:
+                bad = torch.nonzero(~same).flatten().cpu().numpy()
+                sub = rays.view(-1, 8)[torch.from_numpy(bad).cuda()].cpu().numpy().reshape(-1).view(oracle.RAY_DTYPE)
+                got = quant[torch.from_numpy(bad).cuda()].cpu().numpy().view(np.uint32)
+                want = exact[torch.from_numpy(bad).cuda()].cpu().numpy().view(np.uint32)
+                # route the differing rays through the fp64 arbiter (reusing the helper: `want` plays the oracle)
+                assert_tolerance_parity(got, want.view(oracle.RESULT_DTYPE).reshape(-1), sub, verts, idx, name, max_id_mismatch=1.0)
+            print(f"quantised vs exact, {name}: {differing} of {count} ids differ")
+    finally:
+        rb.set_tuning(**{**DEFAULT, "sort": 2, "smem_stack": -1})
+        soup.destroy()
+
+
+def test_quantised_nodes_hand_built_scenes(gpu):
+    from kat_scenes import KAT_CASES, build_kat_scene, deep_stack_scene
+    rb.set_tuning(**{**DEFAULT, "variant": 4})
+    try:
+        for case in KAT_CASES:
+            if case["name"] == "coplanar_duplicates_later_pair_wins":
+                continue  # an exact tie by construction: the one thing the format leaves open
+            images, rays = build_kat_scene(case)
+            pairs = np.concatenate([images.pairs, np.repeat(images.pairs[:1], (-images.pairs.shape[0]) % 32 or 32, axis=0)])
+            s = rb.create_scene_from_images(images.nodes, pairs, images.remap)
+            assert_bit_exact(trace_dev(s, None, rays), oracle.traverse(images, rays), case["name"])
+            s.destroy()
+        images, rays, _ = deep_stack_scene(n_rays=20_000)
+        s = rb.create_scene_from_images(images.nodes, images.pairs, images.remap)
+        assert_bit_exact(trace_dev(s, None, rays), oracle.traverse(images, rays), "deep stack, quantised nodes")
+        s.destroy()
+    finally:
+        rb.set_tuning(**DEFAULT)
+
+
+def test_eight_bounces_bit_exact(scene, env, images, battlefield):
+    """BASELINE.json configs[2]'s depth at reduced size: 480x270 primaries followed by EIGHT diffuse bounces, every wave
+    against the oracle (deep bounces are the short, incoherent streams; the waves shrink to a few thousand rays)."""
+    w, h = 480, 270
+    d_rays = device_primary(battlefield, w, h, 1, seed=3)
+    n = w * h
+    sizes = []
+    for bounce in range(9):
+        rays_np = d_rays[: n * 8].cpu().numpy().view(oracle.RAY_DTYPE)
+        d_res = torch.empty(n * 4, dtype=torch.float32, device="cuda")
+        rb.trace_device(scene, env, [(d_rays.data_ptr(), d_res.data_ptr(), n)])
+        torch.cuda.synchronize()
+        assert_bit_exact(d_res.cpu().numpy().view(np.uint32).reshape(-1, 4), oracle.traverse(images, rays_np), f"bounce {bounce}")
+        sizes.append(n)
+        d_rays, n = device_bounce(scene, d_rays, d_res, n, seed=20 + bounce)
+        assert n > 0
+    assert sizes[8] < sizes[0] // 50, sizes
+
+
+def test_hundreds_of_tiny_host_streams_in_one_call(scene, env, images, battlefield):
+    """A flush of many partially filled API streams: 700 HOST streams of 1..3000 rays (and a few empty ones) in ONE
+    racc_cuda_trace call. They share staging chunks -- a chunk takes as many stream segments as fit, not 64 -- so the
+    call stays a handful of launches, and every stream's results land in its own buffer, bit-exact."""
+    lo = battlefield.vertices[:, :3].min(0)
+    hi = battlefield.vertices[:, :3].max(0)
+    rng = np.random.default_rng(123)
+    sizes = [int(x) for x in rng.integers(1, 3000, size=700)]
+    for k in (5, 77, 300):
+        sizes[k] = 0
+    total = sum(sizes)
+    all_rays = random_rays(total, lo, hi, seed=321)
+    want = oracle.traverse(images, all_rays)
+    pin_r = torch.from_numpy(all_rays.view(np.float32).reshape(-1).copy()).pin_memory()
+    pin_o = torch.full((total * 4 + 4,), 7.0, dtype=torch.float32).pin_memory()
+    descs, off = [], 0
+    for n in sizes:
+        descs.append((pin_r.data_ptr() + off * 32, pin_o.data_ptr() + off * 16, n))
+        off += n
+    before = rb.launch_count()
+    rb.trace_host_ptrs(scene, env, descs)
+    rb.sync()
+    launches = rb.launch_count() - before
+    assert launches <= 3, f"{launches} launches for {total} rays in {len(sizes)} streams"
+    got = pin_o.numpy()[: total * 4].view(np.uint32).reshape(-1, 4)
+    assert_bit_exact(got, want, "tiny host streams")
+    assert float(pin_o[total * 4]) == 7.0  # nothing written past the last stream
+
+
+def test_trees_deeper_than_the_stack_are_refused(gpu):
+    from test_library_on_cpu import deep_chain_images
+    nodes, pairs, remap = deep_chain_images(70)
+    with pytest.raises(rb.EngineError, match="levels deep"):
+        rb.create_scene_from_images(nodes, pairs, remap)
+
+
+def test_tiny_scenes_trace(gpu):
+    """Scenes whose root stays a leaf: a cube and a single triangle now get a synthetic root and trace."""
+    c = np.array([[x, y, z, 1] for x in (0, 1) for y in (0, 1) for z in (0, 1)], np.float32)
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    cube_i = np.array([[a, b, cc, a, cc, d] for a, b, cc, d in quads], np.uint32).ravel()
+    tri_v = np.array([[0, 0, 0, 1], [1, 0, 0, 1], [0, 1, 0, 1]], np.float32)
+    for v, i, name in ((c, cube_i, "cube"), (tri_v, np.arange(3, dtype=np.uint32), "one triangle")):
+        for build in (0, 2):
+            rb.set_tuning(build_device=build)
+            try:
+                s = rb.create_scene(v, i)
+            finally:
+                rb.set_tuning(build_device=3)
+            nodes, pairs, remap = s.download()
+            rays = random_rays(20_000, v[:, :3].min(0) - 1, v[:, :3].max(0) + 1, seed=9)
+            got = trace_dev(s, None, rays)
+            assert_bit_exact(got, oracle.traverse(oracle.SceneImages(nodes, pairs, remap), rays), name)
+            assert (got[:, 0] != rb.INVALID_TRIANGLE).any()
+            s.destroy()
 
 
 # ---------------------------------------------------------------------------------------------

@@ -41,14 +41,14 @@ def main():
     block = int(os.environ.get("C4_BLOCK", "16384"))
     runs = sharding.interleaved_blocks(pixels, rank, world, block) if world > 1 else [(0, pixels)]
     n0 = sum(e - b for b, e in runs)
-    frame = torch.zeros(4, dtype=torch.int64, device="cuda")
+    frame = torch.zeros(8, dtype=torch.int64, device="cuda")
     trace_ms = 0.0
     gather_ms = 0.0
     rays_traced = 0
     per_depth = [0] * (BOUNCES + 1)
 
     if world > 1:  # connection set-up of the communicator is not part of a frame
-        sharding.reduce_frame_counters(torch.zeros(4, dtype=torch.int64, device="cuda"))
+        sharding.reduce_frame_counters(torch.zeros(8, dtype=torch.int64, device="cuda"))
         sharding.gather_results_interleaved(torch.zeros(n0 * 4, dtype=torch.float32, device="cuda"), pixels, block)
         torch.cuda.synchronize()
 
@@ -73,7 +73,7 @@ def main():
             if not streams:
                 break
             results = [torch.empty(n * 4, dtype=torch.float32, device="cuda") for _, n in streams]
-            cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+            cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
             ms = timed_trace([(r.data_ptr(), o.data_ptr(), n) for (r, n), o in zip(streams, results)], cnt)
             if not warm:
                 n_all = sum(n for _, n in streams)

@@ -63,7 +63,7 @@ def main():
     rays[:, 3] = 0.0
     rays[:, 7] = 1e6
     res = torch.empty(n * 4, dtype=torch.float32, device="cuda")
-    cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
     rb.trace_device(scene, None, [(rays.data_ptr(), res.data_ptr(), n)], counters_ptr=cnt.data_ptr(), detail=True)
     torch.cuda.synchronize()
     if world > 1:

@@ -39,7 +39,7 @@ def timed_trace(scene, env, descs, iters=3):
 
 
 def counted(scene, env, rays, res, n):
-    cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
     rb.trace_device(scene, env, [(rays.data_ptr(), res.data_ptr(), n)], counters_ptr=cnt.data_ptr(), detail=True)
     torch.cuda.synchronize()
     return [int(x) for x in cnt.cpu().tolist()]

@@ -21,7 +21,7 @@ rb.generate_primary(cam, w, h, spp, 1, rays.data_ptr())
 sets = []
 for bounce in range(4):
     res = torch.empty(n * 4, dtype=torch.float32, device="cuda")
-    cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
     rb.trace_device(scene, env, [(rays.data_ptr(), res.data_ptr(), n)], counters_ptr=cnt.data_ptr(), detail=False)
     torch.cuda.synchronize()
     sets.append((rays, res, n))
@@ -47,7 +47,7 @@ for cfg in (sys.argv[1] if len(sys.argv) > 1 else "variant=0").split(";"):
             ts.append(a.elapsed_time(b))
         print(cfg, name, " ".join(f"{x:.2f}" for x in ts), flush=True)
         for rep in range(3):  # counted launches: does the WORK vary between runs, or only the time?
-            cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+            cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
             rb.debug_warp_stats(True)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)

@@ -27,7 +27,7 @@ rb.set_tuning(variant=1)  # build the streams with the simple kernel so that ncu
 sets = []
 for bounce in range(4):
     res = torch.empty(n * 4, dtype=torch.float32, device="cuda")
-    cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
     rb.trace_device(scene, env, [(rays.data_ptr(), res.data_ptr(), n)], counters_ptr=cnt.data_ptr(), detail=False)
     torch.cuda.synchronize()
     sets.append((rays, res, n))

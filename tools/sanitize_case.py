@@ -34,7 +34,7 @@ for tuning in (dict(variant=3, sort=0, smem_stack=0), dict(variant=3, sort=1, sm
                dict(variant=2, smem_nodes=-1), dict(variant=0, smem_nodes=64), dict(variant=1)):
     rb.set_tuning(**{**dict(variant=3, block=256, ctas_per_sm=5, smem_nodes=0, sort=0, smem_stack=0, sort_dir_bits=0), **tuning})
     o = torch.zeros(n * 4, dtype=torch.float32, device="cuda")
-    cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
     rb.trace_device(scenes[1], None, [(d_rays.data_ptr(), o.data_ptr(), n // 2), (d_rays[(n // 2) * 8:].data_ptr(), o[(n // 2) * 4:].data_ptr(), n - n // 2)],
                     counters_ptr=cnt.data_ptr(), detail=True)
     torch.cuda.synchronize()

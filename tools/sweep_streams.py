@@ -25,7 +25,7 @@ def main():
     sets = []
     for bounce in range(6):
         res = torch.empty(n * 4, dtype=torch.float32, device="cuda")
-        cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+        cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
         rb.trace_device(scene, env, [(rays.data_ptr(), res.data_ptr(), n)], counters_ptr=cnt.data_ptr(), detail=True)
         torch.cuda.synchronize()
         c = [int(x) for x in cnt.tolist()]
