@@ -325,7 +325,11 @@ __device__ __forceinline__ uint32_t innerStepPacked(u64 nodeBase, uint32_t node,
 
 // The same step on a 32-byte quantised node (kQuant). The ray was moved into grid space once (quantRay): r.ix = cell *
 // invDir, r.px = (gridOrigin - origin) * invDir, so a plane's distance is fma(q, r.ix, r.px) with q the plane's 16-bit
-// cell index as a float (I2F.U16 with a half-word selector: the conversions run on the otherwise idle XU pipe).
+// cell index as a float: I2F.U16 with a half-word selector, 12 per node, on the XU pipe (quarter rate). Measured against
+// the alternative that keeps the XU idle -- a 15-bit index dropped into the mantissa of 2^15 by one PRMT, bias folded
+// into r.px -- the conversions on the ALU pipe cost more than they save (that pipe already runs at 64 %) and the
+// coarser grid lets bounce rays into 12 % more nodes: battlefield 6880 vs 7418 Mrays/s, config 5 899 vs 928
+// (profiles/r02_quantised_nodes.md). So: 16 bits, I2F.
 template <bool kCount, typename Stack>
 __device__ __forceinline__ uint32_t innerStepQuant(u64 nodeBase, uint32_t node, const RayState& r, Stack& stack, unsigned& pushes) {
 	u64 a;

@@ -28,6 +28,12 @@
 
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 v = {x, y, z, w}; return v; }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned selector) { // PRMT, default mode
+	const unsigned long long both = ((unsigned long long)b << 32) | a;
+	unsigned r = 0;
+	for (int k = 0; k < 4; ++k) r |= (unsigned)((both >> (8 * ((selector >> (4 * k)) & 7))) & 0xff) << (8 * k);
+	return r;
+}
 struct uint4 { unsigned x, y, z, w; };
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v = {x, y, z, w}; return v; }
 
@@ -384,6 +390,7 @@ inline void pack2(unsigned long long& out, float lo, float hi) {
 	uint32_t a, b; memcpy(&a, &lo, 4); memcpy(&b, &hi, 4);
 	out = (unsigned long long)a | ((unsigned long long)b << 32);
 }
+inline void pack2(unsigned long long& out, unsigned lo, unsigned hi) { out = (unsigned long long)lo | ((unsigned long long)hi << 32); }
 inline void unpack2(float& lo, float& hi, unsigned long long v) {
 	const uint32_t a = (uint32_t)v, b = (uint32_t)(v >> 32); memcpy(&lo, &a, 4); memcpy(&hi, &b, 4);
 }

@@ -39,7 +39,7 @@ static T* alignedArray(size_t n) { return static_cast<T*>(_mm_malloc(n * sizeof(
 
 int main(int argc, char** argv) {
 	bool whitted = false;
-	int width = 0, height = 0, frames = 4, depth = -1, threads = 0, device = 0;
+	int width = 0, height = 0, frames = 4, depth = -1, threads = 0, device = 0, devices = 1;
 	std::string scenePath = "data/battlefield.bin", outPath, dumpPath;
 	for (int i = 1; i < argc; ++i) {
 		auto next = [&]() { return i + 1 < argc ? argv[++i] : "0"; };
@@ -50,6 +50,7 @@ int main(int argc, char** argv) {
 		else if (!strcmp(argv[i], "--depth")) depth = atoi(next());
 		else if (!strcmp(argv[i], "--threads")) threads = atoi(next());
 		else if (!strcmp(argv[i], "--device")) device = atoi(next());
+		else if (!strcmp(argv[i], "--devices")) devices = atoi(next());
 		else if (!strcmp(argv[i], "--scene")) scenePath = next();
 		else if (!strcmp(argv[i], "--out")) outPath = next();
 		else if (!strcmp(argv[i], "--dump")) dumpPath = next();
@@ -104,7 +105,7 @@ int main(int argc, char** argv) {
 	              make_float3(h.up[0], h.up[1], h.up[2]), h.fov, 1e-3f, 1e+6f, sd.viewportWidth, sd.viewportHeight);
 
 	racc::init();
-	racc::Configuration cfg = racc::defaultConfiguration(racc::cudaDevice(device));
+	racc::Configuration cfg = racc::defaultConfiguration(devices > 1 ? racc::cudaDevices(device, devices) : racc::cudaDevice(device));
 	if (threads > 0) cfg.cpuThreads = (uint8_t)threads;
 	racc::Context* context = racc::createContext(cfg);
 	if (!context) return 3;

@@ -1,0 +1,145 @@
+"""Several B200s behind ONE process (VERDICT r01 "missing" 2): the engine library itself replicates scenes, deals HOST
+streams over a device set and sums the devices' frame records with NCCL -- and the reference API drives it through
+racc::cudaDevices. Needs >= 2 GPUs (the driver's single-GPU test run skips this file; `gpurun --gpus 2` runs it)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+import rayaccel_b200 as rb
+from conftest import random_rays
+from test_api_plumbing import run_json  # noqa: F401
+from test_api_plumbing import plumbing_gpu  # noqa: F401  (fixture)
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def devices():
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    yield list(range(min(n, 8)))
+    rb.init(0)
+
+
+def test_one_process_all_devices_host_streams_and_frame_reduce(devices, battlefield):
+    """racc_cuda_init over every GPU of the box: one scene build replicated peer to peer, one racc_cuda_trace call whose HOST
+    streams are dealt over all devices (results bit-exact, every device took part), racc_cuda_frame_reduce = ncclAllReduce
+    over the devices from inside the library."""
+    rb.init(devices)
+    assert rb.current_devices() == devices
+    scene = rb.create_scene(battlefield.vertices, battlefield.indices)
+    env = rb.create_environment(battlefield.environment)
+    nodes, pairs, remap = scene.download()
+    images = oracle.SceneImages(nodes, pairs, remap, battlefield.environment)
+    lo, hi = battlefield.vertices[:, :3].min(0), battlefield.vertices[:, :3].max(0)
+    sizes = [3_000_000, 1, 65535, 49152, 700_001]
+    rays = [random_rays(s, lo, hi, seed=500 + k) for k, s in enumerate(sizes)]
+    pin_r = [torch.from_numpy(r.view(np.float32).reshape(-1).copy()).pin_memory() for r in rays]
+    pin_o = [torch.full((s * 4,), 7.0, dtype=torch.float32).pin_memory() for s in sizes]
+    rb.frame_reduce()
+    rb.trace_host_ptrs(scene, env, [(a.data_ptr(), b.data_ptr(), s) for a, b, s in zip(pin_r, pin_o, sizes)])
+    rb.sync()
+    hits = 0
+    for k, s in enumerate(sizes):
+        want = oracle.traverse(images, rays[k])
+        hits += int((want["triangle"] != oracle.INVALID).sum())
+        assert np.array_equal(pin_o[k].numpy().view(np.uint32).reshape(-1, 4), want.view(np.uint32).reshape(-1, 4)), f"stream {k}"
+    # per-device shares: bind to each device alone and read (and zero) its record
+    shares = []
+    for d in devices:
+        rb.init(d)
+        shares.append(rb.frame_reduce()["rays"])
+    assert sum(shares) == sum(sizes) and all(x > 0 for x in shares), shares
+    # the reduction over the set (NCCL, single process): trace again, reduce once
+    rb.init(devices)
+    rb.trace_host_ptrs(scene, env, [(a.data_ptr(), b.data_ptr(), s) for a, b, s in zip(pin_r, pin_o, sizes)])
+    rb.sync()
+    total = rb.frame_reduce()
+    assert total["rays"] == sum(sizes) and total["hits"] == hits
+    assert rb.frame_reduce()["rays"] == 0
+    # any single device of the set traces the same scene with the same bits (device-resident stream on device 1)
+    rb.init(devices[1])
+    with torch.cuda.device(devices[1]):
+        d_rays = torch.from_numpy(rays[2].view(np.float32).reshape(-1).copy()).cuda()
+        d_res = torch.empty(sizes[2] * 4, dtype=torch.float32, device="cuda")
+        rb.trace_device(scene, env, [(d_rays.data_ptr(), d_res.data_ptr(), sizes[2])])
+        torch.cuda.synchronize()
+        got = d_res.cpu().numpy().view(np.uint32).reshape(-1, 4)
+    assert np.array_equal(got, oracle.traverse(images, rays[2]).view(np.uint32).reshape(-1, 4))
+    rb.init(devices)
+    env.destroy()
+    scene.destroy()
+    rb.thread_release()
+    rb.comm_destroy()
+    rb.init(0)
+
+
+def test_two_contexts_on_different_devices_do_not_disturb_each_other(devices, battlefield):
+    """ADVICE r01 (process-global device binding): two threads, each bound to its own device with its own scene, trace
+    concurrently; both get the oracle's bits."""
+    import threading
+    lo, hi = battlefield.vertices[:, :3].min(0), battlefield.vertices[:, :3].max(0)
+    h = rb.HostImages(battlefield.vertices, battlefield.indices)
+    images = oracle.SceneImages(h.nodes, h.pairs, h.remap, battlefield.environment)
+    errors = []
+
+    def worker(dev):
+        try:
+            rb.init(dev)
+            scene = rb.create_scene(battlefield.vertices, battlefield.indices)
+            env = rb.create_environment(battlefield.environment)
+            for rep in range(4):
+                rays = random_rays(200_000, lo, hi, seed=900 + 10 * dev + rep)
+                got = rb.trace_host(scene, env, rays)
+                if not np.array_equal(got.view(np.uint32), oracle.traverse(images, rays).view(np.uint32)):
+                    errors.append(f"device {dev} rep {rep}: results differ")
+            env.destroy()
+            scene.destroy()
+            rb.thread_release()
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"device {dev}: {e}")
+
+    threads = [threading.Thread(target=worker, args=(d,)) for d in devices[:2]]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
+def test_reference_api_over_all_devices(devices, plumbing_gpu):  # noqa: F811
+    """The plumbing client (written like the reference's renderers) with racc::cudaDevices(0, n): every result still comes
+    back to the right ray, and Stats.raysTraced -- the NCCL sum of the devices' frame records -- equals the expected count."""
+    n = len(devices)
+    rc, out = run_json([plumbing_gpu, "--devices", str(n), "--threads", "8", "--submitters", "2", "--rays", "2000000", "--frames", "3",
+                        "--spawn", "16384", "--shade", "8192", "--batch", "49152", "--inflight", "2097152"])
+    assert rc == 0 and out["ok"], out
+    assert out["rays_traced"] == out["rays_expected"]
+
+
+def test_unmodified_path_tracer_same_rays_on_one_and_on_all_devices(devices):
+    """the reference's unmodified PathTracingRenderer through racc::render() on all GPUs -- its ray count
+    is rand()-seeded, so frames are compared by the invariants the plumbing test uses (rendered size, finite, non-black) and
+    by raysTraced being self-consistent with the submitters' own count (a mismatch prints a warning to stderr)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "racc_render_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/racc_render_gpu not built")
+    outs = []
+    for n in (1, len(devices)):
+        p = subprocess.run([exe, "--width", "1920", "--height", "1080", "--frames", "4", "--devices", str(n)], capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert p.returncode == 0, p.stderr[-500:]
+        assert "devices counted" not in p.stderr, p.stderr[-500:]
+        import json
+        outs.append(json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1]))
+    for o in outs:
+        assert o["rendered_width"] == 1920 and o["rendered_height"] == 1024 and o["nonblack_fraction"] > 0.9 and o["not_finite"] == 0
+    a, b = outs[0]["rays_first_frame"], outs[1]["rays_first_frame"]
+    assert abs(a - b) < 0.01 * a, (a, b)  # same estimator, different rand() draws

@@ -27,12 +27,13 @@ del d
 res = torch.empty(n * 4, dtype=torch.float32, device="cuda")
 desc = [(rays.data_ptr(), res.data_ptr(), n)]
 rb.trace_device(scene, None, desc)  # warm-up (skipped by ncu -s 1)
-for variant in (3, 4):
-    rb.set_tuning(variant=variant)
+for tuning in (dict(variant=3), dict(variant=4)):
+    variant = tuning["variant"]
+    rb.set_tuning(**tuning)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     rb.trace_device(scene, None, desc)
     b.record()
     b.synchronize()
-    print(f"variant {variant}: {a.elapsed_time(b):.3f} ms, {n / a.elapsed_time(b) / 1e3:.1f} Mrays/s (sort + traversal)")
+    print(f"{tuning}: {a.elapsed_time(b):.3f} ms, {n / a.elapsed_time(b) / 1e3:.1f} Mrays/s (sort + traversal)")
 rb.set_tuning(variant=3)
