@@ -555,7 +555,11 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             rb.init(local_rank)
             store.set("racc_one_process_done", "1")
         else:
-            store.wait(["racc_one_process_done"])
+            try:
+                import datetime
+                store.wait(["racc_one_process_done"], datetime.timedelta(seconds=240))
+            except Exception as e:  # noqa: BLE001 -- rank 0's extra took too long: go on, the barrier below still meets it
+                note(f"rank {rank}: still waiting for rank 0's one-process measurement ({type(e).__name__})")
         barrier()
 
     # ---- beside the contract's numbers: frames rendered on the device -- the reference's
@@ -574,8 +578,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
         renders spp_total of its own. Framebuffers summed by one NCCL all-reduce inside the timed region."""
         camr = rb.Camera.for_scene(sf, width, height)
         if strong:
-            lo, hi = sharding.sample_range(spp_total, rank, world)
-            spp, base = hi - lo, lo
+            base, spp = sharding.sample_range(spp_total, rank, world)  # (first sample, count)
         else:
             spp, base = spp_total, rank * spp_total
         fb = torch.zeros(width * height * 4, dtype=torch.float32, device="cuda")

@@ -142,8 +142,9 @@ int racc_cuda_trace_counted(racc_cuda_scene* scene, racc_cuda_env* env, const ra
 
 /* The per-frame hit reduction -- the one collective on the path. Every traversal launch without a
  * caller-supplied counter record adds its rays and hits to its device's frame record. This call sums the records over
- * the calling thread's device set (ncclAllReduce, one communicator per device, this process) and, when the process has
- * joined a rank communicator (below), over all ranks; zeroes them for the next frame; and returns the totals -- what
+ * the calling thread's device set (ncclAllReduce, one communicator per device, this process) or -- for a thread whose set
+ * is the one device the process joined a rank communicator with (below) -- over all ranks, in which case EVERY rank must
+ * call; zeroes them for the next frame; and returns the totals -- what
  * racc::Stats.raysTraced is on the reference's single host (RayAccelerator.cpp:200,372,755-758). totals == NULL: no
  * wait, the sums stay on the device, ordered on cuda_stream. Launches to be counted must have completed or have been
  * enqueued on cuda_stream. NCCL is bound at run time (dlopen) and only when more than one GPU takes part. */

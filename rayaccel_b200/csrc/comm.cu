@@ -6,9 +6,11 @@
 // Every traversal launch adds {rays, hits} to its device's frame record (DeviceState::dFrame, one atomic per warp at
 // kernel exit). racc_cuda_frame_reduce sums the records with ncclAllReduce
 //   * over the devices of the calling thread's device set, one communicator per device in ONE process
-//     (ncclCommInitAll) -- the library drives several B200s itself, e.g. behind racc::render(); and / or
+//     (ncclCommInitAll) -- the library drives several B200s itself, e.g. behind racc::render(); or
 //   * over the ranks of a multi-process job, one device per process (racc_cuda_comm_init_rank: the host application
-//     broadcasts the unique id however it likes -- bench.py uses its torch.distributed store);
+//     broadcasts the unique id however it likes -- bench.py uses its torch.distributed store). The rank communicator
+//     is used by callers whose device set is that one device; a thread that drives a multi-device set reduces over its
+//     set only (a rank-wide collective needs every rank to call, which only the per-rank frame loop guarantees);
 // and zeroes them for the next frame. NCCL is bound at run time (dlopen "libnccl.so.2": in a process that already
 // loaded one -- PyTorch brings its own -- that very library is used, so there is a single NCCL in the address space);
 // a single device without a rank communicator needs no NCCL at all.
@@ -104,9 +106,7 @@ int commFrameReduce(racc_cuda_counters* totals, cudaStream_t stream) {
 	if (!dev) return -1;
 	const std::vector<int> set = currentDeviceSet();
 	std::lock_guard<std::mutex> lock(g_commMutex);
-	const bool ranks = g_rankComm != nullptr;
-	if (ranks && g_rankDevice != dev->ordinal)
-		return fail("racc_cuda_frame_reduce: the rank communicator belongs to CUDA device %d, the calling thread is bound to %d", g_rankDevice, dev->ordinal);
+	const bool ranks = g_rankComm != nullptr && set.size() == 1 && g_rankDevice == dev->ordinal;
 	if (set.size() > 1) {
 		if (loadNccl() || ensureSetComms(set)) return -1;
 		// bound device: the reduction follows the caller's stream; the others reduce on their own streams
@@ -133,7 +133,7 @@ int commFrameReduce(racc_cuda_counters* totals, cudaStream_t stream) {
 		RACC_CUDA_CHECK(cudaMemcpyAsync(dev->dFrameTotal, dev->dFrame, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
 		RACC_CUDA_CHECK(cudaMemsetAsync(dev->dFrame, 0, 8 * sizeof(unsigned long long), stream));
 	}
-	if (ranks) // the sum over this process' devices, summed over the processes
+	if (ranks) // this process' record, summed over the processes
 		RACC_NCCL_CHECK(g_nccl.AllReduce(dev->dFrameTotal, dev->dFrameTotal, 8, kNcclUint64, kNcclSum, g_rankComm, stream));
 	if (totals) {
 		static_assert(sizeof(racc_cuda_counters) == 8 * sizeof(unsigned long long), "counter record is 8 x u64");
