@@ -585,24 +585,28 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
         if spp:
             rb.path_trace(scene, env, shading, camr, width, height, spp, depth, seed=1, framebuffer_ptr=fb.data_ptr(), sample_base=base, stream=stream)
         rb.sync(stream)  # untimed: pool growth, first launches
-        best_ms, waves = 1e30, [0] * (depth + 1)
+        best_ms, best_render_ms, waves = 1e30, 0.0, [0] * (depth + 1)
         for rep in range(3):
             fb.zero_()
             barrier()
-            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0, rm, r1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             r0.record(stream)
             if spp:
                 _, waves = rb.path_trace(scene, env, shading, camr, width, height, spp, depth, seed=1, framebuffer_ptr=fb.data_ptr(),
                                          sample_base=base, stream=stream)
+            rm.record(stream)
             if world > 1:
                 with torch.cuda.stream(stream):
                     sharding.reduce_framebuffer(fb)
             r1.record(stream)
             r1.synchronize()
-            best_ms = min(best_ms, gmax(r0.elapsed_time(r1)))
+            t_all, t_render = gmax(r0.elapsed_time(r1)), gmax(r0.elapsed_time(rm))
+            if t_all < best_ms:
+                best_ms, best_render_ms = t_all, t_render
         n_all = gsum(sum(waves))
         n_secondary_all = gsum(sum(waves[1:]))
-        rec = {"value": round(n_all / best_ms / 1e3, 1), "unit": "Mrays/s", "ms": round(best_ms, 3), "rays": n_all,
+        rec = {"value": round(n_all / best_ms / 1e3, 1), "unit": "Mrays/s", "ms": round(best_ms, 3), "render_ms_slowest_rank": round(best_render_ms, 3),
+               "framebuffer_allreduce_bytes": width * height * 16 if world > 1 else 0, "rays": n_all,
                "secondary_rays": n_secondary_all, "rays_per_depth_rank0": waves, "scaling": "strong" if strong else "weak",
                "spp_this_rank": spp, "max_depth": int(depth),
                "mean_radiance": round(float(fb.view(-1, 4)[:, :3].double().mean().item()) / max(1, spp_total * (1 if strong else world)), 5),

@@ -51,6 +51,20 @@ __device__ __forceinline__ void initRay(const DevRay* rays, uint32_t i, RayState
 	h.index = kMiss; h.t = r.tFar; h.u = 0.0f; h.v = 0.0f;
 }
 
+// Three-input min / max (FMNMX3, new on sm_100): exact operations, so max3(a, b, c) has the bits of fmaxf(fmaxf(a, b), c) --
+// minNum / maxNum are associative, NaN operands are skipped either way and -0 < +0 is a total order. One ALU-pipe
+// instruction instead of two in the slab tests, on a kernel whose ALU pipe runs at 61-74 %.
+__device__ __forceinline__ float max3(float a, float b, float c) {
+	float d;
+	asm("max.ftz.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+	return d;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+	float d;
+	asm("min.ftz.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+	return d;
+}
+
 // aabbIntersect (Kernels.h:117-135): entry distance, or tFar as the miss sentinel.
 __device__ __forceinline__ float slab(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const RayState& r) {
 	const float nx = fmaf(mnx, r.ix, r.px), ny = fmaf(mny, r.iy, r.py), nz = fmaf(mnz, r.iz, r.pz);

@@ -298,10 +298,11 @@ __device__ __forceinline__ uint32_t innerStepPacked(u64 nodeBase, uint32_t node,
 	unpack2(fma2(rz, iz2, pz2), n1z, f1z);
 	const float tRay = r.tFar;
 	// aabbIntersect (Kernels.h:117-135), twice
-	const float a0 = fmaxf(fmaxf(r.tNear, fminf(n0x, f0x)), fmaxf(fminf(n0y, f0y), fminf(n0z, f0z)));
-	const float b0 = fminf(fminf(tRay, fmaxf(n0x, f0x)), fminf(fmaxf(n0y, f0y), fmaxf(n0z, f0z)));
-	const float a1 = fmaxf(fmaxf(r.tNear, fminf(n1x, f1x)), fmaxf(fminf(n1y, f1y), fminf(n1z, f1z)));
-	const float b1 = fminf(fminf(tRay, fmaxf(n1x, f1x)), fminf(fmaxf(n1y, f1y), fmaxf(n1z, f1z)));
+	// same value as max(max(tNear, min(nx,fx)), max(min(ny,fy), min(nz,fz))) of Kernels.h:128-131, one instruction fewer per line
+	const float a0 = max3(fmaxf(r.tNear, fminf(n0x, f0x)), fminf(n0y, f0y), fminf(n0z, f0z));
+	const float b0 = min3(fminf(tRay, fmaxf(n0x, f0x)), fmaxf(n0y, f0y), fmaxf(n0z, f0z));
+	const float a1 = max3(fmaxf(r.tNear, fminf(n1x, f1x)), fminf(n1y, f1y), fminf(n1z, f1z));
+	const float b1 = min3(fminf(tRay, fmaxf(n1x, f1x)), fmaxf(n1y, f1y), fmaxf(n1z, f1z));
 	const float tFirst = a0 > b0 ? tRay : a0;
 	const float tLast = a1 > b1 ? tRay : a1;
 	const float firstDiff = tRay - tFirst;
@@ -351,10 +352,11 @@ __device__ __forceinline__ uint32_t innerStepQuant(u64 nodeBase, uint32_t node, 
 	RACC_QPLANES(w4, r.iy, r.py, n1y, f1y)
 	RACC_QPLANES(w5, r.iz, r.pz, n1z, f1z)
 #undef RACC_QPLANES
-	const float a0 = fmaxf(fmaxf(r.tNear, fminf(n0x, f0x)), fmaxf(fminf(n0y, f0y), fminf(n0z, f0z)));
-	const float b0 = fminf(fminf(tRay, fmaxf(n0x, f0x)), fminf(fmaxf(n0y, f0y), fmaxf(n0z, f0z)));
-	const float a1 = fmaxf(fmaxf(r.tNear, fminf(n1x, f1x)), fmaxf(fminf(n1y, f1y), fminf(n1z, f1z)));
-	const float b1 = fminf(fminf(tRay, fmaxf(n1x, f1x)), fminf(fmaxf(n1y, f1y), fmaxf(n1z, f1z)));
+	// same value as max(max(tNear, min(nx,fx)), max(min(ny,fy), min(nz,fz))) of Kernels.h:128-131, one instruction fewer per line
+	const float a0 = max3(fmaxf(r.tNear, fminf(n0x, f0x)), fminf(n0y, f0y), fminf(n0z, f0z));
+	const float b0 = min3(fminf(tRay, fmaxf(n0x, f0x)), fmaxf(n0y, f0y), fmaxf(n0z, f0z));
+	const float a1 = max3(fmaxf(r.tNear, fminf(n1x, f1x)), fminf(n1y, f1y), fminf(n1z, f1z));
+	const float b1 = min3(fminf(tRay, fmaxf(n1x, f1x)), fmaxf(n1y, f1y), fmaxf(n1z, f1z));
 	const float tFirst = a0 > b0 ? tRay : a0;
 	const float tLast = a1 > b1 ? tRay : a1;
 	const float firstDiff = tRay - tFirst;

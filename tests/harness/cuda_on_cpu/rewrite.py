@@ -58,6 +58,8 @@ PTX_FORMS: list[tuple[re.Pattern, str]] = [
     (re.compile(r"^mov\.b64 \{%(\d+),%(\d+)\}, %(\d+);$"), "::cuda_on_cpu::ptx::unpack2({0}, {1}, {2});"),
     (re.compile(r"^mov\.b64 %(\d+), %(\d+);$"), "{0} = {1};"),
     (re.compile(r"^fma\.rn\.ftz\.f32x2 %(\d+), %(\d+), %(\d+), %(\d+);$"), "::cuda_on_cpu::ptx::fma2({0}, {1}, {2}, {3});"),
+    (re.compile(r"^max\.ftz\.f32 %(\d+), %(\d+), %(\d+), %(\d+);$"), "{0} = fmaxf(fmaxf({1}, {2}), {3});"),
+    (re.compile(r"^min\.ftz\.f32 %(\d+), %(\d+), %(\d+), %(\d+);$"), "{0} = fminf(fminf({1}, {2}), {3});"),
     (re.compile(r"^mad\.wide\.u32 %(\d+), %(\d+), (\d+), %(\d+);$"), "{0} = (unsigned long long)(uint32_t)({1}) * {imm}ull + (unsigned long long)({3});"),
     (re.compile(r"^ld\.global\.nc\.v8\.f32 \{%0,%1,%2,%3,%4,%5,%6,%7\}, " + _MEM + r";$"), "LD8F"),
     (re.compile(r"^ld\.global\.nc\.v8\.u32 \{%0,%1,%2,%3,%4,%5,%6,%7\}, " + _MEM + r";$"), "LD8U"),

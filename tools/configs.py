@@ -113,6 +113,15 @@ def c5(tris=10_000_000, nrays=100_000_000):
     b = alg_bytes(nrays, c)
     scene_mb = (info["node_count"] * 64 + info["pair_count"] * 48 + info["remap_count"] * 4) / 1e6
     ref = None
+    # the checker's answer for a strided sample of >= 1 M rays at FULL scene size (not `same_bits_as_first` alone)
+    import oracle  # noqa: E402  (test infrastructure; this is a development tool, not the product)
+    nodes, pairs, remap = scene.download()
+    img = oracle.SceneImages(nodes, pairs, remap)
+    stride = max(1, nrays // 1_000_000)
+    idx = torch.arange(0, nrays, stride, device="cuda")
+    sample = rays[idx].cpu().numpy().reshape(-1).view(oracle.RAY_DTYPE)
+    want = torch.from_numpy(oracle.traverse(img, sample).view(np.int32).reshape(-1, 4).copy()).cuda()
+    del img, nodes, pairs, remap
     # RACC_CFG_TUNINGS="k=v,k=v;k=v": time the same rays under several tunings (one line each)
     for spec in os.environ.get("RACC_CFG_TUNINGS", "").split(";"):
         tuning = {k: int(v) for k, v in (kv.split("=") for kv in spec.split(",") if kv)}
@@ -123,7 +132,10 @@ def c5(tris=10_000_000, nrays=100_000_000):
             ref = res.clone()
         else:
             same = bool(torch.equal(ref.view(torch.int32), res.view(torch.int32)))
+        got = res.view(-1, 4).view(torch.int32)[idx]
         emit({"config": f"C5 synthetic soup {tris} triangles, {nrays} uniform random rays", "tuning": tuning, "same_bits_as_first": same,
+              "parity_sample_bit_exact": bool(torch.equal(got, want)), "parity_sample_ids_differing": int((got[:, 0] != want[:, 0]).sum()),
+              "parity_sample_rays": int(idx.numel()),
               "rays": nrays, "ms": round(ms, 3), "mrays": round(nrays / ms / 1e3, 1),
               "hit_rate": round(c[1] / nrays, 4), "inner_per_ray": round(c[2] / nrays, 2), "pairs_per_ray": round(c[3] / nrays, 2),
               "alg_bytes_per_ray": round(b / nrays, 1), "alg_gbs": round(b / ms / 1e6, 1), "frac_of_measured_hbm": round(b / ms / 1e6 / PEAK, 4),
