@@ -40,4 +40,22 @@ for tuning in (dict(variant=3, sort=0, smem_stack=0), dict(variant=3, sort=1, sm
     torch.cuda.synchronize()
     outs.append(o.view(torch.int32).cpu())
 assert all(torch.equal(outs[0], o) for o in outs[1:]), "kernel variants disagree"
+# round 2: the quantised-node kernel (both stack flavours, re-binned), HOST streams through the staging pipeline with the tapered
+# tail, the frame record, and thread teardown
+for tuning in (dict(variant=4), dict(variant=4, sort=1, smem_stack=16)):
+    rb.set_tuning(**{**dict(variant=3, block=256, ctas_per_sm=5, smem_nodes=0, sort=0, smem_stack=0, sort_dir_bits=0), **tuning})
+    o = torch.zeros(n * 4, dtype=torch.float32, device="cuda")
+    rb.trace_device(scenes[1], None, [(d_rays.data_ptr(), o.data_ptr(), n)])
+    torch.cuda.synchronize()
+    ids = o.view(torch.int32).cpu().view(-1, 4)[:, 0]
+    assert int((ids != outs[0].view(-1, 4)[:, 0]).sum()) <= 2, "quantised nodes: ids differ beyond ties"
+rb.set_tuning(variant=3, sort=2, smem_stack=-1)
+host_rays = torch.from_numpy(rays.reshape(-1)).pin_memory()
+host_out = torch.zeros(n * 4, dtype=torch.float32).pin_memory()
+rb.frame_reduce()
+rb.trace_host_ptrs(scenes[1], None, [(host_rays.data_ptr(), host_out.data_ptr(), 7), (host_rays.data_ptr() + 7 * 32, host_out.data_ptr() + 7 * 16, n - 7)])
+rb.sync()
+assert torch.equal(host_out.view(torch.int32), outs[0]), "HOST stream results differ"
+assert rb.frame_reduce()["rays"] == n
+rb.thread_release()
 print("sanitize case ok:", n_tris, "triangles,", n, "rays,", int((outs[0].view(-1, 4)[:, 0] != -1).sum()), "hits")
