@@ -278,6 +278,24 @@ def run_reference(args, rank: int, world: int) -> None:
         ref_kernel = {"value": round(m / (time.perf_counter() - t1) / 1e6, 3), "unit": "Mrays/s", "cores": cores, "kind": "reference",
                       "sample": f"first {m} rays of the step", "what": "reference traversal kernel source text run on the CPU through an "
                       "OpenCL C shim, one work-item at a time per thread", "port_results_bit_identical": bool(got.tobytes() == want.tobytes())}
+    # ... and the reference's CPU query path, executeRayQueryCPU (Scene.cpp:374-484), from its own source over the stand-in for
+    # its binary-only Embree 2.7 (oracle/ref_shim/mini_embree.cpp: an unoptimised 8-wide packet traversal, so this rate says
+    # nothing about Embree's speed; it is here for the agreement check)
+    ref_cpu_path = None
+    if oracle.have_ref_cpu_query():
+        m = min(n, 2_000_000)
+        t1 = time.perf_counter()
+        got = oracle.ref_cpu_query(sf.vertices, sf.indices, sf.environment, sample[:m], threads=0)
+        dt1 = time.perf_counter() - t1
+        want = oracle.traverse_avx2(images, sample[:m])
+        hit_a, hit_b = got["triangle"] != oracle.INVALID, want["triangle"] != oracle.INVALID
+        same = hit_a & hit_b & (got["triangle"] == want["triangle"])
+        ref_cpu_path = {"value": round(m / dt1 / 1e6, 3), "unit": "Mrays/s", "cores": cores, "kind": "reference",
+                        "sample": f"first {m} rays of the step (scene set-up included in the time)",
+                        "what": "racc_internal::executeRayQueryCPU run from its own source; rtcIntersect8 served by oracle/ref_shim/mini_embree.cpp",
+                        "hit_miss_disagreements_with_port": int((hit_a != hit_b).sum()),
+                        "prim_ids_differing_from_port": int((hit_a & hit_b & ~same).sum()),
+                        "max_rel_dt": float(np.max(np.abs(got["a"][same] - want["a"][same]) / np.abs(want["a"][same]))) if same.any() else 0.0}
     line = {
         "impl": "reference", "metric": METRIC, "value": round(mrays, 3), "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
@@ -293,6 +311,8 @@ def run_reference(args, rank: int, world: int) -> None:
     }
     if ref_kernel is not None:
         line["reference_kernel_source"] = ref_kernel
+    if ref_cpu_path is not None:
+        line["reference_cpu_query_path"] = ref_cpu_path
     emit(line)
 
 

@@ -223,6 +223,30 @@ def tri_t_f64(verts4: np.ndarray, indices: np.ndarray, rays: np.ndarray, tri_ids
 
 # ---- the unmodified reference (oracle/_ref) ------------------------------------------------
 
+def ref_cpu_query(verts4: np.ndarray, indices: np.ndarray, env: np.ndarray | None, rays: np.ndarray, threads: int = 0) -> np.ndarray:
+    """The reference's CPU query path, executeRayQueryCPU (Scene.cpp:374-484), run from its own source over the stand-in
+    for its binary-only Embree 2.7 (oracle/ref_shim/mini_embree.cpp): RESULT_DTYPE array, Embree conventions (primID =
+    original triangle index, u / v = weights of vertices 1 and 2, misses carry the light probe's radiance)."""
+    verts4 = np.ascontiguousarray(verts4, dtype=np.float32).reshape(-1, 4)
+    indices = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+    rays = np.ascontiguousarray(rays)
+    assert rays.dtype == RAY_DTYPE
+    res = np.zeros(rays.shape[0], dtype=RESULT_DTYPE)
+    e = None if env is None else np.ascontiguousarray(env, dtype=np.float32)
+    fn = ref().ref_cpu_query
+    fn.restype = ctypes.c_int
+    rc = fn(_p(verts4), ctypes.c_uint32(verts4.shape[0]), _p(indices), ctypes.c_uint32(indices.shape[0]),
+            _p(e) if e is not None else None, ctypes.c_uint32(e.shape[1] if e is not None else 0),
+            ctypes.c_uint32(e.shape[0] if e is not None else 0), _p(rays), ctypes.c_uint32(rays.shape[0]), _p(res), ctypes.c_int(threads))
+    if rc:
+        raise RuntimeError("ref_cpu_query failed")
+    return res
+
+
+def have_ref_cpu_query() -> bool:
+    return have_ref() and hasattr(ref(), "ref_cpu_query")
+
+
 def ref_build_scene(verts4: np.ndarray, indices: np.ndarray) -> SceneImages:
     """racc::createScene() of the unmodified reference -> its GPU upload images."""
     verts4 = np.ascontiguousarray(verts4, dtype=np.float32).reshape(-1, 4)

@@ -8,8 +8,10 @@
 //   * the raw Bvh2 the reference builder produces (RayAccelerator/Bvh2.h:15-33);
 //   * the reference's CPU light-probe lookup racc_internal::sample()
 //     (RayAccelerator/Environment.h:27-82).
-// The reference's CPU intersection itself lives inside Embree 2.7 (binary-only, macOS/Windows),
-// so there is no ref_intersect here.
+//   * the reference's CPU query path executeRayQueryCPU (RayAccelerator/Scene.cpp:374-484), run from its own
+//     source: the AoS -> RTCRay8 transposes, the primID / tfar / u / v scatter, the light-probe lookup of misses
+//     and the scalar tail are the reference's. What it calls -- rtcIntersect8 / rtcIntersect -- lives inside
+//     Embree 2.7 (binary-only, macOS/Windows); ref_shim/mini_embree.cpp stands in for that binary.
 #include "Scene.h"
 #include "Bvh2.h"
 #include "Context.h"
@@ -19,6 +21,8 @@
 #include <string.h>
 #include <xmmintrin.h>
 #include <pmmintrin.h>
+#include <thread>
+#include <vector>
 
 namespace {
 	struct FtzScope {
@@ -99,6 +103,56 @@ int ref_build_bvh2(const float* verts4, uint32_t nverts, const uint32_t* indices
 	}
 	_mm_free(v);
 	return n;
+}
+
+// results[i] = what racc's CPU back-end returns for rays[i] (32 B racc::Ray -> 16 B racc::Result): the reference's own
+// executeRayQueryCPU over [0, count), cut into slices of a multiple of 8 rays for `threads` host threads (the reference
+// hands it slices of cpuTestBatch rays, RayAccelerator.cpp:158-244). rgba may be null (misses then keep r=g=b=0... the
+// reference dereferences the environment unconditionally, so a 1x1 black probe is created for it).
+int ref_cpu_query(const float* verts4, uint32_t nverts, const uint32_t* indices, uint32_t nindices, const float* rgba, uint32_t width,
+                  uint32_t height, const void* rays, uint32_t count, void* results, int threads) {
+	FtzScope ftz;
+	racc::Vertex* v = static_cast<racc::Vertex*>(_mm_malloc(sizeof(racc::Vertex) * (size_t)nverts + 64, 64));
+	memcpy(v, verts4, sizeof(racc::Vertex) * (size_t)nverts);
+	racc::Context* ctx = fakeContext(false);
+	racc::Scene* scene = racc::createScene(ctx, v, nverts, indices, nindices);
+	const float black[4] = {0, 0, 0, 0};
+	racc::Environment* env = rgba ? racc::createEnvironment(ctx, reinterpret_cast<const racc::Color*>(rgba), width, height)
+	                              : racc::createEnvironment(ctx, reinterpret_cast<const racc::Color*>(black), 1, 1);
+	int rc = -1;
+	if (scene && env) {
+		// the reference's streams are 4 KiB-aligned slabs (RayAccelerator.cpp:532-568); executeRayQueryCPU uses aligned loads
+		racc::Ray* r = static_cast<racc::Ray*>(_mm_malloc(sizeof(racc::Ray) * (size_t)count + 64, 4096));
+		racc::Result* o = static_cast<racc::Result*>(_mm_malloc(sizeof(racc::Result) * (size_t)count + 64, 4096));
+		memcpy(r, rays, sizeof(racc::Ray) * (size_t)count);
+		memset(o, 0, sizeof(racc::Result) * (size_t)count);
+		racc::RayStream stream = {};
+		stream.index = 0;
+		stream.count = count;
+		stream.rays = r;
+		stream.results = o;
+		if (threads < 1) threads = (int)std::thread::hardware_concurrency();
+		if (threads < 1) threads = 1;
+		const uint32_t slice = ((count / (uint32_t)threads + 8) / 8) * 8;
+		std::vector<std::thread> pool;
+		for (uint32_t begin = 0; begin < count; begin += slice) {
+			const uint32_t end = begin + slice < count ? begin + slice : count;
+			pool.emplace_back([=, &stream] {
+				FtzScope inner; // worker threads of the reference run with FTZ + DAZ (Threading.h:77-79)
+				racc_internal::executeRayQueryCPU(scene, &stream, env, begin, end);
+			});
+		}
+		for (std::thread& t : pool) t.join();
+		memcpy(results, o, sizeof(racc::Result) * (size_t)count);
+		_mm_free(r);
+		_mm_free(o);
+		rc = 0;
+	}
+	if (env) racc::destroy(env);
+	if (scene) racc::destroy(scene);
+	_mm_free(ctx);
+	_mm_free(v);
+	return rc;
 }
 
 // out4[i] = sample(environment, dirs4[i]); dirs4 is n x 4 floats (xyz used).

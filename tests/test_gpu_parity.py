@@ -323,6 +323,36 @@ def test_golden_rays_on_gpu(scene, env):
     assert np.all(np.abs(t[both] - g["t64"][both]) <= 1e-4 * g["t64"][both])  # north_star: t within 1e-4 relative
 
 
+def test_engine_matches_reference_cpu_path(scene, env, battlefield):
+    """north_star's parity statement on the CUDA path: results equal the reference's CPU query path on the same rays --
+    executeRayQueryCPU (Scene.cpp:374-484) run from its own source over the stand-in for its binary-only Embree
+    (oracle/ref_shim/mini_embree.cpp). Committed golden vectors always; when oracle/_ref travelled, also live on 1 M rays
+    of the full-size bench streams (every 8th primary ray of 1920x1080x4spp... and its first bounce)."""
+    from conftest import assert_matches_reference_cpu_path
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "battlefield_rays.npz"))
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cpu_path.npz"))["results"]
+    rays = np.ascontiguousarray(g["rays"]).view(oracle.RAY_DTYPE).reshape(-1)
+    assert_matches_reference_cpu_path(trace_dev(scene, env, rays), ref, rays, battlefield.vertices, battlefield.indices, "golden rays")
+    if not oracle.have_ref_cpu_query():
+        return
+    w, h, spp = 1920, 1080, 4
+    n = w * h * spp
+    d_rays = device_primary(battlefield, w, h, spp, seed=1)
+    d_res = torch.empty(n * 4, dtype=torch.float32, device="cuda")
+    rb.trace_device(scene, env, [(d_rays.data_ptr(), d_res.data_ptr(), n)])
+    torch.cuda.synchronize()
+    d_b, nb = device_bounce(scene, d_rays, d_res, n, seed=2)
+    d_bres = torch.empty(max(nb, 1) * 4, dtype=torch.float32, device="cuda")
+    rb.trace_device(scene, env, [(d_b.data_ptr(), d_bres.data_ptr(), nb)])
+    torch.cuda.synchronize()
+    for name, dr, do, count, stride in (("primary", d_rays, d_res, n, 13), ("bounce", d_b, d_bres, nb, 11)):
+        sub = dr.view(-1, 8)[:count][::stride].contiguous().cpu().numpy().reshape(-1).view(oracle.RAY_DTYPE)
+        got = do.view(-1, 4)[:count][::stride].contiguous().cpu().numpy()
+        want = oracle.ref_cpu_query(battlefield.vertices, battlefield.indices, battlefield.environment, sub)
+        differ, rel = assert_matches_reference_cpu_path(got, want, sub, battlefield.vertices, battlefield.indices, name)
+        print(f"engine vs reference CPU path, {name}: {len(sub)} rays, {differ} primIDs differ (ties), max |dt|/t {rel:.2e}")
+
+
 def test_host_streams_packed_into_shared_launches(scene, env, images, battlefield):
     """Many small HOST streams (the sizes racc::render() submits) in one call: the engine packs them
     into shared staging chunks; every stream's results must land in its own buffer, bit-exact."""
