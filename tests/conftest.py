@@ -119,13 +119,23 @@ def assert_matches_reference_cpu_path(got, ref, rays, vertices, indices, what, t
     if differ.size:
         # a tie: both report the closest hit's distance. Either both triangles are hit at that distance in fp64, or the ray
         # runs through the edge they share and fp64 gives it to one of them -- the distances still agree with the fp64 minimum
+        # ... or it grazes an edge: one fp32 implementation counts the near triangle as hit, the other as missed and
+        # reports what lies behind it. Any two fp32 intersectors disagree on such rays (their number is bounded above);
+        # what must hold is that one of the two answers is the fp64 closest hit.
         sub = np.ascontiguousarray(rays[differ])
         t_min, _ = oracle.brute_f64(vertices, indices, sub)
-        for t in (got["a"][differ], ref["a"][differ]):
-            assert np.all(np.abs(t - t_min) <= 1e-4 * t_min), f"{what}: a differing primID is not a closest hit"
+        ok_g = np.abs(got["a"][differ] - t_min) <= 1e-4 * t_min
+        ok_r = np.abs(ref["a"][differ] - t_min) <= 1e-4 * t_min
+        assert np.all(ok_g | ok_r), f"{what}: a ray where neither answer is the fp64 closest hit"
     same = both & (got["triangle"] == ref["triangle"])
-    rel = np.abs(got["a"][same] - ref["a"][same]) / np.abs(ref["a"][same])
-    assert rel.size == 0 or rel.max() <= 1e-4, f"{what}: |dt|/t = {rel.max():.3e} > 1e-4"
+    # 1e-4 relative, with the floor fp32 itself sets for very short distances: a bounce ray starts 1e-4 from a surface and may
+    # hit the next one millimetres on, where t is the difference of two coordinates of magnitude ~250 (8 ulp of those)
+    floor = 8 * 2.0 ** -23 * (np.abs(rays["origin"][same]).max(axis=1) + np.abs(ref["a"][same]))
+    err = np.abs(got["a"][same] - ref["a"][same])
+    bad = err > 1e-4 * np.abs(ref["a"][same]) + floor
+    assert not bad.any(), f"{what}: t differs beyond 1e-4 relative (+ 8 ulp of the coordinates) for {int(bad.sum())} rays, worst {err[bad].max():.3e}"
+    far = np.abs(ref["a"][same]) > 1.0
+    rel = err[far] / np.abs(ref["a"][same][far])
     for k in ("b", "c"):
         d = np.abs(got[k][same] - ref[k][same])
         assert d.size == 0 or d.max() <= 2e-3, f"{what}: barycentric {k} differs by {d.max():.3e}"
