@@ -497,6 +497,7 @@ static inline cudaError_t cudaSetDevice(int device) {
 }
 static inline cudaError_t cudaMemcpyPeer(void* dst, int, const void* src, int, size_t bytes) { if (bytes) memmove(dst, src, bytes); return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaMemGetInfo(size_t* freeBytes, size_t* totalBytes) { *freeBytes = (size_t)4 << 30; *totalBytes = (size_t)8 << 30; return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) { *pool = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
 static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
