@@ -155,6 +155,15 @@ int racc_cuda_frame_reduce(racc_cuda_counters* totals, void* cuda_stream);
 int racc_cuda_comm_unique_id(void* id128);
 int racc_cuda_comm_init_rank(const void* id128, int rank, int nranks);
 void racc_cuda_comm_destroy(void);
+/* Ranks of the communicator joined (1 without one); *rank (may be NULL) receives this process' rank. */
+int racc_cuda_comm_ranks(int* rank);
+
+/* A ray-sharded frame's hit buffer made whole on every rank: every rank passes the racc::Result slice
+ * of its contiguous ray range -- rays_per_rank records of 16 bytes, the same count on every rank (pad the last slice) -- and
+ * receives all slices in rank order in device_all_results (nranks * rays_per_rank records; may alias the slice of this rank in
+ * place). ncclAllGather over the rank communicator, enqueued on cuda_stream; a copy when there is only one rank. Results stay
+ * index-parallel to the frame's rays, as the reference's clients expect (RayAccelerator.h:66-83). */
+int racc_cuda_gather_results(const void* device_results, uint32_t rays_per_rank, void* device_all_results, void* cuda_stream);
 
 /* Pinned (page-locked) host memory for ray streams: replaces the 4 KiB-aligned stream slab that the
  * reference wraps in zero-copy CL_MEM_USE_HOST_PTR buffers (RayAccelerator.cpp:532-568,636-645).

@@ -61,6 +61,8 @@ SYMBOLS = {
     "racc_cuda_comm_unique_id": (ctypes.c_int, [_P]),
     "racc_cuda_comm_init_rank": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int]),
     "racc_cuda_comm_destroy": (None, []),
+    "racc_cuda_comm_ranks": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "racc_cuda_gather_results": (ctypes.c_int, [_P, _U32, _P, _P]),
     "racc_cuda_abi_version": (ctypes.c_int, []),
     "racc_cuda_last_error": (ctypes.c_char_p, []),
     "racc_cuda_scene_create": (_P, [_P, _U32, _P, _U32]),

@@ -76,6 +76,20 @@ def comm_destroy() -> None:
     _lib.load().racc_cuda_comm_destroy()
 
 
+def comm_ranks() -> tuple[int, int]:
+    """(rank, number of ranks) of the communicator this process joined; (0, 1) without one."""
+    r = ctypes.c_int(0)
+    n = _lib.load().racc_cuda_comm_ranks(ctypes.byref(r))
+    return int(r.value), int(n)
+
+
+def gather_results(results_ptr: int, rays_per_rank: int, all_results_ptr: int, stream=None) -> None:
+    """racc_cuda_gather_results: every rank's Result slice (rays_per_rank x 16 B, device memory) gathered in rank order into
+    all_results_ptr on every rank (ncclAllGather inside the engine library)."""
+    _lib.check(_lib.load().racc_cuda_gather_results(ctypes.c_void_p(results_ptr), rays_per_rank, ctypes.c_void_p(all_results_ptr),
+                                                    _cuda_stream_handle(stream)), "racc_cuda_gather_results")
+
+
 def device_count() -> int:
     return _lib.load().racc_cuda_device_count()
 

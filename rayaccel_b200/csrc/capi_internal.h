@@ -151,6 +151,8 @@ void releaseRenderScratch();
 
 // comm.cu
 int commFrameReduce(racc_cuda_counters* totals, cudaStream_t stream);
+int commAllGather(const void* send, void* recv, size_t bytesPerRank, cudaStream_t stream);
+int commRanks(int* rank);
 void commShutdown();
 
 } // namespace racc_b200

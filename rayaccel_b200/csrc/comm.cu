@@ -39,6 +39,7 @@ struct Nccl {
 	ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*GroupStart)() = nullptr;
 	ncclResult_t (*GroupEnd)() = nullptr;
 	const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -71,6 +72,7 @@ int loadNccl() {
 	BIND(CommInitAll, "ncclCommInitAll")
 	BIND(CommDestroy, "ncclCommDestroy")
 	BIND(AllReduce, "ncclAllReduce")
+	BIND(AllGather, "ncclAllGather")
 	BIND(GroupStart, "ncclGroupStart")
 	BIND(GroupEnd, "ncclGroupEnd")
 	BIND(GetErrorString, "ncclGetErrorString")
@@ -143,6 +145,30 @@ int commFrameReduce(racc_cuda_counters* totals, cudaStream_t stream) {
 	return 0;
 }
 
+// Result slices of a ray-sharded frame gathered so that every rank holds the full, index-parallel hit buffer (SURVEY.md
+// section 8e): rank r's `bytes_per_rank` bytes at recv + r * bytes_per_rank. Ranks of the multi-process communicator only (a
+// single process already sees every device's results in its own address space).
+int commAllGather(const void* send, void* recv, size_t bytesPerRank, cudaStream_t stream) {
+	DeviceState* dev = currentDevice();
+	if (!dev) return -1;
+	std::lock_guard<std::mutex> lock(g_commMutex);
+	if (!g_rankComm) {
+		// one rank: the gather is a copy
+		if (send != recv) RACC_CUDA_CHECK(cudaMemcpyAsync(recv, send, bytesPerRank, cudaMemcpyDeviceToDevice, stream));
+		return 0;
+	}
+	if (g_rankDevice != dev->ordinal)
+		return fail("racc_cuda_gather_results: the rank communicator belongs to CUDA device %d, the calling thread is bound to %d", g_rankDevice, dev->ordinal);
+	RACC_NCCL_CHECK(g_nccl.AllGather(send, recv, bytesPerRank, /*ncclUint8*/ 1, g_rankComm, stream));
+	return 0;
+}
+
+int commRanks(int* rank) {
+	std::lock_guard<std::mutex> lock(g_commMutex);
+	if (rank) *rank = g_rank;
+	return g_ranks;
+}
+
 void commShutdown() {
 	std::lock_guard<std::mutex> lock(g_commMutex);
 	if (!g_nccl.lib) return;
@@ -189,5 +215,12 @@ int racc_cuda_comm_init_rank(const void* id128, int rank, int nranks) {
 }
 
 void racc_cuda_comm_destroy(void) { commShutdown(); }
+
+int racc_cuda_comm_ranks(int* rank) { return commRanks(rank); }
+
+int racc_cuda_gather_results(const void* device_results, uint32_t rays_per_rank, void* device_all_results, void* cuda_stream) {
+	if (!device_results || !device_all_results) return fail("racc_cuda_gather_results: null argument");
+	return commAllGather(device_results, device_all_results, (size_t)rays_per_rank * 16, static_cast<cudaStream_t>(cuda_stream));
+}
 
 } // extern "C"

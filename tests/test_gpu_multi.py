@@ -143,3 +143,19 @@ def test_unmodified_path_tracer_same_rays_on_one_and_on_all_devices(devices):
         assert o["rendered_width"] == 1920 and o["rendered_height"] == 1024 and o["nonblack_fraction"] > 0.9 and o["not_finite"] == 0
     a, b = outs[0]["rays_first_frame"], outs[1]["rays_first_frame"]
     assert abs(a - b) < 0.01 * a, (a, b)  # same estimator, different rand() draws
+
+
+def test_ranks_reduce_and_gather_through_the_library(devices):
+    """One process per GPU (torchrun): the engine's own rank communicator sums the frame records and gathers the Result slices
+    of a ray-sharded frame -- ncclAllReduce and ncclAllGather called from libracc_b200.so. Every rank ends up with
+    the full index-parallel hit buffer, bit-exact against the oracle."""
+    n = min(len(devices), 4)
+    p = subprocess.run(["python", "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(ROOT, "tests", "harness", "rank_gather_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert p.returncode == 0 and lines, p.stdout[-1000:] + p.stderr[-2000:]
+    import json
+    out = json.loads(lines[-1])
+    assert out["ranks"] == n and out["every_rank_holds_the_full_hit_buffer_bit_exact"], out
+    assert out["frame_rays"] == out["frame_rays_expected"] and out["frame_hits"] == out["frame_hits_expected"], out
