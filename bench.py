@@ -148,6 +148,13 @@ def ncu_capture(name: str):
     return float(t["dram_bytes_per_launch"]), t.get("source"), t.get("limiters"), t.get("l1_wavefronts_per_launch")
 
 
+def workload_config(rays_per_step: int, ray_digest: str) -> dict:
+    """`config` of the JSON line, the same dict in both arms: what is traced, how many rays, a digest of their bytes, and the
+    cache policy between timed iterations (the inputs of one step are far larger than L2, nothing is flushed)."""
+    return {"workload": workload_name(), "rays_per_step": rays_per_step, "ray_digest": ray_digest,
+            "l2": "inputs larger than L2: 0.8 GB of rays + results per step vs 126 MB; the 3.2 MB scene is cache-resident by nature"}
+
+
 def workload_name():
     return (f"path tracer wavefront, battlefield.bin, {WIDTH}x{HEIGHT}, {SPP} spp, depth {BOUNCES} "
             f"(primary + {BOUNCES} diffuse bounces)")
@@ -300,7 +307,7 @@ def run_reference(args, rank: int, world: int) -> None:
         "impl": "reference", "metric": METRIC, "value": round(mrays, 3), "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "rays_per_step": n_full, "ray_digest": ray_digest},
+        "config": workload_config(n_full, ray_digest),
         "cpu_baseline": {"value": round(mrays, 3), "unit": "Mrays/s", "cores": cores, "kind": "port",
                          "sample": f"{what}; scene images by the {built_by}; batch generated in {gen_s:.1f} s (untimed)"},
         "e2e": {"value": round(mrays, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -710,7 +717,7 @@ def run_engine(args, rank: int, local_rank: int, world: int) -> None:
             "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(), "rays_per_step": rays_per_step, "ray_digest": ray_digest},
+            "config": workload_config(rays_per_step, ray_digest),
             "workload_detail": {"streams": visit, "rays_per_step_all_ranks": rays_all_ranks,
                                 "l2": "inputs larger than L2 (rays+results 0.8 GB per step vs 126 MB); the 3.2 MB scene is L2-resident by nature",
                                 "parallelism": (f"ray-sharded x{world}, scene replicated, per-frame hit reduction in the engine library (NCCL)"
