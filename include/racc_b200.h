@@ -272,7 +272,7 @@ typedef struct {
 	uint32_t spp;            /* paths per pixel; the reference renders one per frame and accumulates (TiledRenderer.cpp:40-48) */
 	uint32_t max_depth;      /* SceneData::maxDepth: a path is extended while its depth < max_depth (PathTracingRenderer.cpp:126) */
 	uint32_t seed;           /* 0 = primary rays through pixel centres */
-	uint32_t batch_spp;      /* samples traced together, 0 = about 128 M paths (128 B of device memory per path; fewer when less than 64 GB is free) */
+	uint32_t batch_spp;      /* samples traced together, 0 = about 128 M paths (128 B of device memory per path; at most an eighth of the device's memory) */
 	uint32_t flags;
 } racc_cuda_path_desc;
 

@@ -93,6 +93,10 @@ DeviceState* useDevice(int ordinal) {
 		return nullptr;
 	}
 	{
+		size_t freeBytes = 0;
+		if (cudaMemGetInfo(&freeBytes, &d.totalBytes) != cudaSuccess) d.totalBytes = (size_t)16 << 30;
+	}
+	{
 		// stream-ordered scratch (stream tables, re-binning buffers, renderer waves) is recycled instead of being handed
 		// back to the driver at every synchronisation
 		cudaMemPool_t pool = nullptr;

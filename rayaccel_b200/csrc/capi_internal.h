@@ -33,6 +33,7 @@ struct DeviceState {
 	bool ready = false;
 	int ordinal = -1;
 	int smCount = 0;
+	size_t totalBytes = 0; // device memory, noted once
 	// racc_cuda_counters accumulated by every traversal launch on this device since the last racc_cuda_frame_reduce
 	// (rays + hits: one atomic per warp at kernel exit), and the reduced record
 	unsigned long long* dFrame = nullptr;

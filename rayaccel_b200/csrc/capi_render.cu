@@ -199,15 +199,13 @@ int racc_cuda_path_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda
 	if (!pixels || !d->spp) return 0;
 	if (pixels > (1ull << 28)) return fail("racc_cuda_path_trace: viewport too large");
 	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-	// paths per batch: whole samples, about 128 M paths (128 B of device memory each: 16 GB of a B200's 180) unless the caller
-	// says otherwise or less than four times that is free: the deeper waves of a batch are a tenth to a hundredth of its size,
+	// paths per batch: whole samples, about 128 M paths (128 B of device memory each: 16 GB of a B200's 180; never more than an
+	// eighth of the device's memory -- sized from the total noted at device set-up: cudaMemGetInfo costs ~8 ms per call on a
+	// 180 GB part with a warm memory pool, measured) unless the caller says otherwise: the deeper waves of a batch are a tenth to a hundredth of its size,
 	// and a persistent launch over < 1 M rays is mostly tail (1920x1080, 16 spp: 4.4 / 5.8 / 6.3 Gray/s at 2 M / 8 M / 33 M
 	// paths per batch, profiles/r01_render_device.md; 64 spp x 8 bounces: 5.91 / 6.06 / 6.14 Gray/s at 33 M / 66 M / 133 M)
 	uint64_t autoPaths = 128ull << 20;
-	{
-		size_t freeBytes = 0, totalBytes = 0;
-		if (cudaMemGetInfo(&freeBytes, &totalBytes) == cudaSuccess && freeBytes / 512 < autoPaths) autoPaths = freeBytes / 512;
-	}
+	if (dev->totalBytes / 1024 < autoPaths) autoPaths = dev->totalBytes / 1024; // at most an eighth of the device's memory
 	uint32_t batchSpp = d->batch_spp ? d->batch_spp : (uint32_t)(autoPaths / pixels);
 	if (batchSpp < 1) batchSpp = 1;
 	if (batchSpp > d->spp) batchSpp = d->spp;
