@@ -211,9 +211,11 @@ int racc_cuda_set_variant(int variant);
  * and grown per calling thread instead of allocated per wave (default 1: 11 ms instead of 24-31 ms per 1080p x 4 spp frame),
  * 16 a warp sums its rays' fixed-point radiance per pixel before the atomics (same bits; default 0: neutral); 17 staged HOST streams: the
  * last chunks of a call shrink geometrically down to this many K rays (0 = off, default 256); 18 racc_cuda_path_trace waits
- * for every wave's size on the host (1) instead of leaving the sizes on the device (0, default). Returns the previous value. Also settable through
+ * for every wave's size on the host (1) instead of leaving the sizes on the device (0, default); 19 racc_cuda_path_trace as one
+ * persistent kernel per batch that traces, shades and queues the paths' next rays itself (1) instead of one traversal and one
+ * shading launch per bounce (0): same framebuffer bits either way. Returns the previous value. Also settable through
  * RACC_B200_VARIANT / _BLOCK / _CTAS_PER_SM / _SMEM_NODES / _FETCH_THRESHOLD / _LEAF_BAIL / _INNER_BAIL / _SORT /
- * _SORT_ORIGIN_BITS / _SORT_DIR_BITS / _SORT_DIR_MAJOR / _BUILD_DEVICE / _SMEM_STACK / _HOST_ZERO_COPY / _WHITTED_ARENA / _WHITTED_COMBINE / _HOST_TAPER / _PATH_SYNC. Variant 3 (default) is the packed-format kernel;
+ * _SORT_ORIGIN_BITS / _SORT_DIR_BITS / _SORT_DIR_MAJOR / _BUILD_DEVICE / _SMEM_STACK / _HOST_ZERO_COPY / _WHITTED_ARENA / _WHITTED_COMBINE / _HOST_TAPER / _PATH_SYNC / _PATH_STREAM. Variant 3 (default) is the packed-format kernel;
  * 0-2 are the reference-format kernels kept for A/B. */
 int racc_cuda_set_tuning(int key, int value);
 

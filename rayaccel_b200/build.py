@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libracc_b200.so")
 
-SOURCES = ["capi.cu", "capi_render.cu", "comm.cu", "traverse.cu", "traverse_packed.cu", "raysort.cu", "bvh_build.cu", "raygen.cu", "pathtrace.cu", "whitted.cu", "scene_build.cpp", "racc_api.cpp"]
+SOURCES = ["capi.cu", "capi_render.cu", "comm.cu", "traverse.cu", "traverse_packed.cu", "raysort.cu", "bvh_build.cu", "raygen.cu", "pathtrace.cu", "pathstream.cu", "whitted.cu", "scene_build.cpp", "racc_api.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

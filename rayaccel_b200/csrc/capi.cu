@@ -53,6 +53,8 @@ void readTuningFromEnvironment() {
 	t.whittedArena = envInt("RACC_B200_WHITTED_ARENA", t.whittedArena);
 	t.whittedCombine = envInt("RACC_B200_WHITTED_COMBINE", t.whittedCombine);
 	t.pathSync = envInt("RACC_B200_PATH_SYNC", t.pathSync);
+	t.pathStream = envInt("RACC_B200_PATH_STREAM", t.pathStream);
+	t.pathStreamThreshold = envInt("RACC_B200_PATH_STREAM_THRESHOLD", t.pathStreamThreshold);
 }
 
 } // namespace
@@ -368,6 +370,7 @@ int racc_cuda_set_tuning(int key, int value) {
 	case 16: slot = &g_tuning.whittedCombine; break;
 	case 17: slot = &g_tuning.hostTaper; break;
 	case 18: slot = &g_tuning.pathSync; break;
+	case 19: slot = &g_tuning.pathStream; break;
 	default: return fail("unknown tuning key %d", key);
 	}
 	const int previous = *slot;

@@ -118,6 +118,138 @@ struct WhittedArena {
 
 thread_local std::vector<std::unique_ptr<WhittedArena>> t_whittedArenas;
 
+// What the streamed form of racc_cuda_path_trace (pathstream.cu) keeps between calls, one set per calling host thread and
+// device: the queue's flag words -- they hold the epoch numbers of earlier launches, so that no launch has to clear them --
+// its four control words and the per-bounce ray counters.
+struct StreamArena {
+	int device = -1;
+	uint32_t* flags = nullptr;
+	size_t flagWords = 0;
+	uint32_t epoch = 0;
+	uint32_t* ctrl = nullptr;                 // device, 4 words
+	unsigned long long* depthRays = nullptr;  // device, PathLanes::kDepths
+	unsigned long long* hostDepthRays = nullptr; // pinned
+	cudaEvent_t idle = nullptr;               // end of the previous call's work
+	bool idleRecorded = false;
+
+	int begin(cudaStream_t stream) {
+		if (!idle) {
+			RACC_CUDA_CHECK(cudaEventCreateWithFlags(&idle, cudaEventDisableTiming));
+			RACC_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ctrl), 4 * sizeof(uint32_t)));
+			RACC_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&depthRays), PathLanes::kDepths * sizeof(unsigned long long)));
+			RACC_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&hostDepthRays), PathLanes::kDepths * sizeof(unsigned long long), cudaHostAllocPortable));
+		}
+		if (idleRecorded) RACC_CUDA_CHECK(cudaStreamWaitEvent(stream, idle, 0));
+		return 0;
+	}
+	int end(cudaStream_t stream) {
+		RACC_CUDA_CHECK(cudaEventRecord(idle, stream));
+		idleRecorded = true;
+		return 0;
+	}
+	// grows only; new words are zero, which no epoch equals
+	int ensureFlags(size_t words) {
+		if (words <= flagWords) return 0;
+		if (idleRecorded) RACC_CUDA_CHECK(cudaEventSynchronize(idle));
+		if (flags) RACC_CUDA_CHECK(cudaFree(flags));
+		flags = nullptr;
+		flagWords = 0;
+		const size_t want = ((words + words / 4 + (1u << 19)) >> 19) << 19;
+		RACC_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&flags), want * sizeof(uint32_t)));
+		RACC_CUDA_CHECK(cudaMemset(flags, 0, want * sizeof(uint32_t)));
+		flagWords = want;
+		epoch = 0;
+		return 0;
+	}
+	uint32_t nextEpoch() {
+		if (++epoch == 0) { // wrapped: every stale value could collide again
+			cudaMemset(flags, 0, flagWords * sizeof(uint32_t));
+			epoch = 1;
+		}
+		return epoch;
+	}
+	void release() {
+		if (device >= 0) cudaSetDevice(device);
+		if (idle) { cudaEventSynchronize(idle); cudaEventDestroy(idle); }
+		if (flags) cudaFree(flags);
+		if (ctrl) cudaFree(ctrl);
+		if (depthRays) cudaFree(depthRays);
+		if (hostDepthRays) cudaFreeHost(hostDepthRays);
+		flags = nullptr; ctrl = nullptr; depthRays = nullptr; hostDepthRays = nullptr; idle = nullptr;
+		flagWords = 0;
+		idleRecorded = false;
+	}
+	~StreamArena() { /* see HostPipeline */ }
+};
+
+thread_local std::vector<std::unique_ptr<StreamArena>> t_streamArenas;
+
+// racc_cuda_path_trace as one persistent kernel per batch (pathstream.cu): arguments checked by the caller.
+int pathTraceStreamed(DeviceState* dev, const Tuning& tuning, racc_cuda_scene* s, racc_cuda_env* env, const SceneReplica* rep, const EnvReplica* erep,
+                      const racc_cuda_shading* sh, const ShadingReplica* shr, const racc_cuda_camera* camera, const racc_cuda_path_desc* d,
+                      float* framebuffer4, uint64_t* wave_rays, cudaStream_t stream, uint64_t maxBatchPaths) {
+	const uint64_t pixels = (uint64_t)d->width * d->height;
+	StreamArena& ar = *perDevice(t_streamArenas, dev->ordinal);
+	if (ar.begin(stream)) return -1;
+	uint64_t batchSpp = d->batch_spp ? d->batch_spp : maxBatchPaths / pixels;
+	if (batchSpp > maxBatchPaths / pixels) batchSpp = maxBatchPaths / pixels;
+	if (batchSpp > d->spp) batchSpp = d->spp;
+	if (batchSpp < 1) batchSpp = 1;
+	const size_t paths = (size_t)(pixels * batchSpp);
+	const size_t capacity = paths * d->max_depth;
+	if (ar.ensureFlags(capacity)) return -1;
+	const bool hostFb = (d->flags & RACC_CUDA_FRAMEBUFFER_HOST) != 0;
+
+	struct Buffers {
+		cudaStream_t stream;
+		void* p[3] = {};
+		~Buffers() { for (void* q : p) if (q) cudaFreeAsync(q, stream); }
+	} buf;
+	buf.stream = stream;
+	const size_t sizes[3] = {capacity * 48 + 48, paths * 16, hostFb ? (size_t)pixels * 16 : 0};
+	for (int k = 0; k < 3; ++k)
+		if (sizes[k]) RACC_CUDA_CHECK(cudaMallocAsync(&buf.p[k], sizes[k], stream));
+	float4* radiance = static_cast<float4*>(buf.p[1]);
+	float4* fb = hostFb ? static_cast<float4*>(buf.p[2]) : reinterpret_cast<float4*>(framebuffer4);
+	if (hostFb) RACC_CUDA_CHECK(cudaMemcpyAsync(fb, framebuffer4, (size_t)pixels * 16, cudaMemcpyHostToDevice, stream));
+	if (wave_rays) RACC_CUDA_CHECK(cudaMemsetAsync(ar.depthRays, 0, PathLanes::kDepths * sizeof(unsigned long long), stream));
+
+	Tuning t = tuning;
+	if (t.smemStack < 0) t.smemStack = sceneExceedsL2(s) ? 16 : 0;
+	int launches = 0;
+	for (uint32_t done = 0; done < d->spp; done += (uint32_t)batchSpp) {
+		const uint32_t spp = d->spp - done < batchSpp ? d->spp - done : (uint32_t)batchSpp;
+		const uint32_t batchPaths = (uint32_t)(pixels * spp);
+		RACC_CUDA_CHECK(cudaMemsetAsync(radiance, 0, (size_t)batchPaths * 16, stream));
+		PathStreamParams p{};
+		p.tnodes = rep->dTNodes; p.tpairs = rep->dTPairs; p.remap = rep->dRemap;
+		p.envPairs = erep ? erep->dTexelPairs : nullptr; p.envWidth = env ? env->width : 0; p.envHeight = env ? env->height : 0;
+		p.indices = rep->dIndices; p.normals = shr->dNormals; p.triangleNormals = shr->dTriangleNormals;
+		p.triangleMaterials = shr->dTriangleMaterials; p.materials = shr->dMaterials;
+		p.triangleCount = sh->triangleCount; p.materialCount = sh->materialCount;
+		p.camera12 = camera->origin;
+		p.width = d->width; p.pixels = (uint32_t)pixels; p.sampleBase = d->sample_base + done; p.seed = d->seed; p.maxDepth = d->max_depth;
+		p.firstPath = 0; p.paths = batchPaths;
+		p.queue = static_cast<float4*>(buf.p[0]); p.flags = ar.flags; p.capacity = (uint32_t)capacity; p.epoch = ar.nextEpoch(); p.ctrl = ar.ctrl;
+		p.radiance = radiance; p.depthRays = wave_rays ? ar.depthRays : nullptr; p.counters = dev->dFrame;
+		p.smemStack = t.smemStack;
+		RACC_CUDA_CHECK(launchPathStream(p, t, dev->smCount, stream, &launches));
+		RACC_CUDA_CHECK(launchPathAccumulate(radiance, (uint32_t)pixels, spp, fb, stream, &launches));
+	}
+	countLaunches(launches);
+	if (wave_rays) {
+		// the one wait of the call, and only because the caller asked for the ray counts
+		RACC_CUDA_CHECK(cudaMemcpyAsync(ar.hostDepthRays, ar.depthRays, (d->max_depth + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+		RACC_CUDA_CHECK(cudaStreamSynchronize(stream));
+		for (uint32_t k = 0; k <= d->max_depth; ++k) wave_rays[k] += ar.hostDepthRays[k];
+	}
+	if (hostFb) {
+		RACC_CUDA_CHECK(cudaMemcpyAsync(framebuffer4, fb, (size_t)pixels * 16, cudaMemcpyDeviceToHost, stream));
+		RACC_CUDA_CHECK(cudaStreamSynchronize(stream));
+	}
+	return ar.end(stream);
+}
+
 } // namespace
 
 void releaseRenderScratch() {
@@ -125,6 +257,8 @@ void releaseRenderScratch() {
 	t_pathLanes.clear();
 	for (auto& p : t_whittedArenas) p->release();
 	t_whittedArenas.clear();
+	for (auto& p : t_streamArenas) p->release();
+	t_streamArenas.clear();
 }
 
 } // namespace racc_b200
@@ -220,6 +354,18 @@ int racc_cuda_path_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda
 	// larger than L2) and tuning key 18.
 	const bool rebinned = (tuning.variant == 3 || tuning.variant == 4) && (tuning.sortMode == 1 || (tuning.sortMode == 2 && sceneExceedsL2(s)));
 	const bool hostSizes = tuning.pathSync != 0 || rebinned;
+	// The streamed form (Tuning::pathStream, pathstream.cu): one persistent kernel per batch traces, shades and queues. It
+	// walks the exact packed images in arrival order, so the other forms keep the wavefront scheme below. A batch needs
+	// 16 B per path and 48 B per path and bounce; it stays within an eighth of the device's memory.
+	if (tuning.pathStream != 0 && tuning.variant == 3 && !hostSizes) {
+		uint64_t maxBatchPaths = (dev->totalBytes / 8) / (16 + 48ull * d->max_depth);
+		if (maxBatchPaths > pathStreamMaxPaths()) maxBatchPaths = pathStreamMaxPaths();
+		if (d->max_depth && maxBatchPaths > 0xfffffff0ull / d->max_depth) maxBatchPaths = 0xfffffff0ull / d->max_depth;
+		const EnvReplica* erep = env ? env->on(dev->ordinal) : nullptr;
+		if (env && !erep) return fail("racc_cuda_path_trace: the environment has no copy on CUDA device %d", dev->ordinal);
+		if (pixels <= maxBatchPaths)
+			return pathTraceStreamed(dev, tuning, s, env, rep, erep, sh, shr, camera, d, framebuffer4, wave_rays, stream, maxBatchPaths);
+	}
 
 	// Lanes: a batch is cut into contiguous path ranges that advance bounce by bounce on their own streams, so that the
 	// tail of one lane's traversal launch (few long paths left, most SMs idle) is filled by the other lane's kernels.

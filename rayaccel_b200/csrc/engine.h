@@ -80,6 +80,12 @@ struct Tuning {
 	                         // measured neutral with the arena (11.13 vs 11.16 ms) and erratic without it: stays off
 	int pathSync = 0;        // racc_cuda_path_trace: 1 = the host waits for every wave's size (round 1's scheme); 0 = wave sizes stay on
 	                         // the device and the whole batch is enqueued without a host round trip
+	int pathStream = 0;      // racc_cuda_path_trace: 1 = one persistent kernel per batch that traces, shades and queues the paths'
+	                         // next rays itself (pathstream.cu); 0 = a traversal launch and a shading launch per bounce. Same
+	                         // framebuffer bits; measured 31 % slower on the 1920x1080 x 4 spp frame (3.88 vs 2.95 ms,
+	                         // profiles/r02_streamed_path_tracer.md), so it stays opt-in
+	int pathStreamThreshold = 28; // its refill threshold: the idle lanes of a warp also SHADE together, so fuller is better
+	                         // (8 / 16 / 24 / 28 / 32 idle lanes: 5.66 / 4.69 / 4.10 / 3.88 / 3.89 ms)
 };
 
 // counterMode: 0 none, 1 rays+hits only, 2 rays, hits, inner-node and pair visits
@@ -147,6 +153,36 @@ cudaError_t launchPathPrimary(const float* camera12, uint32_t width, uint32_t he
 cudaError_t launchPathShade(const PathShadeParams& p, cudaStream_t stream, int* launches);
 cudaError_t launchPathAccumulate(const float4* radiance, uint32_t pixels, uint32_t spp, float4* framebuffer, cudaStream_t stream,
                                  int* launches);
+
+// the same path tracer as one persistent kernel per launch (pathstream.cu), see there
+struct PathStreamParams {
+	const float4* tnodes;     // packed scene images and light probe of the traversal (TraceParams)
+	const float4* tpairs;
+	const uint32_t* remap;
+	const float4* envPairs;
+	uint32_t envWidth, envHeight;
+	const uint32_t* indices;  // shading data (PathShadeParams)
+	const float4* normals;
+	const float4* triangleNormals;
+	const uint16_t* triangleMaterials;
+	const float4* materials;
+	uint32_t triangleCount, materialCount;
+	const float* camera12;
+	uint32_t width, pixels, sampleBase, seed, maxDepth;
+	uint32_t firstPath, paths; // this launch traces paths firstPath .. firstPath + paths - 1 of the batch (< pathStreamMaxPaths())
+	float4* queue;            // capacity x 48 B
+	uint32_t* flags;          // capacity words holding epochs of earlier launches (or zero)
+	uint32_t capacity;        // >= paths * maxDepth
+	uint32_t epoch;           // differs from every value in flags
+	uint32_t* ctrl;           // 4 words, zeroed by the launch
+	float4* radiance;         // one slot per path of the batch (zeroed by the caller)
+	unsigned long long* depthRays; // [maxDepth + 1] += rays traced per bounce, or null
+	unsigned long long* counters;  // racc_cuda_counters: += rays, hits; or null
+	int smemStack;            // > 0: the tops of the traversal stacks in shared memory (scenes far larger than L2)
+};
+
+uint32_t pathStreamMaxPaths();
+cudaError_t launchPathStream(const PathStreamParams& p, const Tuning& t, int smCount, cudaStream_t stream, int* launches);
 
 // device-side Whitted renderer (whitted.cu), see there
 struct WhittedShadeParams {

@@ -23,74 +23,12 @@
 // reproducible; here every draw is a counter-based hash of (pixel, sample, depth, seed). Its _mm256_rsqrt_ps /
 // _mm256_rcp_ps approximations are exact 1/sqrt and 1/x here. Arithmetic is pinned like the traversal's (DESIGN.md
 // section 3): explicit fmaf, no contraction, IEEE division and square root, FTZ.
-#include "raygen.cuh"
+#include "pathshade.cuh"
 
 namespace racc_b200 {
 namespace {
 
 constexpr int kShadeBlock = 256;
-
-__device__ __forceinline__ float xorSign(float x, uint32_t signBit) { return __uint_as_float(__float_as_uint(x) ^ signBit); }
-
-// Materials.cpp:11-22: parabola through sin(2 pi x), x in [0,1]
-__device__ __forceinline__ float sinApprox(float x) {
-	const float y = fmaf(-16.0f, x, 8.0f);
-	const bool gt = x >= 0.5f;
-	float xy = x * y;
-	if (gt) xy = -xy;
-	return xy + (gt ? y : 0.0f);
-}
-
-// Materials.cpp:24-28
-__device__ __forceinline__ float cosApprox(float x) {
-	const float y = x - 0.75f;
-	x = (__float_as_uint(y) & 0x80000000u) ? x + 0.25f : y;
-	return sinApprox(x);
-}
-
-// Materials.cpp:39-151, one lane. ke = {r, g, b, eta}
-__device__ __forceinline__ void materialSample(const float4 ke, const float rnd[3], const float n[3], const float wo[3], float wi[3],
-                                               float color[3]) {
-	const float nx = n[0], ny = n[1], nz = n[2];
-	const float eta = ke.w;
-	// reflection vector and fresnel term
-	float cosi = fmaf(nz, wo[2], fmaf(ny, wo[1], nx * wo[0]));
-	cosi = cosi > 0.0f ? cosi : 0.0f;
-	const float c2 = 2.0f * cosi;
-	const float rx = fmaf(c2, nx, -wo[0]), ry = fmaf(c2, ny, -wo[1]), rz = fmaf(c2, nz, -wo[2]);
-	const float cosi2m1 = fmaf(cosi, cosi, -1.0f);
-	const float eta2 = eta * eta;
-	const float k = fmaf(eta2, cosi2m1, 1.0f);
-	const float cost = sqrtf(k);
-	const float rper = fmaf(eta, cosi, -cost) * (1.0f / fmaf(eta, cosi, cost));
-	const float rpar = -(fmaf(eta, cost, -cosi) * (1.0f / fmaf(eta, cost, cosi)));
-	float fresnel = 0.5f * fmaf(rpar, rpar, rper * rper);
-	if (__float_as_uint(k) & 0x80000000u) fresnel = 1.0f;
-	// diffuse direction: cosine-weighted about n in the basis (u, v, n)
-	const bool wide = !(fabsf(nx) <= 0.1f);
-	float ux = wide ? -nz : 0.0f, uy = wide ? 0.0f : -nz, uz = wide ? nx : ny;
-	const float fb = 1.0f / sqrtf(fmaf(uz, uz, fmaf(uy, uy, ux * ux)));
-	ux *= fb; uy *= fb; uz *= fb;
-	const float vx = fmaf(ny, uz, -(nz * uy)), vy = fmaf(nz, ux, -(nx * uz)), vz = fmaf(nx, uy, -(ny * ux));
-	const float sinx = sinApprox(rnd[0]), cosx = cosApprox(rnd[0]);
-	const float r2s = sqrtf(rnd[1]);
-	const float sq = sqrtf(1.0f - rnd[1]);
-	float dx = fmaf(nx, sq, fmaf(ux, cosx, vx * sinx) * r2s);
-	float dy = fmaf(ny, sq, fmaf(uy, cosx, vy * sinx) * r2s);
-	float dz = fmaf(nz, sq, fmaf(uz, cosx, vz * sinx) * r2s);
-	const float fd = 1.0f / sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-	dx *= fd; dy *= fd; dz *= fd;
-	// reflection with probability 3 F / (3 F + r + g + b), else diffuse; the weight keeps the estimator unbiased
-	const float s0 = fresnel * 3.0f;
-	const float s1 = ke.z + (ke.x + ke.y);
-	const float sum = s0 + s1;
-	const float uniform = rnd[2] * sum;
-	const bool diffuse = uniform >= s0;
-	wi[0] = diffuse ? dx : rx; wi[1] = diffuse ? dy : ry; wi[2] = diffuse ? dz : rz;
-	const float r = diffuse ? ke.x : fresnel, g = diffuse ? ke.y : fresnel, b = diffuse ? ke.z : fresnel;
-	const float scale = sum * (1.0f / (b + (r + g)));
-	color[0] = r * scale; color[1] = g * scale; color[2] = b * scale;
-}
 
 // paths [firstPath, firstPath + count) of a batch; path i is pixel i % pixels of sample sampleBase + i / pixels
 __global__ void pathPrimaryKernel(CameraArgs cam, uint32_t width, uint32_t pixels, uint32_t sampleBase, uint32_t firstPath, uint32_t count,
@@ -111,12 +49,7 @@ struct ShadeArgs {
 	const uint32_t* countPtr; // non-null: the wave's size lives on the device (<= count); see TraceParams::totalPtr
 	uint32_t depth, maxDepth; // this wave's bounce number; paths are extended while depth < maxDepth
 	uint32_t seed, pixels, sampleBase;
-	const uint32_t* indices;  // scene data of Renderer/SceneData.h
-	const float4* normals;
-	const float4* triangleNormals;
-	const uint16_t* triangleMaterials;
-	const float4* materials;
-	uint32_t triangleCount, materialCount;
+	ShadeScene scene;
 	DevRay* outRays;          // next wave, compacted
 	float4* outStates;
 	uint32_t* outCount;       // zeroed by the caller
@@ -142,51 +75,14 @@ __global__ void __launch_bounds__(kShadeBlock) pathShadeKernel(const ShadeArgs a
 			// PathTracingRenderer.cpp:468-566: the light probe's radiance times the path weight
 			a.radiance[__float_as_uint(state.w)] = make_float4(res.y * state.x, res.z * state.y, res.w * state.z, 0.0f);
 		}
-		else if (tri < a.triangleCount && a.depth < a.maxDepth) {
+		else if (tri < a.scene.triangleCount && a.depth < a.maxDepth) {
 			const DevRay ray = a.rays[i];
-			const float t = res.y, u = res.z, v = res.w;
-			const uint32_t i0 = __ldg(&a.indices[3 * (size_t)tri]), i1 = __ldg(&a.indices[3 * (size_t)tri + 1]), i2 = __ldg(&a.indices[3 * (size_t)tri + 2]);
-			const float4 n0 = __ldg(&a.normals[i0]), n1 = __ldg(&a.normals[i1]), n2 = __ldg(&a.normals[i2]);
-			const float4 gn4 = __ldg(&a.triangleNormals[tri]);
-			uint32_t m = __ldg(&a.triangleMaterials[tri]);
-			if (m >= a.materialCount) m = 0;
-			const float4 ke = __ldg(&a.materials[m]);
-			const float w = 1.0f - (u + v);
-			float n[3] = {fmaf(n2.x, v, fmaf(n1.x, u, n0.x * w)), fmaf(n2.y, v, fmaf(n1.y, u, n0.y * w)), fmaf(n2.z, v, fmaf(n1.z, u, n0.z * w))};
-			const float fn = 1.0f / sqrtf(fmaf(n[2], n[2], fmaf(n[1], n[1], n[0] * n[0])));
-			const float gn[3] = {gn4.x, gn4.y, gn4.z};
 			const float rd[3] = {ray.b.x, ray.b.y, ray.b.z};
 			const float ro[3] = {ray.a.x, ray.a.y, ray.a.z};
-			const float rdgn = fmaf(rd[2], gn[2], fmaf(rd[1], gn[1], rd[0] * gn[0]));
-			const uint32_t sgn0 = __float_as_uint(rdgn) & 0x80000000u;
-			float wo[3], pos[3];
-#pragma unroll
-			for (int k = 0; k < 3; ++k) {
-				n[k] = xorSign(n[k] * fn, sgn0);
-				wo[k] = -rd[k];
-				pos[k] = fmaf(rd[k], t, ro[k]);
-			}
 			const uint32_t path = __float_as_uint(state.w);
-			const uint32_t pixel = path % a.pixels, sample = a.sampleBase + path / a.pixels;
-			uint32_t h = pcg(pixel ^ pcg(sample ^ pcg(a.seed ^ (0x9e3779b9u * (a.depth + 1u)))));
-			float rnd[3];
-			rnd[0] = unitFloat(h); h = pcg(h);
-			rnd[1] = unitFloat(h); h = pcg(h);
-			rnd[2] = unitFloat(h);
-			float wi[3], color[3];
-			materialSample(ke, rnd, n, wo, wi, color);
-			state.x *= color[0]; state.y *= color[1]; state.z *= color[2];
-			go = state.x > 0.01f || state.y > 0.01f || state.z > 0.01f;
-			const float sgn1 = fmaf(wi[2], gn[2], fmaf(wi[1], gn[1], wi[0] * gn[0]));
-			go = go && ((__float_as_uint(sgn1) ^ sgn0) >> 31) != 0; // leaves on the side it arrived from
-			const uint32_t flip = __float_as_uint(sgn1) & 0x80000000u;
-#pragma unroll
-			for (int k = 0; k < 3; ++k) {
-				pos[k] = fmaf(xorSign(gn[k], flip), 1e-4f, pos[k]);
-				go = go && pos[k] == pos[k] && wi[k] == wi[k];
-			}
-			next.a = make_float4(pos[0], pos[1], pos[2], 1e-3f);
-			next.b = make_float4(wi[0], wi[1], wi[2], 1e+6f);
+			float weight[3] = {state.x, state.y, state.z};
+			go = shadeHit(a.scene, tri, res.y, res.z, res.w, ro, rd, path % a.pixels, a.sampleBase + path / a.pixels, a.seed, a.depth, weight, next);
+			state.x = weight[0]; state.y = weight[1]; state.z = weight[2];
 		}
 	}
 	// compaction: one atomic per CTA, arrival order kept inside the CTA
@@ -242,8 +138,8 @@ cudaError_t launchPathShade(const PathShadeParams& p, cudaStream_t stream, int* 
 	ShadeArgs a;
 	a.rays = p.rays; a.results = p.results; a.states = p.states; a.count = p.count; a.countPtr = p.countPtr;
 	a.depth = p.depth; a.maxDepth = p.maxDepth; a.seed = p.seed; a.pixels = p.pixels; a.sampleBase = p.sampleBase;
-	a.indices = p.indices; a.normals = p.normals; a.triangleNormals = p.triangleNormals; a.triangleMaterials = p.triangleMaterials;
-	a.materials = p.materials; a.triangleCount = p.triangleCount; a.materialCount = p.materialCount;
+	a.scene.indices = p.indices; a.scene.normals = p.normals; a.scene.triangleNormals = p.triangleNormals; a.scene.triangleMaterials = p.triangleMaterials;
+	a.scene.materials = p.materials; a.scene.triangleCount = p.triangleCount; a.scene.materialCount = p.materialCount;
 	a.outRays = p.outRays; a.outStates = p.outStates; a.outCount = p.outCount; a.radiance = p.radiance;
 	uint32_t grid = (p.count + kShadeBlock - 1) / kShadeBlock;
 	if (p.gridLimit && grid > p.gridLimit) grid = p.gridLimit;

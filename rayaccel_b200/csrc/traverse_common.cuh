@@ -37,9 +37,8 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
 	float ry = fmaf(az, bx, -(ax * bz));               \
 	float rz = fmaf(ax, by, -(ay * bx));
 
-__device__ __forceinline__ void initRay(const DevRay* rays, uint32_t i, RayState& r, HitState& h) {
-	const float4 a = __ldg(&rays[i].a);
-	const float4 b = __ldg(&rays[i].b);
+// a = origin.xyz, minT; b = direction.xyz, maxT
+__device__ __forceinline__ void initRayFrom(const float4 a, const float4 b, RayState& r, HitState& h) {
 	r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tNear = a.w;
 	r.dx = b.x; r.dy = b.y; r.dz = b.z; r.tFar = b.w;
 	const float epsilon = 1e-10f;
@@ -49,6 +48,10 @@ __device__ __forceinline__ void initRay(const DevRay* rays, uint32_t i, RayState
 	r.ix = __frcp_rn(r.dx); r.iy = __frcp_rn(r.dy); r.iz = __frcp_rn(r.dz);
 	r.px = -r.ox * r.ix; r.py = -r.oy * r.iy; r.pz = -r.oz * r.iz;
 	h.index = kMiss; h.t = r.tFar; h.u = 0.0f; h.v = 0.0f;
+}
+
+__device__ __forceinline__ void initRay(const DevRay* rays, uint32_t i, RayState& r, HitState& h) {
+	initRayFrom(__ldg(&rays[i].a), __ldg(&rays[i].b), r, h);
 }
 
 // Three-input min / max (FMNMX3, new on sm_100): exact operations, so max3(a, b, c) has the bits of fmaxf(fmaxf(a, b), c) --

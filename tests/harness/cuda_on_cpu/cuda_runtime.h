@@ -515,3 +515,11 @@ static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c);
 static inline uint32_t atomicMin(uint32_t* p, uint32_t v) { const uint32_t old = *p; if (v < old) *p = v; return old; }
 static inline uint32_t atomicMax(uint32_t* p, uint32_t v) { const uint32_t old = *p; if (v > old) *p = v; return old; }
 static inline int atomicAdd(int* p, int v) { const int old = *p; *p = old + v; return old; }
+
+// memory-ordering and back-off intrinsics of the streamed path tracer (pathstream.cu): fibers of one CTA share one host
+// thread, so a fence has nothing to order; a sleeping warp lets the other fibers run
+static inline void __threadfence() {}
+static inline void __nanosleep(unsigned) { ::cuda_on_cpu::yield(); }
+template <typename T>
+static inline T __ldcg(const T* p) { return *p; }
+static inline bool __any_sync(unsigned mask, bool predicate) { return __ballot_sync(mask, predicate) != 0; }

@@ -113,6 +113,75 @@ def test_device_framebuffer_accumulates_and_splits_by_sample(scene, env, shading
     assert sorted_fb.tobytes() == whole.tobytes() and sorted_waves == waves
 
 
+@pytest.fixture
+def streamed():
+    """The streamed form of racc_cuda_path_trace (tuning key 19, pathstream.cu) for the duration of a test."""
+    rb.set_tuning(path_stream=1)
+    yield
+    rb.set_tuning(path_stream=0)
+
+
+@pytest.mark.parametrize("width,height,spp,depth,seed,batch", [
+    (256, 128, 4, 3, 11, 0),
+    (256, 128, 5, 3, 11, 2),   # ragged last batch; epochs of the earlier launches in the flag words
+    (200, 96, 2, 8, 3, 0),     # deep paths
+    (64, 64, 3, 0, 0, 0),      # depth 0: no queue at all
+    (33, 17, 1, 1, 9, 0),      # fewer paths than one SM's lanes
+    (640, 360, 4, 3, 5, 0),    # 0.9 M paths: every CTA of the persistent grid takes part in the queue
+])
+def test_streamed_path_trace_equals_oracle(scene, env, shading, checker, battlefield, streamed, width, height, spp, depth, seed, batch):
+    """One persistent kernel per batch that traces, shades and queues the paths' next rays itself: same framebuffer bits and
+    the same rays per bounce as oracle.path_trace (and so as the wavefront form)."""
+    images, sh = checker
+    cam = camera_for(battlefield, width, height)
+    want, want_waves = oracle.path_trace(images, sh, cam, width, height, spp, depth, seed)
+    got, waves = rb.path_trace(scene, env, shading, cam, width, height, spp, depth, seed, batch_spp=batch)
+    assert waves == [int(x) for x in want_waves], "rays traced per bounce differ"
+    bad = np.flatnonzero((got.view(np.uint32) != want.view(np.uint32)).reshape(-1, 4).any(axis=1))
+    assert bad.size == 0, f"{bad.size} of {width * height} pixels differ, first {bad[:5]}: {got.reshape(-1, 4)[bad[:3]]} vs {want.reshape(-1, 4)[bad[:3]]}"
+
+
+def test_streamed_path_trace_synthetic_scene_and_stack_tops(gpu, streamed):
+    verts, indices, normals, tri_normals, tri_materials, materials, env_img, cam = synthetic_shading_case()
+    scene = rb.create_scene(verts, indices)
+    env = rb.create_environment(env_img)
+    shading = rb.create_shading(normals, tri_normals, tri_materials, materials)
+    nodes, pairs, remap = scene.download()
+    images = oracle.SceneImages(nodes, pairs, remap, env_img)
+    sh = oracle.Shading(indices, normals, tri_normals, tri_materials, materials)
+    try:
+        for spp, depth, seed, smem_stack in ((8, 6, 2, -1), (3, 12, 0, 16)):
+            rb.set_tuning(smem_stack=smem_stack)
+            want, want_waves = oracle.path_trace(images, sh, cam, 96, 64, spp, depth, seed)
+            got, waves = rb.path_trace(scene, env, shading, cam, 96, 64, spp, depth, seed)
+            assert waves == [int(x) for x in want_waves]
+            assert got.tobytes() == want.tobytes(), f"{(got.view(np.uint32) != want.view(np.uint32)).reshape(-1, 4).any(axis=1).sum()} pixels differ"
+    finally:
+        rb.set_tuning(smem_stack=-1)
+        shading.destroy(); env.destroy(); scene.destroy()
+
+
+def test_streamed_full_frame_equals_wavefront_form(scene, env, shading, battlefield):
+    """BASELINE.json's 1920x1080 x 4 spp frame, and 16 spp in one batch (33 M paths): the streamed form's framebuffer and
+    rays per bounce are the wavefront form's, bit for bit; device framebuffers accumulate the same way."""
+    w, h = 1920, 1080
+    cam = camera_for(battlefield, w, h)
+    for spp in (4, 16):
+        fb, waves = rb.path_trace(scene, env, shading, cam, w, h, spp, 3, seed=1)
+        rb.set_tuning(path_stream=1)
+        try:
+            got, waves2 = rb.path_trace(scene, env, shading, cam, w, h, spp, 3, seed=1)
+            dev = torch.zeros(h * w * 4, dtype=torch.float32, device="cuda")
+            rb.path_trace(scene, env, shading, cam, w, h, spp // 2, 3, seed=1, framebuffer_ptr=dev.data_ptr())
+            rb.path_trace(scene, env, shading, cam, w, h, spp - spp // 2, 3, seed=1, framebuffer_ptr=dev.data_ptr(), sample_base=spp // 2)
+            rb.sync()
+        finally:
+            rb.set_tuning(path_stream=0)
+        assert waves2 == waves
+        assert got.tobytes() == fb.tobytes()
+        assert dev.cpu().numpy().tobytes() == fb.tobytes()
+
+
 def test_device_path_trace_matches_reference_renderer_image(scene, env, shading, battlefield):
     g = np.load(os.path.join(GOLDEN, "ref_render_tiles.npz"))
     w, h, tile = int(g["width"]), int(g["height"]), int(g["tile"])
