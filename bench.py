@@ -126,7 +126,7 @@ def measured_hbm_peak():
 def kernel_source_sha() -> str:
     """Identity of the traversal kernel's source: a committed ncu capture is only quoted while it still describes this code."""
     h = hashlib.sha256()
-    for name in ("traverse_packed.cu", "traverse_common.cuh", "engine.h"):
+    for name in ("traverse_packed.cu", "traverse_packed.cuh", "traverse_common.cuh", "engine.h"):
         with open(os.path.join(ROOT, "rayaccel_b200", "csrc", name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]
