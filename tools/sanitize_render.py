@@ -23,3 +23,10 @@ _, waves2 = rb.path_trace(scene, env, shading, cam, w, h, 9, 3, seed=5, framebuf
 torch.cuda.synchronize()
 assert waves == waves2 and fb.cpu().numpy().tobytes() == host.tobytes(), "host and device framebuffers differ"
 print("sanitize render ok:", sum(waves), "rays", waves)
+# the same frames as one persistent kernel per batch (tuning key 19, pathstream.cu): queue, tickets, epoch flags
+rb.set_tuning(path_stream=1)
+streamed, waves3 = rb.path_trace(scene, env, shading, cam, w, h, 9, 3, seed=5, batch_spp=4)
+streamed2, waves4 = rb.path_trace(scene, env, shading, cam, w, h, 9, 3, seed=5, batch_spp=3)
+rb.set_tuning(path_stream=0)
+assert waves3 == waves and waves4 == waves and streamed.tobytes() == host.tobytes() and streamed2.tobytes() == host.tobytes(), "streamed form differs"
+print("sanitize streamed render ok:", sum(waves3), "rays")
