@@ -213,9 +213,10 @@ int racc_cuda_set_variant(int variant);
  * last chunks of a call shrink geometrically down to this many K rays (0 = off, default 256); 18 racc_cuda_path_trace waits
  * for every wave's size on the host (1) instead of leaving the sizes on the device (0, default); 19 racc_cuda_path_trace as one
  * persistent kernel per batch that traces, shades and queues the paths' next rays itself (1) instead of one traversal and one
- * shading launch per bounce (0): same framebuffer bits either way. Returns the previous value. Also settable through
+ * shading launch per bounce (0): same framebuffer bits either way; 20 racc_cuda_path_trace's traversal launches use at most this
+ * many CTAs per SM (0 = all that fit; default 4 of 5: the other lane's shading pass then runs beside them). Returns the previous value. Also settable through
  * RACC_B200_VARIANT / _BLOCK / _CTAS_PER_SM / _SMEM_NODES / _FETCH_THRESHOLD / _LEAF_BAIL / _INNER_BAIL / _SORT /
- * _SORT_ORIGIN_BITS / _SORT_DIR_BITS / _SORT_DIR_MAJOR / _BUILD_DEVICE / _SMEM_STACK / _HOST_ZERO_COPY / _WHITTED_ARENA / _WHITTED_COMBINE / _HOST_TAPER / _PATH_SYNC / _PATH_STREAM. Variant 3 (default) is the packed-format kernel;
+ * _SORT_ORIGIN_BITS / _SORT_DIR_BITS / _SORT_DIR_MAJOR / _BUILD_DEVICE / _SMEM_STACK / _HOST_ZERO_COPY / _WHITTED_ARENA / _WHITTED_COMBINE / _HOST_TAPER / _PATH_SYNC / _PATH_STREAM / _PATH_TRACE_CTAS. Variant 3 (default) is the packed-format kernel;
  * 0-2 are the reference-format kernels kept for A/B. */
 int racc_cuda_set_tuning(int key, int value);
 

@@ -298,7 +298,7 @@ def debug_warp_stats(reset: bool = True) -> list[int]:
 def set_tuning(**kw) -> None:
     keys = {"variant": 0, "block": 1, "ctas_per_sm": 2, "smem_nodes": 3, "fetch_threshold": 4, "leaf_bail": 5, "carveout": 6, "inner_bail": 7,
             "sort": 8, "sort_origin_bits": 9, "sort_dir_bits": 10, "sort_dir_major": 11, "build_device": 12, "smem_stack": 13, "host_zero_copy": 14,
-            "whitted_arena": 15, "whitted_combine": 16, "host_taper": 17, "path_sync": 18, "path_stream": 19}
+            "whitted_arena": 15, "whitted_combine": 16, "host_taper": 17, "path_sync": 18, "path_stream": 19, "path_trace_ctas": 20}
     lib = _lib.load()
     unknown = [k for k in kw if k not in keys]
     if unknown:

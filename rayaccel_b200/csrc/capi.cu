@@ -54,6 +54,7 @@ void readTuningFromEnvironment() {
 	t.whittedCombine = envInt("RACC_B200_WHITTED_COMBINE", t.whittedCombine);
 	t.pathSync = envInt("RACC_B200_PATH_SYNC", t.pathSync);
 	t.pathStream = envInt("RACC_B200_PATH_STREAM", t.pathStream);
+	t.pathTraceCtas = envInt("RACC_B200_PATH_TRACE_CTAS", t.pathTraceCtas);
 	t.pathStreamThreshold = envInt("RACC_B200_PATH_STREAM_THRESHOLD", t.pathStreamThreshold);
 }
 
@@ -371,6 +372,7 @@ int racc_cuda_set_tuning(int key, int value) {
 	case 17: slot = &g_tuning.hostTaper; break;
 	case 18: slot = &g_tuning.pathSync; break;
 	case 19: slot = &g_tuning.pathStream; break;
+	case 20: slot = &g_tuning.pathTraceCtas; break;
 	default: return fail("unknown tuning key %d", key);
 	}
 	const int previous = *slot;
@@ -687,12 +689,13 @@ cudaError_t launchAny(const racc_cuda_scene* s, const Tuning& tuning, const Devi
 } // namespace
 
 int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams, void* cuda_stream,
-              void* device_counters, bool fullCounters, const uint32_t* deviceTotal) {
+              void* device_counters, bool fullCounters, const uint32_t* deviceTotal, int gridCtasPerSm) {
 	if (!s) return fail("racc_cuda_trace: null scene");
 	if (!streams && nstreams) return fail("racc_cuda_trace: null stream list");
 	DeviceState* dev = currentDevice();
 	if (!dev) return -1;
-	const Tuning tuning = tuningSnapshot();
+	Tuning tuning = tuningSnapshot();
+	tuning.gridCtasPerSm = gridCtasPerSm;
 	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
 	SceneReplica* rep = s->on(dev->ordinal);
 	if (!rep) return fail("racc_cuda_trace: the scene has no copy on CUDA device %d (it was created for another device set)", dev->ordinal);

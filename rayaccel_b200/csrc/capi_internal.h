@@ -143,7 +143,7 @@ namespace racc_b200 {
 // One traversal of `streams` on the calling thread's bound device (DEVICE streams) / dealt over its device set (HOST
 // streams); capi.cu. deviceTotal: see TraceParams::totalPtr (single DEVICE stream only).
 int traceImpl(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda_stream_desc* streams, uint32_t nstreams, void* cuda_stream,
-              void* device_counters, bool fullCounters, const uint32_t* deviceTotal = nullptr);
+              void* device_counters, bool fullCounters, const uint32_t* deviceTotal = nullptr, int gridCtasPerSm = 0);
 
 bool sceneExceedsL2(const racc_cuda_scene* s);
 

@@ -433,7 +433,7 @@ int racc_cuda_path_trace(racc_cuda_scene* s, racc_cuda_env* env, const racc_cuda
 			sd.results = ln.results;
 			sd.count = upper;
 			sd.flags = 0;
-			if (traceImpl(s, env, &sd, 1, ln.stream, nullptr, false, size)) return -1;
+			if (traceImpl(s, env, &sd, 1, ln.stream, nullptr, false, size, nlanes > 1 ? tuning.pathTraceCtas : 0)) return -1;
 			PathShadeParams p{};
 			p.rays = ln.rays[ln.cur]; p.results = ln.results; p.states = ln.states[ln.cur]; p.count = upper; p.countPtr = size;
 			p.gridLimit = (uint32_t)dev->smCount * 8u;

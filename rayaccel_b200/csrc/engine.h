@@ -80,6 +80,10 @@ struct Tuning {
 	                         // measured neutral with the arena (11.13 vs 11.16 ms) and erratic without it: stays off
 	int pathSync = 0;        // racc_cuda_path_trace: 1 = the host waits for every wave's size (round 1's scheme); 0 = wave sizes stay on
 	                         // the device and the whole batch is enqueued without a host round trip
+	int pathTraceCtas = 4;   // racc_cuda_path_trace, wavefront form: its traversal launches use at most this many CTAs per SM
+	                         // (0 = all that fit), which leaves registers for one CTA of the OTHER lane's shading kernel beside
+	                         // them: the HBM-bound shading pass then overlaps the L1-bound traversal instead of waiting for it
+	int gridCtasPerSm = 0;   // internal (not a tuning key): cap of a persistent launch's grid, set per call by the renderer
 	int pathStream = 0;      // racc_cuda_path_trace: 1 = one persistent kernel per batch that traces, shades and queues the paths'
 	                         // next rays itself (pathstream.cu); 0 = a traversal launch and a shading launch per bounce. Same
 	                         // framebuffer bits; measured 31 % slower on the 1920x1080 x 4 spp frame (3.88 vs 2.95 ms,

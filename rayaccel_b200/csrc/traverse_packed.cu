@@ -261,6 +261,7 @@ cudaError_t launchPacked(const TraceParams& p, const Tuning& t, int smCount, cud
 	}
 	int ctas = resident;
 	if (t.ctasPerSm > 0 && ctas > t.ctasPerSm) ctas = t.ctasPerSm;
+	if (t.gridCtasPerSm > 0 && ctas > t.gridCtasPerSm) ctas = t.gridCtasPerSm; // same instantiation, fewer resident CTAs
 	long long grid = (long long)smCount * ctas;
 	const long long needed = ((long long)p.total + kBlock - 1) / kBlock;
 	if (grid > needed) grid = needed > 0 ? needed : 1;

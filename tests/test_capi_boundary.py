@@ -105,8 +105,8 @@ def test_tuning_keys_documented_and_settable_without_gpu():
     header = open(os.path.join(ROOT, "include", "racc_b200.h")).read()
     for env in ["_WHITTED_ARENA", "_WHITTED_COMBINE", "_HOST_TAPER", "_SMEM_STACK", "_HOST_ZERO_COPY"]:
         assert env in header
-    defaults = {15: 1, 16: 0, 17: 256, 18: 0, 19: 0}
-    for key in range(20):
+    defaults = {15: 1, 16: 0, 17: 256, 18: 0, 19: 0, 20: 4}
+    for key in range(21):
         prev = lib.racc_cuda_set_tuning(key, 1)
         assert lib.racc_cuda_set_tuning(key, prev) == 1, f"key {key} did not keep the value"
         if key in defaults and not os.environ.get("RACC_B200_HOST_TAPER"):
