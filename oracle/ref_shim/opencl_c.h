@@ -157,7 +157,14 @@ inline float3 fmin(const float3& a, const float3& b) { return float3(fmin(a.d[0]
 inline float3 fmax(const float3& a, const float3& b) { return float3(fmax(a.d[0], b.d[0]), fmax(a.d[1], b.d[1]), fmax(a.d[2], b.d[2])); }
 #ifndef RACC_SHIM_RELAXED
 inline float mad(float a, float b, float c) { return ::fmaf(a, b, c); }
-inline float dot(const float3& a, const float3& b) { return ::fmaf(a.d[2], b.d[2], ::fmaf(a.d[1], b.d[1], a.d[0] * b.d[0])); }
+// The result passes through an empty asm so that a unary minus applied to it (Kernels.h:65-66: -dot(R, e1), -dot(R, e3)) stays the
+// separate IEEE negation the OpenCL C source says: g++ otherwise folds it into the last fma (vfnmsub), whose exact-cancellation
+// zero is +0 where -(+0) is -0 -- and that sign decides which of two triangles owns their shared edge.
+inline float dot(const float3& a, const float3& b) {
+	float r = ::fmaf(a.d[2], b.d[2], ::fmaf(a.d[1], b.d[1], a.d[0] * b.d[0]));
+	__asm__("" : "+x"(r));
+	return r;
+}
 #else
 // A second, equally legal reading of what -cl-fast-relaxed-math leaves open, used only to measure how far another
 // implementation's results can lie from the pinned ones (tests/test_oracle_kat.py::test_relaxed_builtin_model_*):

@@ -96,8 +96,13 @@ __device__ __forceinline__ void pairTest(const float4* __restrict__ pairs, uint3
 	const float dRe1 = dot3(Rx, Ry, Rz, t0.x, t0.y, t0.z);
 	const int iU1 = (int)(__float_as_uint(dot3(Rx, Ry, Rz, t1.x, t1.y, t1.z)) ^ s1);
 	const int iV1 = (int)(__float_as_uint(dRe1) ^ s1);
-	const int iU2 = (int)(__float_as_uint(-dRe1) ^ s2);
-	const int iV2 = (int)(__float_as_uint(-dot3(Rx, Ry, Rz, t0.w, t1.w, t2.w)) ^ s2);
+	// The two negations of Kernels.h:65-66 as sign-bit flips. Written as -fma(...), a host compiler (gcc, for the CPU builds of
+	// this source and of the checker) folds the minus into ONE fnmsub; when the products cancel exactly that instruction
+	// returns +0 where -(+0) is -0, and the sign of that zero decides which of two triangles owns their shared edge
+	// (found by tools/fuzz_gpu.py on integer-grid meshes). The flip has one meaning everywhere.
+	const uint32_t flip2 = s2 ^ 0x80000000u;
+	const int iU2 = (int)(__float_as_uint(dRe1) ^ flip2);
+	const int iV2 = (int)(__float_as_uint(dot3(Rx, Ry, Rz, t0.w, t1.w, t2.w)) ^ flip2);
 
 	if (((iU1 | iV1) & (iU2 | iV2)) < 0)
 		return;
