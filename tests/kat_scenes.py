@@ -151,3 +151,65 @@ def deep_stack_scene(levels=60, n_rays=4096, seed=17):
                 expect[r] = 0xFFFFFFFE  # too close to an edge to call by hand
                 break
     return images, rays, expect
+
+
+def shared_edge_mesh_case():
+    """The scene and rays on which the randomised campaign (tools/fuzz_gpu.py, round 2) caught the CHECKER leaving the
+    source's semantics: an integer-grid height field (15 x 6 cells, 180 triangles) and 17 193 rays aimed at its vertices,
+    edge midpoints and interiors. Five of them pass through a shared edge such that dot(R, e3) of Kernels.h:66 cancels to an
+    exact +0; its negation is -0 (sign bit set: outside the pair's second triangle, the neighbour owns the edge). gcc folds
+    that negation into the dot product's last fma (vfnmsub), which yields +0 -- the other triangle. Returns (vertices
+    (N,4) f32, indices u32, rays, {ray index: (triangle, t bits, u bits, v bits)} as the source's semantics give them."""
+    import numpy as np
+    import oracle
+    rng = np.random.default_rng(1368281523)
+    rng.choice(["soup", "mesh", "coincident", "slivers", "quads", "huge", "tiny", "offset", "few"])
+    w, h = int(rng.integers(2, 60)), int(rng.integers(2, 60))
+    xs, ys = np.meshgrid(np.arange(w + 1, dtype=np.float64), np.arange(h + 1, dtype=np.float64))
+    z = rng.normal(0, rng.uniform(0.0, 2.0), xs.shape)
+    v = np.stack([xs, z, ys], -1).reshape(-1, 3)
+    q = (np.arange(h)[:, None] * (w + 1) + np.arange(w)[None, :]).reshape(-1)
+    indices = np.stack([q, q + 1, q + w + 2, q, q + w + 2, q + w + 1], -1).reshape(-1).astype(np.uint32)
+    verts = np.zeros((v.shape[0], 4), np.float32)
+    verts[:, :3] = v.astype(np.float32)
+    rng.choice([0, 2, 3])
+    if rng.random() < 0.6:
+        rng.random((int(rng.integers(1, 9)), int(rng.integers(1, 9)), 4))
+    rng.random()
+    n = int(rng.integers(1, 20000))
+    # the ray recipe of tools/fuzz_gpu.py: rays_for()
+    vv = verts[:, :3].astype(np.float64)
+    tri = vv[indices.reshape(-1, 3).astype(np.int64)]
+    lo, hi = vv.min(0), vv.max(0)
+    ext = np.maximum(hi - lo, 1e-30)
+    pick = tri[rng.integers(0, tri.shape[0], n)]
+    bary = rng.dirichlet([1, 1, 1], n)
+    mode = rng.integers(0, 6, n)
+    target = (pick * bary[:, :, None]).sum(1)
+    target[mode == 1] = pick[mode == 1, rng.integers(0, 3)]
+    target[mode == 2] = 0.5 * (pick[mode == 2, 0] + pick[mode == 2, 1])
+    origin = lo + rng.uniform(-0.5, 1.5, (n, 3)) * ext
+    on = mode == 3
+    origin[on] = target[on]
+    target[on] = lo + rng.uniform(0, 1, (int(on.sum()), 3)) * ext
+    d = target - origin
+    rnd = mode >= 4
+    d[rnd] = rng.normal(size=(int(rnd.sum()), 3))
+    ln = np.linalg.norm(d, axis=1, keepdims=True)
+    d = np.where(ln > 0, d / np.maximum(ln, 1e-300), [[1.0, 0.0, 0.0]])
+    axis = rng.random(n) < 0.08
+    k = rng.integers(0, 3, n)
+    d[axis] = 0.0
+    d[axis, k[axis]] = rng.choice([-1.0, 1.0], int(axis.sum()))
+    rays = np.zeros(n, dtype=oracle.RAY_DTYPE)
+    rays["origin"], rays["dir"] = origin.astype(np.float32), d.astype(np.float32)
+    rays["minT"] = np.where(rng.random(n) < 0.2, rng.choice([1e-3, 1e-6, 1.0]) * float(ext.max()), 0.0).astype(np.float32)
+    rays["maxT"] = np.float32(1e6) * np.float32(max(1.0, float(ext.max())))
+    short = rng.random(n) < 0.1
+    rays["maxT"][short] = (np.linalg.norm(ln[short], axis=1) * rng.uniform(0.3, 1.3, int(short.sum()))).astype(np.float32)
+    empty = rng.random(n) < 0.02
+    rays["maxT"][empty] = rays["minT"][empty]
+    # what the source's semantics (and the B200) give; the folded build said triangles 23, 153, 53, MISS (a crack at a vertex), 142
+    known = {523: (22, 1107818876, 0, 1056964610), 1917: (142, 1103844780, 0, 1065353216), 6883: (55, 1102174747, 1065353212, 0),
+             11445: (142, 1091516065, 884998144, 1065353210), 17187: (145, 1103608929, 869358250, 1065353212)}
+    return verts, indices, rays, known

@@ -595,6 +595,30 @@ def test_hundreds_of_tiny_host_streams_in_one_call(scene, env, images, battlefie
     assert float(pin_o[total * 4]) == 7.0  # nothing written past the last stream
 
 
+def test_shared_edge_zero_keeps_its_sign_on_gpu(gpu):
+    """kat_scenes.shared_edge_mesh_case (the round on which tools/fuzz_gpu.py caught the checker following gcc's fnmsub fold):
+    rays through shared edges whose edge function cancels to an exact zero -- known answers and the checker's bits on all rays,
+    every kernel family, both scene builders."""
+    from kat_scenes import shared_edge_mesh_case
+    verts, indices, rays, known = shared_edge_mesh_case()
+    for build in (0, 2):
+        rb.set_tuning(build_device=build)
+        s = rb.create_scene(verts, indices)
+        rb.set_tuning(build_device=3)
+        nodes, pairs, remap = s.download()
+        want = oracle.traverse(oracle.SceneImages(nodes, pairs, remap), rays)
+        for tuning in (dict(), dict(variant=1), dict(variant=2), dict(variant=0), dict(smem_stack=16), dict(sort=1)):
+            rb.set_tuning(**{**DEFAULT, **tuning})
+            try:
+                got = trace_dev(s, None, rays)
+            finally:
+                rb.set_tuning(**DEFAULT)
+            for k, w in known.items():
+                assert tuple(int(x) for x in got[k]) == w, (build, tuning, k, got[k], w)
+            assert_bit_exact(got, want, f"shared-edge mesh, build {build}, {tuning}")
+        s.destroy()
+
+
 def test_trees_deeper_than_the_stack_are_refused(gpu):
     from test_library_on_cpu import deep_chain_images
     nodes, pairs, remap = deep_chain_images(70)

@@ -129,6 +129,52 @@ def rays_for(rng, verts, indices, n):
     return r
 
 
+def quantised_check(got, want, rays, verts, indices):
+    """Variant 4 walks conservative boxes: same triangle -> same bits; a different triangle must be a closest hit by the fp64
+    brute force (a tie, or a hit the exact fp32 boxes let slip); a miss where the checker hits is never allowed."""
+    same = got[:, 0] == want[:, 0]
+    if not np.array_equal(got[same], want[same]):
+        return "same triangle (or both miss) but different words"
+    bad = np.flatnonzero(~same)
+    if not bad.size:
+        return ""
+    lost = bad[got[bad, 0] == 0xFFFFFFFF]
+    if lost.size:
+        return f"{lost.size} rays miss where the checker hits (first {lost[0]})"
+    # fp64 Moeller-Trumbore with edges that are eps wide: rays of this campaign run ALONG edges and through vertices, where an
+    # fp32 pair test reached through a conservative box may accept what the exact boxes never let it see
+    v = verts[:, :3].astype(np.float64)
+    tri = v[indices.reshape(-1, 3).astype(np.int64)]
+    e1, e2 = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    for k in bad[:64]:
+        o, d = rays["origin"][k].astype(np.float64), rays["dir"][k].astype(np.float64)
+        d = np.where(np.abs(d) < 1e-10, np.copysign(1e-10, d), d)
+        p = np.cross(d, e2)
+        det = (e1 * p).sum(1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = 1.0 / det
+            tv = o - tri[:, 0]
+            u = (tv * p).sum(1) * inv
+            q = np.cross(tv, e1)
+            vv = (q * d).sum(1) * inv
+            t = (e2 * q).sum(1) * inv
+        eps = 1e-5
+        inside = (u >= -eps) & (vv >= -eps) & (u + vv <= 1 + eps) & np.isfinite(t)
+        lo_t, hi_t = float(rays["minT"][k]), float(rays["maxT"][k])
+        ok_t = inside & (t >= lo_t * (1 - 1e-4) - 1e-30) & (t <= hi_t * (1 + 1e-4))
+        g = int(got[k, 0])
+        if g >= tri.shape[0] or not ok_t[g]:
+            return f"ray {k}: triangle {g} is not hit even with eps-wide edges"
+        closest = t[ok_t].min()
+        if t[g] > closest * (1 + 1e-4) + 1e-6 * float(np.abs(v).max()):
+            # nearer triangles that only an eps-wide edge admits are ones the exact kernel may skip as well: compare with the
+            # checker's own answer when it has one
+            wt = want[k, 1:2].copy().view(np.float32)[0] if want[k, 0] != 0xFFFFFFFF else np.inf
+            if not (t[g] <= wt * (1 + 1e-4)):
+                return f"ray {k}: triangle {g} at t {t[g]} lies behind the closest hit {closest} (checker: {wt})"
+    return ""
+
+
 def to_u32(a):
     return np.ascontiguousarray(a).view(np.uint32).reshape(-1, 4)
 
@@ -159,7 +205,7 @@ def main():
     rb.set_tuning(**DEFAULT)
     rng = np.random.default_rng(args.seed)
     t0 = time.time()
-    rounds = rays_total = builds_compared = frames = 0
+    rounds = rays_total = builds_compared = frames = quantised = 0
     kinds = {}
     failures = []
     while time.time() - t0 < args.seconds and len(failures) < 5:
@@ -208,6 +254,16 @@ def main():
         if not np.array_equal(got2, want):
             bad = np.flatnonzero((got2 != want).any(1))
             failures.append(f"{what}: tuning {shape}, {bad.size}/{len(rays)} rays differ, first {bad[0]}")
+        if r.random() < 0.5:  # quantised nodes (variant 4, opt-in): north_star's bar instead of bit-exactness
+            rb.set_tuning(**{**DEFAULT, "variant": 4})
+            try:
+                got4 = trace_device(scene, env, rays)
+            finally:
+                rb.set_tuning(**DEFAULT)
+            msg = quantised_check(got4, want, rays, verts, indices)
+            if msg:
+                failures.append(f"{what}: variant 4: {msg}")
+            quantised += 1
         cuts = np.sort(r.integers(0, len(rays) + 1, int(r.integers(0, 6))))
         parts = [np.ascontiguousarray(p) for p in np.split(rays, cuts)]
         outs = [np.zeros(len(p), dtype=rb.RESULT_DTYPE) for p in parts]
@@ -253,7 +309,7 @@ def main():
             env.destroy()
         scene.destroy()
         rounds += 1
-    print(f"fuzz: {rounds} rounds in {time.time() - t0:.0f} s, {rays_total} rays traced and compared, {builds_compared} builder comparisons, {frames} frames (both renderer forms), families { {str(k): v for k, v in kinds.items()} }")
+    print(f"fuzz: {rounds} rounds in {time.time() - t0:.0f} s, {rays_total} rays traced and compared, {builds_compared} builder comparisons, {frames} frames (both renderer forms), {quantised} rounds also on quantised nodes, families { {str(k): v for k, v in kinds.items()} }")
     for f in failures:
         print("FAIL", f)
     print("fuzz: ok" if not failures else f"fuzz: {len(failures)} failures")
