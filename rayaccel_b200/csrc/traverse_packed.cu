@@ -66,14 +66,14 @@ __global__ void packPairsKernel(const float4* __restrict__ pairs, uint32_t count
 }
 
 // Packed node image -> 32-byte quantised nodes: {Lx Ly Lz Rx Ry Rz | first last}, every box word = (min | max << 16) in
-// cells of a 16-bit grid over the scene bounds. min rounds down and max rounds up after moving a quarter cell outwards:
+// cells of a 16-bit grid over the scene bounds (plus a few cells of padding, launchQuantiseNodes). min rounds down and max rounds up after moving a quarter cell outwards:
 // the quantised box contains the fp32 box with a margin of at least 0.25 cell, ~15x what the kernel's grid-space slab
 // arithmetic can differ from the reference's (both err by about 2^-22 of the scene extent = 0.016 cell). A whole extra
 // cell of padding was measured and dropped: rays that START on flat, axis-aligned geometry (battlefield's ground: its
 // exact boxes have zero thickness, so a bounce ray leaving the ground never enters them) would then begin inside every
 // such box on their way -- +23 % node visits and +82 % pair tests on the first bounce (profiles/r02_quantised_nodes.md).
 // Arithmetic in double: done once per scene.
-struct QuantGrid { float origin[3]; float cell[3]; double inverse[3]; };
+struct QuantGrid { float origin[3]; float cell[3]; double inverse[3]; double margin[3]; };
 
 __global__ void quantiseNodesKernel(const float4* __restrict__ nodes, uint32_t count, QuantGrid g, uint4* __restrict__ out) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -86,8 +86,8 @@ __global__ void quantiseNodesKernel(const float4* __restrict__ nodes, uint32_t c
 	uint32_t w[6];
 	for (int k = 0; k < 6; ++k) {
 		const int a = k % 3;
-		double lo = floor(((double)mn[k] - (double)g.origin[a]) * g.inverse[a] - 0.25);
-		double hi = ceil(((double)mx[k] - (double)g.origin[a]) * g.inverse[a] + 0.25);
+		double lo = floor(((double)mn[k] - (double)g.origin[a]) * g.inverse[a] - g.margin[a]);
+		double hi = ceil(((double)mx[k] - (double)g.origin[a]) * g.inverse[a] + g.margin[a]);
 		if (!(lo > 0.0)) lo = 0.0;          // also NaN
 		if (lo > 65535.0) lo = 65535.0;     // +inf: the synthetic root's unreachable child (scene_build.cpp)
 		if (!(hi > 0.0)) hi = 0.0;
@@ -313,11 +313,27 @@ cudaError_t launchQuantiseNodes(const float4* nodes, uint32_t nodeCount, const f
                                 float qOrigin[3], float qCell[3], cudaStream_t stream, int* launches) {
 	QuantGrid g;
 	for (int a = 0; a < 3; ++a) {
+		// The margin (quantiseNodesKernel) is a quarter cell, or more where fp32 cannot resolve a quarter cell: a scene far from
+		// the origin has coordinates whose ulp exceeds the cell, and the kernel's grid-space slab arithmetic errs by a few of
+		// those ulps. The grid starts `pad` cells below the scene's lower bound so that the margin exists on that side too
+		// (with cell 0 at the bound itself a ray through a vertex ON the bound could slip past the root box: found by
+		// tools/fuzz_gpu.py on a four-triangle scene).
 		const double extent = (double)boundsMax[a] - (double)boundsMin[a];
 		const bool usable = extent > 0.0 && extent < 3.0e38;
-		g.origin[a] = boundsMin[a];
-		g.cell[a] = usable ? (float)(extent / 65533.0) : 0.0f;   // head room for the outward rounding
-		g.inverse[a] = usable ? 65533.0 / extent : 0.0;
+		const double reach = fmax(fabs((double)boundsMin[a]), fabs((double)boundsMax[a]));
+		const double ulp = reach * 1.1920928955078125e-7;
+		double margin = 0.25, pad = 1.0; // the common case: bounds at cells 1 and 65534, planes rounded out to 0 and 65535
+		if (usable) {
+			margin = fmax(0.25, 4.0 * ulp / (extent / 65533.0));
+			if (margin > 8192.0) margin = 8192.0;
+			pad = ceil(margin + 0.75);
+		}
+		const double cells = 65535.0 - 2.0 * pad;
+		const double cell = usable ? extent / cells : 0.0;
+		g.margin[a] = margin;
+		g.cell[a] = (float)cell;
+		g.origin[a] = (float)((double)boundsMin[a] - pad * cell);
+		g.inverse[a] = usable ? cells / extent : 0.0;
 		qOrigin[a] = g.origin[a];
 		qCell[a] = g.cell[a];
 	}

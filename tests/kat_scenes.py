@@ -213,3 +213,24 @@ def shared_edge_mesh_case():
     known = {523: (22, 1107818876, 0, 1056964610), 1917: (142, 1103844780, 0, 1065353216), 6883: (55, 1102174747, 1065353212, 0),
              11445: (142, 1091516065, 884998144, 1065353210), 17187: (145, 1103608929, 869358250, 1065353212)}
     return verts, indices, rays, known
+
+
+def bound_vertex_case(seed=7):
+    """Four random triangles and rays aimed exactly at their vertices -- among them the vertices that ARE the scene's lower
+    and upper bounds, where the quantised-node grid (variant 4) once had no margin: a ray through such a vertex slipped past
+    the root box (tools/fuzz_gpu.py, round 2). Returns (vertices (N,4) f32, indices u32, rays)."""
+    import numpy as np
+    import oracle
+    rng = np.random.default_rng(seed)
+    v = rng.uniform(-5, 5, (12, 3)).astype(np.float32)
+    verts = np.zeros((12, 4), np.float32)
+    verts[:, :3] = v
+    indices = np.arange(12, dtype=np.uint32)
+    n = 12 * 600
+    target = np.repeat(v.astype(np.float64), 600, axis=0)
+    origin = rng.uniform(-12, 12, (n, 3))
+    d = target - origin
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.zeros(n, dtype=oracle.RAY_DTYPE)
+    rays["origin"], rays["dir"], rays["minT"], rays["maxT"] = origin.astype(np.float32), d.astype(np.float32), 0.0, 1e6
+    return verts, indices, rays

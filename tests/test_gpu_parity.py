@@ -527,6 +527,26 @@ def test_quantised_nodes_full_size_and_soup(scene, env, battlefield):
         soup.destroy()
 
 
+def test_quantised_nodes_keep_hits_at_the_scene_bounds(gpu):
+    """kat_scenes.bound_vertex_case: rays through the vertices that are the scene's own bounds. Conservative boxes may find
+    MORE than the exact ones, never less: no ray may miss where the checker hits (three did while cell 0 of the grid sat on
+    the lower bound), and where the triangle agrees so do all the words."""
+    from kat_scenes import bound_vertex_case
+    verts, indices, rays = bound_vertex_case()
+    scene = rb.create_scene(verts, indices)
+    nodes, pairs, remap = scene.download()
+    want = oracle.traverse(oracle.SceneImages(nodes, pairs, remap), rays).view(np.uint32).reshape(-1, 4)
+    rb.set_tuning(variant=4)
+    try:
+        got = trace_dev(scene, None, rays)
+    finally:
+        rb.set_tuning(variant=3)
+        scene.destroy()
+    assert not ((got[:, 0] == 0xFFFFFFFF) & (want[:, 0] != 0xFFFFFFFF)).any(), "a quantised box lost a hit"
+    same = got[:, 0] == want[:, 0]
+    assert same.mean() > 0.99 and np.array_equal(got[same], want[same])
+
+
 def test_quantised_nodes_hand_built_scenes(gpu):
     from kat_scenes import KAT_CASES, build_kat_scene, deep_stack_scene
     rb.set_tuning(**{**DEFAULT, "variant": 4})

@@ -43,3 +43,4 @@ for seed in [int(a) for a in sys.argv[1:]]:
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     np.savez_compressed(os.path.join(ROOT, "gpurun_out", f"fuzz_{seed}.npz"), **out)
     scene.destroy()
+    print(seed, "variant 4 against north_star's bar:", F.quantised_check(out["got_v4"], want, rays, verts, indices) or "ok")
