@@ -161,19 +161,24 @@ def quantised_check(got, want, rays, verts, indices):
         # fp32 pair tests of far, small triangles err by ~1e-3 in barycentrics, those of slivers (edge-on, nearly collinear: tiny
         # determinant) by far more: the width grows with the conditioning. Gross errors are what this looks for.
         eps = 2e-3 + 1e-6 * np.linalg.norm(e1, axis=1) * np.linalg.norm(e2, axis=1) / np.maximum(np.abs(det), 1e-300)
+        degenerate = np.linalg.norm(e1, axis=1) * np.linalg.norm(e2, axis=1) > 1e6 * np.abs(det)  # edge-on / collinear: fp32 cannot decide
         inside = (u >= -eps) & (vv >= -eps) & (u + vv <= 1 + eps) & np.isfinite(t)
         lo_t, hi_t = float(rays["minT"][k]), float(rays["maxT"][k])
         ok_t = inside & (t >= lo_t * (1 - 1e-4) - 1e-30) & (t <= hi_t * (1 + 1e-4))
         g = int(got[k, 0])
-        if g >= tri.shape[0] or not ok_t[g]:
-            return f"ray {k}: triangle {g} is not hit even with eps-wide edges"
-        closest = t[ok_t].min()
-        if t[g] > closest * (1 + 1e-4) + 1e-6 * float(np.abs(v).max()):
-            # nearer triangles that only an eps-wide edge admits are ones the exact kernel may skip as well: compare with the
-            # checker's own answer when it has one
-            wt = want[k, 1:2].copy().view(np.float32)[0] if want[k, 0] != 0xFFFFFFFF else np.inf
-            if not (t[g] <= wt * (1 + 1e-4)):
-                return f"ray {k}: triangle {g} at t {t[g]} lies behind the closest hit {closest} (checker: {wt})"
+        gt = float(got[k, 1:2].copy().view(np.float32)[0])
+        if want[k, 0] != 0xFFFFFFFF:
+            # both hit, different triangles: north_star's bar is the distance (a tie, or a grazing triangle whose fp32 pair test
+            # the exact boxes never reached: its reported t may be off its fp64 t by more than the two answers differ)
+            wt = float(want[k, 1:2].copy().view(np.float32)[0])
+            if abs(gt - wt) <= 1e-4 * abs(wt):
+                continue
+            # ... or a NEARER hit the exact boxes let slip (they are not watertight at corners: a ray through a vertex): genuine by fp64
+            if gt < wt and g < tri.shape[0] and (ok_t[g] or degenerate[g]):
+                continue
+            return f"ray {k}: triangle {g} at t {gt}, the checker's triangle {int(want[k, 0])} at t {wt}"
+        if g >= tri.shape[0] or not (ok_t[g] or degenerate[g]):
+            return f"ray {k}: the checker misses and triangle {g} is not hit even with eps-wide edges"
     return ""
 
 
