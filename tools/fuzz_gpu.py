@@ -39,13 +39,14 @@ SHAPES = [
 def scene_family(rng):
     kind = rng.choice(["soup", "mesh", "coincident", "slivers", "quads", "huge", "tiny", "offset", "few"])
     scale, offset = 1.0, np.zeros(3)
+    big = rng.random() < 0.02  # now and then a scene of the size where the device builder's other code paths run
     if kind == "soup":
-        n = int(rng.integers(3, 4000))
+        n = int(rng.integers(3, 4000)) if not big else int(rng.integers(20000, 250000))
         c = rng.uniform(-50, 50, (n, 1, 3))
         v = (c + rng.normal(0, rng.uniform(0.05, 5.0), (n, 3, 3))).reshape(-1, 3)
         i = np.arange(3 * n, dtype=np.uint32)
     elif kind == "mesh":  # height field: shared vertices and edges, neighbouring triangles become pairs
-        w, h = int(rng.integers(2, 60)), int(rng.integers(2, 60))
+        w, h = (int(rng.integers(2, 60)), int(rng.integers(2, 60))) if not big else (int(rng.integers(100, 350)), int(rng.integers(100, 350)))
         xs, ys = np.meshgrid(np.arange(w + 1, dtype=np.float64), np.arange(h + 1, dtype=np.float64))
         z = rng.normal(0, rng.uniform(0.0, 2.0), xs.shape)
         v = np.stack([xs, z, ys], -1).reshape(-1, 3)
@@ -212,7 +213,7 @@ def main():
     rb.set_tuning(**DEFAULT)
     rng = np.random.default_rng(args.seed)
     t0 = time.time()
-    rounds = rays_total = builds_compared = frames = quantised = 0
+    rounds = rays_total = builds_compared = frames = quantised = counted = 0
     kinds = {}
     failures = []
     while time.time() - t0 < args.seconds and len(failures) < 5:
@@ -251,6 +252,22 @@ def main():
         if not np.array_equal(got, want):
             bad = np.flatnonzero((got != want).any(1))
             failures.append(f"{what}: default tuning, {bad.size}/{len(rays)} rays differ, first {bad[0]}: got {got[bad[0]]} want {want[bad[0]]} ray {rays[bad[0]]}")
+        if torch.cuda.is_available() and r.random() < 0.3:  # several DEVICE streams in one counted launch: results and the visit counters
+            cuts = np.sort(r.integers(0, len(rays) + 1, int(r.integers(1, 5))))
+            parts = [np.ascontiguousarray(p) for p in np.split(rays, cuts)]
+            d_parts = [torch.from_numpy(p.view(np.float32).reshape(-1).copy()).cuda() for p in parts]
+            d_outs = [torch.full((max(len(p), 1) * 4,), 7.0, dtype=torch.float32, device="cuda") for p in parts]
+            cnt = torch.zeros(8, dtype=torch.int64, device="cuda")
+            rb.trace_device(scene, env, [(a.data_ptr(), b.data_ptr(), len(p)) for a, b, p in zip(d_parts, d_outs, parts)], counters_ptr=cnt.data_ptr(), detail=True)
+            torch.cuda.synchronize()
+            gotm = np.concatenate([b[: len(p) * 4].cpu().numpy().view(np.uint32).reshape(-1, 4) for b, p in zip(d_outs, parts)])
+            _, oc = oracle.traverse(images, rays, counters=True)
+            c = cnt.cpu().numpy()
+            sums = (len(rays), int((want[:, 0] != 0xFFFFFFFF).sum()), int(oc["inner"].astype(np.int64).sum()), int(oc["pairs"].astype(np.int64).sum()),
+                    int(oc["pushes"].astype(np.int64).sum()), int(oc["leaves"].astype(np.int64).sum()))
+            if not np.array_equal(gotm, want) or tuple(int(x) for x in c[:6]) != sums:
+                failures.append(f"{what}: counted launch over DEVICE streams {[len(p) for p in parts]}: results equal {np.array_equal(gotm, want)}, counters {c[:6].tolist()} vs {sums}")
+            counted += 1
         shapes = SHAPES if torch.cuda.is_available() else [x for x in SHAPES if x.get("smem_nodes", 0) == 0]  # no TMA on the CPU build
         shape = shapes[int(r.integers(0, len(shapes)))]
         rb.set_tuning(**{**DEFAULT, **shape})
@@ -309,6 +326,11 @@ def main():
                     rb.set_tuning(path_stream=0)
                 if waves != [int(x) for x in want_waves] or fb.tobytes() != want_fb.tobytes():
                     failures.append(f"{what}: frame {w}x{h} spp {spp} depth {depth} seed {fseed} form {form} differs from the checker")
+            ww, hh = max(8, w // 2), max(8, h // 2)
+            want_w, want_ww = oracle.whitted_trace(images, sh, cam, ww, hh, 1, min(depth, 5), fseed)
+            fbw, wavesw = rb.whitted_trace(scene, env, shading, cam, ww, hh, 1, min(depth, 5), fseed)
+            if wavesw != [int(x) for x in want_ww] or fbw.tobytes() != want_w.tobytes():
+                failures.append(f"{what}: Whitted frame {ww}x{hh} depth {min(depth, 5)} seed {fseed} differs from the checker")
             shading.destroy()
             frames += 1
         kinds[kind] = kinds.get(kind, 0) + 1
@@ -316,7 +338,7 @@ def main():
             env.destroy()
         scene.destroy()
         rounds += 1
-    print(f"fuzz: {rounds} rounds in {time.time() - t0:.0f} s, {rays_total} rays traced and compared, {builds_compared} builder comparisons, {frames} frames (both renderer forms), {quantised} rounds also on quantised nodes, families { {str(k): v for k, v in kinds.items()} }")
+    print(f"fuzz: {rounds} rounds in {time.time() - t0:.0f} s, {rays_total} rays traced and compared, {builds_compared} builder comparisons, {frames} frames (both path-tracer forms + Whitted), {quantised} rounds also on quantised nodes, {counted} counted multi-stream launches, families { {str(k): v for k, v in kinds.items()} }")
     for f in failures:
         print("FAIL", f)
     print("fuzz: ok" if not failures else f"fuzz: {len(failures)} failures")
