@@ -206,11 +206,14 @@ def main():
     ap.add_argument("--seconds", type=float, default=240.0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--rays", type=int, default=20000)
+    ap.add_argument("--devices", type=int, default=1, help="the calling thread's device set: scenes replicated, HOST streams dealt over them")
     args = ap.parse_args()
     if torch.cuda.is_available():
         torch.cuda.set_device(0)
-    rb.init(0)
+    rb.init(list(range(args.devices)) if args.devices > 1 else 0)
     rb.set_tuning(**DEFAULT)
+    if args.devices > 1:
+        rb.set_tuning(host_taper=1)  # with RACC_B200_HOST_CHUNK=2048 in the environment: every device of the set gets chunks of each call
     rng = np.random.default_rng(args.seed)
     t0 = time.time()
     rounds = rays_total = builds_compared = frames = quantised = counted = 0
