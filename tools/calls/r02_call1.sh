@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, first GPU call: the questions round 1 left for the hardware (VERDICT "next round" items 4 and 9).
-# Outputs -> gpurun_out/r02c1_*. Run as: gpurun --timeout 1200 -- 'bash tools/r02_call1.sh'
+# Outputs -> gpurun_out/r02c1_*. Run as: gpurun --timeout 1200 -- 'bash tools/calls/r02_call1.sh'
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/r02c1_gpu.txt 2>&1
 # 1. does the texture path / the constant path have a wavefront budget of its own? (tools/micro/l1_wavefronts.cu modes 8-15)
