@@ -196,7 +196,7 @@ static inline float pair_intersect(const float* pairs, uint32_t index, const ray
 	/* Kernels.h:65-66 negate two dot products. The minus is a sign-bit flip here: written as -dot3(...), gcc folds it into the
 	 * last fma of the dot product (vfnmsub), and when the products cancel exactly that instruction returns +0 where the
 	 * source's -(+0) is -0 -- the sign of that zero decides which of two triangles owns their shared edge (a ray aimed at an
-	 * edge of an integer-grid mesh; found by tools/fuzz_gpu.py, where the B200 followed the source and this file did not). */
+	 * edge of an integer-grid mesh; found by tests/fuzz/fuzz_gpu.py, where the B200 followed the source and this file did not). */
 	uint32_t flip2 = sgnDet2 ^ 0x80000000u;
 	int32_t iU2 = (int32_t)(f2u(dRe1) ^ flip2);
 	int32_t iV2 = (int32_t)(f2u(dot3(R, e3)) ^ flip2);

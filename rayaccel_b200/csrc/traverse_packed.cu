@@ -317,7 +317,7 @@ cudaError_t launchQuantiseNodes(const float4* nodes, uint32_t nodeCount, const f
 		// the origin has coordinates whose ulp exceeds the cell, and the kernel's grid-space slab arithmetic errs by a few of
 		// those ulps. The grid starts `pad` cells below the scene's lower bound so that the margin exists on that side too
 		// (with cell 0 at the bound itself a ray through a vertex ON the bound could slip past the root box: found by
-		// tools/fuzz_gpu.py on a four-triangle scene).
+		// tests/fuzz/fuzz_gpu.py on a four-triangle scene).
 		const double extent = (double)boundsMax[a] - (double)boundsMin[a];
 		const bool usable = extent > 0.0 && extent < 3.0e38;
 		const double reach = fmax(fabs((double)boundsMin[a]), fabs((double)boundsMax[a]));

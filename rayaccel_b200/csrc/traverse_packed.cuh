@@ -97,7 +97,7 @@ __device__ __forceinline__ void pairTestPacked(u64 pairBase, uint32_t index, Ray
 	// The two negations of Kernels.h:65-66 as sign-bit flips. Written as -fma(...), a host compiler (gcc, for the CPU builds of
 	// this source and of the checker) folds the minus into ONE fnmsub; when the products cancel exactly that instruction
 	// returns +0 where -(+0) is -0, and the sign of that zero decides which of two triangles owns their shared edge
-	// (found by tools/fuzz_gpu.py on integer-grid meshes). The flip has one meaning everywhere.
+	// (found by tests/fuzz/fuzz_gpu.py on integer-grid meshes). The flip has one meaning everywhere.
 	const uint32_t flip2 = s2 ^ 0x80000000u;
 	const int iU2 = (int)(__float_as_uint(dRe1) ^ flip2);
 	const int iV2 = (int)(__float_as_uint(dot3(Rx, Ry, Rz, t0.w, t1.w, t2.w)) ^ flip2);

@@ -1,8 +1,8 @@
 """CPU-only campaign: our host scene builder (racc_cuda_build_images, csrc/scene_build.cpp) against the UNMODIFIED reference builder
-compiled from /root/reference (oracle/_ref/libracc_ref.so) on the random scene families of tools/fuzz_gpu.py: the
+compiled from /root/reference (oracle/_ref/libracc_ref.so) on the random scene families of tests/fuzz/fuzz_gpu.py: the
 numbering-independent digest of nodes, pairs and remap must be equal. Needs oracle/_ref (this container).
 
-    python tools/fuzz_builder_cpu.py [--seconds 120] [--seed 1]
+    python tests/fuzz/fuzz_builder_cpu.py [--seconds 120] [--seed 1]
 """
 import argparse
 import os
@@ -11,9 +11,9 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "fuzz"))
 import oracle  # noqa: E402
 import rayaccel_b200 as rb  # noqa: E402
 from fuzz_gpu import scene_family  # noqa: E402

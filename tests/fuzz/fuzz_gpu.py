@@ -8,7 +8,7 @@ them (a) as one DEVICE stream under the default tuning, (b) under a second tunin
 use, (c) as ragged HOST streams. All three must equal oracle.traverse on the images the kernel walks, as 32-bit words.
 A few rounds render a small frame with racc_cuda_path_trace (both forms) against oracle.path_trace.
 
-    python tools/fuzz_gpu.py [--seconds 240] [--seed 1]      # development tool; log copied to profiles/ by hand
+    python tests/fuzz/fuzz_gpu.py [--seconds 240] [--seed 1]      # development tool; log copied to profiles/ by hand
 """
 import argparse
 import os
@@ -18,7 +18,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import oracle  # noqa: E402  (the checker; this is a test tool)
 import rayaccel_b200 as rb  # noqa: E402

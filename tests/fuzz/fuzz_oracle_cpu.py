@@ -1,8 +1,8 @@
 """CPU-only campaign: the checker (oracle/racc_oracle.c) against the reference's OWN kernel source (Kernels.h compiled over
 oracle/ref_shim/opencl_c.h into oracle/_ref/libkernel_ref.so) on the random scene families and adversarial rays of
-tools/fuzz_gpu.py: triangle id, t, u, v and miss radiance bit for bit. This is what pins the checker. Needs oracle/_ref.
+tests/fuzz/fuzz_gpu.py: triangle id, t, u, v and miss radiance bit for bit. This is what pins the checker. Needs oracle/_ref.
 
-    python tools/fuzz_oracle_cpu.py [--seconds 120] [--seed 1]
+    python tests/fuzz/fuzz_oracle_cpu.py [--seconds 120] [--seed 1]
 """
 import argparse
 import os
@@ -11,9 +11,9 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "fuzz"))
 import oracle  # noqa: E402
 import rayaccel_b200 as rb  # noqa: E402
 from fuzz_gpu import rays_for, scene_family  # noqa: E402

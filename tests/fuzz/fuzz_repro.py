@@ -1,4 +1,4 @@
-"""Re-creates one round of tools/fuzz_gpu.py from its seed, traces its rays under every kernel variant and writes scene, rays,
+"""Re-creates one round of tests/fuzz/fuzz_gpu.py from its seed, traces its rays under every kernel variant and writes scene, rays,
 images, the checker's results and each variant's results to gpurun_out/fuzz_<seed>.npz for offline analysis."""
 import os
 import sys
@@ -6,9 +6,9 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "fuzz"))
 import fuzz_gpu as F  # noqa: E402
 import oracle  # noqa: E402
 import rayaccel_b200 as rb  # noqa: E402

@@ -154,7 +154,7 @@ def deep_stack_scene(levels=60, n_rays=4096, seed=17):
 
 
 def shared_edge_mesh_case():
-    """The scene and rays on which the randomised campaign (tools/fuzz_gpu.py, round 2) caught the CHECKER leaving the
+    """The scene and rays on which the randomised campaign (tests/fuzz/fuzz_gpu.py, round 2) caught the CHECKER leaving the
     source's semantics: an integer-grid height field (15 x 6 cells, 180 triangles) and 17 193 rays aimed at its vertices,
     edge midpoints and interiors. Five of them pass through a shared edge such that dot(R, e3) of Kernels.h:66 cancels to an
     exact +0; its negation is -0 (sign bit set: outside the pair's second triangle, the neighbour owns the edge). gcc folds
@@ -177,7 +177,7 @@ def shared_edge_mesh_case():
         rng.random((int(rng.integers(1, 9)), int(rng.integers(1, 9)), 4))
     rng.random()
     n = int(rng.integers(1, 20000))
-    # the ray recipe of tools/fuzz_gpu.py: rays_for()
+    # the ray recipe of tests/fuzz/fuzz_gpu.py: rays_for()
     vv = verts[:, :3].astype(np.float64)
     tri = vv[indices.reshape(-1, 3).astype(np.int64)]
     lo, hi = vv.min(0), vv.max(0)
@@ -218,7 +218,7 @@ def shared_edge_mesh_case():
 def bound_vertex_case(seed=7):
     """Four random triangles and rays aimed exactly at their vertices -- among them the vertices that ARE the scene's lower
     and upper bounds, where the quantised-node grid (variant 4) once had no margin: a ray through such a vertex slipped past
-    the root box (tools/fuzz_gpu.py, round 2). Returns (vertices (N,4) f32, indices u32, rays)."""
+    the root box (tests/fuzz/fuzz_gpu.py, round 2). Returns (vertices (N,4) f32, indices u32, rays)."""
     import numpy as np
     import oracle
     rng = np.random.default_rng(seed)

@@ -616,7 +616,7 @@ def test_hundreds_of_tiny_host_streams_in_one_call(scene, env, images, battlefie
 
 
 def test_shared_edge_zero_keeps_its_sign_on_gpu(gpu):
-    """kat_scenes.shared_edge_mesh_case (the round on which tools/fuzz_gpu.py caught the checker following gcc's fnmsub fold):
+    """kat_scenes.shared_edge_mesh_case (the round on which tests/fuzz/fuzz_gpu.py caught the checker following gcc's fnmsub fold):
     rays through shared edges whose edge function cancels to an exact zero -- known answers and the checker's bits on all rays,
     every kernel family, both scene builders."""
     from kat_scenes import shared_edge_mesh_case

@@ -1,7 +1,7 @@
 #!/bin/bash
-# randomised parity campaign (tools/fuzz_gpu.py), then the ncu JSONs for the current kernel-source hash
+# randomised parity campaign (tests/fuzz/fuzz_gpu.py), then the ncu JSONs for the current kernel-source hash
 mkdir -p gpurun_out
-timeout -s KILL 500 python tools/fuzz_gpu.py --seconds 300 --seed 1 > gpurun_out/r02_fuzz_gpu.log 2>&1; echo "fuzz rc=$?"; tail -8 gpurun_out/r02_fuzz_gpu.log | cut -c1-400
+timeout -s KILL 500 python tests/fuzz/fuzz_gpu.py --seconds 300 --seed 1 > gpurun_out/r02_fuzz_gpu.log 2>&1; echo "fuzz rc=$?"; tail -8 gpurun_out/r02_fuzz_gpu.log | cut -c1-400
 bash tools/profile.sh > gpurun_out/r02c24_profile.log 2>&1; tail -2 gpurun_out/r02c24_profile.log
 python -c "
 import json
