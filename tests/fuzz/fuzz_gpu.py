@@ -36,10 +36,13 @@ SHAPES = [
 ]
 
 
+BIG_SHARE = 0.02  # --big raises it
+
+
 def scene_family(rng):
     kind = rng.choice(["soup", "mesh", "coincident", "slivers", "quads", "huge", "tiny", "offset", "few"])
     scale, offset = 1.0, np.zeros(3)
-    big = rng.random() < 0.02  # now and then a scene of the size where the device builder's other code paths run
+    big = rng.random() < BIG_SHARE  # now and then a scene of the size where the device builder's other code paths run
     if kind == "soup":
         n = int(rng.integers(3, 4000)) if not big else int(rng.integers(20000, 250000))
         c = rng.uniform(-50, 50, (n, 1, 3))
@@ -206,8 +209,11 @@ def main():
     ap.add_argument("--seconds", type=float, default=240.0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--rays", type=int, default=20000)
+    ap.add_argument("--big", type=float, default=0.02, help="share of rounds with a 20-250 K-triangle soup or mesh")
     ap.add_argument("--devices", type=int, default=1, help="the calling thread's device set: scenes replicated, HOST streams dealt over them")
     args = ap.parse_args()
+    global BIG_SHARE
+    BIG_SHARE = args.big
     if torch.cuda.is_available():
         torch.cuda.set_device(0)
     rb.init(list(range(args.devices)) if args.devices > 1 else 0)
