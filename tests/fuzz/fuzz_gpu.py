@@ -165,6 +165,13 @@ def quantised_check(got, want, rays, verts, indices):
         # fp32 pair tests of far, small triangles err by ~1e-3 in barycentrics, those of slivers (edge-on, nearly collinear: tiny
         # determinant) by far more: the width grows with the conditioning. Gross errors are what this looks for.
         eps = 2e-3 + 1e-6 * np.linalg.norm(e1, axis=1) * np.linalg.norm(e2, axis=1) / np.maximum(np.abs(det), 1e-300)
+        # ... and with distance over size: the hit point is known to ~16 ulp of the largest coordinate or distance involved, which a
+        # thin triangle's height turns into a barycentric error
+        longest = np.maximum(np.maximum(np.linalg.norm(e1, axis=1), np.linalg.norm(e2, axis=1)), np.linalg.norm(e2 - e1, axis=1))
+        height = np.linalg.norm(np.cross(e1, e2), axis=1) / np.maximum(longest, 1e-300)
+        reach = max(float(np.abs(o).max()), float(np.abs(v).max()))
+        with np.errstate(invalid="ignore"):
+            eps = eps + 16 * 1.2e-7 * np.maximum(reach, np.where(np.isfinite(t), np.abs(t), 0.0)) / np.maximum(height, 1e-300)
         degenerate = np.linalg.norm(e1, axis=1) * np.linalg.norm(e2, axis=1) > 1e6 * np.abs(det)  # edge-on / collinear: fp32 cannot decide
         inside = (u >= -eps) & (vv >= -eps) & (u + vv <= 1 + eps) & np.isfinite(t)
         lo_t, hi_t = float(rays["minT"][k]), float(rays["maxT"][k])
