@@ -268,7 +268,8 @@ def trace_device(scene: Scene, environment: Environment | None, streams, stream=
                  detail: bool = True) -> None:
     """Launch ONE traversal over a list of device-resident streams [(rays_ptr, results_ptr, count), ...]
     (or a PackedStreams). Asynchronous on `stream`. counters_ptr: device pointer to a zeroed Counters record
-    (4 x u64); detail=False accumulates rays+hits only (free), detail=True also node/pair visits (slower)."""
+    (racc_cuda_counters: 8 x u64 -- rays, hits, inner nodes, pairs, stack pushes, leaf visits, 2 reserved); detail=False
+    accumulates rays+hits only (free), detail=True also the visit counters (slower)."""
     packed = streams if isinstance(streams, PackedStreams) else pack_streams(streams)
     arr, n = packed.arr, packed.n
     lib = _lib.load()

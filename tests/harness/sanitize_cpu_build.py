@@ -3,7 +3,7 @@
 host code's own source, compiled by g++ with -fsanitize=..., driven through the C-ABI -- host staging (both tail
 policies), every traversal variant, re-binning, both device renderers (with and without tuning keys 15/16) and the device
 scene builder. compute-sanitizer does this on the B200 (tools/sanitize.sh); this is the same question asked where there is
-no GPU.   python tests/harness/sanitize_cpu_build.py address|undefined
+no GPU.   python tests/harness/sanitize_cpu_build.py address|undefined [seconds of tests/fuzz/fuzz_gpu.py on top]
 First run `python -m pytest tests/test_library_on_cpu.py -k builds` so that the rewritten sources exist."""
 import subprocess
 SAN = (__import__("sys").argv[1:] or ["address"])[0]
@@ -18,7 +18,7 @@ if __import__("os").environ.get("RACC_SANITIZE_CHILD") != "1":
                    srcs + ["-o", OUT], check=True)
     rt = subprocess.check_output(["gcc", "-print-file-name=" + ("libasan.so" if SAN == "address" else "libubsan.so")], text=True).strip()
     env = dict(os.environ, RACC_SANITIZE_CHILD="1", LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1")
-    sys.exit(subprocess.run([sys.executable, __file__, SAN], env=env).returncode)
+    sys.exit(subprocess.run([sys.executable, __file__, SAN] + sys.argv[2:], env=env).returncode)
 import sys, os, ctypes
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 os.environ["RACC_B200_BUILD_DEVICE"] = "0"; os.environ["RACC_B200_HOST_CHUNK"] = "1024"
@@ -46,7 +46,7 @@ rb.set_tuning(host_taper=0)
 print("variants", flush=True)
 for variant, sort, ss in [(3,0,0),(3,1,0),(3,1,16),(0,0,0),(1,0,0),(2,0,0)]:
     rb.set_tuning(variant=variant, sort=sort, smem_stack=ss)
-    s = np.ascontiguousarray(np.concatenate([primary, bounce])); o = np.zeros(len(s), dtype=oracle.RESULT_DTYPE); c = np.zeros(4, np.uint64)
+    s = np.ascontiguousarray(np.concatenate([primary, bounce])); o = np.zeros(len(s), dtype=oracle.RESULT_DTYPE); c = np.zeros(8, np.uint64)
     rb.trace_device(scene, env, [(s.ctypes.data, o.ctypes.data, len(s))], counters_ptr=c.ctypes.data); rb.sync()
 rb.set_tuning(variant=3, sort=2, smem_stack=-1)
 print("renderers", flush=True)
@@ -62,4 +62,11 @@ print("device build", flush=True)
 v, i = rb.synthetic_triangles(300, seed=11, extent=50.0, edge=4.0)
 rb.set_tuning(build_device=2); s2 = rb.create_scene(v, i); s2.destroy(); rb.set_tuning(build_device=0)
 sh.destroy(); env.destroy(); scene.destroy()
+if len(sys.argv) > 2:  # ... and N seconds of the randomised campaign (tests/fuzz/fuzz_gpu.py) through the same sanitised library:
+    print("randomised campaign", flush=True)  # degenerate scenes, ragged streams, quantised nodes, both renderer forms, Whitted
+    sys.path.insert(0, "/root/repo/tests/fuzz")
+    import fuzz_gpu
+    sys.argv = ["fuzz", "--seconds", sys.argv[2], "--rays", "300", "--seed", "31"]
+    if fuzz_gpu.main():
+        sys.exit(1)
 print(f"sanitizer run complete ({SAN}): no report above means clean", flush=True)
