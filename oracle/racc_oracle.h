@@ -44,6 +44,10 @@
  *     spec formula (section 8.2) in binary32, see oracle_env_sample()
  *   - flush-to-zero / denormals-are-zero ON (RayAccelerator.cpp:417-420, Threading.h:77-79)
  *   - fmin/fmax: IEEE minNum/maxNum with -0 < +0 (what CUDA's FMNMX implements)
+ *   - unary minus on a float (Kernels.h:65-66: -dot(R,e1), -dot(R,e3)) -> a flip of the sign bit, AFTER the dot product was
+ *     rounded. gcc folds -fma(a,b,c) into one fnmsub, whose exact-cancellation zero is +0 where -(+0) is -0; that sign decides
+ *     who owns a shared edge. nvcc keeps the negation, so the B200 had it right and this file did not until the randomised
+ *     campaign (tests/fuzz/fuzz_gpu.py) met a ray through an edge of an integer-grid mesh.
  */
 #ifndef RACC_ORACLE_H
 #define RACC_ORACLE_H
