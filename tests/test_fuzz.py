@@ -1,7 +1,6 @@
-"""Short runs of the randomised campaigns (tests/fuzz/) inside the test suites, so that every `pytest` pass draws fresh
-adversarial scenes and rays as well as the fixed ones: a different seed per day, printed on failure. The long runs and what they
-found: profiles/r02_fuzz_*.txt, DESIGN.md section 3."""
-import datetime
+"""Short runs of the randomised campaigns (tests/fuzz/) inside the test suites: the first seconds of seeds whose long runs are on
+record (profiles/r02_fuzz_*.txt), so a suite run is reproducible; RACC_FUZZ_SEED=<n> draws other scenes. What the campaigns
+found: DESIGN.md section 3."""
 import os
 import sys
 
@@ -11,7 +10,7 @@ import oracle
 
 FUZZ = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz")
 sys.path.insert(0, FUZZ)
-SEED = str(int(datetime.date.today().strftime("%Y%m%d")))
+SEED = os.environ.get("RACC_FUZZ_SEED", "7")
 
 
 def _run(module, argv):
